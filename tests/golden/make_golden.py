@@ -1,0 +1,330 @@
+"""Generates tests/golden/*.npz from the reference itself. Run in the BUILD container only:
+
+    python tests/golden/make_golden.py
+
+It imports /root/reference/mot3d UNMODIFIED (imageio / matplotlib / the Boost wrapper are stubbed in
+sys.modules: they are not installed here; the wrapper stub calls the real vendored muSSP through
+oracle/_ref/libmussp_ref.so, fed the same text lines wrapper.solve would receive) and freezes, per vector:
+inputs (sorted detections as arrays, cost parameters), the reference graph (arcs in graph_to_text order with the
+float weights, their "{:0.7f}" quantisation, sha of the text) and the reference answer (K, path costs, total,
+per-arc flow, trajectories as indices into the sorted detections).
+The reference's own tests pin nothing; these files are the parity anchor.
+/root/reference does not exist on the GPU box, hence the committed fixtures.
+"""
+import json
+import os
+import re
+import sys
+import types
+import zipfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from oracle import oracle  # noqa: E402
+from oracle import build_ref  # noqa: E402
+
+
+def import_reference():
+    assert build_ref.build(), "oracle/_ref could not be built"
+    for name in ("imageio", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    wrapper = types.ModuleType("mot3d.solvers.wrappers.muSSP.wrapper")
+    wrapper.solve = oracle.wrapper_solve
+    sys.modules["mot3d.solvers.wrappers.muSSP.wrapper"] = wrapper
+    sys.path.insert(0, REF)
+    import mot3d  # the reference package
+    import mot3d.solvers.wrappers.muSSP as pkg
+    pkg.wrapper = wrapper
+    return mot3d
+
+
+def parse_text(lines):
+    n, m = [int(x) for x in lines[0].split()[2:4]]
+    tail, head, w, c = [], [], [], []
+    for l in lines[1:]:
+        if l[0] != "a":
+            continue
+        _, s, t, x = l.split()
+        tail.append(int(s))
+        head.append(int(t))
+        w.append(float(x))
+        neg = x.startswith("-")
+        whole, frac = x.lstrip("-").split(".")
+        v = int(whole) * 10 ** 7 + int(frac)
+        c.append(-v if neg else v)
+    return n, np.array(tail, np.int32), np.array(head, np.int32), np.array(w), np.array(c, np.int64)
+
+
+def solve_reference(lines):
+    n, tail, head, w, c = parse_text(lines)
+    res = oracle.mussp_solve_text(lines, len(tail))
+    return dict(n_nodes=n, tail=tail, head=head, w_text=w, cost=c, flow=res["flow"], K=res["K"],
+                path_cost=res["path_cost"], total=res["total"], sha=oracle.text_sha(lines))
+
+
+def freeze_detection_case(mot3d, name, detections, build_kwargs, spec, extra=None):
+    """Run reference build_graph + solve_graph on Detection objects; store everything."""
+    g = mot3d.build_graph(detections, verbose=False, **build_kwargs)
+    assert g is not None
+    lines = mot3d.graph_to_text(g)
+    sol = solve_reference(lines)
+    # exact float weights of the arcs (before text rounding), in g.edges() order
+    w_float = np.array([d["weight"] for _, _, d in g.edges(data=True)], dtype=np.float64)
+    trajectories = mot3d.solve_graph(g, verbose=False, method="muSSP")
+    # sorted order = node order in g
+    sorted_dets = [data["detection"] for _, data in g.nodes(data=True) if data.get("label") == "pre-node"]
+    index_of = {id(d): i for i, d in enumerate(sorted_dets)}
+    tracks = [[index_of[id(d)] for d in t] for t in trajectories]
+    frame = np.array([d.index for d in sorted_dets], dtype=np.int64)
+    pos = np.array([np.asarray(d.position, dtype=np.float64) for d in sorted_dets])
+    conf = np.array([d.confidence for d in sorted_dets], dtype=np.float64)
+    out = dict(sol)
+    out.update(frame=frame, pos=pos, conf=conf, w_float=w_float,
+               track_ptr=np.cumsum([0] + [len(t) for t in tracks]).astype(np.int64),
+               track_det=np.array([i for t in tracks for i in t], dtype=np.int64),
+               spec=json.dumps(spec))
+    if extra:
+        out.update(extra(sorted_dets))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-22s V=%d E=%d K=%d total=%.7f sha=%s (%d KB)" % (name, sol["n_nodes"], len(sol["tail"]), sol["K"],
+                                                              sol["total"], sol["sha"], os.path.getsize(path) // 1024))
+    return g, trajectories
+
+
+def freeze_graph_case(name, lines, extra=None):
+    sol = solve_reference(lines)
+    if extra:
+        sol.update(extra)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **sol)
+    print("%-22s V=%d E=%d K=%d total=%.7f sha=%s (%d KB)" % (name, sol["n_nodes"], len(sol["tail"]), sol["K"],
+                                                              sol["total"], sol["sha"], os.path.getsize(path) // 1024))
+
+
+def gen_synth(F, P, seed, extent=1000.0):
+    """SURVEY.md 8(d) generator gen(F,P,seed)."""
+    rng = np.random.RandomState(seed)
+    pos = rng.rand(P, 2) * extent
+    vel = rng.randn(P, 2) * 1.0
+    frames, positions = [], []
+    for f in range(F):
+        pos = pos + vel + rng.randn(P, 2) * 0.2
+        frames.append(np.full(P, f, dtype=np.int64))
+        positions.append(pos.copy())
+    return np.concatenate(frames), np.concatenate(positions)
+
+
+def main():
+    mot3d = import_reference()
+    import mot3d.weight_functions as wf
+    from mot3d.utils import utils as ref_utils
+    from mot3d.utils import trajectory as ref_traj
+
+    # ---- (0) the wrapper's own smoke graph (mot3d/solvers/wrappers/muSSP/test.py:3-71)
+    src = open(os.path.join(REF, "mot3d/solvers/wrappers/muSSP/test.py")).read()
+    lines = [l for l in re.findall(r'"([^"]+)"', src) if l[0] in "pac"]
+    freeze_graph_case("wrapper_test_graph", lines)
+
+    # ---- (1) C1 simple_2d (examples/simple_2d/example.py:17-58), jitter seeded
+    ex = os.path.join(REF, "examples/simple_2d")
+    ps1 = np.array(ref_utils.json_read(os.path.join(ex, "track_line1.json")))
+    ps2 = np.array(ref_utils.json_read(os.path.join(ex, "track_line2.json")))
+    ps2 = ps2 - np.array([[4, 0]])
+    rng = np.random.RandomState(0)
+    ps1[4] = ps1[4] + rng.randn(2)
+    ps2[4] = ps2[4] + rng.randn(2)
+    dummy_hist = [np.ones((128,))] * 3
+    dummy_bbox = [0, 0, 1, 1]
+    dets = []
+    for index, pair in enumerate(zip(ps1, ps2)):
+        for position in pair:
+            dets.append(mot3d.Detection2D(index, position, color_histogram=dummy_hist, bbox=dummy_bbox))
+    spec = dict(kind="2d", sigma_jump=1, sigma_distance=10, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                max_distance=15, use_color_histogram=True, use_bbox=True, mul=1, bias=0,
+                weight_source_sink=0.1, max_jump=4)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, sigma_jump=1, sigma_distance=10,
+                                                         sigma_color_histogram=0.3, sigma_box_size=0.3,
+                                                         max_distance=15, use_color_histogram=True, use_bbox=True)
+    wc = lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0)
+
+    def extra_2d(sorted_dets):
+        return dict(bbox=np.array([d.bbox for d in sorted_dets], dtype=np.float64),
+                    hist=np.array([np.asarray(d.color_histogram, dtype=np.float64) for d in sorted_dets]))
+
+    g, trajectories = freeze_detection_case(mot3d, "c1_simple_2d", dets,
+                                            dict(weight_source_sink=0.1, max_jump=4, weight_confidence=wc,
+                                                 weight_distance=wd), spec, extra_2d)
+
+    # ---- (2) C2 simple_2d_tracklets pass 2 (examples/simple_2d_tracklets/example.py:78-108)
+    tracklets = []
+    for traj in trajectories:
+        tracklets += mot3d.split_trajectory_modulo(traj, length=5)
+    tracklets = mot3d.remove_short_trajectories(tracklets, th_length=2)
+    dts = [mot3d.DetectionTracklet2D(t) for t in tracklets]
+    wdt = lambda t1, t2: wf.weight_distance_tracklets_2d(t1, t2, max_distance=None, sigma_color_histogram=0.3,
+                                                         sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
+                                                         cutoff_appearance=0.1, use_color_histogram=True)
+    wct = lambda t: wf.weight_confidence_tracklets_2d(t, mul=1, bias=0)
+    g2 = mot3d.build_graph(dts, weight_source_sink=0.1, max_jump=20, verbose=False, weight_confidence=wct,
+                           weight_distance=wdt)
+    freeze_graph_case("c2_tracklets_pass2", mot3d.graph_to_text(g2))
+
+    # ---- (3) C3 soldiers_3d (examples/soldiers_3d/example.py:25-101)
+    ex = os.path.join(REF, "examples/soldiers_3d")
+    det3d = ref_utils.json_read(os.path.join(ex, "detections_3d_head.json"))
+    from mot3d.utils import filt as ref_filt
+    dets = []
+    for index, index_frame in enumerate(range(49650, 50000)):
+        positions = ref_filt.merge_close_points(det3d[str(index_frame)], eps=0.25)
+        for position in positions:
+            dets.append(mot3d.Detection3D(index, position))
+    spec = dict(kind="3d", sigma_jump=2, sigma_distance=0.15, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                max_distance=0.4, use_color_histogram=False, use_bbox=False, mul=1, bias=0,
+                weight_source_sink=50, max_jump=8)
+    wd = lambda d1, d2: wf.weight_distance_detections_3d(d1, d2, sigma_jump=2, sigma_distance=0.15,
+                                                         sigma_color_histogram=0.3, sigma_box_size=0.3,
+                                                         max_distance=0.4, use_color_histogram=False,
+                                                         use_bbox=False)
+    wc = lambda d: wf.weight_confidence_detections_3d(d, mul=1, bias=0)
+    g, trajectories = freeze_detection_case(mot3d, "c3_soldiers_pass1", dets,
+                                            dict(weight_source_sink=50, max_jump=8, weight_confidence=wc,
+                                                 weight_distance=wd), spec)
+    tracklets = []
+    for traj in trajectories:
+        tracklets += mot3d.split_trajectory_modulo(traj, length=10)
+    tracklets = mot3d.remove_short_trajectories(tracklets, th_length=2)
+    dts = [mot3d.DetectionTracklet3D(t) for t in tracklets]
+    wdt = lambda t1, t2: wf.weight_distance_tracklets_3d(t1, t2, sigma_color_histogram=0.3, sigma_motion=3,
+                                                         alpha=0.7, cutoff_motion=0.1, cutoff_appearance=0.1,
+                                                         max_distance=None, use_color_histogram=False)
+    wct = lambda t: wf.weight_confidence_tracklets_3d(t, mul=1, bias=0)
+    g2 = mot3d.build_graph(dts, weight_source_sink=0.1, max_jump=30, verbose=False, weight_confidence=wct,
+                           weight_distance=wdt)
+    freeze_graph_case("c3_soldiers_pass2", mot3d.graph_to_text(g2))
+
+    # ---- (4) C4-real: PETS View_001 detections JSON, two 50-frame windows, bbox term on, no histograms
+    #      (feeder logic of projects/PETS2009S2L1/feeders.py:51-124; parameters of
+    #       config/config_singleview_PETS2009S2L1_View_001.yaml:24-38 with use_color_histogram=False)
+    pets = ref_utils.json_read(os.path.join(REF, "projects/PETS2009S2L1/detections",
+                                            "keypointsrcnn_resnet50_fpn_View_001_finetuned_2.json"))
+    spec = dict(kind="2d", sigma_jump=4, sigma_distance=10, sigma_color_histogram=0.1, sigma_box_size=0.1,
+                max_distance=30, use_color_histogram=False, use_bbox=True, mul=0, bias=0,
+                weight_source_sink=1, max_jump=4)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, sigma_distance=10, sigma_jump=4,
+                                                         sigma_color_histogram=0.1, sigma_box_size=0.1,
+                                                         max_distance=30, use_color_histogram=False, use_bbox=True)
+    wc = lambda d: wf.weight_confidence_detections_2d(d, mul=0, bias=0)
+
+    def extra_bbox(sorted_dets):
+        return dict(bbox=np.array([d.bbox for d in sorted_dets], dtype=np.float64))
+
+    def pets_window(f0, f1):
+        dets = []
+        for idx in range(f0, f1):
+            boxes = [[max(int(x), 0) for x in box] for box in pets["bboxes"][idx]]
+            kpss = [[p[:2] for p in kps] for kps in pets["keypoints"][idx]]
+            for box, kps, score, label in zip(boxes, kpss, pets["scores"][idx], pets["labels"][idx]):
+                if label == 1 and score > 0.75:
+                    position = np.mean(np.reshape(kps, (-1, 2)), axis=0)[:2]
+                    dets.append(mot3d.Detection2D(idx, position, confidence=score, bbox=tuple(box)))
+        return dets
+
+    for k, (f0, f1) in enumerate([(0, 50), (50, 100)]):
+        freeze_detection_case(mot3d, "c4_pets_view1_w%d" % k, pets_window(f0, f1),
+                              dict(weight_source_sink=1, max_jump=4, weight_confidence=wc, weight_distance=wd),
+                              spec, extra_bbox)
+
+    # ---- (4b) synthetic appearance case: random mean-subtracted histograms (3 x 32 bins) + bboxes, both terms on
+    rng = np.random.RandomState(7)
+    dets = []
+    P, F = 6, 20
+    base = rng.rand(P, 2) * 200
+    vel = rng.randn(P, 2) * 2
+    proto = rng.rand(P, 3, 32)
+    for f in range(F):
+        base = base + vel + rng.randn(P, 2) * 0.5
+        for p in range(P):
+            if rng.rand() < 0.1:
+                continue
+            h = proto[p] + 0.15 * rng.rand(3, 32)
+            h = h - h.mean(axis=1, keepdims=True)
+            w, hh = 30 + rng.randn() * 3, 80 + rng.randn() * 8
+            x, y = base[p]
+            dets.append(mot3d.Detection2D(f, base[p].copy(), confidence=0.75 + 0.25 * rng.rand(),
+                                          color_histogram=[h[0], h[1], h[2]],
+                                          bbox=(x - w / 2, y - hh / 2, x + w / 2, y + hh / 2)))
+    spec = dict(kind="2d", sigma_jump=1, sigma_distance=10, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                max_distance=30, use_color_histogram=True, use_bbox=True, mul=1, bias=0.05,
+                weight_source_sink=0.8, max_jump=3)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, sigma_jump=1, sigma_distance=10,
+                                                         sigma_color_histogram=0.3, sigma_box_size=0.3,
+                                                         max_distance=30, use_color_histogram=True, use_bbox=True)
+    wc = lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0.05)
+    freeze_detection_case(mot3d, "c4_synth_appearance", dets,
+                          dict(weight_source_sink=0.8, max_jump=3, weight_confidence=wc, weight_distance=wd),
+                          spec, extra_2d)
+
+    # ---- (5) C5 window: gen(F=50, P=100, seed 0) = one 50-frame window of the batched config
+    spec = dict(kind="2d", sigma_jump=1, sigma_distance=10, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                max_distance=30, use_color_histogram=False, use_bbox=False, mul=1, bias=0,
+                weight_source_sink=1, max_jump=8)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, sigma_jump=1, sigma_distance=10,
+                                                         max_distance=30, use_color_histogram=False, use_bbox=False)
+    wc = lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0)
+    for nm, F, P in (("c5_window_f50_p100", 50, 100), ("c5_small_f30_p12", 30, 12)):
+        frame, pos = gen_synth(F, P, 0, extent=1000.0 if P == 100 else 120.0)
+        dets = [mot3d.Detection2D(int(f), p, confidence=0.9) for f, p in zip(frame, pos)]
+        freeze_detection_case(mot3d, nm, dets,
+                              dict(weight_source_sink=1, max_jump=8, weight_confidence=wc, weight_distance=wd),
+                              spec)
+
+    # ---- (6) quirk: lone detection whose only path costs +0.5 is still returned (wrapper.cpp:205,220)
+    dets = [mot3d.Detection2D(0, np.array([1.0, 2.0]), confidence=0.5)]
+    spec = dict(kind="2d", sigma_jump=1, sigma_distance=2, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                max_distance=20, use_color_histogram=False, use_bbox=False, mul=1, bias=0,
+                weight_source_sink=1.0, max_jump=4)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, use_color_histogram=False, use_bbox=False)
+    freeze_detection_case(mot3d, "quirk_single_detection", dets,
+                          dict(weight_source_sink=1.0, max_jump=4, weight_confidence=wc, weight_distance=wd), spec)
+
+    # ---- (7) muSSP's own sample graph (zip!/muSSP-master/input_MOT_seq07_followme.txt): solver-only vector
+    with zipfile.ZipFile(os.path.join(REF, "mussp-master-6cf61b8.zip")) as z:
+        txt = z.read("muSSP-master/input_MOT_seq07_followme.txt").decode()
+    lines = [l for l in txt.split("\n") if l and l[0] in "pa"]
+    n, tail, head, w, c = parse_text(lines)
+    res = oracle.mussp_solve(n, tail, head, w)
+    # the file carries 6 decimals at most? keep exact ints at 1e-7 via decimal parsing of the text
+    out = dict(n_nodes=n, tail=tail, head=head, cost=c, K=res["K"], total=res["total"], path_cost=res["path_cost"],
+               flow=res["flow"].astype(np.int8))
+    path = os.path.join(HERE, "mussp_seq07.npz")
+    np.savez_compressed(path, **out)
+    print("%-22s V=%d E=%d K=%d total=%.7f (%d KB)" % ("mussp_seq07", n, len(tail), res["K"], res["total"],
+                                                       os.path.getsize(path) // 1024))
+
+    # ---- (8) C5 whole (F=1000, P=100): arcs from the numpy oracle (validated above on the window), real muSSP
+    frame, pos = gen_synth(1000, 100, 0)
+    ospec = oracle.CostSpec(sigma_jump=1, sigma_distance=10, max_distance=30, mul=1, bias=0, weight_source_sink=1,
+                            max_jump=8)
+    row_ptr, col, w = oracle.build_transitions(frame, pos, ospec)
+    nw = oracle.node_weights(np.full(frame.shape[0], 0.9), ospec)
+    tail, head, ww = oracle.graph_arcs(frame.shape[0], 1.0, nw, 0.0, row_ptr, col, w)
+    c = oracle.quantise(ww)
+    res = oracle.mussp_solve(2 * frame.shape[0] + 2, tail, head, c.astype(np.float64) * 1e-7)
+    out = dict(n_nodes=2 * frame.shape[0] + 2, n_arcs=len(tail), n_transitions=len(col), K=res["K"],
+               total=res["total"], path_cost=res["path_cost"], cost_sum_check=int(c.sum()),
+               total_units=oracle.flow_cost(c, res["flow"]))
+    path = os.path.join(HERE, "c5_whole_summary.npz")
+    np.savez_compressed(path, **out)
+    print("%-22s V=%d E=%d K=%d total=%.7f (%d KB)" % ("c5_whole_summary", out["n_nodes"], out["n_arcs"], res["K"],
+                                                       res["total"], os.path.getsize(path) // 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""CPU tests: pin the oracle (oracle/ssp_oracle.c + oracle/oracle.py) to the reference's own outputs
+(tests/golden, produced by the unmodified reference Python + vendored muSSP) and, when oracle/_ref was built
+from the vendored sources, to the real muSSP run live."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+import golden_util as gu
+
+
+@pytest.mark.parametrize("name", gu.GRAPH_CASES)
+def test_ssp_restatement_matches_mussp(name):
+    d = gu.load(name)
+    r = oracle.ssp_solve(int(d["n_nodes"]), d["tail"], d["head"], d["cost"])
+    assert r["K"] == int(d["K"])
+    assert oracle.flow_cost(d["cost"], r["flow"]) == r["total"] == int(r["path_cost"].sum())
+    if name in gu.MUSSP_BOGUS_COST:
+        assert r["total"] == 5000000
+    else:
+        gap = gu.MUSSP_SUBOPTIMAL.get(name, 0)
+        assert gu.ref_total_units(d) - r["total"] == gap  # exact optimum <= muSSP, equal where tolerances are silent
+        if gap == 0:
+            assert (r["path_cost"] == gu.ref_path_units(d)).all()
+            assert (r["flow"] == d["flow"]).all()
+    # successive path costs never decrease (convexity) and all but the first are negative
+    assert (np.diff(r["path_cost"]) >= 0).all()
+    assert (r["path_cost"][1:] < 0).all()
+
+
+@pytest.mark.parametrize("name", ["c1_simple_2d", "c4_pets_view1_w0", "c4_pets_view1_w1", "c4_synth_appearance",
+                                  "c5_small_f30_p12", "wrapper_test_graph", "c2_tracklets_pass2"])
+def test_exact_optimum_network_simplex(name):
+    """Independent second oracle: min-cost circulation with a free T->S arc."""
+    import networkx as nx
+    d = gu.load(name)
+    n = int(d["n_nodes"])
+    g = nx.DiGraph()
+    for t, h, c in zip(d["tail"].tolist(), d["head"].tolist(), d["cost"].tolist()):
+        g.add_edge(t, h, weight=c, capacity=1)
+    g.add_edge(n, 1, weight=0, capacity=10 ** 9)
+    cost, flow = nx.network_simplex(g)
+    r = oracle.ssp_solve(n, d["tail"], d["head"], d["cost"])
+    assert cost == r["total"]
+    assert flow[n][1] == r["K"]
+
+
+@pytest.mark.parametrize("name", gu.DETECTION_CASES)
+def test_build_restatement_matches_reference(name):
+    d = gu.load(name)
+    s = d["spec"]
+    spec = oracle.CostSpec(**{k: v for k, v in s.items() if k != "kind"})
+    row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], spec, bbox=d.get("bbox"), hist=d.get("hist"))
+    n = len(d["frame"])
+    tail, head, ww = oracle.graph_arcs(n, float(spec.weight_source_sink), oracle.node_weights(d["conf"], spec), 0.0,
+                                       row_ptr, col, w)
+    assert (tail == d["tail"]).all() and (head == d["head"]).all()  # same arcs, same order
+    np.testing.assert_allclose(ww, d["w_float"], rtol=1e-12, atol=0)
+    gu.assert_costs_match(oracle.quantise(ww), d["cost"], d["w_float"])
+    assert (oracle.quantise(d["w_float"]) == d["cost"]).all()
+    if name != "c5_window_f50_p100":  # text of 64k arcs: slow, sha checked on the others
+        assert oracle.text_sha(oracle.arcs_to_text(2 * n + 2, tail, head, d["w_float"])) == str(d["sha"])
+
+
+@pytest.mark.parametrize("name", gu.DETECTION_CASES)
+def test_tracks_from_flow_matches_reference(name):
+    d = gu.load(name)
+    tr = oracle.tracks_from_flow(len(d["frame"]), d["tail"], d["head"], d["flow"])
+    assert np.cumsum([0] + [len(t) for t in tr]).tolist() == d["track_ptr"].tolist()
+    assert [i for t in tr for i in t] == d["track_det"].tolist()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["wrapper_test_graph", "c1_simple_2d", "c3_soldiers_pass1", "c4_pets_view1_w1",
+                                  "mussp_seq07"])
+def test_live_mussp_reproduces_golden(name):
+    d = gu.load(name)
+    r = oracle.mussp_solve(int(d["n_nodes"]), d["tail"], d["head"], d["cost"].astype(np.float64) * 1e-7)
+    assert r["K"] == int(d["K"])
+    assert round(r["total"] * 1e7) == gu.ref_total_units(d)
+    assert (r["flow"] == d["flow"]).all()
+
+
+def test_c5_whole_summary():
+    d = gu.load("c5_whole_summary")
+    assert int(d["K"]) == 100 and int(d["n_arcs"]) == 1187969 and int(d["n_nodes"]) == 200002
+    assert int(d["total_units"]) == gu.ref_total_units(d) == -1878765227978
