@@ -1,0 +1,177 @@
+/* mot3d_b200 -- C ABI of the B200-native mot3d tracking hot path (graph build + min-cost-flow solve + tracks).
+ *
+ * This is the drop-in boundary: it replaces the reference's only native interface,
+ *     wrapper.solve(graph_as_text: list[str], verbose: int) -> list[(tail, head)]
+ *     (/root/reference/mot3d/solvers/wrappers/muSSP/wrapper.cpp:171, 319-324; called from mot3d/mot3d.py:160-161),
+ * and moves the Python work either side of it (build_graph's loops, mot3d/mot3d.py:75-141; graph_to_text, :218-226;
+ * path enumeration, :165-184) behind the same boundary.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns MOT3D_OK (0) or a negative MOT3D_E_* code; mot3d_last_error() gives a thread-local
+ *     message.  Nothing is printed, nothing throws across the ABI.
+ *   - unless a name ends in _host, every pointer is a DEVICE pointer owned by the caller (e.g. tensor.data_ptr());
+ *     the library allocates no user-visible memory.  `stream` is a cudaStream_t passed as void*; calls are
+ *     asynchronous with respect to the host.
+ *   - a batch is a concatenation of independent graphs (windows / views / sequences): graph g owns detections
+ *     [graph_ptr[g], graph_ptr[g+1]).  Inside a graph detections are in the reference's node order: stable sort
+ *     by frame index (mot3d/mot3d.py:61-64); detection m of a graph is pre-node 2+2m / post-node 3+2m there.
+ *   - costs are int64 in units of 1e-7, the precision the reference hands to muSSP ("{:0.7f}", mot3d/mot3d.py:224).
+ *   - no global mutable state: safe from several host threads on different streams/devices.
+ */
+#ifndef MOT3D_B200_H
+#define MOT3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOT3D_OK 0
+#define MOT3D_E_INVALID (-1)     /* bad argument */
+#define MOT3D_E_CUDA (-2)        /* a CUDA call failed (message has the CUDA error string) */
+#define MOT3D_E_CAPACITY (-3)    /* caller-provided buffer too small */
+#define MOT3D_E_UNSUPPORTED (-4) /* valid in the reference, not built here (message says what) */
+
+#define MOT3D_MAX_JUMP 256
+#define MOT3D_INF_COST ((int64_t)1 << 60) /* "no arc" for entry/exit costs */
+
+#define MOT3D_DIR_IN 0  /* CSR rows = arc heads (pre_j), columns = tails (post_i), ascending: what the solver pulls from */
+#define MOT3D_DIR_OUT 1 /* CSR rows = arc tails (post_i), columns = heads (pre_j), ascending: graph_to_text order */
+
+#define MOT3D_FLAG_ENTRY 1 /* Detection.entry_points (mot3d/types.py:24, mot3d/mot3d.py:90-91) */
+#define MOT3D_FLAG_EXIT 2  /* Detection.exit_point   (mot3d/types.py:25, mot3d/mot3d.py:98-99) */
+
+/* Packed detections, structure of arrays (replaces the Detection2D/Detection3D objects of mot3d/types.py:11-45). */
+typedef struct mot3d_dets {
+    int64_t n;            /* detections in the whole batch */
+    int32_t dim;          /* 2 (Detection2D) or 3 (Detection3D) */
+    int32_t hist_channels; /* C, 0 when hist == NULL */
+    int32_t hist_bins;    /* B */
+    int32_t reserved;
+    const int32_t *tkey;  /* [n] time keys made by mot3d_make_keys: frame index shifted per graph so that the batch is
+                             one non-decreasing sequence and keys of different graphs differ by more than max_jump */
+    const double *pos;    /* [dim][n] planar positions */
+    const double *conf;   /* [n] Detection.confidence */
+    const uint8_t *flags; /* [n] MOT3D_FLAG_*; NULL = entry and exit allowed everywhere (the reference default) */
+    const double *bbox;   /* [4][n] planar xmin,ymin,xmax,ymax; NULL unless use_bbox */
+    const double *hist;   /* [n][C][B] colour histograms (mean-subtracted, mot3d/distance_functions.py:10-19); NULL unless use_hist */
+} mot3d_dets;
+
+/* Parameters of the built-in costs (mot3d/weight_functions.py:13-17,37-38,43-47) and of build_graph
+ * (mot3d/mot3d.py:20-23), pre-digested by the host so that the device reproduces the reference's float64 values:
+ *   sq_dist_max      largest s with sqrt(s) <= max_distance in IEEE double (the reference tests dist > max_distance)
+ *   sigma_*_sq       sigma**2 as the reference evaluates it
+ *   neg_exp_jump[k]  -exp(-(k)*sigma_jump) for k = jump-1 = 0..max_jump-1, evaluated by the host's numpy exp */
+typedef struct mot3d_cost_spec {
+    int32_t max_jump;
+    int32_t use_bbox;
+    int32_t use_hist;
+    int32_t reserved;
+    double sq_dist_max;
+    double sigma_distance_sq;
+    double sigma_hist_sq;
+    double sigma_bbox_sq;
+    double conf_mul;
+    double conf_bias;
+    int64_t entry_cost; /* quantised weight_source_sink */
+    int64_t exit_cost;  /* 0 in the reference (mot3d/mot3d.py:99) */
+    double neg_exp_jump[MOT3D_MAX_JUMP];
+} mot3d_cost_spec;
+
+const char *mot3d_version(void);
+const char *mot3d_last_error(void);
+
+/* ---- graph build: replaces build_graph's loops (mot3d/mot3d.py:75-141) + graph_to_text (:218-226) ------------ */
+
+/* tkey[i] = frame[i] - frame[first of graph] + base(graph), base = running sum of (frame span + max_jump + 1).
+ * graph_base_ws: scratch of n_graphs int64. */
+int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, int32_t max_jump,
+                        int32_t *tkey_out, int64_t *graph_base_ws, void *stream);
+
+/* per-detection arc costs: entry (S->pre), node (pre->post, weight_confidence_detections, weight_functions.py:37-38),
+ * exit (post->T).  MOT3D_INF_COST where flags forbid the arc. */
+int32_t mot3d_node_costs(const mot3d_dets *dets, const mot3d_cost_spec *spec, int64_t *entry_cost_out,
+                         int64_t *node_cost_out, int64_t *exit_cost_out, void *stream);
+
+/* pass 1 of the windowed all-pairs kernel: row_count[r] = number of transition arcs of row r
+ * (pairs with 0 < frame[j]-frame[i] <= max_jump and dist <= max_distance; mot3d/mot3d.py:122-127). */
+int32_t mot3d_edge_count(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction, int32_t *row_count_out,
+                         void *stream);
+
+size_t mot3d_scan_workspace_bytes(int64_t n);
+/* out[0] = 0, out[i+1] = in[0] + ... + in[i]  (n+1 outputs). */
+int32_t mot3d_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, void *ws, size_t ws_bytes, void *stream);
+
+/* pass 2: columns (ascending), float64 weights (NULL to skip) and quantised costs of every arc.
+ * When spec->use_hist is set, `weight_out` is required and receives the distance factor only; finish with
+ * mot3d_edge_appearance.  Arcs beyond edge_capacity are not written and *overflow_flag (device int32) is set to 1. */
+int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction, const int32_t *row_ptr,
+                        int64_t edge_capacity, int32_t *col_out, int64_t *cost_out, double *weight_out,
+                        int32_t *overflow_flag, void *stream);
+
+/* colour-histogram factor (color_histogram_similarity, mot3d/distance_functions.py:21-34) multiplied in, then the
+ * bbox and jump factors, then quantisation. One warp per row. */
+int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction,
+                              const int32_t *row_ptr, const int32_t *col, double *weight_inout, int64_t *cost_out,
+                              void *stream);
+
+/* ---- solve: replaces wrapper.solve (wrapper.cpp:171-317) and the muSSP core it drives ------------------------ */
+
+size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs);
+
+/* Successive shortest paths per graph on the residual network, one thread block per graph.
+ *   in_ptr/in_src/in_cost : MOT3D_DIR_IN CSR of the transition arcs over the whole batch (in_src = global indices)
+ *   next_out[i]  : successor of detection i on its track (global index), -2 if the track ends at i, -1 if i is unused
+ *   prev_out[i]  : predecessor, -2 if a track starts at i, -1 if unused
+ *   n_paths_out[g], total_cost_out[g] : K and the sum of accepted path costs
+ *   path_cost_out : optional [n_total]; graph g's k-th path cost at graph_ptr[g]+k
+ * Acceptance rule of wrapper.cpp:199-267 on integers: path 1 always, then while cost < 0. */
+int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
+                          const int32_t *tkey,
+                          const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
+                          const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
+                          int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
+                          int64_t *path_cost_out, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- trajectories: replaces _run_ssp's tail (mot3d/mot3d.py:165-184) ---------------------------------------- */
+
+/* Tracks of graph g, ordered by their first detection (= the reference's DFS order over SOURCE's successors):
+ *   track_count_out[g] = K
+ *   track_ptr_out[graph_ptr[g] + g + k] (k = 0..K) = start of track k inside the graph's slice of track_det_out
+ *   track_det_out[graph_ptr[g] + ...]   = detection indices LOCAL to the graph (0-based position in sorted order) */
+int32_t mot3d_extract_tracks(int32_t n_graphs, const int32_t *graph_ptr, const int32_t *next, const int32_t *prev,
+                             int32_t *track_count_out, int32_t *track_ptr_out, int32_t *track_det_out, void *stream);
+
+/* ---- one call with HOST buffers: pack -> H2D -> build -> solve -> tracks -> D2H ------------------------------ */
+
+typedef struct mot3d_host_batch {
+    int32_t n_graphs;
+    int32_t dim;
+    int64_t n;                 /* total detections */
+    const int32_t *graph_ptr;  /* host [n_graphs+1] */
+    const int32_t *frame;      /* host [n], sorted inside each graph */
+    const double *pos;         /* host [dim][n] */
+    const double *conf;        /* host [n] */
+    const uint8_t *flags;      /* host [n] or NULL */
+    const double *bbox;        /* host [4][n] or NULL */
+} mot3d_host_batch;
+
+typedef struct mot3d_host_result {
+    int32_t *track_count; /* host [n_graphs] */
+    int32_t *track_ptr;   /* host [n + n_graphs] */
+    int32_t *track_det;   /* host [n] */
+    int64_t *total_cost;  /* host [n_graphs] */
+    int64_t n_edges;      /* out: transition arcs built */
+} mot3d_host_result;
+
+size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity);
+/* Synchronous on `stream` (returns after the results are in host memory). Host buffers should be pinned. */
+int32_t mot3d_track_batch_host(const mot3d_host_batch *batch, const mot3d_cost_spec *spec, mot3d_host_result *result,
+                               void *device_ws, size_t ws_bytes, int64_t edge_capacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOT3D_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of libmot3d_b200.so (include/mot3d_b200.h). No fallback: if the CUDA library is missing or a call
+fails, this raises. PyTorch only supplies device memory and the stream."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmot3d_b200.so")
+
+MAX_JUMP = 256
+INF_COST = 1 << 60
+DIR_IN, DIR_OUT = 0, 1
+FLAG_ENTRY, FLAG_EXIT = 1, 2
+
+E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4
+
+
+class Mot3dError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "mot3d_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Dets(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("dim", ctypes.c_int32), ("hist_channels", ctypes.c_int32),
+                ("hist_bins", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tkey", ctypes.c_void_p),
+                ("pos", ctypes.c_void_p), ("conf", ctypes.c_void_p), ("flags", ctypes.c_void_p),
+                ("bbox", ctypes.c_void_p), ("hist", ctypes.c_void_p)]
+
+
+class CostSpecC(ctypes.Structure):
+    _fields_ = [("max_jump", ctypes.c_int32), ("use_bbox", ctypes.c_int32), ("use_hist", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("sq_dist_max", ctypes.c_double),
+                ("sigma_distance_sq", ctypes.c_double), ("sigma_hist_sq", ctypes.c_double),
+                ("sigma_bbox_sq", ctypes.c_double), ("conf_mul", ctypes.c_double), ("conf_bias", ctypes.c_double),
+                ("entry_cost", ctypes.c_int64), ("exit_cost", ctypes.c_int64),
+                ("neg_exp_jump", ctypes.c_double * MAX_JUMP)]
+
+
+class HostBatch(ctypes.Structure):
+    _fields_ = [("n_graphs", ctypes.c_int32), ("dim", ctypes.c_int32), ("n", ctypes.c_int64),
+                ("graph_ptr", ctypes.c_void_p), ("frame", ctypes.c_void_p), ("pos", ctypes.c_void_p),
+                ("conf", ctypes.c_void_p), ("flags", ctypes.c_void_p), ("bbox", ctypes.c_void_p)]
+
+
+class HostResult(ctypes.Structure):
+    _fields_ = [("track_count", ctypes.c_void_p), ("track_ptr", ctypes.c_void_p), ("track_det", ctypes.c_void_p),
+                ("total_cost", ctypes.c_void_p), ("n_edges", ctypes.c_int64)]
+
+
+_vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+_PD, _PS = ctypes.POINTER(Dets), ctypes.POINTER(CostSpecC)
+
+# name -> (restype, argtypes); every symbol declared in include/mot3d_b200.h
+SIGNATURES = {
+    "mot3d_version": (ctypes.c_char_p, []),
+    "mot3d_last_error": (ctypes.c_char_p, []),
+    "mot3d_make_keys": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "mot3d_node_costs": (_i32, [_PD, _PS, _vp, _vp, _vp, _vp]),
+    "mot3d_edge_count": (_i32, [_PD, _PS, _i32, _vp, _vp]),
+    "mot3d_scan_workspace_bytes": (_sz, [_i64]),
+    "mot3d_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "mot3d_edge_fill": (_i32, [_PD, _PS, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32]),
+    "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _sz, _vp]),
+    "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "mot3d_track_batch_host": (_i32, [ctypes.POINTER(HostBatch), _PS, ctypes.POINTER(HostResult), _vp, _sz, _i64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it was not built (python __graft_entry__.py build / build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("mot3d_b200: CUDA library %s is missing; build it with `python -c 'import "
+                              "__graft_entry__ as g; g.build()'`. There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise Mot3dError(code, lib().mot3d_last_error().decode())
+
+
+def version():
+    return lib().mot3d_version().decode()

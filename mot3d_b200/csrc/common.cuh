@@ -1,0 +1,145 @@
+// Shared device/host helpers for the mot3d_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mot3d_b200.h"
+
+namespace m3 {
+
+// ---------------------------------------------------------------------------------------- error plumbing
+void set_error(const char *fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char *what);
+
+#define M3_CHECK_ARG(cond, msg)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            m3::set_error("%s", msg);          \
+            return MOT3D_E_INVALID;            \
+        }                                      \
+    } while (0)
+
+#define M3_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return m3::cuda_fail(e__, #call); \
+    } while (0)
+
+#define M3_LAUNCH_CHECK(name)                                     \
+    do {                                                          \
+        cudaError_t e__ = cudaGetLastError();                     \
+        if (e__ != cudaSuccess) return m3::cuda_fail(e__, name);  \
+    } while (0)
+
+constexpr int64_t INF = MOT3D_INF_COST;
+constexpr int64_t INF_CUT = MOT3D_INF_COST / 2;  // anything >= this is "unreachable"
+
+// ---------------------------------------------------------------------------------------- warp / block primitives
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane_id() >= d) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one int per thread over the whole block; returns the exclusive prefix, *total gets the block sum.
+// `scratch` = 33 ints of shared memory. Ends with a barrier, so it may be called back to back.
+__device__ __forceinline__ int block_excl_scan(int v, int *scratch, int *total) {
+    int incl = warp_incl_scan(v);
+    int w = warp_id(), l = lane_id();
+    int nw = (blockDim.x + 31) >> 5;
+    if (l == 31) scratch[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = (l < nw) ? scratch[l] : 0;
+        int si = warp_incl_scan(s);
+        scratch[l] = si - s;
+        if (l == 31) scratch[32] = si;
+    }
+    __syncthreads();
+    int base = scratch[w];
+    *total = scratch[32];
+    __syncthreads();
+    return base + incl - v;
+}
+
+struct KeyIdx {
+    int64_t key;
+    int idx;
+};
+__device__ __forceinline__ KeyIdx min_ki(KeyIdx a, KeyIdx b) {
+    // ties -> smaller index, so results do not depend on the reduction shape
+    return (b.key < a.key || (b.key == a.key && b.idx < a.idx)) ? b : a;
+}
+__device__ __forceinline__ KeyIdx shfl_down_ki(KeyIdx a, int d, unsigned mask = 0xffffffffu) {
+    KeyIdx r;
+    r.key = __shfl_down_sync(mask, a.key, d);
+    r.idx = __shfl_down_sync(mask, a.idx, d);
+    return r;
+}
+__device__ __forceinline__ KeyIdx shfl_xor_ki(KeyIdx a, int d, unsigned mask = 0xffffffffu) {
+    KeyIdx r;
+    r.key = __shfl_xor_sync(mask, a.key, d);
+    r.idx = __shfl_xor_sync(mask, a.idx, d);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------- TMA bulk copy (1-D) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy through the TMA unit (SASS: UBLKCP). dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------- exact quantisation
+// Nearest integer to w * 1e7 evaluated exactly (ties to even) = what "{:0.7f}".format(w) prints
+// (mot3d/mot3d.py:224), without the double rounding of llrint(w * 1e7).
+__device__ __forceinline__ int64_t quantise_1e7(double w) {
+    const double S = 1e7;
+    double p = __dmul_rn(w, S);
+    double n = rint(p);
+    double r = fma(w, S, -n);  // exact w*S - n up to one rounding of a tiny value
+    if (r > 0.5)
+        n += 1.0;
+    else if (r < -0.5)
+        n -= 1.0;
+    else if (r == 0.5) {
+        if (fmod(n, 2.0) != 0.0) n += 1.0;
+    } else if (r == -0.5) {
+        if (fmod(n, 2.0) != 0.0) n -= 1.0;
+    }
+    return (int64_t)n;
+}
+
+}  // namespace m3

@@ -1,0 +1,317 @@
+"""The reference's public API (reference mot3d/mot3d.py:18: build_graph, solve_graph, graph_to_text, save_graph),
+backed by the CUDA kernels. Same names, arguments, defaults, return conventions and error behaviour:
+
+    g = build_graph(detections, weight_source_sink=1, max_jump=12, verbose=True,
+                    weight_confidence=..., weight_distance=...)        -> graph handle or None
+    trajectories = solve_graph(g, verbose=True, method='muSSP')         -> list[list[Detection]]
+
+The graph handle owns device tensors; it materialises a networkx.DiGraph identical to the reference's only when a
+caller asks for nodes/edges (plot_graph, graph_to_text).
+"""
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from . import spec as _spec
+from .types import Detection, Detection2D, Detection3D, DetectionTracklet
+from .weight_functions import weight_distance_detections_2d, weight_confidence_detections_2d
+
+__all__ = ["build_graph", "solve_graph", "graph_to_text", "save_graph"]
+
+
+class _ProbeMixin(object):
+    _m3_probe = True
+
+
+class _Probe2D(_ProbeMixin, Detection2D):
+    pass
+
+
+class _Probe3D(_ProbeMixin, Detection3D):
+    pass
+
+
+def _recover_spec(detections, weight_source_sink, max_jump, weight_confidence, weight_distance):
+    """Find out which built-in costs (and kwargs) the user's callables stand for; see spec.probe_callable."""
+    first = detections[0]
+    if isinstance(first, Detection3D):
+        p1, p2 = _Probe3D(0, (0.0, 0.0, 0.0)), _Probe3D(1, (0.0, 0.0, 0.0))
+    else:
+        p1, p2 = _Probe2D(0, (0.0, 0.0)), _Probe2D(1, (0.0, 0.0))
+    rd = _spec.probe_callable(weight_distance, p1, p2)
+    rc = _spec.probe_callable(weight_confidence, p1)
+    if rc.name != "confidence":
+        raise TypeError("weight_confidence must be one of the built-in weight_confidence_* functions")
+    if rd.name not in ("detections_2d", "detections_3d"):
+        raise TypeError("weight_distance resolved to %r, which does not apply to detections" % rd.name)
+    return _spec.CostSpec(kind=rd.name, distance=rd.kwargs, confidence=rc.kwargs,
+                          weight_source_sink=weight_source_sink, max_jump=max_jump)
+
+
+def _pack(sorted_dets, cspec):
+    """Detection objects (already in node order) -> DetectionBatch on the host (one graph)."""
+    from .batch import DetectionBatch
+    n = len(sorted_dets)
+    dim = cspec.dim
+    frame = np.fromiter((d.index for d in sorted_dets), dtype=np.int64, count=n)
+    if n and (frame.min() < -2 ** 31 or frame.max() >= 2 ** 31):
+        raise ValueError("frame indices must fit in int32")
+    pos = np.empty((n, dim), dtype=np.float64)
+    for i, d in enumerate(sorted_dets):
+        pos[i] = np.asarray(d.position, dtype=np.float64).reshape(-1)[:dim]
+    conf = np.fromiter((d.confidence for d in sorted_dets), dtype=np.float64, count=n)
+    flags = None
+    if any((not d.entry_points) or (not d.exit_point) for d in sorted_dets):
+        flags = np.fromiter(((_lib.FLAG_ENTRY if d.entry_points else 0) | (_lib.FLAG_EXIT if d.exit_point else 0)
+                             for d in sorted_dets), dtype=np.uint8, count=n)
+    bbox = hist = None
+    if cspec.kind == "detections_3d" and (cspec.use_bbox or cspec.use_hist):
+        raise NotImplementedError("weight_distance_detections_3d with use_color_histogram/use_bbox averages over the "
+                                  "shared 2D views (reference mot3d/weight_functions.py:55-71); only the position "
+                                  "term is built for 3D detections so far")
+    if cspec.use_bbox:
+        bbox = np.array([d.bbox for d in sorted_dets], dtype=np.float64).reshape(n, 4)
+    if cspec.use_hist:
+        hist = np.array([np.asarray(d.color_histogram, dtype=np.float64) for d in sorted_dets])
+        if hist.ndim != 3:
+            raise ValueError("color_histogram must be a list of C arrays of B bins for every detection")
+    gp = np.array([0, n], dtype=np.int32)
+    return DetectionBatch(gp, frame.astype(np.int32), np.ascontiguousarray(pos.T), conf, flags,
+                          None if bbox is None else np.ascontiguousarray(bbox.T), hist)
+
+
+class TrackingGraph(object):
+    """What build_graph returns. Quacks like the reference's networkx graph where callers touch it:
+    len(g) == number of nodes; g.edges(), g.nodes[...], g.has_edge(...) etc. are served by a lazily built
+    networkx.DiGraph with the reference's node ids, attributes and edge order."""
+
+    def __init__(self, detections, cspec, graphs):
+        self.detections = detections  # the caller's objects, in node order
+        self.spec = cspec
+        self.graphs = graphs          # batch.GraphBatch (one graph, DIR_IN CSR on the device)
+        self._nx = None
+        self._out = None
+        self._solution = None
+
+    def __len__(self):
+        return 2 * len(self.detections) + 2
+
+    @property
+    def n_transitions(self):
+        return self.graphs.n_edges
+
+    def out_csr(self):
+        """(row_ptr, col, weight float64, cost int64) on the host, rows = tails, reference emission order."""
+        if self._out is None:
+            from .batch import build_graphs
+            gb = build_graphs(self.graphs.dets, self.spec, direction=_lib.DIR_OUT, with_weights=True,
+                              keys=self.graphs.tkey)
+            e = gb.n_edges
+            self._out = (gb.row_ptr.cpu().numpy().astype(np.int64), gb.col[:e].cpu().numpy().astype(np.int64),
+                         gb.weight[:e].cpu().numpy(), gb.cost[:e].cpu().numpy())
+        return self._out
+
+    def arcs(self):
+        """Every arc as (tail, head, weight) arrays, 1-based node ids, in graph_to_text order
+        (reference mot3d/mot3d.py:75-104,218-226)."""
+        n = len(self.detections)
+        row_ptr, col, w, _ = self.out_csr()
+        gb = self.graphs
+        en = gb.entry_cost[:n].cpu().numpy()
+        ex = gb.exit_cost[:n].cpu().numpy()
+        conf = gb.dets.conf.cpu().numpy()
+        node_w = -(conf * self.spec.confidence["mul"] + self.spec.confidence["bias"])
+        has_en = en < _lib.INF_COST
+        has_ex = ex < _lib.INF_COST
+        T = 2 * n + 2
+        m = np.arange(n)
+        deg = np.diff(row_ptr)
+        per = 1 + has_ex.astype(np.int64) + deg
+        n_en = int(has_en.sum())
+        E = n_en + int(per.sum())
+        tail = np.empty(E, dtype=np.int64)
+        head = np.empty(E, dtype=np.int64)
+        ww = np.empty(E, dtype=np.float64)
+        tail[:n_en] = 1
+        head[:n_en] = 2 + 2 * m[has_en]
+        ww[:n_en] = self.spec.weight_source_sink
+        base = n_en + np.concatenate(([0], np.cumsum(per)[:-1])) if n else np.zeros(0, dtype=np.int64)
+        tail[base] = 2 + 2 * m
+        head[base] = 3 + 2 * m
+        ww[base] = node_w
+        xi = base[has_ex] + 1
+        tail[xi] = 3 + 2 * m[has_ex]
+        head[xi] = T
+        ww[xi] = 0
+        if len(col):
+            src = np.repeat(m, deg)
+            within = np.arange(len(col)) - np.repeat(row_ptr[:-1], deg)
+            at = np.repeat(base + 1 + has_ex.astype(np.int64), deg) + within
+            tail[at] = 3 + 2 * src
+            head[at] = 2 + 2 * col
+            ww[at] = w
+        return tail, head, ww
+
+    def to_networkx(self):
+        """The reference's DiGraph: nodes SOURCE=1, SINK=2N+2, pre=2+2m, post=3+2m with label/detection/idet
+        attributes, edges with 'weight', same insertion order (reference mot3d/mot3d.py:75-141)."""
+        if self._nx is None:
+            import networkx as nx
+            n = len(self.detections)
+            g = nx.DiGraph()
+            g.add_node(1, label="source")
+            g.add_node(2 * n + 2, label="sink")
+            for m, d in enumerate(self.detections):
+                g.add_node(2 + 2 * m, detection=d, label="pre-node", idet=m)
+                g.add_node(3 + 2 * m, detection=d, label="post-node", idet=m)
+            tail, head, w = self.arcs()
+            g.add_weighted_edges_from(zip(tail.tolist(), head.tolist(), w.tolist()))
+            self._nx = g
+        return self._nx
+
+    def __getattr__(self, name):  # nodes, edges, has_edge, ... -> the materialised networkx graph
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.to_networkx(), name)
+
+    def __iter__(self):
+        return iter(self.to_networkx())
+
+    def __contains__(self, node):
+        return 1 <= node <= len(self)
+
+    def __getitem__(self, node):
+        return self.to_networkx()[node]
+
+
+def build_graph(detections, weight_source_sink=1, max_jump=12, verbose=True,
+                weight_confidence=weight_confidence_detections_2d, weight_distance=weight_distance_detections_2d):
+    """Build the flow graph on the GPU (reference mot3d/mot3d.py:20-150).
+
+    detections : list/tuple of Detection2D / Detection3D in any order.
+    Returns a TrackingGraph, or None when there is no detection or no path from source to sink, exactly like the
+    reference (mot3d/mot3d.py:49-50,147-150). Sets detection.pre_node / detection.post_node (:89,:97).
+    """
+    assert isinstance(detections, (list, tuple))
+    if len(detections) == 0:
+        return None
+    if isinstance(detections[0], DetectionTracklet):
+        raise NotImplementedError("build_graph on DetectionTracklet lists (tracklet linking, reference "
+                                  "mot3d/weight_functions.py:80-160) is not built yet; no CPU fallback")
+    if not isinstance(detections[0], Detection):
+        raise TypeError("detections must be Detection2D/Detection3D objects")
+    from .batch import build_graphs, solve_graphs
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mot3d_b200.build_graph needs a CUDA device (B200); there is no CPU fallback")
+    cspec = _recover_spec(detections, weight_source_sink, max_jump, weight_confidence, weight_distance)
+    # stable ascending sort by frame index = the reference's cmp sort on -a.diff_index(b) (mot3d/mot3d.py:61-64)
+    ordered = sorted(detections, key=lambda d: d.index)
+    n = len(ordered)
+    if verbose:
+        print("Number of frames: {}".format(len(set(d.index for d in ordered))))
+        print("Number of detections: {}".format(n))
+    node = 2
+    for d in ordered:
+        d.pre_node = node
+        d.post_node = node + 1
+        node += 2
+    host = _pack(ordered, cspec)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    graphs = build_graphs(host.to(dev), cspec)
+    g = TrackingGraph(ordered, cspec, graphs)
+    if verbose:
+        print("Number of post-pre nodes edges created: {}".format(graphs.n_edges))
+        n_arcs = graphs.n_edges + 3 * n if host.flags is None else None
+        if n_arcs is not None:
+            print("Fraction of edges per detection: {}".format(n_arcs / n))
+    if host.flags is not None:
+        # a source->sink path exists iff the solver finds a first path; keep the solution for solve_graph
+        sol = solve_graphs(graphs)
+        if int(sol.n_paths[0].item()) == 0:
+            return None
+        g._solution = sol
+    return g
+
+
+def _run_ssp(g, verbose=1, method="muSSP"):
+    """GPU successive shortest paths + flow following -> list of tracks as lists of node ids (post-nodes), in the
+    reference's order (reference mot3d/mot3d.py:152-184)."""
+    if method != "muSSP":
+        raise NotImplementedError(method)
+    from .batch import solve_graphs, extract_tracks, tracks_to_lists
+    sol = g._solution if g._solution is not None else solve_graphs(g.graphs)
+    extract_tracks(g.graphs, sol)
+    n = len(g.detections)
+    tracks = tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                             sol.track_det.cpu().numpy())[0]
+    g._solution = sol
+    if verbose:
+        used = sum(len(t) for t in tracks) * 2
+        print("[muSSP] {} out of {} nodes unused".format(2 * n - used, 2 * n))
+    return [[3 + 2 * m for m in t] for t in tracks]
+
+
+def solve_graph(g, verbose=True, method="muSSP"):
+    """Solve the flow graph (reference mot3d/mot3d.py:197-216). method 'muSSP' runs the CUDA solver;
+    'FollowMe'/'SSP' raise NotImplementedError as in the reference (:159-163); 'ILP' is the reference's slow
+    PuLP path and is not provided; anything else raises ValueError (:205-206)."""
+    start_time = time.time()
+    if method in ["muSSP", "FollowMe", "SSP"]:
+        if not isinstance(g, TrackingGraph):
+            raise TypeError("solve_graph expects the graph returned by mot3d_b200.build_graph")
+        tracks_nodes = _run_ssp(g, verbose, method)
+    elif method == "ILP":
+        raise NotImplementedError("method='ILP' (reference mot3d/solvers/ilp/ilp.py, PuLP/CBC) is outside the "
+                                  "GPU hot path; use method='muSSP'")
+    else:
+        raise ValueError("Unrecognazed method '{}'. Choose 'muSSP' or 'ILP'".format(method))
+    trajectories = [[g.detections[(node - 3) // 2] for node in nodes] for nodes in tracks_nodes]
+    if verbose:
+        print("Graph solved in {:0.4f}s using {}.".format(time.time() - start_time, method))
+    return trajectories
+
+
+def graph_to_text(g):
+    """DIMACS-like lines, weights with 7 decimals, arcs in the graph's edge order (reference mot3d/mot3d.py:218-226)."""
+    if isinstance(g, TrackingGraph):
+        tail, head, w = g.arcs()
+        lines = ["p min {} {}".format(len(g), len(tail))]
+        for s, t, x in zip(tail.tolist(), head.tolist(), w.tolist()):
+            lines.append("a {} {} {:0.7f}".format(s, t, x))
+        return lines
+    lines = ["p min {} {}".format(len(g), len(g.edges()))]
+    for s, t, data in g.edges(data=True):
+        lines.append("a {} {} {:0.7f}".format(s, t, data["weight"]))
+    return lines
+
+
+def save_graph(graph_as_text, filename="/tmp/graph.txt"):
+    """Write the lines to a file (reference mot3d/mot3d.py:255-265)."""
+    flags = os.O_RDWR | os.O_CREAT | os.O_TRUNC
+    if os.name != "nt":
+        flags |= os.O_SYNC
+    fd = os.open(filename, flags)
+    try:
+        for line in graph_as_text:
+            os.write(fd, str.encode(line + "\n"))
+    finally:
+        os.close(fd)
+
+
+def _evaluate_pair(kind, d1, d2, kwargs):
+    """weight_distance_detections_*(d1, d2, **kwargs) for one real pair, on the GPU: a 2-detection graph."""
+    import torch
+    from .batch import build_graphs
+    jump = int(d2.index - d1.index)
+    if not (1 <= jump <= _lib.MAX_JUMP):
+        raise ValueError("weight of a pair is only defined here for 1 <= jump <= %d (got %d)" % (_lib.MAX_JUMP, jump))
+    cs = _spec.CostSpec(kind=kind, distance=kwargs, max_jump=jump)
+    host = _pack([d1, d2], cs)
+    gb = build_graphs(host.to(torch.device("cuda", torch.cuda.current_device())), cs, direction=_lib.DIR_OUT,
+                      with_weights=True)
+    if gb.n_edges == 0:
+        return None
+    return float(gb.weight[0].item())

@@ -1,0 +1,132 @@
+"""Built-in arc costs, with the reference's names and keyword arguments (reference mot3d/weight_functions.py).
+
+In this package they are *cost descriptors*: the arithmetic runs in the CUDA kernels (csrc/edge_build.cu).
+build_graph calls the user's callable once with probe objects; a built-in reached with probes records its name and
+keyword arguments (spec.record) so that lambdas / functools.partial wrappers keep working unmodified.  Called on
+real detections they evaluate that single pair on the GPU through the same kernels; there is no CPU arithmetic.
+
+    w_ij = -exp(-(jump-1)*sigma_jump) * exp(-dist^2/sigma_distance^2) [* exp(-(1-NCC)^2/sigma_ch^2)]
+                                                                       [* exp(-(1-bss)^2/sigma_bs^2)]
+           or None when dist > max_distance                      (reference mot3d/weight_functions.py:13-35, 43-75)
+    w_i  = -(confidence*mul + bias)                              (reference mot3d/weight_functions.py:37-38)
+"""
+from . import spec as _spec
+
+__all__ = ["weight_distance_detections_2d", "weight_confidence_detections", "weight_confidence_detections_2d",
+           "weight_distance_detections_3d", "weight_confidence_detections_3d", "weight_distance_tracklets_2d",
+           "weight_confidence_tracklets_2d", "weight_distance_tracklets_3d", "weight_confidence_tracklets_3d",
+           "weight_distance_detections_auto", "weight_confidence_detections_auto",
+           "weight_distance_tracklets_auto", "weight_confidence_tracklets_auto"]
+
+
+def _pair_on_gpu(kind, d1, d2, kwargs):
+    from .mot3d import _evaluate_pair
+    return _evaluate_pair(kind, d1, d2, kwargs)
+
+
+def weight_distance_detections_2d(d1, d2, sigma_jump=1, sigma_distance=2, sigma_color_histogram=0.3,
+                                  sigma_box_size=0.3, max_distance=20, use_color_histogram=True, use_bbox=True):
+    kw = dict(sigma_jump=sigma_jump, sigma_distance=sigma_distance, sigma_color_histogram=sigma_color_histogram,
+              sigma_box_size=sigma_box_size, max_distance=max_distance, use_color_histogram=use_color_histogram,
+              use_bbox=use_bbox)
+    if _spec.is_probe(d1):
+        return _spec.record("detections_2d", kw)
+    return _pair_on_gpu("detections_2d", d1, d2, kw)
+
+
+def weight_distance_detections_3d(d1, d2, sigma_jump=1, sigma_distance=2, sigma_color_histogram=0.3,
+                                  sigma_box_size=0.3, max_distance=5, use_color_histogram=True, use_bbox=True):
+    kw = dict(sigma_jump=sigma_jump, sigma_distance=sigma_distance, sigma_color_histogram=sigma_color_histogram,
+              sigma_box_size=sigma_box_size, max_distance=max_distance, use_color_histogram=use_color_histogram,
+              use_bbox=use_bbox)
+    if _spec.is_probe(d1):
+        return _spec.record("detections_3d", kw)
+    return _pair_on_gpu("detections_3d", d1, d2, kw)
+
+
+def weight_confidence_detections(detection, mul=1, bias=0):
+    if _spec.is_probe(detection):
+        return _spec.record("confidence", dict(mul=mul, bias=bias))
+    raise TypeError("weight_confidence_detections is a cost descriptor for build_graph; the value for a detection "
+                    "is -(confidence*mul + bias) and is computed by the CUDA build kernel")
+
+
+def weight_confidence_detections_2d(detection, **kwargs):
+    return weight_confidence_detections(detection, **kwargs)
+
+
+def weight_confidence_detections_3d(detection, **kwargs):
+    return weight_confidence_detections(detection, **kwargs)
+
+
+def _tracklets_pending(name):
+    raise NotImplementedError(
+        "%s: the tracklet-linking cost kernel (reference mot3d/weight_functions.py:80-160) is scheduled after the "
+        "detection path (SURVEY.md 8a row a18); this build has no CPU fallback for it" % name)
+
+
+def weight_distance_tracklets_2d(t1, t2, sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
+                                 cutoff_appearance=0.1, max_distance=None, use_color_histogram=True, debug=False):
+    kw = dict(sigma_color_histogram=sigma_color_histogram, sigma_motion=sigma_motion, alpha=alpha,
+              cutoff_motion=cutoff_motion, cutoff_appearance=cutoff_appearance, max_distance=max_distance,
+              use_color_histogram=use_color_histogram)
+    if _spec.is_probe(t1):
+        return _spec.record("tracklets_2d", kw)
+    _tracklets_pending("weight_distance_tracklets_2d")
+
+
+def weight_distance_tracklets_3d(t1, t2, sigma_color_histogram=0.3, sigma_motion=5, alpha=0.7, cutoff_motion=0.1,
+                                 cutoff_appearance=0.1, max_distance=None, use_color_histogram=True):
+    kw = dict(sigma_color_histogram=sigma_color_histogram, sigma_motion=sigma_motion, alpha=alpha,
+              cutoff_motion=cutoff_motion, cutoff_appearance=cutoff_appearance, max_distance=max_distance,
+              use_color_histogram=use_color_histogram)
+    if _spec.is_probe(t1):
+        return _spec.record("tracklets_3d", kw)
+    _tracklets_pending("weight_distance_tracklets_3d")
+
+
+def weight_confidence_tracklets_2d(tracklet, **kwargs):
+    return weight_confidence_detections(tracklet, **kwargs)
+
+
+def weight_confidence_tracklets_3d(tracklet, **kwargs):
+    return weight_confidence_detections(tracklet, **kwargs)
+
+
+def _is(obj, name):
+    return getattr(obj, "_m3_kind", None) == name or type(obj).__name__ == name or any(
+        c.__name__ == name for c in type(obj).__mro__)
+
+
+def weight_distance_detections_auto(d1, d2, config2d={}, config3d={}):
+    """Type dispatch of the reference (mot3d/weight_functions.py:237-256)."""
+    if _is(d1, "Detection2D") and _is(d2, "Detection2D"):
+        return weight_distance_detections_2d(d1, d2, **config2d)
+    if _is(d1, "Detection3D") and _is(d2, "Detection3D"):
+        return weight_distance_detections_3d(d1, d2, **config3d)
+    raise RuntimeError("Combination not possible or not implemented [{},{}].".format(type(d1), type(d2)))
+
+
+def weight_confidence_detections_auto(d, config2d={}, config3d={}):
+    if _is(d, "Detection2D"):
+        return weight_confidence_detections_3d(d, **config2d)
+    if _is(d, "Detection3D"):
+        return weight_confidence_detections_3d(d, **config3d)
+    raise RuntimeError("Unable to pick the pick the correct weight confidence for detections [{}].".format(type(d)))
+
+
+def weight_distance_tracklets_auto(t1, t2, config2d={}, config3d={}, calib={}):
+    if _is(t1, "DetectionTracklet2D") and _is(t2, "DetectionTracklet2D"):
+        return weight_distance_tracklets_2d(t1, t2, **config2d)
+    if _is(t1, "DetectionTracklet3D") and _is(t2, "DetectionTracklet3D"):
+        return weight_distance_tracklets_3d(t1, t2, **config3d)
+    raise NotImplementedError("mixed 2D/3D tracklet costs (reference mot3d/weight_functions.py:177-201) need camera "
+                              "projection; out of scope of the hot path")
+
+
+def weight_confidence_tracklets_auto(t, config2d={}, config3d={}):
+    if _is(t, "DetectionTracklet2D"):
+        return weight_confidence_tracklets_2d(t, **config2d)
+    if _is(t, "DetectionTracklet3D"):
+        return weight_confidence_tracklets_3d(t, **config3d)
+    raise RuntimeError("Unable to pick the pick the correct weight confidence for tracklets [{}].".format(type(t)))

@@ -1,0 +1,193 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/mot3d_b200.h declares, argument
+errors are reported through the ABI without touching CUDA, and the host-side logic (cost-spec recovery from
+callables, quantisation, thresholds, packing order, scheduler + gather over gloo with world_size 2)."""
+import ctypes
+import functools
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    from mot3d_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "mot3d_b200.h")).read()
+    declared = set(re.findall(r"\b(mot3d_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mot3d_last_error"} - {"mot3d_last_error"}
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(built.SIGNATURES), declared ^ set(built.SIGNATURES)
+    assert built.version().startswith("mot3d_b200")
+
+
+def test_argument_errors_without_gpu(built):
+    L = built.lib()
+    assert L.mot3d_edge_count(None, None, 0, None, None) == built.E_INVALID
+    assert b"NULL" in L.mot3d_last_error()
+    d = built.Dets()
+    d.n, d.dim = 4, 5
+    s = built.CostSpecC()
+    s.max_jump = 3
+    assert L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(s), 0, None, None) == built.E_INVALID
+    assert b"dim" in L.mot3d_last_error()
+    d.dim = 2
+    s.max_jump = 100000
+    assert L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(s), 0, None, 0, None, None, None, None, None) == built.E_INVALID
+    assert b"max_jump" in L.mot3d_last_error()
+    assert L.mot3d_solve_batch(-1, 0, None, 0, None, None, None, None, None, None, None, None, None, None, None, None,
+                               None, 0, None) == built.E_INVALID
+    assert L.mot3d_scan_workspace_bytes(1 << 20) >= 8 * ((1 << 20) // 4096)
+    assert L.mot3d_solve_workspace_bytes(1000, 3) >= 1000 * 40
+    # empty batches are fine and touch nothing
+    d.n = 0
+    s.max_jump = 3
+    assert L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(s), 0, None, None) == 0
+    assert L.mot3d_extract_tracks(0, None, None, None, None, None, None, None) == 0
+
+
+def test_spec_recovery_from_callables(built):
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    from mot3d_b200.mot3d import _recover_spec
+    dets = [mot3d.Detection2D(0, (0, 0))]
+    lam = lambda a, b: wf.weight_distance_detections_2d(a, b, sigma_jump=4, sigma_distance=10, max_distance=30,
+                                                        use_color_histogram=False, use_bbox=True, sigma_box_size=0.1)
+    conf = functools.partial(wf.weight_confidence_detections_2d, mul=0, bias=0.11)
+    s = _recover_spec(dets, 1, 4, conf, lam)
+    assert s.kind == "detections_2d" and s.distance["sigma_jump"] == 4 and s.distance["max_distance"] == 30
+    assert s.use_bbox and not s.use_hist and s.confidence == dict(mul=0, bias=0.11)
+    c = s.to_c()
+    assert c.entry_cost == 10 ** 7 and c.max_jump == 4 and c.sigma_bbox_sq == 0.1 ** 2
+    assert c.neg_exp_jump[0] == -1.0 and c.neg_exp_jump[3] == float(-np.exp(-3 * 4))
+    # defaults of the bare functions (reference mot3d/mot3d.py:22-23)
+    s = _recover_spec(dets, 1, 12, wf.weight_confidence_detections_2d, wf.weight_distance_detections_2d)
+    assert s.distance["max_distance"] == 20 and s.use_hist and s.confidence == dict(mul=1, bias=0)
+    # 3D detections, auto dispatch
+    d3 = [mot3d.Detection3D(0, (0, 0, 0))]
+    auto = lambda a, b: wf.weight_distance_detections_auto(a, b, config2d={}, config3d=dict(max_distance=0.4))
+    s = _recover_spec(d3, 50, 8, lambda d: wf.weight_confidence_detections_auto(d), auto)
+    assert s.kind == "detections_3d" and s.distance["max_distance"] == 0.4 and s.dim == 3
+    with pytest.raises(TypeError):
+        _recover_spec(dets, 1, 4, conf, lambda a, b: -1.0)
+    with pytest.raises(TypeError):
+        _recover_spec(dets, 1, 4, conf, lambda a, b: a.position[0] * b.nothing)
+    with pytest.raises(TypeError):
+        wf.weight_distance_detections_2d(dets[0], dets[0], bogus=1)
+
+
+def test_quantisation_and_threshold(built):
+    from mot3d_b200 import spec
+    assert spec.quantise_scalar(0.1) == 1000000 and spec.quantise_scalar(-0.00000004) == 0
+    assert spec.quantise_scalar(-0.00000005) == -1 or spec.quantise_scalar(-0.00000005) == 0  # binary value decides
+    assert spec.quantise_scalar(50) == 500000000
+    rng = np.random.RandomState(0)
+    for m in [15, 30, 0.4, 20, 5, 1e-3, 12345.678] + rng.rand(50).tolist():
+        s = spec.sq_dist_max(m)
+        assert np.sqrt(np.float64(s)) <= m and np.sqrt(np.nextafter(np.float64(s), np.inf)) > m
+
+
+def test_packing_order_is_the_reference_sort(built):
+    import mot3d_b200 as mot3d
+    frame = np.array([3, 1, 2, 1, 3, 0, 2, 1])
+    pos = np.arange(16, dtype=float).reshape(8, 2)
+    b, order = mot3d.DetectionBatch.from_arrays(np.array([0, 5, 8]), frame, pos)
+    # graph 0 = items 0..4 sorted stably by frame, graph 1 = items 5..7
+    assert order.tolist() == [1, 3, 2, 0, 4, 5, 7, 6]
+    assert b.frame.tolist() == [1, 1, 2, 3, 3, 0, 1, 2] and b.pos.shape == (2, 8)
+    assert b.pos[:, 0].tolist() == pos[1].tolist()
+
+
+def test_types_api(built):
+    import mot3d_b200 as mot3d
+    a, b = mot3d.Detection2D(3, (1, 2)), mot3d.Detection2D(7, (2, 2), confidence=0.9)
+    assert a.diff_index(b) == 4 and a.confidence == 0.5 and a.entry_points and a.exit_point and a.pre_node is None
+    chain = [mot3d.Detection2D(i, (float(i), 0.0), bbox=(0, 0, 1 + i, 2)) for i in range(10)]
+    t1, t2 = mot3d.DetectionTracklet2D(chain[:4], window=2), mot3d.DetectionTracklet2D(chain[6:])
+    assert t1.diff_index(t2) == 6 - 3 and t1.head.indexes == [2, 3] and t1.tail.indexes == [0, 1]
+    assert t2.tail.index == 6 and t2.head.position == (9.0, 0.0)
+    with pytest.raises(ValueError):
+        mot3d.DetectionTracklet3D(chain[:2])
+    assert abs(mot3d.bbox_size_similarity((0, 0, 1, 1), (0, 0, 1, 1)) - 1) < 1e-12
+    h = [np.ones(8)] * 3
+    assert abs(mot3d.color_histogram_similarity(h, h) - 1) < 1e-12
+    assert mot3d.linear_motion([0, 1], [(0, 0), (1, 0)], [2, 3], [(2, 0), (3, 0)]) < 1e-9
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under mot3d_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "mot3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("test oracle", ""), os.path.join(dirpath, f)
+
+
+def test_no_gpu_means_loud_failure(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mot3d_b200 as mot3d
+    with pytest.raises(RuntimeError):
+        mot3d.build_graph([mot3d.Detection2D(0, (0, 0))], verbose=False,
+                          weight_distance=lambda a, b: mot3d.weight_distance_detections_2d(a, b, use_color_histogram=False, use_bbox=False))
+
+
+def test_lpt_sharding(built):
+    import mot3d_b200 as mot3d
+    sizes = [5000] * 20 + [300] * 16 + [26, 3385]
+    for w in (1, 2, 4, 8):
+        parts = mot3d.shard_graphs(sizes, w)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(sizes)))
+        loads = [sum(sizes[g] ** 1.5 for g in p) for p in parts]
+        assert max(loads) <= min(loads) + max(s ** 1.5 for s in sizes)
+        assert [p.tolist() for p in parts] == [p.tolist() for p in mot3d.shard_graphs(sizes, w)]
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import mot3d_b200 as mot3d
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+sizes = [7, 3, 9, 4, 5]
+parts = mot3d.shard_graphs(sizes, 2)
+mine = parts[rank]
+tracks = [[[g, g + 1, g + 2], [10 * g]] if g %% 2 == 0 else [] for g in mine]
+costs = [-(g + 1) * 1000 for g in mine]
+out = mot3d.gather_tracks(mine, tracks, costs, len(sizes))
+if rank == 0:
+    tr, co = out
+    assert co == [-(g + 1) * 1000 for g in range(5)], co
+    assert tr == [[[g, g + 1, g + 2], [10 * g]] if g %% 2 == 0 else [] for g in range(5)], tr
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_gather_tracks_gloo_world2(built, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % dict(root=ROOT, port=29500 + os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]

@@ -1,0 +1,317 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes, mot3d_b200/_lib.py), against
+ - the golden vectors frozen from the reference itself (tests/golden, see make_golden.py), and
+ - the CPU oracle (oracle/) on the same seeded inputs.
+Bar: integer work bit-exact (arc sets and order, quantised costs away from rounding ties, total cost, K, path costs,
+tracks); float64 weights within 1e-6 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # float edge weights, BASELINE.json north_star
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _spec_from(s, mot3d):
+    kind = "detections_2d" if s["kind"] == "2d" else "detections_3d"
+    dist = {k: s[k] for k in ("sigma_jump", "sigma_distance", "sigma_color_histogram", "sigma_box_size",
+                              "max_distance", "use_color_histogram", "use_bbox")}
+    return mot3d.CostSpec(kind=kind, distance=dist, confidence=dict(mul=s["mul"], bias=s["bias"]),
+                          weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"])
+
+
+def _batch_from(d, mot3d, flags=None):
+    n = len(d["frame"])
+    b, order = mot3d.DetectionBatch.from_arrays(np.array([0, n]), d["frame"], d["pos"], d["conf"], flags=flags,
+                                                bbox=d.get("bbox"), hist=d.get("hist"))
+    assert (order == np.arange(n)).all()  # fixtures are stored in node order
+    return b
+
+
+def _golden_transitions(d):
+    """(row_ptr, col, w, cost) of the post_i -> pre_j arcs in reference order, from the golden arc list."""
+    n = len(d["frame"])
+    tail, head = d["tail"].astype(np.int64), d["head"].astype(np.int64)
+    m = (tail % 2 == 1) & (head != 2 * n + 2) & (tail != 1)
+    src = (tail[m] - 3) // 2
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(row_ptr, src + 1, 1)
+    return np.cumsum(row_ptr), (head[m] - 2) // 2, d["w_float"][m], d["cost"][m]
+
+
+@pytest.mark.parametrize("name", gu.DETECTION_CASES)
+def test_edge_build_matches_reference(name):
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    torch = _torch()
+    d = gu.load(name)
+    spec = _spec_from(d["spec"], mot3d)
+    b = _batch_from(d, mot3d).to("cuda")
+    row_ptr, col, w, cost = _golden_transitions(d)
+    out = mot3d.build_graphs(b, spec, direction=_lib.DIR_OUT, with_weights=True)
+    assert out.n_edges == len(col)
+    assert (out.row_ptr.cpu().numpy() == row_ptr).all()
+    e = out.n_edges
+    assert (out.col[:e].cpu().numpy() == col).all()                      # same arcs, same order
+    np.testing.assert_allclose(out.weight[:e].cpu().numpy(), w, rtol=RTOL, atol=0)
+    gu.assert_costs_match(out.cost[:e].cpu().numpy(), cost, w)
+    # the solver's orientation is the transpose of the same arc set
+    inn = mot3d.build_graphs(b, spec, direction=_lib.DIR_IN, with_weights=True)
+    assert inn.n_edges == e
+    rp = inn.row_ptr.cpu().numpy().astype(np.int64)
+    dst = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    srcs = inn.col[:e].cpu().numpy().astype(np.int64)
+    o = np.lexsort((dst, srcs))
+    assert (srcs[o] == np.repeat(np.arange(len(row_ptr) - 1), np.diff(row_ptr))).all()
+    assert (dst[o] == col).all()
+    assert (inn.cost[:e].cpu().numpy()[o] == out.cost[:e].cpu().numpy()).all()
+    # per-detection arcs
+    n = len(d["frame"])
+    tail, head = d["tail"], d["head"]
+    node_ref = d["cost"][(tail % 2 == 0) & (head == tail + 1)]
+    assert (out.node_cost[:n].cpu().numpy() == node_ref).all()
+    assert (out.entry_cost[:n].cpu().numpy() == d["cost"][tail == 1]).all()
+    assert (out.exit_cost[:n].cpu().numpy() == 0).all()
+
+
+def _solve_checks(name, d, sol, n, perm=None):
+    from oracle import oracle
+    ref = oracle.ssp_solve(int(d["n_nodes"]), d["tail"], d["head"], d["cost"])
+    K = int(sol.n_paths[0].item())
+    total = int(sol.total_cost[0].item())
+    assert total == ref["total"]                         # exact optimum in 1e-7 units
+    assert K == ref["K"] == int(d["K"])
+    assert (sol.path_cost[:K].cpu().numpy() == ref["path_cost"]).all()
+    if name not in gu.MUSSP_BOGUS_COST:
+        assert gu.ref_total_units(d) - total == gu.MUSSP_SUBOPTIMAL.get(name, 0)   # vs the real muSSP
+    return ref
+
+
+@pytest.mark.parametrize("name", gu.DETECTION_CASES)
+def test_build_solve_extract_matches_mussp(name):
+    import mot3d_b200 as mot3d
+    from oracle import oracle
+    d = gu.load(name)
+    spec = _spec_from(d["spec"], mot3d)
+    b = _batch_from(d, mot3d).to("cuda")
+    gb, sol = mot3d.track_batch(b, spec)
+    n = len(d["frame"])
+    ref = _solve_checks(name, d, sol, n)
+    tracks = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                   sol.track_det.cpu().numpy())[0]
+    ref_tracks = oracle.tracks_from_flow(n, d["tail"], d["head"], ref["flow"])
+    assert tracks == ref_tracks                                       # oracle (exact optimum)
+    if gu.MUSSP_SUBOPTIMAL.get(name, 0) == 0:                         # and the reference's own trajectories
+        gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist()
+                for k in range(len(d["track_ptr"]) - 1)]
+        assert tracks == gold
+    # flow consistency: next/prev are inverse of each other, tracks cover exactly the used detections
+    nxt, prv = sol.next[:n].cpu().numpy(), sol.prev[:n].cpu().numpy()
+    for i in np.flatnonzero(nxt >= 0).tolist():
+        assert prv[nxt[i]] == i
+    assert sorted(i for t in tracks for i in t) == np.flatnonzero(prv != -1).tolist()
+
+
+@pytest.mark.parametrize("name", ["wrapper_test_graph", "c2_tracklets_pass2", "c3_soldiers_pass2", "mussp_seq07"])
+def test_solver_on_reference_graphs(name):
+    """Solver-only vectors: the wrapper's own smoke graph, the two tracklet-linking graphs (not frame sorted,
+    backward-numbered arcs) and muSSP's sample graph (20 210 detections: the global-memory state path)."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import dimacs
+    d = gu.load(name)
+    gb, perm = dimacs.graph_from_arcs(int(d["n_nodes"]), d["tail"], d["head"], d["cost"])
+    sol = mot3d.solve_graphs(gb)
+    ref = _solve_checks(name, d, sol, len(perm))
+    # same flow as muSSP (these optima are unique): successor of every detection
+    n = len(perm)
+    nxt = sol.next[:n].cpu().numpy()
+    tail, head, flow = d["tail"].astype(np.int64), d["head"].astype(np.int64), ref["flow"]
+    T = int(d["n_nodes"])
+    exp = np.full(n, -1, dtype=np.int64)
+    m = (flow != 0) & (tail % 2 == 1)
+    exp[(tail[m] - 3) // 2] = np.where(head[m] == T, -2, (head[m] - 2) // 2)
+    got = np.full(n, -1, dtype=np.int64)
+    got[perm] = np.where(nxt >= 0, perm[np.maximum(nxt, 0)], nxt)
+    assert (got == exp).all()
+
+
+def test_public_api_drop_in():
+    """The reference's own call sequence (examples/simple_2d/example.py:41-75) on the C1 vector, through
+    build_graph / solve_graph with lambdas around the built-in costs; text identical to the reference's."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    from oracle import oracle
+    d = gu.load("c1_simple_2d")
+    rng = np.random.RandomState(1)
+    n = len(d["frame"])
+    shuffled = rng.permutation(n)
+    hist = d["hist"]
+    dets_sorted = [mot3d.Detection2D(int(d["frame"][i]), d["pos"][i], confidence=float(d["conf"][i]),
+                                     color_histogram=[hist[i, 0], hist[i, 1], hist[i, 2]], bbox=list(d["bbox"][i]))
+                   for i in range(n)]
+    # any input order: equal frames keep their relative order (stable sort), so shuffle whole frames only
+    frames = np.unique(d["frame"])
+    dets = [dets_sorted[i] for f in rng.permutation(frames) for i in np.flatnonzero(d["frame"] == f)]
+    weight_distance = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, sigma_jump=1, sigma_distance=10,
+                                                                      sigma_color_histogram=0.3, sigma_box_size=0.3,
+                                                                      max_distance=15, use_color_histogram=True,
+                                                                      use_bbox=True)
+    weight_confidence = lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0)
+    g = mot3d.build_graph(dets, weight_source_sink=0.1, max_jump=4, verbose=False,
+                          weight_confidence=weight_confidence, weight_distance=weight_distance)
+    assert g is not None and len(g) == int(d["n_nodes"])
+    assert [x.pre_node for x in dets_sorted] == [2 + 2 * m for m in range(n)]
+    assert [x.post_node for x in dets_sorted] == [3 + 2 * m for m in range(n)]
+    lines = mot3d.graph_to_text(g)
+    assert oracle.text_sha(lines) == str(d["sha"])
+    trajectories = mot3d.solve_graph(g, verbose=False, method="muSSP")
+    got = [[dets_sorted.index(x) for x in t] for t in trajectories]
+    gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
+    assert got == gold
+    # networkx view used by plot_graph (reference mot3d/utils/vis.py:78-113)
+    assert g.nodes[2]["label"] == "pre-node" and g.nodes[3]["detection"] is dets_sorted[0]
+    assert len(g.edges()) == len(d["tail"]) and g.has_edge(1, 2)
+    with pytest.raises(ValueError):
+        mot3d.solve_graph(g, verbose=False, method="nope")
+    with pytest.raises(NotImplementedError):
+        mot3d.solve_graph(g, verbose=False, method="SSP")
+    assert mot3d.build_graph([], verbose=False) is None
+    with pytest.raises(TypeError):
+        mot3d.build_graph(dets, verbose=False, weight_distance=lambda a, b: -1.0)
+    # a single pair evaluated on the GPU
+    w = wf.weight_distance_detections_2d(dets_sorted[0], dets_sorted[2], sigma_jump=1, sigma_distance=10,
+                                         max_distance=15, use_color_histogram=False, use_bbox=False)
+    tail, head = d["tail"], d["head"]
+    k = np.flatnonzero((tail == 3) & (head == 6))
+    assert (w is None and len(k) == 0) or abs(w - d["w_float"][k[0]]) <= RTOL * abs(d["w_float"][k[0]])
+
+
+def test_batched_graphs_equal_single_graphs():
+    """Several different graphs (ragged sizes, one of them empty) in one batch = the same graphs one by one."""
+    import mot3d_b200 as mot3d
+    names = ["c5_small_f30_p12", "quirk_single_detection", "c5_small_f30_p12", "c5_window_f50_p100"]
+    ds = [gu.load(n) for n in names]
+    spec = _spec_from(ds[0]["spec"], mot3d)
+    sizes = [len(d["frame"]) for d in ds]
+    sizes.insert(2, 0)  # an empty graph in the middle
+    gp = np.cumsum([0] + sizes)
+    frame = np.concatenate([d["frame"] for d in ds])
+    pos = np.concatenate([d["pos"] for d in ds])
+    conf = np.concatenate([d["conf"] for d in ds])
+    b, order = mot3d.DetectionBatch.from_arrays(gp, frame, pos, conf)
+    gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+    tracks = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                   sol.track_det.cpu().numpy())
+    totals = sol.total_cost.cpu().numpy()
+    gi = 0
+    for k, sz in enumerate(sizes):
+        if sz == 0:
+            assert tracks[k] == [] and totals[k] == 0
+            continue
+        d = ds[gi]
+        gi += 1
+        if names[gi - 1] == "quirk_single_detection":
+            assert tracks[k] == [[0]]  # first path kept although its cost is +0.5 (wrapper.cpp:205,220)
+            continue
+        assert totals[k] == gu.ref_total_units(d)
+        gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist()
+                for t in range(len(d["track_ptr"]) - 1)]
+        assert tracks[k] == gold
+
+
+def test_host_buffer_entry_point():
+    """mot3d_track_batch_host (pinned host buffers in/out, copies inside the call) = the device path."""
+    import mot3d_b200 as mot3d
+    d = gu.load("c5_small_f30_p12")
+    spec = _spec_from(d["spec"], mot3d)
+    n = len(d["frame"])
+    gp = np.array([0, n, 2 * n])
+    b, _ = mot3d.DetectionBatch.from_arrays(gp, np.r_[d["frame"], d["frame"]], np.r_[d["pos"], d["pos"]],
+                                            np.r_[d["conf"], d["conf"]])
+    ht = mot3d.HostTracker(n_max=2 * n + 7, g_max=3, edge_capacity=20000, dim=2)
+    ht.load(b)
+    n_edges = ht.run(spec.to_c())
+    assert n_edges == 2 * int(((d["tail"] % 2 == 1) & (d["head"] != int(d["n_nodes"]))).sum())
+    gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist() for t in range(len(d["track_ptr"]) - 1)]
+    assert ht.tracks() == [gold, gold]
+    assert ht.h_total[:2].tolist() == [gu.ref_total_units(d)] * 2
+    # too small an arc buffer is reported, not silently truncated
+    small = mot3d.HostTracker(n_max=2 * n, g_max=2, edge_capacity=100, dim=2)
+    small.load(b)
+    with pytest.raises(mot3d.Mot3dError) as e:
+        small.run(spec.to_c())
+    assert e.value.code == -3
+
+
+def test_entry_exit_flags_against_oracle():
+    """entry_points / exit_point = False (mot3d/mot3d.py:90-99): muSSP cannot run such graphs (UB), the
+    integer oracle can."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    from oracle import oracle
+    d = gu.load("c5_small_f30_p12")
+    n = len(d["frame"])
+    rng = np.random.RandomState(5)
+    flags = (rng.rand(n) < 0.6).astype(np.uint8) * _lib.FLAG_ENTRY | (rng.rand(n) < 0.6).astype(np.uint8) * _lib.FLAG_EXIT
+    spec = _spec_from(d["spec"], mot3d)
+    b = _batch_from(d, mot3d, flags=flags).to("cuda")
+    gb, sol = mot3d.track_batch(b, spec)
+    s = d["spec"]
+    ospec = oracle.CostSpec(**{k: v for k, v in s.items() if k != "kind"})
+    row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], ospec)
+    tail, head, ww = oracle.graph_arcs(n, 1.0, oracle.node_weights(d["conf"], ospec), 0.0, row_ptr, col, w,
+                                       entry_mask=(flags & 1) != 0, exit_mask=(flags & 2) != 0)
+    ref = oracle.ssp_solve(2 * n + 2, tail, head, oracle.quantise(ww))
+    assert int(sol.total_cost[0].item()) == ref["total"] and int(sol.n_paths[0].item()) == ref["K"]
+    tracks = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                   sol.track_det.cpu().numpy())[0]
+    assert tracks == oracle.tracks_from_flow(n, tail, head, ref["flow"])
+    for t in tracks:
+        assert flags[t[0]] & 1 and flags[t[-1]] & 2
+
+
+def test_full_size_c5_whole_graph():
+    """BASELINE config 5 as ONE graph: 100 000 detections / 1 000 frames / max_jump 8. Size-independent checks:
+    arc count, K and total cost equal the real muSSP's (golden summary), rows sorted, every track time-ordered and
+    within max_jump / max_distance."""
+    import mot3d_b200 as mot3d
+    torch = _torch()
+    g = gu.load("c5_whole_summary")
+    rng = np.random.RandomState(0)
+    P, F = 100, 1000
+    pos = rng.rand(P, 2) * 1000.0
+    vel = rng.randn(P, 2) * 1.0
+    frames, positions = [], []
+    for f in range(F):
+        pos = pos + vel + rng.randn(P, 2) * 0.2
+        frames.append(np.full(P, f))
+        positions.append(pos.copy())
+    frame, xy = np.concatenate(frames), np.concatenate(positions)
+    spec = mot3d.CostSpec(kind="detections_2d",
+                          distance=dict(sigma_jump=1, sigma_distance=10, max_distance=30, use_color_histogram=False,
+                                        use_bbox=False),
+                          confidence=dict(mul=1, bias=0), weight_source_sink=1, max_jump=8)
+    b, _ = mot3d.DetectionBatch.from_arrays(np.array([0, len(frame)]), frame, xy, np.full(len(frame), 0.9))
+    gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+    assert gb.n_edges == int(g["n_transitions"])
+    assert int(sol.n_paths[0].item()) == int(g["K"])
+    assert int(sol.total_cost[0].item()) == int(g["total_units"])
+    rp = gb.row_ptr.cpu().numpy()
+    col = gb.col[:gb.n_edges].cpu().numpy()
+    seg = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    same = seg[1:] == seg[:-1]
+    assert (col[1:][same] > col[:-1][same]).all()          # sources ascend inside every row
+    tracks = mot3d.tracks_to_lists(np.array([0, len(frame)]), sol.track_count.cpu().numpy(),
+                                   sol.track_ptr.cpu().numpy(), sol.track_det.cpu().numpy())[0]
+    assert [t[0] for t in tracks] == sorted(t[0] for t in tracks)
+    for t in tracks:
+        t = np.array(t)
+        dt = np.diff(frame[t])
+        assert (dt > 0).all() and (dt <= 8).all()
+        assert (np.linalg.norm(np.diff(xy[t], axis=0), axis=1) <= 30).all()
