@@ -35,6 +35,7 @@ struct SolveParams {
     int32_t *n_paths;
     int64_t *total;
     int64_t *path_cost;
+    int32_t *stats;  // optional [n_graphs][4]: forward sweeps, track-walk phases, layers, arcs
     // global workspace
     int64_t *ws_dpre;
     int64_t *ws_dpost;
@@ -113,6 +114,7 @@ __global__ void k_ssp_solve(const SolveParams p) {
 
     int K = 0;
     int64_t total = 0;
+    int n_fwd = 0, n_bwd = 0;
     const int sub = tid % LPN;
     const int grp = tid / LPN;
     const int ngrp = T / LPN;
@@ -126,6 +128,7 @@ __global__ void k_ssp_solve(const SolveParams p) {
         __syncthreads();
         for (int round = 0; round < 4 * n + 8; round++) {  // fix-point; the bound only guards against bad input
             int changed = 0;
+            n_fwd++;
             // ---- forward sweep over the frame layers (all forward arcs, pull mode)
             for (int l = 0; l < L; l++) {
                 const int a = lvl[l], b = lvl[l + 1];
@@ -180,6 +183,7 @@ __global__ void k_ssp_solve(const SolveParams p) {
             if (!__syncthreads_or(changed) && round > 0) break;
             // ---- reversed arcs only exist along tracks: walk each track from its end to its start
             int ch2 = 0;
+            n_bwd++;
             for (int t = tid; t < K; t += T) {
                 int j = ends[t];
                 for (int step = 0; step < n; step++) {
@@ -300,6 +304,12 @@ __global__ void k_ssp_solve(const SolveParams p) {
     if (tid == 0) {
         p.n_paths[g] = K;
         p.total[g] = total;
+        if (p.stats) {
+            p.stats[4 * g + 0] = n_fwd;
+            p.stats[4 * g + 1] = n_bwd;
+            p.stats[4 * g + 2] = L;
+            p.stats[4 * g + 3] = in_ptr[n] - in_ptr[0];
+        }
     }
     for (int i = tid; i < n; i += T) {
         const int a = nxt[i], b = prv[i];
@@ -373,7 +383,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
                           const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
-                          int64_t *path_cost_out, void *ws, size_t ws_bytes, void *stream) {
+                          int64_t *path_cost_out, int32_t *stats_out, void *ws, size_t ws_bytes, void *stream) {
     M3_CHECK_ARG(n_graphs >= 0 && max_graph_nodes >= 0, "negative sizes");
     if (n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(graph_ptr && tkey && in_ptr && entry_cost && node_cost && exit_cost, "NULL input");
@@ -401,6 +411,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.n_paths = n_paths_out;
     p.total = total_cost_out;
     p.path_cost = path_cost_out;
+    p.stats = stats_out;
     p.ws_dpre = (int64_t *)w;
     w += a256(n_cap * 8);
     p.ws_dpost = (int64_t *)w;

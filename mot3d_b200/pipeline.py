@@ -1,0 +1,103 @@
+"""TrackPipeline: the whole hot path on the device with preallocated buffers and no host synchronisation between
+stages -- keys -> node costs -> arc count -> row scan -> arc fill -> solve -> tracks. All graphs of a batch go
+through each kernel in one launch (one thread block per graph in the solver). This is what the batch scheduler runs
+per rank; bench.py times it stage by stage with CUDA events on the launching stream."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
+
+STAGES = ["make_keys", "node_costs", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 3 + 1 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
+
+
+class TrackPipeline(object):
+    def __init__(self, n_max, g_max, edge_capacity, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = self.device
+        self.n_max, self.g_max, self.edge_capacity = int(n_max), int(g_max), int(edge_capacity)
+        L = _lib.lib()
+        i32 = dict(dtype=torch.int32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        n, G, E = self.n_max, self.g_max, self.edge_capacity
+        self.tkey = torch.empty(n, **i32)
+        self.gbase = torch.empty(G, **i64)
+        self.entry_cost = torch.empty(n, **i64)
+        self.node_cost = torch.empty(n, **i64)
+        self.exit_cost = torch.empty(n, **i64)
+        self.row_count = torch.empty(n, **i32)
+        self.row_ptr = torch.empty(n + 1, **i32)
+        self.scan_ws_bytes = L.mot3d_scan_workspace_bytes(n)
+        self.scan_ws = torch.empty(self.scan_ws_bytes, dtype=torch.uint8, device=dev)
+        self.col = torch.empty(E, **i32)
+        self.cost = torch.empty(E, **i64)
+        self.overflow = torch.zeros(1, **i32)
+        self.next = torch.empty(n, **i32)
+        self.prev = torch.empty(n, **i32)
+        self.n_paths = torch.empty(G, **i32)
+        self.total_cost = torch.empty(G, **i64)
+        self.stats = torch.zeros(4 * G, **i32)
+        self.solve_ws_bytes = L.mot3d_solve_workspace_bytes(n, G)
+        self.solve_ws = torch.empty(self.solve_ws_bytes, dtype=torch.uint8, device=dev)
+        self.track_count = torch.empty(G, **i32)
+        self.track_ptr = torch.empty(n + G + 1, **i32)
+        self.track_det = torch.empty(n, **i32)
+
+    def run(self, batch, spec, spec_c=None, events=None):
+        """batch: DetectionBatch on self.device. events: optional list of len(STAGES)+1 torch.cuda.Event recorded
+        around every stage on the current stream. Asynchronous: call check_overflow()/synchronize afterwards."""
+        L = _lib.lib()
+        dev = self.device
+        n, G = batch.n, batch.n_graphs
+        if n > self.n_max or G > self.g_max:
+            raise ValueError("batch larger than the pipeline was sized for")
+        if spec.use_hist:
+            raise NotImplementedError("TrackPipeline: the appearance pass is wired through build_graphs only")
+        cs = spec.to_c() if spec_c is None else spec_c
+        st = _stream(dev)
+        rec = (lambda k: events[k].record(torch.cuda.current_stream(dev))) if events is not None else (lambda k: None)
+        max_nodes = getattr(batch, "_max_nodes", None)
+        if max_nodes is None:
+            max_nodes = batch.max_graph_nodes()
+        rec(0)
+        _lib.check(L.mot3d_make_keys(_ptr(batch.frame), _ptr(batch.graph_ptr), G, spec.max_jump, _ptr(self.tkey),
+                                     _ptr(self.gbase), st))
+        rec(1)
+        d = _dets_struct(batch, self.tkey, spec)
+        _lib.check(L.mot3d_node_costs(ctypes.byref(d), ctypes.byref(cs), _ptr(self.entry_cost), _ptr(self.node_cost),
+                                      _ptr(self.exit_cost), st))
+        rec(2)
+        _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
+        rec(3)
+        _lib.check(L.mot3d_exclusive_scan_i32(_ptr(self.row_count), n, _ptr(self.row_ptr), _ptr(self.scan_ws),
+                                              self.scan_ws_bytes, st))
+        rec(4)
+        _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_ptr),
+                                     self.edge_capacity, _ptr(self.col), _ptr(self.cost), None, _ptr(self.overflow),
+                                     st))
+        rec(5)
+        _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), _ptr(self.row_ptr),
+                                       _ptr(self.col), _ptr(self.cost), _ptr(self.entry_cost), _ptr(self.node_cost),
+                                       _ptr(self.exit_cost), _ptr(self.next), _ptr(self.prev), _ptr(self.n_paths),
+                                       _ptr(self.total_cost), None, _ptr(self.stats), _ptr(self.solve_ws),
+                                       self.solve_ws_bytes, st))
+        rec(6)
+        _lib.check(L.mot3d_extract_tracks(G, _ptr(batch.graph_ptr), _ptr(self.next), _ptr(self.prev),
+                                          _ptr(self.track_count), _ptr(self.track_ptr), _ptr(self.track_det), st))
+        rec(7)
+        self._n, self._G = n, G
+
+    def check_overflow(self):
+        if int(self.overflow.item()) != 0:
+            raise _lib.Mot3dError(_lib.E_CAPACITY, "edge capacity %d too small (batch has %d arcs)" %
+                                  (self.edge_capacity, int(self.row_ptr[self._n].item())))
+
+    def n_edges(self):
+        return int(self.row_ptr[self._n].item())
+
+    def tracks(self, graph_ptr_host):
+        return tracks_to_lists(graph_ptr_host, self.track_count.cpu().numpy(), self.track_ptr.cpu().numpy(),
+                               self.track_det.cpu().numpy())
