@@ -122,20 +122,22 @@ int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spe
 size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs);
 
 /* Successive shortest paths per graph on the residual network, one thread block per graph.
- *   in_ptr/in_src/in_cost : MOT3D_DIR_IN CSR of the transition arcs over the whole batch (in_src = global indices)
+ *   in_ptr/in_src/in_cost : MOT3D_DIR_IN CSR of the transition arcs over the whole batch (in_src = global indices);
+ *                   arc_capacity = entries present in in_src/in_cost: a graph whose rows reach beyond it (arc buffer
+ *                   overflow during the build) is skipped and gets n_paths = -1
  *   next_out[i]  : successor of detection i on its track (global index), -2 if the track ends at i, -1 if i is unused
  *   prev_out[i]  : predecessor, -2 if a track starts at i, -1 if unused
  *   n_paths_out[g], total_cost_out[g] : K and the sum of accepted path costs
  *   path_cost_out : optional [n_total]; graph g's k-th path cost at graph_ptr[g]+k
- *   stats_out     : optional [n_graphs][4] = forward sweeps, track-walk phases, frame layers, transition arcs
+ *   stats_out     : optional int64 [n_graphs][4] = ascending sweeps, descending sweeps, node pulls, arc pulls
  *                   (what the roofline accounting of bench.py needs)
  * Acceptance rule of wrapper.cpp:199-267 on integers: path 1 always, then while cost < 0. */
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
-                          const int32_t *tkey,
+                          const int32_t *tkey, int64_t arc_capacity,
                           const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
                           const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
-                          int64_t *path_cost_out, int32_t *stats_out, void *ws, size_t ws_bytes, void *stream);
+                          int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- trajectories: replaces _run_ssp's tail (mot3d/mot3d.py:165-184) ---------------------------------------- */
 

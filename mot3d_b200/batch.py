@@ -200,13 +200,14 @@ def solve_graphs(gb, want_path_costs=True):
     sol.n_paths = torch.zeros(max(G, 1), **i32)
     sol.total_cost = torch.zeros(max(G, 1), **i64)
     sol.path_cost = torch.zeros(max(n, 1), **i64) if want_path_costs else None
-    sol.stats = torch.zeros(max(G, 1) * 4, **i32)
+    sol.stats = torch.zeros(max(G, 1) * 4, **i64)
     ws_bytes = L.mot3d_solve_workspace_bytes(n, G)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     max_nodes = getattr(b, "_max_nodes", None)
     if max_nodes is None:
         max_nodes = b.max_graph_nodes()
-    _lib.check(L.mot3d_solve_batch(G, n, _ptr(b.graph_ptr), max_nodes, _ptr(gb.tkey), _ptr(gb.row_ptr), _ptr(gb.col),
+    _lib.check(L.mot3d_solve_batch(G, n, _ptr(b.graph_ptr), max_nodes, _ptr(gb.tkey), max(gb.n_edges, 0),
+                                   _ptr(gb.row_ptr), _ptr(gb.col),
                                    _ptr(gb.cost), _ptr(gb.entry_cost), _ptr(gb.node_cost), _ptr(gb.exit_cost),
                                    _ptr(sol.next), _ptr(sol.prev), _ptr(sol.n_paths), _ptr(sol.total_cost),
                                    _ptr(sol.path_cost), _ptr(sol.stats), _ptr(ws), ws_bytes, st))

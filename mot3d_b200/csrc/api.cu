@@ -158,7 +158,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     if ((rc = mot3d_exclusive_scan_i32(d_rowcnt, n, d_rowptr, d_scan, scan_b, st))) return rc;
     if ((rc = mot3d_edge_fill(&d, spec, MOT3D_DIR_IN, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over, st)))
         return rc;
-    if ((rc = mot3d_solve_batch(G, n, d_gptr, max_nodes, d_tkey, d_rowptr, d_col, d_cost, d_en, d_cn, d_ex, d_next, d_prev,
+    if ((rc = mot3d_solve_batch(G, n, d_gptr, max_nodes, d_tkey, edge_capacity, d_rowptr, d_col, d_cost, d_en, d_cn, d_ex, d_next, d_prev,
                                 d_np, d_total, nullptr, nullptr, d_solve, solve_b, st)))
         return rc;
     if ((rc = mot3d_extract_tracks(G, d_gptr, d_next, d_prev, d_tcount, d_tptr, d_tdet, st))) return rc;

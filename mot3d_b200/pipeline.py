@@ -39,7 +39,7 @@ class TrackPipeline(object):
         self.prev = torch.empty(n, **i32)
         self.n_paths = torch.empty(G, **i32)
         self.total_cost = torch.empty(G, **i64)
-        self.stats = torch.zeros(4 * G, **i32)
+        self.stats = torch.zeros(4 * G, **i64)
         self.solve_ws_bytes = L.mot3d_solve_workspace_bytes(n, G)
         self.solve_ws = torch.empty(self.solve_ws_bytes, dtype=torch.uint8, device=dev)
         self.track_count = torch.empty(G, **i32)
@@ -79,7 +79,8 @@ class TrackPipeline(object):
                                      self.edge_capacity, _ptr(self.col), _ptr(self.cost), None, _ptr(self.overflow),
                                      st))
         rec(5)
-        _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), _ptr(self.row_ptr),
+        _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), self.edge_capacity,
+                                       _ptr(self.row_ptr),
                                        _ptr(self.col), _ptr(self.cost), _ptr(self.entry_cost), _ptr(self.node_cost),
                                        _ptr(self.exit_cost), _ptr(self.next), _ptr(self.prev), _ptr(self.n_paths),
                                        _ptr(self.total_cost), None, _ptr(self.stats), _ptr(self.solve_ws),

@@ -49,8 +49,8 @@ def test_argument_errors_without_gpu(built):
     s.max_jump = 100000
     assert L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(s), 0, None, 0, None, None, None, None, None) == built.E_INVALID
     assert b"max_jump" in L.mot3d_last_error()
-    assert L.mot3d_solve_batch(-1, 0, None, 0, None, None, None, None, None, None, None, None, None, None, None, None,
-                               None, None, 0, None) == built.E_INVALID
+    assert L.mot3d_solve_batch(-1, 0, None, 0, None, 0, None, None, None, None, None, None, None, None, None, None,
+                               None, None, None, 0, None) == built.E_INVALID
     assert L.mot3d_scan_workspace_bytes(1 << 20) >= 8 * ((1 << 20) // 4096)
     assert L.mot3d_solve_workspace_bytes(1000, 3) >= 1000 * 40
     # empty batches are fine and touch nothing
