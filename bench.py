@@ -307,7 +307,7 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    stats = pipe.stats.cpu().numpy().reshape(-1, 4)[:G]
+    stats = pipe.stats.cpu().numpy().reshape(-1, 12)[:G]
     # relaxation work actually done (k_ssp_solve only touches the branch it has to re-label):
     # every arc pull reads 4 B source + 8 B cost, every node pull moves 8 B dist + 8 B dist + 4 B parent
     solve_bytes = float(np.sum(stats[:, 3] * 12 + stats[:, 2] * 20))
@@ -322,7 +322,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": float(stage_ms[i_solve]),
                 "ascending_sweeps_per_graph_mean": float(stats[:, 0].mean()),
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
-                "arc_pulls_per_graph_mean": float(stats[:, 3].mean())}
+                "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
+                "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(
+                    ["sink_argmin", "collect_branch", "stage", "walk", "sweeps", "write_back", "first_tree"])}}
     roofline_build = {"bound": "hbm", "kernel": "k_edge_build<count>+<fill>", "achieved": build_gbs, "peak": peak,
                       "unit": "GB/s", "frac": build_gbs / peak, "traffic": None,
                       "algorithmic_bytes_per_launch": build_bytes, "launch_ms": float(build_ms)}

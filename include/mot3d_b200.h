@@ -40,6 +40,8 @@ extern "C" {
 #define MOT3D_DIR_IN 0  /* CSR rows = arc heads (pre_j), columns = tails (post_i), ascending: what the solver pulls from */
 #define MOT3D_DIR_OUT 1 /* CSR rows = arc tails (post_i), columns = heads (pre_j), ascending: graph_to_text order */
 
+#define MOT3D_SOLVE_STATS 12 /* int64 per graph written to mot3d_solve_batch's stats_out */
+
 #define MOT3D_FLAG_ENTRY 1 /* Detection.entry_points (mot3d/types.py:24, mot3d/mot3d.py:90-91) */
 #define MOT3D_FLAG_EXIT 2  /* Detection.exit_point   (mot3d/types.py:25, mot3d/mot3d.py:98-99) */
 
@@ -119,7 +121,7 @@ int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spe
 
 /* ---- solve: replaces wrapper.solve (wrapper.cpp:171-317) and the muSSP core it drives ------------------------ */
 
-size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs);
+size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t arc_capacity);
 
 /* Successive shortest paths per graph on the residual network, one thread block per graph.
  *   in_ptr/in_src/in_cost : MOT3D_DIR_IN CSR of the transition arcs over the whole batch (in_src = global indices);
@@ -129,8 +131,9 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs);
  *   prev_out[i]  : predecessor, -2 if a track starts at i, -1 if unused
  *   n_paths_out[g], total_cost_out[g] : K and the sum of accepted path costs
  *   path_cost_out : optional [n_total]; graph g's k-th path cost at graph_ptr[g]+k
- *   stats_out     : optional int64 [n_graphs][4] = ascending sweeps, descending sweeps, node pulls, arc pulls
- *                   (what the roofline accounting of bench.py needs)
+ *   stats_out     : optional int64 [n_graphs][MOT3D_SOLVE_STATS]: [0..3] = ascending sweeps, descending sweeps, node
+ *                   pulls, arc pulls (what bench.py's roofline accounting needs); [4..10] = SM cycles spent in:
+ *                   sink arg-min, branch collection, staging, path walk, re-labelling sweeps, write-back, first tree
  * Acceptance rule of wrapper.cpp:199-267 on integers: path 1 always, then while cost < 0. */
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                           const int32_t *tkey, int64_t arc_capacity,

@@ -72,7 +72,7 @@ size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t ed
     b += align256((size_t)n1 * 4) * 2;          // next, prev
     b += align256((size_t)g1 * 4);              // n_paths
     b += align256((size_t)g1 * 8);              // total
-    b += align256(mot3d_solve_workspace_bytes(n1, g1));
+    b += align256(mot3d_solve_workspace_bytes(n1, g1, e1));
     b += align256((size_t)g1 * 4);              // track_count
     b += align256((size_t)(n1 + g1) * 4);       // track_ptr
     b += align256((size_t)n1 * 4);              // track_det
@@ -124,7 +124,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     int32_t *d_prev = A.take<int32_t>(n);
     int32_t *d_np = A.take<int32_t>(G);
     int64_t *d_total = A.take<int64_t>(G);
-    size_t solve_b = mot3d_solve_workspace_bytes(n, G);
+    size_t solve_b = mot3d_solve_workspace_bytes(n, G, edge_capacity);
     char *d_solve = A.take<char>((int64_t)solve_b);
     int32_t *d_tcount = A.take<int32_t>(G);
     int32_t *d_tptr = A.take<int32_t>(n + G);

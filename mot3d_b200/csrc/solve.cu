@@ -30,22 +30,40 @@ constexpr int PAR_POST = -2;  // pre reached from its own post (reversed node ar
 constexpr int PAR_NONE = -3;
 constexpr int DL_PRE = 1 << 29;  // work-record flags: the detection's pre / post node is to be re-labelled
 constexpr int DL_POST = 1 << 30;
-constexpr int DL_MASK = DL_PRE - 1;
+constexpr int DL_FIRST = 1 << 28;  // first record of its frame layer (set while staging)
+constexpr int DL_MASK = DL_FIRST - 1;
 
-// One detection of the branch being re-labelled, with everything the sweeps need so that they never leave
-// shared memory: node id + flags, frame layer key, where its in-arcs sit, its S->pre and pre->post costs.
+// Staging area for the branch being re-labelled: nd records + their in-arcs from inside the branch. It lives in
+// shared memory when the branch fits (the common case: ~150 of 10 000 nodes on a C5 window) and in the global
+// workspace otherwise. A record = one detection of the branch with everything the path walk and the sweeps need,
+// packed in 16-byte groups so that a step is a handful of 128-bit shared-memory loads:
+//   A  node | flags, (a0 << 16 | adeg) = its staged in-arcs, pslot = slot of prev, prv = prev (node id / marker)
+//   B  nslot = slot of next, parslot = slot of the parent, bpar / banc = parent and branch of the best candidate
+//      that cannot change during the fix-point (in-arcs from outside the branch, own post node outside the branch)
+//   C  bkey = that candidate's distance, en = S->pre cost        D  cn = pre->post cost, mc = cost of prev->this
+//   E  dpre, dpost (the labels being recomputed)                 F  par, apre, apost (labels), nxt (node id / marker)
 struct __align__(16) Rec {
-    int32_t jf;   // detection | DL_PRE | DL_POST
-    int32_t tk;   // time key (frame layer)
-    int32_t a0;   // first in-arc in the staged arc arrays, or -(1 + global arc index) when they did not fit
-    int32_t deg;  // number of in-arcs (0 unless DL_PRE)
-    int64_t en;
-    int64_t cn;
+    int4 A, B;
+    longlong2 C, D, E;
+    int4 F;
 };
+struct __align__(16) StArc {
+    long long cost;
+    int src;  // slot of the source record
+    int pad;
+};
+struct Stage {
+    Rec *rec;
+    StArc *arc;
+    int32_t *tk;  // frame-layer key per record (only used to flag the first record of every layer)
+};
+constexpr int REC_BYTES = sizeof(Rec) + 4;
+constexpr int ARC_BYTES = sizeof(StArc);
+static_assert(sizeof(Rec) == 96, "record layout");
 
 struct SolveParams {
     int32_t n_graphs;
-    int32_t rec_cap;  // work records / staged arcs that fit in shared memory
+    int32_t rec_cap;  // records / arcs of the shared-memory staging area
     int32_t arc_cap;
     int32_t pad;
     const int32_t *graph_ptr;
@@ -56,162 +74,501 @@ struct SolveParams {
     const int64_t *en;
     const int64_t *cn;
     const int64_t *ex;
-    int32_t *next_out;
+    int32_t *next_out;  // also the solver's next[] (local indices while solving, globalised at the end)
     int32_t *prev_out;
     int32_t *n_paths;
     int64_t *total;
     int64_t *path_cost;
-    int64_t *stats;        // optional [n_graphs][4]: ascending sweeps, descending sweeps, node pulls, arc pulls
+    int64_t *stats;        // optional [n_graphs][MOT3D_SOLVE_STATS], see include/mot3d_b200.h
     int64_t arc_capacity;  // arcs actually present in in_src/in_cost (graphs reaching beyond it are skipped)
-    // global workspace
+    // global workspace: per-node state (exact distances, parent, branch labels) ...
     int64_t *ws_dpre;
     int64_t *ws_dpost;
     int64_t *ws_mcost;
-    int32_t *ws_idx;  // 5 index arrays of n_total each (global-state mode)
+    int32_t *ws_par;
+    int32_t *ws_anc_pre;
+    int32_t *ws_anc_post;
+    int32_t *ws_slot_of;
+    int32_t *ws_dl;
+    int32_t *ws_dla0;
     int32_t *ws_lvl;  // [n_total + n_graphs]
-    Rec *ws_rec;      // [n_total] work records when the branch does not fit in shared memory
-    int32_t *ws_fix;  // [n_total]
-    int64_t n_total;
+    // ... and the fallback staging area for branches that do not fit in shared memory
+    Rec *ws_rec;      // n_total
+    int32_t *ws_tk;   // n_total
+    StArc *ws_arc;    // arc_capacity
 };
 
-// Per-graph solver state. Distances are exact shortest distances from S in the current residual network for EVERY
-// node (the invariant the incremental update relies on); anc_* = the detection whose S->pre arc starts the node's
-// path in the shortest-path tree (its "branch"; muSSP's ancestor_node_id, Graph.cpp:160-161).
-template <typename IdxT>
-struct State {
-    int64_t *dpre, *dpost, *mcost;
-    IdxT *par, *nxt, *prv, *anc_pre, *anc_post;
-    int32_t *asrc;  // staged in-arcs of the branch: source (local index) and cost
-    int64_t *acost;
-    const int32_t *in_src;  // global CSR (fallback when the branch's arcs did not fit)
-    const int64_t *in_cost;
-    int g0;
-};
-
-// pull for post_i: its only residual in-arc is pre_i -> post_i (detection unused) or pre_next -> post_i (reversed
-// transition arc, cost -c). One lane.
-template <typename IdxT>
-__device__ __forceinline__ bool pull_post(const State<IdxT> &s, int i, int64_t cn_i) {
-    int64_t c = INF;
-    int a = -1;
-    const int pi = s.prv[i];
-    if (pi == NONE) {
-        const int64_t d = s.dpre[i];
-        if (d < INF_CUT) {
-            c = d + cn_i;
-            a = s.anc_pre[i];
-        }
-    } else {
-        const int j = s.nxt[i];
-        if (j >= 0) {
-            const int64_t d = s.dpre[j];
-            if (d < INF_CUT) {
-                c = d - s.mcost[j];
-                a = s.anc_pre[j];
-            }
-        }
-    }
-    if (c < s.dpost[i]) {
-        s.dpost[i] = c;
-        s.anc_post[i] = (IdxT)a;
-        return true;
-    }
-    return false;
-}
-
-// finish the pull for pre_j given the best forward in-arc found by the lane group; adds S -> pre_j and the reversed
-// node arc post_j -> pre_j. One lane.
-template <typename IdxT>
-__device__ __forceinline__ bool finish_pre(const State<IdxT> &s, int j, KeyIdx best, bool with_forward, int64_t en_j,
-                                           int64_t cn_j) {
-    const int pj = s.prv[j];
-    int anc = -1;
-    if (with_forward) {
-        if (best.idx >= 0) anc = s.anc_post[best.idx];
-        if (pj != TERM && en_j < best.key) {
-            best.key = en_j;
-            best.idx = PAR_S;
-            anc = j;
-        }
-    }
-    if (pj != NONE) {
-        const int64_t d = s.dpost[j];
-        if (d < INF_CUT) {
-            const int64_t c = d - cn_j;
-            if (c < best.key) {
-                best.key = c;
-                best.idx = PAR_POST;
-                anc = s.anc_post[j];
-            }
-        }
-    }
-    if (best.key < s.dpre[j]) {
-        s.dpre[j] = best.key;
-        s.par[j] = (IdxT)best.idx;
-        s.anc_pre[j] = (IdxT)anc;
-        return true;
-    }
-    return false;
-}
-
-// best forward in-arc of pre_j seen by this lane (the lanes of a group stride over the row).
-// a0 >= 0: staged arcs in shared memory; a0 < 0: -(1 + index) into the global CSR.
-template <typename IdxT>
-__device__ __forceinline__ KeyIdx scan_in_arcs(const State<IdxT> &s, int j, int a0, int deg, int sub) {
-    KeyIdx best;
-    best.key = INF;
-    best.idx = PAR_NONE;
-    const int pj = s.prv[j];
-    if (a0 >= 0) {
-        for (int k = sub; k < deg; k += LPN) {
-            const int i = s.asrc[a0 + k];
-            const int64_t di = s.dpost[i];
-            if (i != pj && di < INF_CUT) {
-                const int64_t cand = di + s.acost[a0 + k];
-                if (cand < best.key) {  // sources ascend, so the first minimum has the lowest index
-                    best.key = cand;
-                    best.idx = i;
-                }
-            }
-        }
-    } else {
-        const int e0 = -(a0 + 1);
-        for (int k = sub; k < deg; k += LPN) {
-            const int i = s.in_src[e0 + k] - s.g0;
-            const int64_t di = s.dpost[i];
-            if (i != pj && di < INF_CUT) {
-                const int64_t cand = di + s.in_cost[e0 + k];
-                if (cand < best.key) {
-                    best.key = cand;
-                    best.idx = i;
-                }
-            }
-        }
-    }
-    return best;
-}
-
-__device__ __forceinline__ KeyIdx group_min(KeyIdx best) {
+__device__ __forceinline__ KeyIdx group_min(KeyIdx best, unsigned mask) {
 #pragma unroll
     for (int d = 1; d < LPN; d <<= 1) {
-        KeyIdx o = shfl_xor_ki(best, d);
+        KeyIdx o = shfl_xor_ki(best, d, mask);
         if (o.key < best.key || (o.key == best.key && o.idx >= 0 && (best.idx < 0 || o.idx < best.idx))) best = o;
     }
     return best;
 }
 
-template <typename IdxT, bool SMEM_STATE>
-__global__ void k_ssp_solve(const SolveParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_scan[33];
+// Block-wide exclusive scan with ONE barrier: every warp publishes its total, every thread sums the totals of the
+// warps before it. `scratch` must hold 2 * 32 ints; `phase` alternates 0/1 between consecutive calls.
+__device__ __forceinline__ int block_excl_scan1(int v, int *scratch, int phase, int *total) {
+    const int incl = warp_incl_scan(v);
+    const int w = warp_id(), l = lane_id();
+    const int nw = (blockDim.x + 31) >> 5;
+    int *sc = scratch + 32 * phase;
+    if (l == 31) sc[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int k = 0; k < nw; k++) {
+        const int t = sc[k];
+        if (k < w) base += t;
+        tot += t;
+    }
+    *total = tot;
+    return base + incl - v;
+}
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+// Everything the per-augmentation work needs (pointers are already offset to the graph).
+struct Ctx {
+    const SolveParams *p;
+    int g0, n, arc0;
+    int64_t *dpre, *dpost, *mcost;
+    int32_t *par, *anc_pre, *anc_post, *slot_of, *dl, *dla0, *nxt, *prv;
+    const int32_t *tkey, *in_ptr;
+    const int64_t *en, *cn;
+};
+
+struct Counters {
+    int64_t n_asc, n_desc, n_node, n_arc;
+    long long t_phase[7];  // cycles (thread 0): arg-min, collect, stage, walk, sweeps, write-back, first tree
+    long long t_mark;
+    __device__ __forceinline__ void tick(int k) {
+        const long long now = clock64();
+        t_phase[k] += now - t_mark;
+        t_mark = now;
+    }
+};
+
+// Stage the branch (nd records, listed in dl[]), flip the path that ends in `sink_node`, re-label the branch,
+// write it back. SM = the staging area is in shared memory (the compiler then emits LDS/STS), otherwise in the
+// global workspace. Returns false if the walk found an inconsistent state (cannot happen).
+template <bool SM>
+__device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, int root, int sink_node, int *s_ok,
+                                               long long *s_work, int sweep_warp, Counters &cnt) {
+    const SolveParams &p = *c.p;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
+    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);  // the lanes of this thread's group
+    const int gshift = (tid & 31) / LPN * LPN;
+    Stage st;
+    if (SM) {
+        st.rec = (Rec *)smem_raw;
+        st.arc = (StArc *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec));
+        st.tk = (int32_t *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec) + (size_t)(p.arc_cap + 8) * sizeof(StArc));
+    } else {
+        st.rec = p.ws_rec + c.g0;
+        st.arc = p.ws_arc + c.arc0 + c.g0 + 8 * (size_t)blockIdx.x;  // all in-arcs + a marker per detection + pad
+        st.tk = p.ws_tk + c.g0;
+    }
+    // ---- stage the branch: one lane group per record
+    for (int sb = 0; sb < nd; sb += ngrp) {
+        const int s = sb + grp;
+        const bool valid = s < nd;
+        const int ent = valid ? c.dl[s] : 0;
+        const int j = ent & DL_MASK;
+        KeyIdx cbest;  // best in-arc from outside the branch
+        cbest.key = INF;
+        cbest.idx = PAR_NONE;
+        int nda = 0, a0 = 0;
+        if (valid && (ent & DL_PRE)) {
+            a0 = c.dla0[s];
+            const int e0 = c.in_ptr[j], deg = c.in_ptr[j + 1] - e0;
+            for (int k0 = 0; k0 < deg; k0 += LPN) {
+                const int k = k0 + sub;
+                const bool has = k < deg;
+                int i = -1, a = -2;
+                int64_t w = 0, di = INF;
+                if (has) {
+                    i = p.in_src[e0 + k] - c.g0;
+                    w = p.in_cost[e0 + k];
+                    a = c.anc_post[i];
+                    di = c.dpost[i];
+                }
+                const bool inside = has && a == root;
+                const unsigned m = (__ballot_sync(gmask, inside) >> gshift) & 0xFu;
+                if (inside) {
+                    StArc x;
+                    x.cost = w;
+                    x.src = c.slot_of[i];
+                    x.pad = 0;
+                    st.arc[a0 + nda + __popc(m & ((1u << sub) - 1u))] = x;
+                } else if (has && di < INF_CUT) {
+                    const int64_t cand = di + w;
+                    if (cand < cbest.key) {
+                        cbest.key = cand;
+                        cbest.idx = i;
+                    }
+                }
+                nda += __popc(m);
+            }
+        }
+        cbest = group_min(cbest, gmask);
+        if (valid && sub == 0) {
+            const int64_t dpre_j = c.dpre[j], dpost_j = c.dpost[j], cn_j = c.cn[j];
+            const int prv_j = c.prv[j], nxt_j = c.nxt[j], par_j = c.par[j];
+            const int apost_j = c.anc_post[j];
+            int64_t bkey = cbest.key;
+            int bpar = cbest.idx, banc = cbest.idx >= 0 ? c.anc_post[cbest.idx] : -1;
+            if ((ent & DL_PRE) && !(ent & DL_POST) && prv_j != NONE && dpost_j < INF_CUT) {
+                const int64_t v = dpost_j - cn_j;  // own post node is outside the branch: a constant candidate
+                if (v < bkey) {
+                    bkey = v;
+                    bpar = PAR_POST;
+                    banc = apost_j;
+                }
+            }
+            Rec r;
+            r.A = make_int4(ent, a0, ((ent & DL_PRE) && prv_j >= 0) ? c.slot_of[prv_j] : -1, prv_j);
+            if (ent & DL_PRE) {
+                StArc x;
+                x.cost = 0;
+                x.src = -1;  // end of this record's arc list
+                x.pad = 0;
+                st.arc[a0 + nda] = x;
+                st.arc[a0].pad = nda;  // the first slot also carries the length of the list
+            }
+            r.B = make_int4(((ent & DL_POST) && nxt_j >= 0) ? c.slot_of[nxt_j] : -1,
+                            ((ent & DL_PRE) && par_j >= 0) ? c.slot_of[par_j] : -1, bpar, banc);
+            r.C = make_longlong2(bkey, c.en[j]);
+            r.D = make_longlong2(cn_j, c.mcost[j]);
+            r.E = make_longlong2(dpre_j, dpost_j);
+            r.F = make_int4(par_j, c.anc_pre[j], apost_j, nxt_j);
+            st.rec[s] = r;
+            st.tk[s] = c.tkey[j];
+        }
+    }
+    __syncthreads();
+    cnt.tick(2);
+    // ---- augment: walk the path back from T inside the staged branch and rewrite next/prev
+    //      (Graph::flip_path, Graph.cpp:266-335). One thread.
+    if (tid == 0) {
+        int ok = 0, nhop = 0;
+        int nxt_new = TERM, nxt_new_slot = -1;
+        int cur = c.slot_of[sink_node];
+        for (int step = 0; step <= nd; step++) {
+            int m;
+            const int cur_prv = st.rec[cur].A.w, cur_ns = st.rec[cur].B.x;
+            st.rec[cur].F.w = nxt_new;
+            st.rec[cur].B.x = nxt_new_slot;
+            if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
+                m = cur;
+            } else {  // post_cur came from pre_m, m = its old successor: the arc cur->m is cancelled
+                m = cur_ns;
+                while (m >= 0 && st.rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
+                    const int m2 = st.rec[m].B.x;
+                    st.rec[m].F.w = NONE;
+                    st.rec[m].B.x = -1;
+                    st.rec[m].A.w = NONE;
+                    st.rec[m].A.z = -1;
+                    m = m2;
+                }
+            }
+            if (m < 0) break;  // cannot happen on a consistent residual state
+            const int4 mA = st.rec[m].A;
+            const int q = st.rec[m].F.x, qs = st.rec[m].B.y;
+            if (q < 0) {  // PAR_S: the path starts here
+                st.rec[m].A.w = TERM;
+                st.rec[m].A.z = -1;
+                ok = 1;
+                break;
+            }
+            st.rec[m].A.w = q;
+            st.rec[m].A.z = qs;
+            c.dla0[nhop++] = m;  // the cost of the newly matched arc q -> m is looked up in parallel below
+            nxt_new = mA.x & DL_MASK;
+            nxt_new_slot = m;
+            cur = qs;
+        }
+        *s_ok = ok;
+        s_ok[1] = nhop;
+    }
+    __syncthreads();
+    cnt.tick(3);
+    if (!*s_ok) return false;
+    for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
+        const int m = c.dla0[h];
+        const int qs = st.rec[m].A.z, b0 = st.rec[m].A.y;
+        const int deg = st.arc[b0].pad;
+        for (int k = 0; k < deg; k++) {
+            const StArc x = st.arc[b0 + k];
+            if (x.src == qs) {
+                st.rec[m].D.y = x.cost;
+                break;
+            }
+        }
+    }
+    // ---- un-label the branch; flag the first record of every layer (DL_FIRST) for the sweeps
+    for (int s = tid; s < nd; s += T) {
+        int ent = st.rec[s].A.x;
+        if (s == 0 || st.tk[s] != st.tk[s - 1]) {
+            ent |= DL_FIRST;
+            st.rec[s].A.x = ent;
+        }
+        if (ent & DL_PRE) {
+            st.rec[s].E.x = INF;
+            st.rec[s].F.x = PAR_NONE;
+            st.rec[s].F.y = -1;
+        }
+        if (ent & DL_POST) {
+            st.rec[s].E.y = INF;
+            st.rec[s].F.z = -1;
+        }
+    }
+    __syncthreads();
+    // ---- re-label it: exact Bellman-Ford fix-point in pull mode by ONE warp, one lane per record of the current
+    //      layer. Ascending layer order settles forward arcs, descending order the reversed arcs (they run
+    //      backwards in time along tracks); alternate until nothing moves.
+    if (warp_id() == sweep_warp) {
+        const int lane = lane_id();
+        int n_node32 = 0, n_arc32 = 0, n_asc32 = 0, n_desc32 = 0;
+        for (int round = 0; round < 2 * nd + 4; round++) {
+            bool ch = false;
+            n_asc32++;
+            for (int q = 0; q < nd;) {
+                // one step = the records of one layer, at most 4 at a time, 8 lanes per record (one per in-arc)
+                const int r8 = lane >> 3, a8 = lane & 7;
+                const int s = q + r8;
+                const bool in_range = s < nd;
+                int4 A = make_int4(DL_FIRST, 0, -1, NONE), B = make_int4(-1, -1, PAR_NONE, -1), F = make_int4(0, 0, 0, 0);
+                longlong2 C = make_longlong2(INF, INF), D = make_longlong2(0, 0), E = make_longlong2(INF, INF);
+                if (in_range) {
+                    const Rec *r = st.rec + s;
+                    A = r->A;
+                    B = r->B;
+                    C = r->C;
+                    D = r->D;
+                    E = r->E;
+                    F = r->F;
+                }
+                const unsigned brk = __ballot_sync(0xffffffffu, lane >= 8 && a8 == 0 && (A.x & DL_FIRST));
+                const int cn_t = brk ? (__ffs(brk) - 1) >> 3 : 4;
+                const bool valid = r8 < cn_t;
+                const int ent = valid ? A.x : 0;
+                // next record on the track (higher layer, not in this step) and this record's in-arcs from inside
+                // the branch: all loads are issued before anything is decided
+                int64_t nx_dpre = INF, nx_mc = 0;
+                int nx_apre = -1;
+                KeyIdx best;
+                best.key = INF;
+                best.idx = -1;
+                int deg = 0;
+                if (ent & DL_PRE) {
+                    const StArc x0 = st.arc[A.y + a8];  // speculative: issued together with the list length
+                    deg = st.arc[A.y].pad;
+                    if (a8 < deg) {
+                        const int64_t d = st.rec[x0.src].E.y;
+                        if (x0.src != A.z && d < INF_CUT) {
+                            best.key = d + x0.cost;
+                            best.idx = x0.src;
+                        }
+                    }
+                    for (int k = a8 + 8; k < deg; k += 8) {
+                        const StArc x = st.arc[A.y + k];
+                        const int64_t d = st.rec[x.src].E.y;
+                        if (x.src != A.z && d < INF_CUT && d + x.cost < best.key) {
+                            best.key = d + x.cost;
+                            best.idx = x.src;
+                        }
+                    }
+                }
+                if (valid && B.x >= 0 && a8 == 0) {
+                    const Rec *r = st.rec + B.x;
+                    nx_dpre = r->E.x;
+                    nx_mc = r->D.y;
+                    nx_apre = r->F.y;
+                }
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {  // slots ascend with the detection index: lowest slot wins ties
+                    const KeyIdx o = shfl_xor_ki(best, d);
+                    if (o.idx >= 0 && (best.idx < 0 || o.key < best.key || (o.key == best.key && o.idx < best.idx)))
+                        best = o;
+                }
+                if (valid && a8 == 0) {
+                    int64_t dpre_s = E.x, dpost_s = E.y;
+                    bool upd = false;
+                    if (ent & DL_PRE) {
+                        int64_t key = INF;
+                        int par = PAR_NONE, anc = -1;
+                        if (best.idx >= 0) {
+                            key = best.key;
+                            par = st.rec[best.idx].A.x & DL_MASK;
+                            anc = st.rec[best.idx].F.z;
+                        }
+                        if (C.x < key || (C.x == key && B.z >= 0 && B.z < par)) {
+                            key = C.x;
+                            par = B.z;
+                            anc = B.w;
+                        }
+                        if (A.w != TERM && C.y < key) {
+                            key = C.y;
+                            par = PAR_S;
+                            anc = ent & DL_MASK;
+                        }
+                        if ((ent & DL_POST) && A.w != NONE && dpost_s < INF_CUT && dpost_s - D.x < key) {
+                            key = dpost_s - D.x;
+                            par = PAR_POST;
+                            anc = F.z;
+                        }
+                        if (key < dpre_s) {
+                            dpre_s = key;
+                            F.x = par;
+                            F.y = anc;
+                            upd = true;
+                        }
+                        n_arc32 += deg;
+                    }
+                    if (ent & DL_POST) {
+                        int64_t v = INF;
+                        int a = -1;
+                        if (A.w == NONE) {
+                            if (dpre_s < INF_CUT) {
+                                v = dpre_s + D.x;
+                                a = F.y;
+                            }
+                        } else if (nx_dpre < INF_CUT) {
+                            v = nx_dpre - nx_mc;
+                            a = nx_apre;
+                        }
+                        if (v < dpost_s) {
+                            dpost_s = v;
+                            F.z = a;
+                            upd = true;
+                        }
+                    }
+                    if (upd) {
+                        st.rec[s].E = make_longlong2(dpre_s, dpost_s);
+                        st.rec[s].F = F;
+                        ch = true;
+                    }
+                }
+                n_node32 += cn_t;
+                q += cn_t;
+                __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, ch) && round > 0) break;
+            bool ch2 = false;
+            n_desc32++;
+            for (int q = nd; q > 0;) {
+                // walking down: the records of one layer (until the one flagged DL_FIRST), one lane each
+                const int s = q - 1 - lane;
+                const bool in_range = s >= 0;
+                int4 A = make_int4(DL_FIRST, 0, -1, NONE), F = make_int4(0, 0, 0, 0);
+                int ns = -1;
+                longlong2 D = make_longlong2(0, 0), E = make_longlong2(INF, INF);
+                if (in_range) {
+                    const Rec *r = st.rec + s;
+                    A = r->A;
+                    ns = r->B.x;
+                    D = r->D;
+                    E = r->E;
+                    F = r->F;
+                }
+                const unsigned fst = __ballot_sync(0xffffffffu, (A.x & DL_FIRST) != 0);
+                const int cn_t = fst ? __ffs(fst) : 32;  // lanes 0 .. ffs-1 (the layer's first record included)
+                if (lane < cn_t && in_range) {
+                    const int ent = A.x;
+                    int64_t dpre_s = E.x, dpost_s = E.y;
+                    bool upd = false;
+                    if (ent & DL_POST) {
+                        int64_t v = INF;
+                        int a = -1;
+                        if (A.w == NONE) {
+                            if (dpre_s < INF_CUT) {
+                                v = dpre_s + D.x;
+                                a = F.y;
+                            }
+                        } else if (ns >= 0) {
+                            const Rec *r = st.rec + ns;
+                            const int64_t d = r->E.x;
+                            if (d < INF_CUT) {
+                                v = d - r->D.y;
+                                a = r->F.y;
+                            }
+                        }
+                        if (v < dpost_s) {
+                            dpost_s = v;
+                            F.z = a;
+                            upd = true;
+                        }
+                    }
+                    if ((ent & DL_PRE) && (ent & DL_POST) && A.w != NONE && dpost_s < INF_CUT &&
+                        dpost_s - D.x < dpre_s) {
+                        dpre_s = dpost_s - D.x;
+                        F.x = PAR_POST;
+                        F.y = F.z;
+                        upd = true;
+                    }
+                    if (upd) {
+                        st.rec[s].E = make_longlong2(dpre_s, dpost_s);
+                        st.rec[s].F = F;
+                        ch2 = true;
+                    }
+                }
+                const int done = cn_t < q ? cn_t : q;
+                n_node32 += done;
+                q -= done;
+                __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, ch2)) break;
+        }
+        // work counters of this branch (the leaders of the lane groups counted the arcs)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) n_arc32 += __shfl_xor_sync(0xffffffffu, n_arc32, d);
+        if (lane == 0) {
+            s_work[0] += n_asc32;
+            s_work[1] += n_desc32;
+            s_work[2] += n_node32;
+            s_work[3] += n_arc32;
+        }
+    }
+    __syncthreads();
+    cnt.tick(4);
+    // ---- write the branch back
+    for (int s = tid; s < nd; s += T) {
+        const Rec r = st.rec[s];
+        const int ent = r.A.x;
+        const int j = ent & DL_MASK;
+        if (ent & DL_PRE) {
+            c.dpre[j] = r.E.x;
+            c.par[j] = r.F.x;
+            c.anc_pre[j] = r.F.y;
+        }
+        if (ent & DL_POST) {
+            c.dpost[j] = r.E.y;
+            c.anc_post[j] = r.F.z;
+        }
+        c.nxt[j] = r.F.w;
+        c.prv[j] = r.A.w;
+        c.mcost[j] = r.D.y;
+    }
+    if (tid == 0) cnt.n_arc += atot;  // arcs read while staging
+    __syncthreads();
+    cnt.tick(5);
+    return true;
+}
+
+__global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
+    __shared__ int s_scan[64];
     __shared__ KeyIdx s_red[33];
-    __shared__ int s_nfix, s_root;
+    __shared__ int s_ok[2], s_sweep_warp;
+    __shared__ long long s_work[4];  // ascending sweeps, descending sweeps, node pulls, arc pulls (sweep warp)
 
     const int g = blockIdx.x;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
     const int T = blockDim.x;
     const int tid = threadIdx.x;
+    int32_t *nxt = p.next_out + g0, *prv = p.prev_out + g0;
     if (n <= 0 || (int64_t)p.in_ptr[g0 + n] > p.arc_capacity) {
         // empty graph, or the arc buffer overflowed during the build (reported by the fill kernel's flag)
         if (tid == 0) {
@@ -219,56 +576,71 @@ __global__ void k_ssp_solve(const SolveParams p) {
             p.total[g] = 0;
         }
         for (int i = tid; i < n; i += T) {
-            p.next_out[g0 + i] = NONE;
-            p.prev_out[g0 + i] = NONE;
+            nxt[i] = NONE;
+            prv[i] = NONE;
         }
         return;
     }
-    State<IdxT> s;
-    unsigned char *sm = smem_raw;
-    if (SMEM_STATE) {
-        s.dpre = (int64_t *)sm;
-        s.dpost = s.dpre + n;
-        s.mcost = s.dpost + n;
-        s.par = (IdxT *)(s.mcost + n);
-        s.nxt = s.par + n;
-        s.prv = s.nxt + n;
-        s.anc_pre = s.prv + n;
-        s.anc_post = s.anc_pre + n;
-        sm = (unsigned char *)(((uintptr_t)(s.anc_post + n) + 15) & ~(uintptr_t)15);
-    } else {
-        s.dpre = p.ws_dpre + g0;
-        s.dpost = p.ws_dpost + g0;
-        s.mcost = p.ws_mcost + g0;
-        s.par = (IdxT *)(p.ws_idx + g0);
-        s.nxt = (IdxT *)(p.ws_idx + p.n_total + g0);
-        s.prv = (IdxT *)(p.ws_idx + 2 * p.n_total + g0);
-        s.anc_pre = (IdxT *)(p.ws_idx + 3 * p.n_total + g0);
-        s.anc_post = (IdxT *)(p.ws_idx + 4 * p.n_total + g0);
+    // Which warp runs the sequential sweeps: blocks sharing an SM should use different SM sub-partitions (warp
+    // schedulers), otherwise their sweep warps fight for one issue port. %warpid is the hardware warp slot; slots
+    // of a block are consecutive, slot % 4 = sub-partition. Pick the warp whose sub-partition equals the block's
+    // slot group.
+    if (tid < 4) s_work[tid] = 0;
+    if (tid % 32 == 0) {
+        unsigned hw;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
+        if (tid == 0) s_sweep_warp = 0;
+        s_scan[warp_id()] = (int)hw;
     }
-    // staging area for the branch being re-labelled
-    Rec *rec_sm = (Rec *)sm;
-    s.acost = (int64_t *)(rec_sm + p.rec_cap);
-    s.asrc = (int32_t *)(s.acost + p.arc_cap);
-    s.in_src = p.in_src;
-    s.in_cost = p.in_cost;
-    s.g0 = g0;
-    Rec *rec_gl = p.ws_rec + g0;
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = (T + 31) >> 5;
+        const int want = (s_scan[0] / (nw > 0 ? nw : 1)) & 3;
+        for (int w = 0; w < nw; w++)
+            if ((s_scan[w] & 3) == want) {
+                s_sweep_warp = w;
+                break;
+            }
+    }
+    __syncthreads();
+    const int sweep_warp = s_sweep_warp;
+    Ctx c;
+    c.p = &p;
+    c.g0 = g0;
+    c.n = n;
+    c.dpre = p.ws_dpre + g0;
+    c.dpost = p.ws_dpost + g0;
+    c.mcost = p.ws_mcost + g0;
+    c.par = p.ws_par + g0;
+    c.anc_pre = p.ws_anc_pre + g0;
+    c.anc_post = p.ws_anc_post + g0;
+    c.slot_of = p.ws_slot_of + g0;
+    c.dl = p.ws_dl + g0;
+    c.dla0 = p.ws_dla0 + g0;
+    c.nxt = nxt;
+    c.prv = prv;
+    c.tkey = p.tkey + g0;
+    c.in_ptr = p.in_ptr + g0;
+    c.en = p.en + g0;
+    c.cn = p.cn + g0;
+    c.arc0 = c.in_ptr[0];
+    int64_t *dpre = c.dpre, *dpost = c.dpost;
+    int32_t *par = c.par, *anc_pre = c.anc_pre, *anc_post = c.anc_post;
     int32_t *lvl = p.ws_lvl + g0 + g;
-    int32_t *fix = p.ws_fix + g0;
-    const int32_t *tkey = p.tkey + g0;
-    const int32_t *in_ptr = p.in_ptr + g0;
-    const int64_t *en = p.en + g0, *cn = p.cn + g0, *ex = p.ex + g0;
+    const int32_t *tkey = c.tkey, *in_ptr = c.in_ptr;
+    const int64_t *en = c.en, *cn = c.cn, *ex = p.ex + g0;
+    const int n_arcs_graph = in_ptr[n] - c.arc0;
 
     // ---- prologue: empty flow, nothing labelled, frame layers
     for (int i = tid; i < n; i += T) {
-        s.nxt[i] = (IdxT)NONE;
-        s.prv[i] = (IdxT)NONE;
-        s.dpre[i] = INF;
-        s.dpost[i] = INF;
-        s.par[i] = (IdxT)PAR_NONE;
-        s.anc_pre[i] = (IdxT)-1;
-        s.anc_post[i] = (IdxT)-1;
+        nxt[i] = NONE;
+        prv[i] = NONE;
+        dpre[i] = INF;
+        dpost[i] = INF;
+        par[i] = PAR_NONE;
+        anc_pre[i] = -1;
+        anc_post[i] = -1;
+        c.mcost[i] = 0;
     }
     int L = 0;
     for (int base = 0; base < n; base += T) {
@@ -284,13 +656,19 @@ __global__ void k_ssp_solve(const SolveParams p) {
 
     int K = 0;
     int64_t total = 0;
-    int64_t n_asc = 0, n_desc = 0, n_node = 0, n_arc = 0;
+    Counters cnt;
+    cnt.n_asc = 1;
+    cnt.n_desc = 0;
+    cnt.n_node = 2 * (int64_t)n;
+    cnt.n_arc = 0;
+    for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
+    cnt.t_mark = clock64();
     const int sub = tid % LPN;
     const int grp = tid / LPN;
     const int ngrp = T / LPN;
 
-    // ---- first tree: no flow yet, the network is a DAG: one sweep over the frame layers with the whole block
-    //      (Graph::shortest_path_dag, Graph.cpp:139-187)
+    // ---- first tree: no flow yet, the network is a DAG: one pull sweep over the frame layers with the whole block
+    //      (Graph::shortest_path_dag, Graph.cpp:139-187); branch label = the detection whose S arc starts the path
     for (int l = 0; l < L; l++) {
         const int a = lvl[l], b = lvl[l + 1];
         for (int jb = a; jb < b; jb += ngrp) {
@@ -300,34 +678,56 @@ __global__ void k_ssp_solve(const SolveParams p) {
             best.key = INF;
             best.idx = PAR_NONE;
             if (valid) {
-                const int e0 = in_ptr[j];
-                best = scan_in_arcs(s, j, -(e0 + 1), in_ptr[j + 1] - e0, sub);
+                const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
+                for (int k = sub; k < deg; k += LPN) {
+                    const int i = p.in_src[e0 + k] - g0;
+                    const int64_t di = dpost[i];
+                    if (di < INF_CUT) {
+                        const int64_t cand = di + p.in_cost[e0 + k];
+                        if (cand < best.key) {  // sources ascend: the first minimum has the lowest index
+                            best.key = cand;
+                            best.idx = i;
+                        }
+                    }
+                }
             }
-            best = group_min(best);
+            best = group_min(best, 0xffffffffu);
             if (valid && sub == 0) {
-                const int64_t cn_j = cn[j];
-                finish_pre(s, j, best, true, en[j], cn_j);
-                pull_post(s, j, cn_j);
+                int anc = best.idx >= 0 ? anc_post[best.idx] : -1;
+                const int64_t e_ = en[j];
+                if (e_ < best.key) {
+                    best.key = e_;
+                    best.idx = PAR_S;
+                    anc = j;
+                }
+                if (best.key < INF_CUT) {
+                    dpre[j] = best.key;
+                    par[j] = best.idx;
+                    anc_pre[j] = anc;
+                    dpost[j] = best.key + cn[j];
+                    anc_post[j] = anc;
+                }
             }
         }
         __syncthreads();
     }
-    n_asc = 1;
-    n_node = 2 * (int64_t)n;
-    const int64_t first_arcs = in_ptr[n] - in_ptr[0];
+    cnt.n_arc = (tid == 0) ? n_arcs_graph : 0;
+    cnt.tick(6);
 
     for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
         // ---- cheapest way into T (Graph::update_sink_info's job, Graph.cpp:508-541; here a block-wide arg-min)
         KeyIdx best;
         best.key = INF;
         best.idx = -1;
+#pragma unroll 4
         for (int i = tid; i < n; i += T) {
-            const int64_t d = s.dpost[i], x = ex[i];
-            if (s.nxt[i] != TERM && d < INF_CUT && x < INF_CUT) {
-                KeyIdx c;
-                c.key = d + x;
-                c.idx = i;
-                best = min_ki(best, c);
+            const int64_t d = dpost[i], x = ex[i];
+            const int nx = nxt[i];
+            if (nx != TERM && d < INF_CUT && x < INF_CUT) {
+                KeyIdx v;
+                v.key = d + x;
+                v.idx = i;
+                best = min_ki(best, v);
             }
         }
 #pragma unroll
@@ -337,230 +737,88 @@ __global__ void k_ssp_solve(const SolveParams p) {
         }
         if (lane_id() == 0) s_red[warp_id()] = best;
         __syncthreads();
-        if (warp_id() == 0) {
+        KeyIdx sink;
+        {
             const int nw = (T + 31) >> 5;
-            KeyIdx b2;
-            b2.key = INF;
-            b2.idx = -1;
-            if (lane_id() < nw) b2 = s_red[lane_id()];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                KeyIdx o = shfl_xor_ki(b2, d);
-                if (o.idx >= 0 && (b2.idx < 0 || o.key < b2.key || (o.key == b2.key && o.idx < b2.idx))) b2 = o;
+            sink.key = INF;
+            sink.idx = -1;
+            for (int k = 0; k < nw; k++) {
+                const KeyIdx o = s_red[k];
+                if (o.idx >= 0 && (sink.idx < 0 || o.key < sink.key || (o.key == sink.key && o.idx < sink.idx)))
+                    sink = o;
             }
-            if (lane_id() == 0) s_red[32] = b2;
         }
-        __syncthreads();
-        const KeyIdx sink = s_red[32];
+        __syncthreads();  // s_red is rewritten next iteration
+        cnt.tick(0);
         if (sink.idx < 0) break;             // T unreachable
         if (K >= 1 && sink.key >= 0) break;  // wrapper.cpp:263-267: stop when the next path does not pay
-        // ---- augment: walk the path back from T and rewrite next/prev (Graph::flip_path, Graph.cpp:266-335)
-        if (tid == 0) {
-            int nfix = 0;
-            int nxt_new = TERM;
-            int cur = sink.idx;
-            int root = -1;
-            for (int step = 0; step <= n; step++) {
-                int m;
-                if (s.prv[cur] == NONE) {  // post_cur came from pre_cur: detection cur joins a track
-                    s.nxt[cur] = (IdxT)nxt_new;
-                    m = cur;
-                } else {  // post_cur came from pre_m, m = its old successor: the arc cur->m is cancelled
-                    m = s.nxt[cur];
-                    s.nxt[cur] = (IdxT)nxt_new;
-                    while (m >= 0 && s.par[m] == PAR_POST) {  // pre_m came from post_m: m leaves its track
-                        const int m2 = s.nxt[m];
-                        s.nxt[m] = (IdxT)NONE;
-                        s.prv[m] = (IdxT)NONE;
-                        m = m2;
+        const int root = anc_post[sink.idx];
+        if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        // ---- the path lies in the branch hanging from S -> pre_root, and that branch is exactly what loses its
+        //      labels when the path is flipped (Graph::find_node_set4update, Graph.cpp:341-343): collect it in
+        //      layer order (= ascending detection index). One scan carries both counts: records and their in-arcs.
+        // Every thread owns a contiguous chunk of detections, so one block scan suffices.
+        int nd = 0, atot = 0;
+        {
+            const int chunk = (n + T - 1) / T;
+            const int i0 = tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
+            int my_nd = 0, my_arcs = 0;
+            for (int i = i0; i < i1; i++) {
+                const bool fp = anc_pre[i] == root, fo = anc_post[i] == root;
+                my_nd += (fp || fo) ? 1 : 0;
+                if (fp) my_arcs += in_ptr[i + 1] - in_ptr[i] + 1;  // + 1: end-of-list marker
+            }
+            int tot_nd, tot_arcs;
+            int slot = block_excl_scan1(my_nd, s_scan, 0, &tot_nd);
+            int a0 = block_excl_scan1(my_arcs, s_scan, 1, &tot_arcs);
+            nd = tot_nd;
+            atot = tot_arcs;
+            if (my_nd)
+                for (int i = i0; i < i1; i++) {
+                    int f = 0;
+                    if (anc_pre[i] == root) f |= DL_PRE;
+                    if (anc_post[i] == root) f |= DL_POST;
+                    if (f) {
+                        c.dl[slot] = i | f;
+                        c.dla0[slot] = a0;
+                        c.slot_of[i] = slot;
+                        slot++;
+                        if (f & DL_PRE) a0 += in_ptr[i + 1] - in_ptr[i] + 1;
                     }
                 }
-                if (m < 0) break;  // cannot happen on a consistent residual state
-                const int q = s.par[m];
-                if (q < 0) {  // PAR_S (anything else cannot happen)
-                    s.prv[m] = (IdxT)TERM;
-                    root = m;
-                    break;
-                }
-                s.prv[m] = (IdxT)q;
-                fix[nfix++] = m;
-                nxt_new = m;
-                cur = q;
-            }
-            s_nfix = nfix;
-            s_root = root;
-            if (p.path_cost) p.path_cost[g0 + K] = sink.key;
         }
         __syncthreads();
-        // cost of every newly matched arc prev[m] -> m (used by the reversed arcs)
-        const int nfix = s_nfix;
-        for (int t = tid; t < nfix; t += T) {
-            const int m = fix[t];
-            const int src = s.prv[m] + g0;
-            const int e1 = in_ptr[m + 1];
-            for (int e = in_ptr[m]; e < e1; e++)
-                if (p.in_src[e] == src) {
-                    s.mcost[m] = p.in_cost[e];
-                    break;
-                }
-        }
+        cnt.tick(1);
+        if (tid == 0 && p.path_cost) p.path_cost[g0 + K] = sink.key;
+        const bool in_smem = nd <= p.rec_cap && atot <= p.arc_cap;
+        const bool ok = in_smem ? relabel_branch<true>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt)
+                                : relabel_branch<false>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt);
+        if (!ok) break;  // defensive: inconsistent state, stop with what we have
         K++;
         total += sink.key;
-        const int root = s_root;
-        if (root < 0) break;
-        // ---- only the branch of the tree that hung from S -> pre_root lost its labels
-        //      (Graph::find_node_set4update, Graph.cpp:341-343). Pass 1: count it.
-        int nd = 0;
-        for (int base = 0; base < n; base += T) {
-            const int i = base + tid;
-            const int f = (i < n && (s.anc_pre[i] == root || s.anc_post[i] == root)) ? 1 : 0;
-            nd += __syncthreads_count(f);
-        }
-        Rec *rec = (nd <= p.rec_cap) ? rec_sm : rec_gl;
-        // Pass 2: work records in layer order (ascending detection index), labels reset, arc offsets by a scan of
-        // the in-degrees; arcs that do not fit in shared memory are read from the global CSR by the sweeps.
-        int pos = 0, aoff = 0;
-        for (int base = 0; base < n; base += T) {
-            const int i = base + tid;
-            int f = 0, deg = 0, e0 = 0;
-            if (i < n) {
-                if (s.anc_pre[i] == root) f |= DL_PRE;
-                if (s.anc_post[i] == root) f |= DL_POST;
-                if (f & DL_PRE) {
-                    e0 = in_ptr[i];
-                    deg = in_ptr[i + 1] - e0;
-                }
-            }
-            int tot, atot;
-            const int slot = pos + block_excl_scan(f ? 1 : 0, s_scan, &tot);
-            const int a0 = aoff + block_excl_scan(deg, s_scan, &atot);
-            if (f) {
-                Rec r;
-                r.jf = i | f;
-                r.tk = tkey[i];
-                r.deg = deg;
-                r.a0 = (a0 + deg <= p.arc_cap) ? a0 : -(e0 + 1);
-                r.en = en[i];
-                r.cn = cn[i];
-                rec[slot] = r;
-                if (r.a0 >= 0)
-                    for (int k = 0; k < deg; k++) {
-                        s.asrc[a0 + k] = p.in_src[e0 + k] - g0;
-                        s.acost[a0 + k] = p.in_cost[e0 + k];
-                    }
-                if (f & DL_PRE) {
-                    s.dpre[i] = INF;
-                    s.par[i] = (IdxT)PAR_NONE;
-                    s.anc_pre[i] = (IdxT)-1;
-                }
-                if (f & DL_POST) {
-                    s.dpost[i] = INF;
-                    s.anc_post[i] = (IdxT)-1;
-                }
-            }
-            pos += tot;
-            aoff += atot;
-        }
-        __syncthreads();
-        // ---- re-label the branch: exact Bellman-Ford fix-point over its nodes, warp 0 only (few nodes per layer).
-        if (warp_id() == 0) {
-            const int lane = lane_id();
-            constexpr int NPC = 32 / LPN;  // nodes per ascending chunk
-            for (int round = 0; round < 2 * n + 4; round++) {
-                bool ch = false;
-                n_asc++;
-                for (int q = 0; q < nd;) {
-                    // chunk = up to NPC consecutive records of one layer, LPN lanes each
-                    Rec r;
-                    r.jf = 0;
-                    r.tk = 0;
-                    r.a0 = 0;
-                    r.deg = 0;
-                    r.en = 0;
-                    r.cn = 0;
-                    const int my = lane / LPN;
-                    const bool in_range = q + my < nd;
-                    if (in_range) r = rec[q + my];
-                    const int tk0 = __shfl_sync(0xffffffffu, r.tk, 0);
-                    const unsigned same = __ballot_sync(0xffffffffu, in_range && r.tk == tk0);
-                    // lanes of group k occupy bits [k*LPN, (k+1)*LPN); count the leading groups of the same layer
-                    int cnt = 0;
-#pragma unroll
-                    for (int k = 0; k < NPC; k++)
-                        if (cnt == k && ((same >> (k * LPN)) & 1u)) cnt = k + 1;
-                    const bool valid = my < cnt;
-                    const int j = r.jf & DL_MASK;
-                    KeyIdx best;
-                    best.key = INF;
-                    best.idx = PAR_NONE;
-                    if (valid && (r.jf & DL_PRE)) best = scan_in_arcs(s, j, r.a0, r.deg, lane % LPN);
-                    best = group_min(best);
-                    if (valid && lane % LPN == 0) {
-                        if (r.jf & DL_PRE) {
-                            ch |= finish_pre(s, j, best, true, r.en, r.cn);
-                            n_arc += r.deg;
-                        }
-                        if (r.jf & DL_POST) ch |= pull_post(s, j, r.cn);
-                    }
-                    n_node += cnt;
-                    q += cnt;
-                    __syncwarp();
-                }
-                if (!__any_sync(0xffffffffu, ch) && round > 0) break;
-                bool ch2 = false;
-                n_desc++;
-                for (int q = nd; q > 0;) {
-                    // chunk = up to 32 consecutive records of one layer, one lane each (O(1) work per node)
-                    Rec r;
-                    r.jf = 0;
-                    r.tk = 0;
-                    r.a0 = 0;
-                    r.deg = 0;
-                    r.en = 0;
-                    r.cn = 0;
-                    const bool in_range = q - 1 - lane >= 0;
-                    if (in_range) r = rec[q - 1 - lane];
-                    const int tk0 = __shfl_sync(0xffffffffu, r.tk, 0);
-                    const unsigned same = __ballot_sync(0xffffffffu, in_range && r.tk == tk0);
-                    const int cnt = (same == 0xffffffffu) ? 32 : __ffs(~same) - 1;
-                    if (lane < cnt) {
-                        const int j = r.jf & DL_MASK;
-                        if (r.jf & DL_POST) ch2 |= pull_post(s, j, r.cn);
-                        KeyIdx none;
-                        none.key = INF;
-                        none.idx = PAR_NONE;
-                        if (r.jf & DL_PRE) ch2 |= finish_pre(s, j, none, false, r.en, r.cn);
-                    }
-                    n_node += cnt;
-                    q -= cnt;
-                    __syncwarp();
-                }
-                if (!__any_sync(0xffffffffu, ch2)) break;
-            }
-        }
-        __syncthreads();
     }
     // ---- results
-    if (p.stats && warp_id() == 0) {
-        // arc pulls of the sweeps were counted by the group leaders of warp 0
-        int64_t v = n_arc;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if (p.stats) {
         if (tid == 0) {
-            p.stats[4 * g + 0] = n_asc;
-            p.stats[4 * g + 1] = n_desc;
-            p.stats[4 * g + 2] = n_node;
-            p.stats[4 * g + 3] = v + first_arcs;
+            int64_t *o = p.stats + (size_t)MOT3D_SOLVE_STATS * g;
+            o[0] = cnt.n_asc + s_work[0];
+            o[1] = cnt.n_desc + s_work[1];
+            o[2] = cnt.n_node + s_work[2];
+            o[3] = cnt.n_arc + s_work[3];
+            for (int k = 0; k < 7; k++) o[4 + k] = cnt.t_phase[k];
+            o[11] = 0;
         }
     }
     if (tid == 0) {
         p.n_paths[g] = K;
         p.total[g] = total;
     }
+    __syncthreads();
     for (int i = tid; i < n; i += T) {
-        const int a = s.nxt[i], b = s.prv[i];
-        p.next_out[g0 + i] = a >= 0 ? a + g0 : a;
-        p.prev_out[g0 + i] = b >= 0 ? b + g0 : b;
+        const int a = nxt[i], b = prv[i];
+        nxt[i] = a >= 0 ? a + g0 : a;
+        prv[i] = b >= 0 ? b + g0 : b;
     }
 }
 
@@ -612,18 +870,18 @@ __global__ void k_extract_tracks(int n_graphs, const int32_t *__restrict__ graph
 
 static size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-constexpr size_t SMEM_BUDGET = 227 * 1024 - 1024;  // dynamic shared memory we ask for at most (static use ~700 B)
-
 }  // namespace m3
 
 using namespace m3;
 
 extern "C" {
 
-size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs) {
-    if (n_total < 0 || n_graphs < 0) return 0;
+size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t arc_capacity) {
+    if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
-    return a256(n * 8) * 3 + a256(n * 4 * 5) + a256((n + g) * 4) + a256(n * sizeof(Rec)) + a256(n * 4) + 256;
+    size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
+    return a256(n * 8) * 3 + a256(n * 4) * 6 + a256((n + g) * 4) + a256(n * sizeof(Rec)) + a256(n * 4) +
+           a256((e + n + 8 * g + 8) * sizeof(StArc)) + 256;
 }
 
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
@@ -632,18 +890,20 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           const int64_t *exit_cost, int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out,
                           int64_t *total_cost_out, int64_t *path_cost_out, int64_t *stats_out, void *ws,
                           size_t ws_bytes, void *stream) {
-    M3_CHECK_ARG(n_graphs >= 0 && max_graph_nodes >= 0, "negative sizes");
+    M3_CHECK_ARG(n_graphs >= 0 && max_graph_nodes >= 0 && arc_capacity >= 0, "negative sizes");
     if (n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(graph_ptr && tkey && in_ptr && entry_cost && node_cost && exit_cost, "NULL input");
     M3_CHECK_ARG(next_out && prev_out && n_paths_out && total_cost_out && ws, "NULL output/workspace");
     M3_CHECK_ARG(n_total >= max_graph_nodes, "n_total < max_graph_nodes");
-    M3_CHECK_ARG(max_graph_nodes < DL_PRE, "graph too large");
-    if (ws_bytes < mot3d_solve_workspace_bytes(n_total, n_graphs)) {
-        set_error("solve workspace too small: %zu < %zu", ws_bytes, mot3d_solve_workspace_bytes(n_total, n_graphs));
+    M3_CHECK_ARG(max_graph_nodes < DL_FIRST, "graph too large");
+    if (ws_bytes < mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity)) {
+        set_error("solve workspace too small: %zu < %zu", ws_bytes,
+                  mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity));
         return MOT3D_E_CAPACITY;
     }
     const size_t g = (size_t)n_graphs;
     const size_t n_cap = (size_t)(n_total > 0 ? n_total : 1);
+    const size_t e_cap = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     char *w = (char *)ws;
     SolveParams p;
     p.n_graphs = n_graphs;
@@ -663,55 +923,46 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.path_cost = path_cost_out;
     p.stats = stats_out;
     p.arc_capacity = arc_capacity;
-    p.n_total = (int64_t)n_cap;
     p.ws_dpre = (int64_t *)w;
     w += a256(n_cap * 8);
     p.ws_dpost = (int64_t *)w;
     w += a256(n_cap * 8);
     p.ws_mcost = (int64_t *)w;
     w += a256(n_cap * 8);
-    p.ws_idx = (int32_t *)w;
-    w += a256(n_cap * 4 * 5);
+    p.ws_par = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_anc_pre = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_anc_post = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_slot_of = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_dl = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_dla0 = (int32_t *)w;
+    w += a256(n_cap * 4);
     p.ws_lvl = (int32_t *)w;
     w += a256((n_cap + g) * 4);
     p.ws_rec = (Rec *)w;
     w += a256(n_cap * sizeof(Rec));
-    p.ws_fix = (int32_t *)w;
+    p.ws_tk = (int32_t *)w;
+    w += a256(n_cap * 4);
+    p.ws_arc = (StArc *)w;
 
-    // Shared memory plan: per-node state (24 B distances/costs + 5 indices of 2 or 4 B) when the largest graph fits,
-    // the rest for the branch staging area (32 B records, 12 B arcs).
-    const size_t nmax = (size_t)max_graph_nodes;
-    const bool idx16 = nmax < 32000;
-    const size_t state_bytes = nmax * (24 + 5 * (idx16 ? 2 : 4)) + 16;
-    const size_t min_stage = 64 * sizeof(Rec) + 512 * 12;
-    const bool smem_state = state_bytes + min_stage <= SMEM_BUDGET;
-    size_t stage = smem_state ? SMEM_BUDGET - state_bytes : (size_t)96 * 1024;
-    // small graphs: do not hog the SM, several blocks should fit
-    const size_t want_stage = nmax * sizeof(Rec) / 2 + nmax * 6 * 12 + min_stage;
-    if (stage > want_stage) stage = want_stage;
-    size_t rec_cap = stage / 3 / sizeof(Rec);
-    if (rec_cap > nmax) rec_cap = nmax;
-    if (rec_cap < 64) rec_cap = 64;
-    size_t arc_cap = (stage - rec_cap * sizeof(Rec)) / 12;
+    // Shared memory per block: only the staging area for one branch. Sized so that several blocks (graphs) share
+    // an SM: per-node state lives in global memory (L2), the sequential re-labelling never leaves shared memory.
+    size_t rec_cap = (size_t)max_graph_nodes < 320 ? (size_t)max_graph_nodes : 320;
+    if (rec_cap < 32) rec_cap = 32;
+    size_t arc_cap = rec_cap * 9 / 2 + 32;  // room reserved by in-degree (+1) of the branch's pre nodes
+    if (arc_cap > 1400) arc_cap = 1400;
     p.rec_cap = (int32_t)rec_cap;
     p.arc_cap = (int32_t)arc_cap;
-    const size_t smem = (smem_state ? state_bytes : 16) + rec_cap * sizeof(Rec) + arc_cap * 12 + 16;
-    const int threads = max_graph_nodes <= 256 ? 128 : (max_graph_nodes <= 2048 ? 256 : 512);
+    const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
+    const int threads = max_graph_nodes <= 512 ? 128 : 256;
     cudaStream_t st = (cudaStream_t)stream;
-#define M3_LAUNCH_SOLVE(IDX, SM)                                                                                   \
-    do {                                                                                                           \
-        if (smem > 48 * 1024)                                                                                      \
-            M3_CUDA(cudaFuncSetAttribute(k_ssp_solve<IDX, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                         (int)smem));                                                              \
-        k_ssp_solve<IDX, SM><<<n_graphs, threads, smem, st>>>(p);                                                  \
-    } while (0)
-    if (smem_state && idx16)
-        M3_LAUNCH_SOLVE(int16_t, true);
-    else if (smem_state)
-        M3_LAUNCH_SOLVE(int32_t, true);
-    else
-        M3_LAUNCH_SOLVE(int32_t, false);
-#undef M3_LAUNCH_SOLVE
+    if (smem > 48 * 1024)
+        M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ssp_solve<<<n_graphs, threads, smem, st>>>(p);
     M3_LAUNCH_CHECK("k_ssp_solve");
     return MOT3D_OK;
 }

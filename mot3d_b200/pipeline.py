@@ -39,8 +39,8 @@ class TrackPipeline(object):
         self.prev = torch.empty(n, **i32)
         self.n_paths = torch.empty(G, **i32)
         self.total_cost = torch.empty(G, **i64)
-        self.stats = torch.zeros(4 * G, **i64)
-        self.solve_ws_bytes = L.mot3d_solve_workspace_bytes(n, G)
+        self.stats = torch.zeros(12 * G, **i64)
+        self.solve_ws_bytes = L.mot3d_solve_workspace_bytes(n, G, E)
         self.solve_ws = torch.empty(self.solve_ws_bytes, dtype=torch.uint8, device=dev)
         self.track_count = torch.empty(G, **i32)
         self.track_ptr = torch.empty(n + G + 1, **i32)

@@ -52,7 +52,7 @@ def test_argument_errors_without_gpu(built):
     assert L.mot3d_solve_batch(-1, 0, None, 0, None, 0, None, None, None, None, None, None, None, None, None, None,
                                None, None, None, 0, None) == built.E_INVALID
     assert L.mot3d_scan_workspace_bytes(1 << 20) >= 8 * ((1 << 20) // 4096)
-    assert L.mot3d_solve_workspace_bytes(1000, 3) >= 1000 * 40
+    assert L.mot3d_solve_workspace_bytes(1000, 3, 5000) >= 1000 * 40 + 5000 * 12
     # empty batches are fine and touch nothing
     d.n = 0
     s.max_jump = 3
