@@ -193,27 +193,15 @@ __global__ void __launch_bounds__(EB_TPB) k_edge_build(const __grid_constant__ E
                     }
                     if (s <= p.sq_dist_max) {  // <=> not (sqrt(s) > max_distance)
                         if (FILL) {
+                            // only the column and the squared distance are stored here (two plain stores); the
+                            // weight needs sqrt/exp/div and is computed by k_edge_cost for the ~1 % of pairs that
+                            // survive, instead of dragging the whole warp through it at every hit
                             const int64_t e = out_base + cnt;
                             if (e < p.edge_capacity) {
-                                const int64_t other = c0 + c;
-                                double prod = distance_factor(s, p.sigma_distance_sq);
-                                double w;
-                                if (p.use_hist) {
-                                    w = prod;  // finished by k_edge_appearance (hist factor comes before bbox)
-                                } else {
-                                    if (p.use_bbox) {
-                                        const int64_t a = (DIR == MOT3D_DIR_OUT) ? r : other;
-                                        const int64_t b = (DIR == MOT3D_DIR_OUT) ? other : r;
-                                        const double bss = 1.0 - bbox_similarity(p.bbox, n, a, b);
-                                        prod = prod * exp(-(bss * bss) / p.sigma_bbox_sq);
-                                    }
-                                    w = p.jt.v[dk - 1] * prod;
-                                    p.cost[e] = quantise_1e7(w);
-                                }
-                                p.col[e] = (int32_t)other;
-                                if (p.weight) p.weight[e] = w;
-                            } else {
-                                if (p.overflow) *p.overflow = 1;
+                                p.col[e] = (int32_t)(c0 + c);
+                                p.cost[e] = __double_as_longlong(s);
+                            } else if (p.overflow) {
+                                *p.overflow = 1;
                             }
                         }
                         cnt++;
@@ -224,6 +212,41 @@ __global__ void __launch_bounds__(EB_TPB) k_edge_build(const __grid_constant__ E
         __syncthreads();  // everyone done with this chunk before it is overwritten
     }
     if (!FILL && active) p.row_count[r] = cnt;
+}
+
+// Second half of the fill: one thread per row turns (column, squared distance) into the arc weight
+//   w = (-exp(-(jump-1)*sigma_jump)) * ((exp(-dist^2/sigma_d^2) [* w_hist]) * w_bbox)
+// (reference mot3d/weight_functions.py:13-35) and its exact quantisation (mot3d/mot3d.py:224).
+// With use_hist the distance factor alone is stored in weight[]: k_edge_appearance finishes (the reference
+// multiplies the histogram factor in before the bbox factor).
+template <int DIR>
+__global__ void __launch_bounds__(128) k_edge_cost(const __grid_constant__ EdgeParams p) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n) return;
+    const int64_t n = p.n;
+    int64_t e0 = p.row_ptr[r], e1 = p.row_ptr[r + 1];
+    if (e1 > p.edge_capacity) e1 = p.edge_capacity;
+    const int key_r = p.tkey[r];
+    for (int64_t e = e0; e < e1; e++) {
+        const int64_t other = p.col[e];
+        const double s = __longlong_as_double(p.cost[e]);
+        const int dk = (DIR == MOT3D_DIR_OUT) ? (p.tkey[other] - key_r) : (key_r - p.tkey[other]);
+        double prod = distance_factor(s, p.sigma_distance_sq);
+        double w;
+        if (p.use_hist) {
+            w = prod;
+        } else {
+            if (p.use_bbox) {
+                const int64_t a = (DIR == MOT3D_DIR_OUT) ? r : other;
+                const int64_t b = (DIR == MOT3D_DIR_OUT) ? other : r;
+                const double bss = 1.0 - bbox_similarity(p.bbox, n, a, b);
+                prod = prod * exp(-(bss * bss) / p.sigma_bbox_sq);
+            }
+            w = p.jt.v[dk - 1] * prod;
+            p.cost[e] = quantise_1e7(w);
+        }
+        if (p.weight) p.weight[e] = w;
+    }
 }
 
 // One warp per row: multiply the colour-histogram factor in, then bbox and jump factors, then quantise.
@@ -550,6 +573,13 @@ int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int
     else
         k_edge_build<MOT3D_DIR_OUT, true><<<grid, EB_TPB, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_edge_build<fill>");
+    if (edge_capacity > 0) {
+        if (direction == MOT3D_DIR_IN)
+            k_edge_cost<MOT3D_DIR_IN><<<grid, EB_TPB, 0, st>>>(p);
+        else
+            k_edge_cost<MOT3D_DIR_OUT><<<grid, EB_TPB, 0, st>>>(p);
+        M3_LAUNCH_CHECK("k_edge_cost");
+    }
     return MOT3D_OK;
 }
 

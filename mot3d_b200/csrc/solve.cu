@@ -331,26 +331,22 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
     if (warp_id() == sweep_warp) {
         const int lane = lane_id();
         int n_node32 = 0, n_arc32 = 0, n_asc32 = 0, n_desc32 = 0;
+        // A sweep only has to revisit what can still change: the ascending sweep starts at the lowest record the
+        // previous descending sweep changed, the descending sweep at the highest record the ascending one changed.
+        int asc_from = 0;
         for (int round = 0; round < 2 * nd + 4; round++) {
-            bool ch = false;
+            int hi_ch = -1;
             n_asc32++;
-            for (int q = 0; q < nd;) {
+            for (int q = asc_from; q < nd;) {
                 // one step = the records of one layer, at most 4 at a time, 8 lanes per record (one per in-arc)
                 const int r8 = lane >> 3, a8 = lane & 7;
                 const int s = q + r8;
                 const bool in_range = s < nd;
-                int4 A = make_int4(DL_FIRST, 0, -1, NONE), B = make_int4(-1, -1, PAR_NONE, -1), F = make_int4(0, 0, 0, 0);
-                longlong2 C = make_longlong2(INF, INF), D = make_longlong2(0, 0), E = make_longlong2(INF, INF);
-                if (in_range) {
-                    const Rec *r = st.rec + s;
-                    A = r->A;
-                    B = r->B;
-                    C = r->C;
-                    D = r->D;
-                    E = r->E;
-                    F = r->F;
-                }
-                const unsigned brk = __ballot_sync(0xffffffffu, lane >= 8 && a8 == 0 && (A.x & DL_FIRST));
+                const Rec *rp = st.rec + (in_range ? s : nd - 1);
+                int4 A = rp->A, B = rp->B, F = rp->F;
+                const longlong2 C = rp->C, D = rp->D, E = rp->E;
+                const unsigned brk =
+                    __ballot_sync(0xffffffffu, lane >= 8 && a8 == 0 && (!in_range || (A.x & DL_FIRST)));
                 const int cn_t = brk ? (__ffs(brk) - 1) >> 3 : 4;
                 const bool valid = r8 < cn_t;
                 const int ent = valid ? A.x : 0;
@@ -448,32 +444,27 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                     if (upd) {
                         st.rec[s].E = make_longlong2(dpre_s, dpost_s);
                         st.rec[s].F = F;
-                        ch = true;
+                        hi_ch = s;
                     }
                 }
                 n_node32 += cn_t;
                 q += cn_t;
                 __syncwarp();
             }
-            if (!__any_sync(0xffffffffu, ch) && round > 0) break;
-            bool ch2 = false;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) hi_ch = max(hi_ch, __shfl_xor_sync(0xffffffffu, hi_ch, d));
+            if (hi_ch < 0) break;  // nothing moved: fix-point
+            int lo_ch = nd;
             n_desc32++;
-            for (int q = nd; q > 0;) {
+            for (int q = hi_ch + 1; q > 0;) {
                 // walking down: the records of one layer (until the one flagged DL_FIRST), one lane each
                 const int s = q - 1 - lane;
                 const bool in_range = s >= 0;
-                int4 A = make_int4(DL_FIRST, 0, -1, NONE), F = make_int4(0, 0, 0, 0);
-                int ns = -1;
-                longlong2 D = make_longlong2(0, 0), E = make_longlong2(INF, INF);
-                if (in_range) {
-                    const Rec *r = st.rec + s;
-                    A = r->A;
-                    ns = r->B.x;
-                    D = r->D;
-                    E = r->E;
-                    F = r->F;
-                }
-                const unsigned fst = __ballot_sync(0xffffffffu, (A.x & DL_FIRST) != 0);
+                const Rec *rp = st.rec + (in_range ? s : 0);
+                int4 A = rp->A, F = rp->F;
+                const int ns = rp->B.x;
+                const longlong2 D = rp->D, E = rp->E;
+                const unsigned fst = __ballot_sync(0xffffffffu, !in_range || (A.x & DL_FIRST) != 0);
                 const int cn_t = fst ? __ffs(fst) : 32;  // lanes 0 .. ffs-1 (the layer's first record included)
                 if (lane < cn_t && in_range) {
                     const int ent = A.x;
@@ -511,7 +502,7 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                     if (upd) {
                         st.rec[s].E = make_longlong2(dpre_s, dpost_s);
                         st.rec[s].F = F;
-                        ch2 = true;
+                        lo_ch = s;
                     }
                 }
                 const int done = cn_t < q ? cn_t : q;
@@ -519,7 +510,10 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                 q -= done;
                 __syncwarp();
             }
-            if (!__any_sync(0xffffffffu, ch2)) break;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) lo_ch = min(lo_ch, __shfl_xor_sync(0xffffffffu, lo_ch, d));
+            if (lo_ch >= nd) break;  // nothing moved: fix-point
+            asc_from = lo_ch;
         }
         // work counters of this branch (the leaders of the lane groups counted the arcs)
 #pragma unroll

@@ -11,7 +11,7 @@ from . import _lib
 from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
 
 STAGES = ["make_keys", "node_costs", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
-LAUNCHES_PER_RUN = 2 + 1 + 1 + 3 + 1 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 3 + 2 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
 
 
 class TrackPipeline(object):
