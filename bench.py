@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=29, help="sequences (of 20 windows) per GPU and step")
+    ap.add_argument("--seqs", type=int, default=60, help="sequences (of 20 windows) per GPU and step")
     ap.add_argument("--cpu-windows", type=int, default=40, help="windows in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -16,6 +16,8 @@
 //                  capacities the residual state is just next[]/prev[] per detection
 //   acceptance     path 1 always; path k >= 2 while its cost < 0     (wrapper.cpp:199-267 on integers)
 // Flow read-out (make_output2, wrapper.cpp:139-169) is unnecessary: next[]/prev[] are the flow.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace m3 {
@@ -945,14 +947,21 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 
     // Shared memory per block: only the staging area for one branch. Sized so that several blocks (graphs) share
     // an SM: per-node state lives in global memory (L2), the sequential re-labelling never leaves shared memory.
-    size_t rec_cap = (size_t)max_graph_nodes < 320 ? (size_t)max_graph_nodes : 320;
+    // tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / MOT3D_SOLVE_THREADS override the plan below
+    size_t rec_target = 320;
+    if (const char *e = getenv("MOT3D_SOLVE_RECCAP")) rec_target = (size_t)atoi(e) > 31 ? (size_t)atoi(e) : 32;
+    size_t rec_cap = (size_t)max_graph_nodes < rec_target ? (size_t)max_graph_nodes : rec_target;
     if (rec_cap < 32) rec_cap = 32;
     size_t arc_cap = rec_cap * 9 / 2 + 32;  // room reserved by in-degree (+1) of the branch's pre nodes
     if (arc_cap > 1400) arc_cap = 1400;
     p.rec_cap = (int32_t)rec_cap;
     p.arc_cap = (int32_t)arc_cap;
     const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
-    const int threads = max_graph_nodes <= 512 ? 128 : 256;
+    int threads = max_graph_nodes <= 512 ? 128 : 256;
+    if (const char *e = getenv("MOT3D_SOLVE_THREADS")) {
+        const int t = atoi(e);
+        if (t == 64 || t == 128 || t == 192 || t == 256) threads = t;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
