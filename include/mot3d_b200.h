@@ -119,6 +119,55 @@ int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spe
                               const int32_t *row_ptr, const int32_t *col, double *weight_inout, int64_t *cost_out,
                               void *stream);
 
+/* ---- tracklet linking (second pass): replaces build_graph on DetectionTracklet lists (mot3d/mot3d.py:106-141)
+ *      with weight_distance_tracklets_2d/_3d (mot3d/weight_functions.py:80-160) and linear_motion
+ *      (mot3d/distance_functions.py:47-63) ------------------------------------------------------------------- */
+
+/* One graph of n tracklets in the caller's order (the reference does not sort tracklets). Every tracklet brings the
+ * window of detections at its head (most recent end) and at its tail (oldest end): DetectionTracklet2D/3D,
+ * mot3d/types.py:94-184. */
+typedef struct mot3d_tracklets {
+    int32_t n;
+    int32_t dim;
+    int32_t hist_channels;
+    int32_t hist_bins;
+    int64_t n_head_points;        /* head_ptr[n] */
+    int64_t n_tail_points;        /* tail_ptr[n] */
+    const int32_t *head_ptr;      /* [n+1] */
+    const int32_t *tail_ptr;      /* [n+1] */
+    const int32_t *head_idx;      /* frame index of every head-window point, ascending inside a tracklet */
+    const int32_t *tail_idx;
+    const double *head_pos;       /* [dim][n_head_points] planar */
+    const double *tail_pos;       /* [dim][n_tail_points] planar */
+    const uint8_t *tail_access_point; /* [n] tail.access_point (2-D only) or NULL */
+    const uint8_t *head_has_hist; /* [n] head.color_histogram is not None; NULL = all have one */
+    const uint8_t *tail_has_hist;
+    const double *head_hist;      /* [n][C][B] median histogram of the head window; NULL unless use_hist */
+    const double *tail_hist;
+    double *head_fit_ws;          /* scratch [n][dim][2]: line fits, written by mot3d_tracklet_edge_count */
+    double *tail_fit_ws;
+} mot3d_tracklets;
+
+typedef struct mot3d_tracklet_spec {
+    int32_t max_jump;
+    int32_t use_hist;
+    int32_t check_access_point; /* 1 for weight_distance_tracklets_2d (:101-102), 0 for _3d */
+    int32_t reserved;
+    double sq_dist_max;         /* largest squared head-tail distance accepted; negative = max_distance is None */
+    double sigma_motion_sq;
+    double sigma_hist_sq;
+    double alpha;
+    double cutoff_motion;
+    double cutoff_appearance;
+} mot3d_tracklet_spec;
+
+/* rows = tail tracklet t1, columns = head tracklet t2 (ascending), i.e. the reference's arc order */
+int32_t mot3d_tracklet_edge_count(const mot3d_tracklets *trk, const mot3d_tracklet_spec *spec, int32_t *row_count_out,
+                                  void *stream);
+int32_t mot3d_tracklet_edge_fill(const mot3d_tracklets *trk, const mot3d_tracklet_spec *spec, const int32_t *row_ptr,
+                                 int64_t edge_capacity, int32_t *col_out, int64_t *cost_out, double *weight_out,
+                                 int32_t *overflow_flag, void *stream);
+
 /* ---- solve: replaces wrapper.solve (wrapper.cpp:171-317) and the muSSP core it drives ------------------------ */
 
 size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t arc_capacity);

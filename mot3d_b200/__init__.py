@@ -9,9 +9,9 @@ from .types import *            # noqa: F401,F403
 from .weight_functions import *  # noqa: F401,F403
 from .distance_functions import *  # noqa: F401,F403
 from .mot3d import *            # noqa: F401,F403
-from .mot3d import TrackingGraph  # noqa: F401
+from .mot3d import TrackingGraph, TrackletGraph  # noqa: F401
 from . import weight_functions, distance_functions, types  # noqa: F401
-from .spec import CostSpec  # noqa: F401
+from .spec import CostSpec, TrackletCostSpec  # noqa: F401
 from .batch import (DetectionBatch, GraphBatch, HostTracker, build_graphs, solve_graphs, extract_tracks,  # noqa: F401
                     track_batch, tracks_to_lists)
 from .scheduler import shard_graphs, gather_tracks  # noqa: F401

@@ -36,6 +36,23 @@ class CostSpecC(ctypes.Structure):
                 ("neg_exp_jump", ctypes.c_double * MAX_JUMP)]
 
 
+class Tracklets(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("dim", ctypes.c_int32), ("hist_channels", ctypes.c_int32),
+                ("hist_bins", ctypes.c_int32), ("n_head_points", ctypes.c_int64), ("n_tail_points", ctypes.c_int64),
+                ("head_ptr", ctypes.c_void_p), ("tail_ptr", ctypes.c_void_p), ("head_idx", ctypes.c_void_p),
+                ("tail_idx", ctypes.c_void_p), ("head_pos", ctypes.c_void_p), ("tail_pos", ctypes.c_void_p),
+                ("tail_access_point", ctypes.c_void_p), ("head_has_hist", ctypes.c_void_p),
+                ("tail_has_hist", ctypes.c_void_p), ("head_hist", ctypes.c_void_p), ("tail_hist", ctypes.c_void_p),
+                ("head_fit_ws", ctypes.c_void_p), ("tail_fit_ws", ctypes.c_void_p)]
+
+
+class TrackletSpecC(ctypes.Structure):
+    _fields_ = [("max_jump", ctypes.c_int32), ("use_hist", ctypes.c_int32), ("check_access_point", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("sq_dist_max", ctypes.c_double), ("sigma_motion_sq", ctypes.c_double),
+                ("sigma_hist_sq", ctypes.c_double), ("alpha", ctypes.c_double), ("cutoff_motion", ctypes.c_double),
+                ("cutoff_appearance", ctypes.c_double)]
+
+
 class HostBatch(ctypes.Structure):
     _fields_ = [("n_graphs", ctypes.c_int32), ("dim", ctypes.c_int32), ("n", ctypes.c_int64),
                 ("graph_ptr", ctypes.c_void_p), ("frame", ctypes.c_void_p), ("pos", ctypes.c_void_p),
@@ -61,6 +78,9 @@ SIGNATURES = {
     "mot3d_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "mot3d_edge_fill": (_i32, [_PD, _PS, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_tracklet_edge_count": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _vp]),
+    "mot3d_tracklet_edge_fill": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _i64, _vp, _vp,
+                                        _vp, _vp, _vp]),
     "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),

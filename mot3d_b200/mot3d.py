@@ -50,6 +50,111 @@ def _recover_spec(detections, weight_source_sink, max_jump, weight_confidence, w
                           weight_source_sink=weight_source_sink, max_jump=max_jump)
 
 
+def _recover_tracklet_spec(tracklets, weight_source_sink, max_jump, weight_confidence, weight_distance):
+    from .types import DetectionTracklet2D, DetectionTracklet3D
+
+    class _PT2(_ProbeMixin, DetectionTracklet2D):
+        def __init__(self):
+            pass
+
+    class _PT3(_ProbeMixin, DetectionTracklet3D):
+        def __init__(self):
+            pass
+
+    cls = _PT3 if isinstance(tracklets[0], DetectionTracklet3D) else _PT2
+    rd = _spec.probe_callable(weight_distance, cls(), cls())
+    rc = _spec.probe_callable(weight_confidence, cls())
+    if rc.name != "confidence":
+        raise TypeError("weight_confidence must be one of the built-in weight_confidence_* functions")
+    if rd.name not in ("tracklets_2d", "tracklets_3d"):
+        raise TypeError("weight_distance resolved to %r, which does not apply to tracklets" % rd.name)
+    return _spec.TrackletCostSpec(kind=rd.name, distance=rd.kwargs, confidence=rc.kwargs,
+                                  weight_source_sink=weight_source_sink, max_jump=max_jump)
+
+
+class TrackletGraph(object):
+    """Graph handle for a list of DetectionTracklet objects (nodes in the caller's order, reference
+    mot3d/mot3d.py:134-135). Same surface as TrackingGraph."""
+
+    def __init__(self, tracklets, tspec, packed, out):
+        self.detections = tracklets
+        self.spec = tspec
+        self.packed = packed
+        self._out = out  # (row_ptr, col, weight, cost) on the host, reference arc order
+        n = len(tracklets)
+        flags = packed["flags"]
+        en = np.full(n, _spec.quantise_scalar(tspec.weight_source_sink), dtype=np.int64)
+        ex = np.zeros(n, dtype=np.int64)
+        if flags is not None:
+            en[(flags & _lib.FLAG_ENTRY) == 0] = _lib.INF_COST
+            ex[(flags & _lib.FLAG_EXIT) == 0] = _lib.INF_COST
+        self.entry_cost, self.exit_cost = en, ex
+        self.node_weight = -(packed["conf"] * tspec.confidence["mul"] + tspec.confidence["bias"])
+        self.node_cost = np.array([_spec.quantise_scalar(w) for w in self.node_weight.tolist()], dtype=np.int64)
+        self._nx = None
+        self._solution = None
+
+    def __len__(self):
+        return 2 * len(self.detections) + 2
+
+    @property
+    def n_transitions(self):
+        return len(self._out[1])
+
+    def out_csr(self):
+        return self._out
+
+    def arcs(self):
+        n = len(self.detections)
+        row_ptr, col, w, _ = self._out
+        return _arcs_in_reference_order(n, row_ptr, col, w, self.entry_cost < _lib.INF_COST,
+                                        self.exit_cost < _lib.INF_COST, self.spec.weight_source_sink, self.node_weight)
+
+    def solve(self):
+        from .tracklets import solve_tracklet_graph
+        row_ptr, col, _, cost = self._out
+        tracks, total, K, sol = solve_tracklet_graph(len(self.detections), row_ptr, col, cost, self.entry_cost,
+                                                     self.node_cost, self.exit_cost)
+        self._solution = sol
+        self.total_cost, self.n_paths = total, K
+        return tracks
+
+    to_networkx = None  # bound below (shared with TrackingGraph)
+
+
+def _arcs_in_reference_order(n, row_ptr, col, w, has_en, has_ex, weight_source_sink, node_w):
+    """Every arc as (tail, head, weight), 1-based node ids, in graph_to_text order (reference
+    mot3d/mot3d.py:75-104,218-226): all S->pre first, then per item pre->post, post->T, post->pre_j (j ascending)."""
+    T = 2 * n + 2
+    m = np.arange(n)
+    deg = np.diff(row_ptr)
+    per = 1 + has_ex.astype(np.int64) + deg
+    n_en = int(has_en.sum())
+    E = n_en + int(per.sum())
+    tail = np.empty(E, dtype=np.int64)
+    head = np.empty(E, dtype=np.int64)
+    ww = np.empty(E, dtype=np.float64)
+    tail[:n_en] = 1
+    head[:n_en] = 2 + 2 * m[has_en]
+    ww[:n_en] = weight_source_sink
+    base = n_en + np.concatenate(([0], np.cumsum(per)[:-1])) if n else np.zeros(0, dtype=np.int64)
+    tail[base] = 2 + 2 * m
+    head[base] = 3 + 2 * m
+    ww[base] = node_w
+    xi = base[has_ex] + 1
+    tail[xi] = 3 + 2 * m[has_ex]
+    head[xi] = T
+    ww[xi] = 0
+    if len(col):
+        src = np.repeat(m, deg)
+        within = np.arange(len(col)) - np.repeat(row_ptr[:-1], deg)
+        at = np.repeat(base + 1 + has_ex.astype(np.int64), deg) + within
+        tail[at] = 3 + 2 * src
+        head[at] = 2 + 2 * col
+        ww[at] = w
+    return tail, head, ww
+
+
 def _pack(sorted_dets, cspec):
     """Detection objects (already in node order) -> DetectionBatch on the host (one graph)."""
     from .batch import DetectionBatch
@@ -123,36 +228,18 @@ class TrackingGraph(object):
         ex = gb.exit_cost[:n].cpu().numpy()
         conf = gb.dets.conf.cpu().numpy()
         node_w = -(conf * self.spec.confidence["mul"] + self.spec.confidence["bias"])
-        has_en = en < _lib.INF_COST
-        has_ex = ex < _lib.INF_COST
-        T = 2 * n + 2
-        m = np.arange(n)
-        deg = np.diff(row_ptr)
-        per = 1 + has_ex.astype(np.int64) + deg
-        n_en = int(has_en.sum())
-        E = n_en + int(per.sum())
-        tail = np.empty(E, dtype=np.int64)
-        head = np.empty(E, dtype=np.int64)
-        ww = np.empty(E, dtype=np.float64)
-        tail[:n_en] = 1
-        head[:n_en] = 2 + 2 * m[has_en]
-        ww[:n_en] = self.spec.weight_source_sink
-        base = n_en + np.concatenate(([0], np.cumsum(per)[:-1])) if n else np.zeros(0, dtype=np.int64)
-        tail[base] = 2 + 2 * m
-        head[base] = 3 + 2 * m
-        ww[base] = node_w
-        xi = base[has_ex] + 1
-        tail[xi] = 3 + 2 * m[has_ex]
-        head[xi] = T
-        ww[xi] = 0
-        if len(col):
-            src = np.repeat(m, deg)
-            within = np.arange(len(col)) - np.repeat(row_ptr[:-1], deg)
-            at = np.repeat(base + 1 + has_ex.astype(np.int64), deg) + within
-            tail[at] = 3 + 2 * src
-            head[at] = 2 + 2 * col
-            ww[at] = w
-        return tail, head, ww
+        return _arcs_in_reference_order(n, row_ptr, col, w, en < _lib.INF_COST, ex < _lib.INF_COST,
+                                        self.spec.weight_source_sink, node_w)
+
+    def solve(self):
+        """Tracks as lists of detection indices (node order), in the reference's order."""
+        from .batch import solve_graphs, extract_tracks, tracks_to_lists
+        sol = self._solution if self._solution is not None else solve_graphs(self.graphs)
+        extract_tracks(self.graphs, sol)
+        self._solution = sol
+        n = len(self.detections)
+        return tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                               sol.track_det.cpu().numpy())[0]
 
     def to_networkx(self):
         """The reference's DiGraph: nodes SOURCE=1, SINK=2N+2, pre=2+2m, post=3+2m with label/detection/idet
@@ -186,6 +273,33 @@ class TrackingGraph(object):
         return self.to_networkx()[node]
 
 
+for _name in ("to_networkx", "__getattr__", "__iter__", "__contains__", "__getitem__"):
+    setattr(TrackletGraph, _name, TrackingGraph.__dict__[_name])
+
+
+def _build_tracklet_graph(tracklets, weight_source_sink, max_jump, verbose, weight_confidence, weight_distance):
+    from .tracklets import pack_tracklets, build_tracklet_arcs
+    tspec = _recover_tracklet_spec(tracklets, weight_source_sink, max_jump, weight_confidence, weight_distance)
+    n = len(tracklets)
+    if verbose:
+        print("Number of tracklets: {}".format(n))
+    node = 2
+    for t in tracklets:
+        t.pre_node = node
+        t.post_node = node + 1
+        node += 2
+    packed = pack_tracklets(tracklets, tspec)
+    out = build_tracklet_arcs(packed, tspec)
+    g = TrackletGraph(list(tracklets), tspec, packed, out)
+    if verbose:
+        print("Number of post-pre nodes edges created: {}".format(len(out[1])))
+    if packed["flags"] is not None:
+        g._tracks = g.solve()
+        if g.n_paths == 0:
+            return None
+    return g
+
+
 def build_graph(detections, weight_source_sink=1, max_jump=12, verbose=True,
                 weight_confidence=weight_confidence_detections_2d, weight_distance=weight_distance_detections_2d):
     """Build the flow graph on the GPU (reference mot3d/mot3d.py:20-150).
@@ -197,13 +311,15 @@ def build_graph(detections, weight_source_sink=1, max_jump=12, verbose=True,
     assert isinstance(detections, (list, tuple))
     if len(detections) == 0:
         return None
+    import torch
     if isinstance(detections[0], DetectionTracklet):
-        raise NotImplementedError("build_graph on DetectionTracklet lists (tracklet linking, reference "
-                                  "mot3d/weight_functions.py:80-160) is not built yet; no CPU fallback")
+        if not torch.cuda.is_available():
+            raise RuntimeError("mot3d_b200.build_graph needs a CUDA device (B200); there is no CPU fallback")
+        return _build_tracklet_graph(detections, weight_source_sink, max_jump, verbose, weight_confidence,
+                                     weight_distance)
     if not isinstance(detections[0], Detection):
         raise TypeError("detections must be Detection2D/Detection3D objects")
     from .batch import build_graphs, solve_graphs
-    import torch
     if not torch.cuda.is_available():
         raise RuntimeError("mot3d_b200.build_graph needs a CUDA device (B200); there is no CPU fallback")
     cspec = _recover_spec(detections, weight_source_sink, max_jump, weight_confidence, weight_distance)
@@ -241,13 +357,10 @@ def _run_ssp(g, verbose=1, method="muSSP"):
     reference's order (reference mot3d/mot3d.py:152-184)."""
     if method != "muSSP":
         raise NotImplementedError(method)
-    from .batch import solve_graphs, extract_tracks, tracks_to_lists
-    sol = g._solution if g._solution is not None else solve_graphs(g.graphs)
-    extract_tracks(g.graphs, sol)
+    tracks = getattr(g, "_tracks", None)
+    if tracks is None:
+        tracks = g.solve()
     n = len(g.detections)
-    tracks = tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
-                             sol.track_det.cpu().numpy())[0]
-    g._solution = sol
     if verbose:
         used = sum(len(t) for t in tracks) * 2
         print("[muSSP] {} out of {} nodes unused".format(2 * n - used, 2 * n))
@@ -260,7 +373,7 @@ def solve_graph(g, verbose=True, method="muSSP"):
     PuLP path and is not provided; anything else raises ValueError (:205-206)."""
     start_time = time.time()
     if method in ["muSSP", "FollowMe", "SSP"]:
-        if not isinstance(g, TrackingGraph):
+        if not isinstance(g, (TrackingGraph, TrackletGraph)):
             raise TypeError("solve_graph expects the graph returned by mot3d_b200.build_graph")
         tracks_nodes = _run_ssp(g, verbose, method)
     elif method == "ILP":
@@ -276,7 +389,7 @@ def solve_graph(g, verbose=True, method="muSSP"):
 
 def graph_to_text(g):
     """DIMACS-like lines, weights with 7 decimals, arcs in the graph's edge order (reference mot3d/mot3d.py:218-226)."""
-    if isinstance(g, TrackingGraph):
+    if isinstance(g, (TrackingGraph, TrackletGraph)):
         tail, head, w = g.arcs()
         lines = ["p min {} {}".format(len(g), len(tail))]
         for s, t, x in zip(tail.tolist(), head.tolist(), w.tolist()):

@@ -98,6 +98,59 @@ class CostSpec(object):
         return c
 
 
+class TrackletCostSpec(object):
+    """kind: 'tracklets_2d' | 'tracklets_3d'; distance = kwargs of weight_distance_tracklets_2d/_3d, confidence =
+    kwargs of weight_confidence_tracklets_* (reference mot3d/weight_functions.py:80-84,125-132)."""
+
+    DIST_DEFAULTS = {
+        "tracklets_2d": dict(sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
+                             cutoff_appearance=0.1, max_distance=None, use_color_histogram=True),
+        "tracklets_3d": dict(sigma_color_histogram=0.3, sigma_motion=5, alpha=0.7, cutoff_motion=0.1,
+                             cutoff_appearance=0.1, max_distance=None, use_color_histogram=True),
+    }
+
+    def __init__(self, kind="tracklets_2d", distance=None, confidence=None, weight_source_sink=1, max_jump=12):
+        if kind not in self.DIST_DEFAULTS:
+            raise TypeError("unsupported cost kind %r" % (kind,))
+        self.kind = kind
+        d = dict(self.DIST_DEFAULTS[kind])
+        for k, v in (distance or {}).items():
+            if k not in d:
+                raise TypeError("unexpected keyword argument %r for weight_distance_%s" % (k, kind))
+            d[k] = v
+        c = dict(mul=1, bias=0)
+        for k, v in (confidence or {}).items():
+            if k not in c:
+                raise TypeError("unexpected keyword argument %r for weight_confidence_tracklets" % (k,))
+            c[k] = v
+        self.distance = d
+        self.confidence = c
+        self.weight_source_sink = weight_source_sink
+        self.max_jump = int(max_jump)
+
+    @property
+    def dim(self):
+        return 2 if self.kind == "tracklets_2d" else 3
+
+    @property
+    def use_hist(self):
+        return bool(self.distance["use_color_histogram"])
+
+    def to_c(self):
+        d = self.distance
+        c = _lib.TrackletSpecC()
+        c.max_jump = self.max_jump
+        c.use_hist = int(self.use_hist)
+        c.check_access_point = 1 if self.kind == "tracklets_2d" else 0
+        c.sq_dist_max = -1.0 if d["max_distance"] is None else sq_dist_max(d["max_distance"])
+        c.sigma_motion_sq = float(d["sigma_motion"] ** 2)
+        c.sigma_hist_sq = float(d["sigma_color_histogram"] ** 2)
+        c.alpha = float(d["alpha"])
+        c.cutoff_motion = float(d["cutoff_motion"])
+        c.cutoff_appearance = float(d["cutoff_appearance"])
+        return c
+
+
 # ---- recovering the spec from opaque callables -------------------------------------------------------------------
 # The reference takes arbitrary callables (in practice lambdas closing over kwargs of the built-ins,
 # examples/simple_2d/example.py:52-58). build_graph calls the user's callable once on probe objects; the built-in

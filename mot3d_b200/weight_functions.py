@@ -60,9 +60,9 @@ def weight_confidence_detections_3d(detection, **kwargs):
 
 
 def _tracklets_pending(name):
-    raise NotImplementedError(
-        "%s: the tracklet-linking cost kernel (reference mot3d/weight_functions.py:80-160) is scheduled after the "
-        "detection path (SURVEY.md 8a row a18); this build has no CPU fallback for it" % name)
+    raise TypeError(
+        "%s is a cost descriptor for build_graph: the arithmetic runs in the CUDA kernel "
+        "(mot3d_b200/csrc/tracklet.cu) for all pairs at once; there is no CPU evaluation of a single pair" % name)
 
 
 def weight_distance_tracklets_2d(t1, t2, sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,

@@ -280,6 +280,79 @@ def text_sha(lines):
     return hashlib.sha256(txt.encode()).hexdigest()[:16]
 
 
+
+# ------------------------------------------------------------------------------------------- tracklet linking
+class TrackletSpec(object):
+    """Parameters of weight_distance_tracklets_2d/_3d (mot3d/weight_functions.py:80-84, 128-132)."""
+
+    def __init__(self, kind="tracklets_2d", sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
+                 cutoff_appearance=0.1, max_distance=None, use_color_histogram=True, mul=1, bias=0,
+                 weight_source_sink=1, max_jump=12):
+        self.kind = kind
+        self.sigma_color_histogram = sigma_color_histogram
+        self.sigma_motion = sigma_motion
+        self.alpha = alpha
+        self.cutoff_motion = cutoff_motion
+        self.cutoff_appearance = cutoff_appearance
+        self.max_distance = max_distance
+        self.use_color_histogram = use_color_histogram
+        self.mul = mul
+        self.bias = bias
+        self.weight_source_sink = weight_source_sink
+        self.max_jump = max_jump
+
+
+def build_tracklet_transitions(d, spec):
+    """Arcs between tracklets exactly as build_graph + weight_distance_tracklets_* make them (mot3d/mot3d.py:106-141,
+    mot3d/weight_functions.py:80-160, mot3d/distance_functions.py:47-63), from the flat arrays of
+    tests/golden/make_golden.py:tracklet_arrays. Returns out-CSR (row_ptr, col, w) in the reference's arc order
+    (tracklets in input order). np.polyfit is called once per end instead of once per pair (same fit)."""
+    hp, tp = d["t_head_ptr"], d["t_tail_ptr"]
+    n = len(hp) - 1
+    hidx, tidx, hpos, tpos = d["t_head_idx"], d["t_tail_idx"], d["t_head_pos"], d["t_tail_pos"]
+    fit_h = [np.polyfit(hidx[hp[i]:hp[i + 1]], hpos[hp[i]:hp[i + 1]], 1) for i in range(n)]
+    fit_t = [np.polyfit(tidx[tp[i]:tp[i + 1]], tpos[tp[i]:tp[i + 1]], 1) for i in range(n)]
+
+    def deviation(polys, idx2, pts2):
+        pred = np.vstack([np.polyval(q, idx2) for q in polys.T]).T
+        return np.linalg.norm(pred - pts2, axis=1).mean()
+
+    has_hist = d.get("t_has_hist")
+    rows, cols, ws = [], [], []
+    for i in range(n):
+        head_index = hidx[hp[i + 1] - 1]
+        for j in range(n):
+            if i == j:
+                continue
+            jump = tidx[tp[j]] - head_index
+            if not (0 < jump <= spec.max_jump):
+                continue
+            if spec.max_distance is not None:
+                dist = np.sqrt(sum((a - b) ** 2 for a, b in zip(hpos[hp[i + 1] - 1], tpos[tp[j]])))
+                if dist > spec.max_distance:
+                    continue
+            if spec.kind == "tracklets_2d" and d["t_tail_access"][j]:
+                continue
+            dev = deviation(fit_h[i], tidx[tp[j]:tp[j + 1]], tpos[tp[j]:tp[j + 1]]) + \
+                deviation(fit_t[j], hidx[hp[i]:hp[i + 1]], hpos[hp[i]:hp[i + 1]])
+            wm = np.exp(-dev ** 2 / spec.sigma_motion ** 2)
+            if wm < spec.cutoff_motion:
+                continue
+            if spec.use_color_histogram and has_hist is not None and has_hist[i] and has_hist[j]:
+                chs = 1 - _hist_similarity(d["t_head_hist"][i], d["t_tail_hist"][j])
+                wa = np.exp(-chs ** 2 / spec.sigma_color_histogram ** 2)
+                if wa < spec.cutoff_appearance:
+                    continue
+                w = -((1 - spec.alpha) * wm + spec.alpha * wa)
+            else:
+                w = -wm
+            rows.append(i)
+            cols.append(j)
+            ws.append(w)
+    row_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(row_ptr, np.asarray(rows, dtype=np.int64) + 1, 1)
+    return np.cumsum(row_ptr), np.asarray(cols, dtype=np.int64), np.asarray(ws, dtype=np.float64)
+
 # ------------------------------------------------------------------------------------------------- solve
 def ssp_solve(n_nodes, tail1, head1, cost_units, path_cap=None):
     """C restatement on int64 units. tail1/head1 are 1-based as in the text. -> dict(flow, K, path_cost, total)."""

@@ -108,6 +108,56 @@ def freeze_graph_case(name, lines, extra=None):
                                                               sol["total"], sol["sha"], os.path.getsize(path) // 1024))
 
 
+
+def tracklet_arrays(dts, dim):
+    """Inputs of a tracklet graph as flat arrays: per tracklet the head / tail windows (indexes, positions), the
+    median histograms of both ends (or absence), tail access flag, confidence."""
+    hp, tp = [0], [0]
+    hidx, tidx, hpos, tpos = [], [], [], []
+    hh, th, has_h = [], [], []
+    for t in dts:
+        hidx += list(t.head.indexes)
+        hpos += [np.asarray(p_, dtype=np.float64)[:dim] for p_ in t.head.positions]
+        hp.append(len(hidx))
+        tidx += list(t.tail.indexes)
+        tpos += [np.asarray(p_, dtype=np.float64)[:dim] for p_ in t.tail.positions]
+        tp.append(len(tidx))
+        h1 = getattr(t.head, "color_histogram", None)
+        h2 = getattr(t.tail, "color_histogram", None)
+        has_h.append(h1 is not None and h2 is not None)
+        hh.append(None if h1 is None else np.asarray(h1, dtype=np.float64))
+        th.append(None if h2 is None else np.asarray(h2, dtype=np.float64))
+    out = dict(t_head_ptr=np.array(hp), t_tail_ptr=np.array(tp), t_head_idx=np.array(hidx), t_tail_idx=np.array(tidx),
+               t_head_pos=np.array(hpos), t_tail_pos=np.array(tpos),
+               t_conf=np.array([t.confidence for t in dts], dtype=np.float64),
+               t_tail_access=np.array([bool(getattr(t.tail, "access_point", False)) for t in dts]),
+               t_has_hist=np.array(has_h))
+    if any(has_h):
+        shape = next(h.shape for h in hh if h is not None)
+        out["t_head_hist"] = np.array([np.zeros(shape) if h is None else h for h in hh])
+        out["t_tail_hist"] = np.array([np.zeros(shape) if h is None else h for h in th])
+    return out
+
+
+def freeze_tracklet_case(mot3d, name, dts, build_kwargs, spec, dim):
+    g = mot3d.build_graph(dts, verbose=False, **build_kwargs)
+    assert g is not None
+    lines = mot3d.graph_to_text(g)
+    sol = solve_reference(lines)
+    sol["w_float"] = np.array([d["weight"] for _, _, d in g.edges(data=True)], dtype=np.float64)
+    trajectories = mot3d.solve_graph(g, verbose=False, method="muSSP")
+    index_of = {id(d): i for i, d in enumerate(dts)}
+    tracks = [[index_of[id(d)] for d in t] for t in trajectories]
+    sol.update(track_ptr=np.cumsum([0] + [len(t) for t in tracks]).astype(np.int64),
+               track_det=np.array([i for t in tracks for i in t], dtype=np.int64), spec=json.dumps(spec))
+    sol.update(tracklet_arrays(dts, dim))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **sol)
+    print("%-22s V=%d E=%d K=%d total=%.7f sha=%s (%d KB)" % (name, sol["n_nodes"], len(sol["tail"]), sol["K"],
+                                                              sol["total"], sol["sha"], os.path.getsize(path) // 1024))
+    return trajectories
+
+
 def gen_synth(F, P, seed, extent=1000.0):
     """SURVEY.md 8(d) generator gen(F,P,seed)."""
     rng = np.random.RandomState(seed)
@@ -172,9 +222,11 @@ def main():
                                                          sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
                                                          cutoff_appearance=0.1, use_color_histogram=True)
     wct = lambda t: wf.weight_confidence_tracklets_2d(t, mul=1, bias=0)
-    g2 = mot3d.build_graph(dts, weight_source_sink=0.1, max_jump=20, verbose=False, weight_confidence=wct,
-                           weight_distance=wdt)
-    freeze_graph_case("c2_tracklets_pass2", mot3d.graph_to_text(g2))
+    tspec = dict(kind="tracklets_2d", sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
+                 cutoff_appearance=0.1, max_distance=None, use_color_histogram=True, mul=1, bias=0,
+                 weight_source_sink=0.1, max_jump=20)
+    freeze_tracklet_case(mot3d, "c2_tracklets_pass2", dts,
+                         dict(weight_source_sink=0.1, max_jump=20, weight_confidence=wct, weight_distance=wdt), tspec, 2)
 
     # ---- (3) C3 soldiers_3d (examples/soldiers_3d/example.py:25-101)
     ex = os.path.join(REF, "examples/soldiers_3d")
@@ -205,9 +257,11 @@ def main():
                                                          alpha=0.7, cutoff_motion=0.1, cutoff_appearance=0.1,
                                                          max_distance=None, use_color_histogram=False)
     wct = lambda t: wf.weight_confidence_tracklets_3d(t, mul=1, bias=0)
-    g2 = mot3d.build_graph(dts, weight_source_sink=0.1, max_jump=30, verbose=False, weight_confidence=wct,
-                           weight_distance=wdt)
-    freeze_graph_case("c3_soldiers_pass2", mot3d.graph_to_text(g2))
+    tspec = dict(kind="tracklets_3d", sigma_color_histogram=0.3, sigma_motion=3, alpha=0.7, cutoff_motion=0.1,
+                 cutoff_appearance=0.1, max_distance=None, use_color_histogram=False, mul=1, bias=0,
+                 weight_source_sink=0.1, max_jump=30)
+    freeze_tracklet_case(mot3d, "c3_soldiers_pass2", dts,
+                         dict(weight_source_sink=0.1, max_jump=30, weight_confidence=wct, weight_distance=wdt), tspec, 3)
 
     # ---- (4) C4-real: PETS View_001 detections JSON, two 50-frame windows, bbox term on, no histograms
     #      (feeder logic of projects/PETS2009S2L1/feeders.py:51-124; parameters of
@@ -270,6 +324,47 @@ def main():
     freeze_detection_case(mot3d, "c4_synth_appearance", dets,
                           dict(weight_source_sink=0.8, max_jump=3, weight_confidence=wc, weight_distance=wd),
                           spec, extra_2d)
+
+    # ---- (4c) synthetic tracklet linking with everything on: end windows, histograms on some tracklets only,
+    #      access points, max_distance gate (PETS pass-2 shaped: config_singleview_*.yaml:40-55)
+    rng = np.random.RandomState(11)
+    dts = []
+    P = 7
+    base = rng.rand(P, 2) * 300
+    vel = rng.randn(P, 2) * 1.5
+    proto = rng.rand(P, 3, 16)
+    for p_ in range(P):
+        f = int(rng.randint(0, 6))
+        pos = base[p_].copy()
+        while f < 70:
+            ln = int(rng.randint(3, 9))
+            chain = []
+            with_hist = rng.rand() < 0.8
+            for k in range(ln):
+                pos = pos + vel[p_] + rng.randn(2) * 0.4
+                h = None
+                if with_hist:
+                    hh_ = proto[p_] + 0.2 * rng.rand(3, 16)
+                    hh_ = hh_ - hh_.mean(axis=1, keepdims=True)
+                    h = [hh_[0], hh_[1], hh_[2]]
+                chain.append(mot3d.Detection2D(f + k, pos.copy(), confidence=0.9, color_histogram=h,
+                                               bbox=(pos[0] - 15, pos[1] - 40, pos[0] + 15, pos[1] + 40)))
+            dts.append(mot3d.DetectionTracklet2D(chain, window=4, confidence=0.5 + 0.5 * rng.rand(),
+                                                 tail_access_point=bool(rng.rand() < 0.1)))
+            gap = int(rng.randint(1, 6))
+            pos = pos + vel[p_] * gap
+            f += ln + gap
+    order = rng.permutation(len(dts))
+    dts = [dts[i] for i in order]
+    tspec = dict(kind="tracklets_2d", sigma_color_histogram=0.3, sigma_motion=20, alpha=0.2, cutoff_motion=0.1,
+                 cutoff_appearance=0.1, max_distance=60, use_color_histogram=True, mul=0, bias=0.11,
+                 weight_source_sink=0.1, max_jump=12)
+    wdt = lambda t1, t2: wf.weight_distance_tracklets_2d(t1, t2, sigma_color_histogram=0.3, sigma_motion=20, alpha=0.2,
+                                                         cutoff_motion=0.1, cutoff_appearance=0.1, max_distance=60,
+                                                         use_color_histogram=True)
+    wct = lambda t: wf.weight_confidence_tracklets_2d(t, mul=0, bias=0.11)
+    freeze_tracklet_case(mot3d, "c4_synth_tracklets", dts,
+                         dict(weight_source_sink=0.1, max_jump=12, weight_confidence=wct, weight_distance=wdt), tspec, 2)
 
     # ---- (5) C5 window: gen(F=50, P=100, seed 0) = one 50-frame window of the batched config
     spec = dict(kind="2d", sigma_jump=1, sigma_distance=10, sigma_color_histogram=0.3, sigma_box_size=0.3,

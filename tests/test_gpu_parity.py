@@ -330,3 +330,101 @@ def test_full_size_c5_whole_graph():
         dt = np.diff(frame[t])
         assert (dt > 0).all() and (dt <= 8).all()
         assert (np.linalg.norm(np.diff(xy[t], axis=0), axis=1) <= 30).all()
+
+
+# ----------------------------------------------------------------------------------------------- tracklet linking
+def _tracklet_spec_from(s, mot3d):
+    dist = {k: s[k] for k in ("sigma_color_histogram", "sigma_motion", "alpha", "cutoff_motion", "cutoff_appearance",
+                              "max_distance", "use_color_histogram")}
+    return mot3d.TrackletCostSpec(kind=s["kind"], distance=dist, confidence=dict(mul=s["mul"], bias=s["bias"]),
+                                  weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"])
+
+
+def _packed_from_fixture(d, dim):
+    n = len(d["t_conf"])
+    out = dict(n=n, dim=dim, head_ptr=d["t_head_ptr"].astype(np.int32), tail_ptr=d["t_tail_ptr"].astype(np.int32),
+               head_idx=d["t_head_idx"].astype(np.int32), tail_idx=d["t_tail_idx"].astype(np.int32),
+               head_pos=np.ascontiguousarray(d["t_head_pos"].reshape(-1, dim).T),
+               tail_pos=np.ascontiguousarray(d["t_tail_pos"].reshape(-1, dim).T), conf=d["t_conf"],
+               tail_access=d["t_tail_access"].astype(np.uint8), flags=None)
+    if "t_head_hist" in d:
+        out.update(head_hist=d["t_head_hist"], tail_hist=d["t_tail_hist"],
+                   head_has_hist=d["t_has_hist"].astype(np.uint8), tail_has_hist=d["t_has_hist"].astype(np.uint8))
+    return out
+
+
+@pytest.mark.parametrize("name", gu.TRACKLET_CASES)
+def test_tracklet_build_and_solve_match_reference(name):
+    """Row a18: weight_distance_tracklets_2d/_3d + linear_motion on the GPU, then the same solver."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import tracklets as trk, spec as mspec
+    d = gu.load(name)
+    tspec = _tracklet_spec_from(d["spec"], mot3d)
+    dim = tspec.dim
+    packed = _packed_from_fixture(d, dim)
+    row_ptr, col, w, cost = trk.build_tracklet_arcs(packed, tspec)
+    # golden transitions
+    n = packed["n"]
+    tail, head = d["tail"].astype(np.int64), d["head"].astype(np.int64)
+    m = (tail % 2 == 1) & (tail != 1) & (head != 2 * n + 2)
+    src = (tail[m] - 3) // 2
+    rp = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rp, src + 1, 1)
+    assert (row_ptr == np.cumsum(rp)).all()
+    assert (col == (head[m] - 2) // 2).all()                     # same arcs, same order
+    np.testing.assert_allclose(w, d["w_float"][m], rtol=RTOL, atol=0)
+    gu.assert_costs_match(cost, d["cost"][m], d["w_float"][m])
+    # solve on the reference's own quantised arc costs (bit-identical input), compare with muSSP
+    s = d["spec"]
+    en = np.full(n, mspec.quantise_scalar(s["weight_source_sink"]), dtype=np.int64)
+    node_cost = d["cost"][(tail % 2 == 0) & (head == tail + 1)]
+    tracks, total, K, _ = trk.solve_tracklet_graph(n, row_ptr, col, d["cost"][m], en, node_cost,
+                                                   np.zeros(n, dtype=np.int64))
+    assert total == gu.ref_total_units(d) and K == int(d["K"])
+    gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
+    assert tracks == gold
+
+
+@pytest.mark.parametrize("name", ["c2_tracklets_pass2", "c3_soldiers_pass2"])
+def test_tracklet_public_api_drop_in(name):
+    """build_graph / solve_graph on DetectionTracklet2D/3D objects, as examples/simple_2d_tracklets/example.py:78-108
+    and examples/soldiers_3d/example.py:81-101 call them."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    from oracle import oracle
+    d = gu.load(name)
+    s = d["spec"]
+    n = len(d["t_conf"])
+    hp = d["t_head_ptr"]
+    tracklets = []
+    for i in range(n):
+        idx = d["t_head_idx"][hp[i]:hp[i + 1]]       # window=None: the head window is the whole tracklet
+        pts = d["t_head_pos"][hp[i]:hp[i + 1]]
+        if s["kind"] == "tracklets_2d":
+            hist = [h for h in d["t_head_hist"][i]] if "t_head_hist" in d else None
+            chain = [mot3d.Detection2D(int(f), p, color_histogram=hist, bbox=[0, 0, 1, 1]) for f, p in zip(idx, pts)]
+            tracklets.append(mot3d.DetectionTracklet2D(chain))
+        else:
+            chain = [mot3d.Detection3D(int(f), p) for f, p in zip(idx, pts)]
+            tracklets.append(mot3d.DetectionTracklet3D(chain))
+    kw = {k: s[k] for k in ("sigma_color_histogram", "sigma_motion", "alpha", "cutoff_motion", "cutoff_appearance",
+                            "max_distance", "use_color_histogram")}
+    if s["kind"] == "tracklets_2d":
+        wd = lambda t1, t2: wf.weight_distance_tracklets_2d(t1, t2, **kw)
+        wc = lambda t: wf.weight_confidence_tracklets_2d(t, mul=s["mul"], bias=s["bias"])
+    else:
+        wd = lambda t1, t2: wf.weight_distance_tracklets_3d(t1, t2, **kw)
+        wc = lambda t: wf.weight_confidence_tracklets_3d(t, mul=s["mul"], bias=s["bias"])
+    g = mot3d.build_graph(tracklets, weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"], verbose=False,
+                          weight_confidence=wc, weight_distance=wd)
+    assert g is not None and len(g) == int(d["n_nodes"])
+    tail, head, w = g.arcs()
+    assert (tail == d["tail"]).all() and (head == d["head"]).all()
+    np.testing.assert_allclose(w, d["w_float"], rtol=RTOL, atol=0)
+    if name == "c2_tracklets_pass2":
+        assert oracle.text_sha(mot3d.graph_to_text(g)) == str(d["sha"])
+    trajectories = mot3d.solve_graph(g, verbose=False)
+    got = [[tracklets.index(t) for t in tr] for tr in trajectories]
+    gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
+    assert got == gold
+    assert g.total_cost == gu.ref_total_units(d)

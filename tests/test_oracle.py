@@ -84,3 +84,17 @@ def test_c5_whole_summary():
     d = gu.load("c5_whole_summary")
     assert int(d["K"]) == 100 and int(d["n_arcs"]) == 1187969 and int(d["n_nodes"]) == 200002
     assert int(d["total_units"]) == gu.ref_total_units(d) == -1878765227978
+
+
+@pytest.mark.parametrize("name", ["c2_tracklets_pass2", "c3_soldiers_pass2", "c4_synth_tracklets"])
+def test_tracklet_build_restatement_matches_reference(name):
+    d = gu.load(name)
+    s = d["spec"]
+    spec = oracle.TrackletSpec(**s)
+    row_ptr, col, w = oracle.build_tracklet_transitions(d, spec)
+    n = len(d["t_conf"])
+    node_w = -(d["t_conf"] * spec.mul + spec.bias)
+    tail, head, ww = oracle.graph_arcs(n, float(spec.weight_source_sink), node_w, 0.0, row_ptr, col, w)
+    assert (tail == d["tail"]).all() and (head == d["head"]).all()
+    np.testing.assert_allclose(ww, d["w_float"], rtol=1e-9, atol=0)
+    gu.assert_costs_match(oracle.quantise(ww), d["cost"], d["w_float"])
