@@ -59,6 +59,10 @@ typedef struct mot3d_dets {
     const uint8_t *flags; /* [n] MOT3D_FLAG_*; NULL = entry and exit allowed everywhere (the reference default) */
     const double *bbox;   /* [4][n] planar xmin,ymin,xmax,ymax; NULL unless use_bbox */
     const double *hist;   /* [n][C][B] colour histograms (mean-subtracted, mot3d/distance_functions.py:10-19); NULL unless use_hist */
+    double *sorted_pos;   /* optional scratch [dim][n]: positions sorted by x inside every frame, made by mot3d_frame_sort */
+    int32_t *sorted_perm; /* optional scratch [n]: original index of every sorted entry. When both are set,
+                             mot3d_edge_count / mot3d_edge_fill search x-windows instead of testing every pair
+                             (same arcs, same order); NULL = brute force */
 } mot3d_dets;
 
 /* Parameters of the built-in costs (mot3d/weight_functions.py:13-17,37-38,43-47) and of build_graph
@@ -96,6 +100,9 @@ int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t 
  * exit (post->T).  MOT3D_INF_COST where flags forbid the arc. */
 int32_t mot3d_node_costs(const mot3d_dets *dets, const mot3d_cost_spec *spec, int64_t *entry_cost_out,
                          int64_t *node_cost_out, int64_t *exit_cost_out, void *stream);
+
+/* fills dets->sorted_pos / dets->sorted_perm (both must be set): per frame, detections ranked by (x, index). */
+int32_t mot3d_frame_sort(const mot3d_dets *dets, void *stream);
 
 /* pass 1 of the windowed all-pairs kernel: row_count[r] = number of transition arcs of row r
  * (pairs with 0 < frame[j]-frame[i] <= max_jump and dist <= max_distance; mot3d/mot3d.py:122-127). */

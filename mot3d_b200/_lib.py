@@ -24,7 +24,8 @@ class Dets(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int64), ("dim", ctypes.c_int32), ("hist_channels", ctypes.c_int32),
                 ("hist_bins", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tkey", ctypes.c_void_p),
                 ("pos", ctypes.c_void_p), ("conf", ctypes.c_void_p), ("flags", ctypes.c_void_p),
-                ("bbox", ctypes.c_void_p), ("hist", ctypes.c_void_p)]
+                ("bbox", ctypes.c_void_p), ("hist", ctypes.c_void_p), ("sorted_pos", ctypes.c_void_p),
+                ("sorted_perm", ctypes.c_void_p)]
 
 
 class CostSpecC(ctypes.Structure):
@@ -73,6 +74,7 @@ SIGNATURES = {
     "mot3d_last_error": (ctypes.c_char_p, []),
     "mot3d_make_keys": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "mot3d_node_costs": (_i32, [_PD, _PS, _vp, _vp, _vp, _vp]),
+    "mot3d_frame_sort": (_i32, [_PD, _vp]),
     "mot3d_edge_count": (_i32, [_PD, _PS, _i32, _vp, _vp]),
     "mot3d_scan_workspace_bytes": (_sz, [_i64]),
     "mot3d_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),

@@ -107,8 +107,11 @@ class GraphBatch(object):
         self.n_edges = 0
 
 
-def _dets_struct(b, tkey, spec):
+def _dets_struct(b, tkey, spec, sorted_pos=None, sorted_perm=None):
     d = _lib.Dets()
+    if sorted_pos is not None:
+        d.sorted_pos = sorted_pos.data_ptr()
+        d.sorted_perm = sorted_perm.data_ptr()
     d.n = b.n
     d.dim = b.dim
     d.tkey = tkey.data_ptr()
@@ -127,8 +130,9 @@ def _dets_struct(b, tkey, spec):
     return d
 
 
-def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=None):
-    """Graph build on the device. `batch` must already live on a CUDA device (DetectionBatch.to)."""
+def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=None, pruned=True):
+    """Graph build on the device. `batch` must already live on a CUDA device (DetectionBatch.to).
+    pruned=True: per-frame x-sorted copies + window search (csrc/edge_pruned.cu); False: test every pair."""
     L = _lib.lib()
     dev = batch.frame.device
     if dev.type != "cuda":
@@ -148,7 +152,13 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
     else:
         tkey = keys
     gb.tkey = tkey
-    d = _dets_struct(batch, tkey, spec)
+    spos = sperm = None
+    if pruned and n:
+        spos = torch.empty(batch.dim * n, dtype=torch.float64, device=dev)
+        sperm = torch.empty(n, **i32)
+    d = _dets_struct(batch, tkey, spec, spos, sperm)
+    if spos is not None:
+        _lib.check(L.mot3d_frame_sort(ctypes.byref(d), st))
     gb.entry_cost = torch.empty(max(n, 1), **i64)
     gb.node_cost = torch.empty(max(n, 1), **i64)
     gb.exit_cost = torch.empty(max(n, 1), **i64)

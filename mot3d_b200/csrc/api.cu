@@ -62,6 +62,7 @@ size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t ed
     b += align256((size_t)n1);                  // flags
     b += align256((size_t)n1 * 8 * 4);          // bbox
     b += align256((size_t)g1 * 8);              // graph base
+    b += align256((size_t)n1 * 8 * 3) + align256((size_t)n1 * 4);  // x-sorted copies + permutation
     b += align256((size_t)n1 * 8) * 3;          // entry/node/exit cost
     b += align256((size_t)n1 * 4);              // row_count
     b += align256((size_t)(n1 + 1) * 4);        // row_ptr
@@ -110,6 +111,8 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     uint8_t *d_flags = hb->flags ? A.take<uint8_t>(n) : nullptr;
     double *d_bbox = (spec->use_bbox) ? A.take<double>(n * 4) : nullptr;
     int64_t *d_gbase = A.take<int64_t>(G);
+    double *d_spos = A.take<double>(n * hb->dim);
+    int32_t *d_sperm = A.take<int32_t>(n);
     int64_t *d_en = A.take<int64_t>(n);
     int64_t *d_cn = A.take<int64_t>(n);
     int64_t *d_ex = A.take<int64_t>(n);
@@ -153,7 +156,10 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     d.conf = d_conf;
     d.flags = d_flags;
     d.bbox = d_bbox;
+    d.sorted_pos = d_spos;
+    d.sorted_perm = d_sperm;
     if ((rc = mot3d_node_costs(&d, spec, d_en, d_cn, d_ex, st))) return rc;
+    if ((rc = mot3d_frame_sort(&d, st))) return rc;
     if ((rc = mot3d_edge_count(&d, spec, MOT3D_DIR_IN, d_rowcnt, st))) return rc;
     if ((rc = mot3d_exclusive_scan_i32(d_rowcnt, n, d_rowptr, d_scan, scan_b, st))) return rc;
     if ((rc = mot3d_edge_fill(&d, spec, MOT3D_DIR_IN, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over, st)))

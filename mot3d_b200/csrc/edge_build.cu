@@ -221,13 +221,32 @@ __global__ void __launch_bounds__(EB_TPB) k_edge_build(const __grid_constant__ E
 // multiplies the histogram factor in before the bbox factor).
 template <int DIR>
 __global__ void __launch_bounds__(128) k_edge_cost(const __grid_constant__ EdgeParams p) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.n) return;
+    // one warp per 32 consecutive rows: their arcs are one contiguous range, walked with coalesced accesses; the
+    // row of an arc is found by a binary search over the 32 row starts held one per lane
     const int64_t n = p.n;
-    int64_t e0 = p.row_ptr[r], e1 = p.row_ptr[r + 1];
-    if (e1 > p.edge_capacity) e1 = p.edge_capacity;
-    const int key_r = p.tkey[r];
-    for (int64_t e = e0; e < e1; e++) {
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id()) * 32;
+    if (r0 >= n) return;
+    const int lane = lane_id();
+    const int64_t r_lane = (r0 + lane < n) ? r0 + lane : n - 1;
+    const int rp = p.row_ptr[(r0 + lane <= n) ? r0 + lane : n];  // lanes past the end repeat the final offset
+    const int key_lane = p.tkey[r_lane];
+    int64_t e_begin = __shfl_sync(0xffffffffu, rp, 0);
+    int64_t e_end = p.row_ptr[(r0 + 32 < n) ? r0 + 32 : n];
+    if (e_end > p.edge_capacity) e_end = p.edge_capacity;
+    for (int64_t e0 = e_begin; e0 < e_end; e0 += 32) {
+        const int64_t e = e0 + lane;
+        const bool act = e < e_end;
+        // largest lane l with rp[l] <= e
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int cand = lo + step;
+            const int v = __shfl_sync(0xffffffffu, rp, cand & 31);
+            if (cand < 32 && v <= (int)e) lo = cand;
+        }
+        const int key_r = __shfl_sync(0xffffffffu, key_lane, lo);
+        if (!act) continue;
+        const int64_t r = r0 + lo;
         const int64_t other = p.col[e];
         const double s = __longlong_as_double(p.cost[e]);
         const int dk = (DIR == MOT3D_DIR_OUT) ? (p.tkey[other] - key_r) : (key_r - p.tkey[other]);
@@ -506,6 +525,25 @@ int32_t mot3d_node_costs(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
 }
 
 
+}  // extern "C"
+
+namespace m3 {
+int32_t launch_frame_sort(const mot3d_dets *d, cudaStream_t st);
+int32_t launch_pruned(const mot3d_dets *d, const mot3d_cost_spec *s, int direction, bool fill, int32_t *row_count,
+                      const int32_t *row_ptr, int64_t edge_capacity, int32_t *col, int64_t *cost, int32_t *overflow,
+                      cudaStream_t st);
+}  // namespace m3
+
+extern "C" {
+
+int32_t mot3d_frame_sort(const mot3d_dets *dets, void *stream) {
+    M3_CHECK_ARG(dets, "dets is NULL");
+    if (dets->n == 0) return MOT3D_OK;
+    M3_CHECK_ARG(dets->tkey && dets->pos && dets->sorted_pos && dets->sorted_perm, "NULL pointer");
+    M3_CHECK_ARG(dets->dim == 2 || dets->dim == 3, "dim must be 2 or 3");
+    return launch_frame_sort(dets, (cudaStream_t)stream);
+}
+
 static void fill_params(EdgeParams &p, const mot3d_dets *d, const mot3d_cost_spec *s) {
     p.n = d->n;
     p.dim = d->dim;
@@ -540,6 +578,8 @@ int32_t mot3d_edge_count(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     p.row_count = row_count_out;
     unsigned grid = (unsigned)((dets->n + EB_TPB - 1) / EB_TPB);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dets->sorted_pos && dets->sorted_perm)
+        return launch_pruned(dets, spec, direction, false, row_count_out, nullptr, 0, nullptr, nullptr, nullptr, st);
     if (direction == MOT3D_DIR_IN)
         k_edge_build<MOT3D_DIR_IN, false><<<grid, EB_TPB, 0, st>>>(p);
     else
@@ -568,16 +608,23 @@ int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int
     p.overflow = overflow_flag;
     unsigned grid = (unsigned)((dets->n + EB_TPB - 1) / EB_TPB);
     cudaStream_t st = (cudaStream_t)stream;
-    if (direction == MOT3D_DIR_IN)
-        k_edge_build<MOT3D_DIR_IN, true><<<grid, EB_TPB, 0, st>>>(p);
-    else
-        k_edge_build<MOT3D_DIR_OUT, true><<<grid, EB_TPB, 0, st>>>(p);
-    M3_LAUNCH_CHECK("k_edge_build<fill>");
-    if (edge_capacity > 0) {
+    if (dets->sorted_pos && dets->sorted_perm) {
+        rc = launch_pruned(dets, spec, direction, true, nullptr, row_ptr, edge_capacity, col_out, cost_out,
+                           overflow_flag, st);
+        if (rc) return rc;
+    } else {
         if (direction == MOT3D_DIR_IN)
-            k_edge_cost<MOT3D_DIR_IN><<<grid, EB_TPB, 0, st>>>(p);
+            k_edge_build<MOT3D_DIR_IN, true><<<grid, EB_TPB, 0, st>>>(p);
         else
-            k_edge_cost<MOT3D_DIR_OUT><<<grid, EB_TPB, 0, st>>>(p);
+            k_edge_build<MOT3D_DIR_OUT, true><<<grid, EB_TPB, 0, st>>>(p);
+        M3_LAUNCH_CHECK("k_edge_build<fill>");
+    }
+    if (edge_capacity > 0) {
+        const unsigned cgrid = (unsigned)((dets->n + 127) / 128);  // 4 warps x 32 rows per block
+        if (direction == MOT3D_DIR_IN)
+            k_edge_cost<MOT3D_DIR_IN><<<cgrid, 128, 0, st>>>(p);
+        else
+            k_edge_cost<MOT3D_DIR_OUT><<<cgrid, 128, 0, st>>>(p);
         M3_LAUNCH_CHECK("k_edge_cost");
     }
     return MOT3D_OK;

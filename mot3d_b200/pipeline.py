@@ -10,12 +10,12 @@ import torch
 from . import _lib
 from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
 
-STAGES = ["make_keys", "node_costs", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
-LAUNCHES_PER_RUN = 2 + 1 + 1 + 3 + 2 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
+STAGES = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 3 + 2 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
 
 
 class TrackPipeline(object):
-    def __init__(self, n_max, g_max, edge_capacity, device=None):
+    def __init__(self, n_max, g_max, edge_capacity, device=None, dim=2, pruned=True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         dev = self.device
         self.n_max, self.g_max, self.edge_capacity = int(n_max), int(g_max), int(edge_capacity)
@@ -29,6 +29,9 @@ class TrackPipeline(object):
         self.node_cost = torch.empty(n, **i64)
         self.exit_cost = torch.empty(n, **i64)
         self.row_count = torch.empty(n, **i32)
+        self.pruned = pruned
+        self.sorted_pos = torch.empty(dim * n, dtype=torch.float64, device=dev) if pruned else None
+        self.sorted_perm = torch.empty(n, **i32) if pruned else None
         self.row_ptr = torch.empty(n + 1, **i32)
         self.scan_ws_bytes = L.mot3d_scan_workspace_bytes(n)
         self.scan_ws = torch.empty(self.scan_ws_bytes, dtype=torch.uint8, device=dev)
@@ -66,29 +69,32 @@ class TrackPipeline(object):
         _lib.check(L.mot3d_make_keys(_ptr(batch.frame), _ptr(batch.graph_ptr), G, spec.max_jump, _ptr(self.tkey),
                                      _ptr(self.gbase), st))
         rec(1)
-        d = _dets_struct(batch, self.tkey, spec)
+        d = _dets_struct(batch, self.tkey, spec, self.sorted_pos, self.sorted_perm)
         _lib.check(L.mot3d_node_costs(ctypes.byref(d), ctypes.byref(cs), _ptr(self.entry_cost), _ptr(self.node_cost),
                                       _ptr(self.exit_cost), st))
         rec(2)
-        _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
+        if self.pruned:
+            _lib.check(L.mot3d_frame_sort(ctypes.byref(d), st))
         rec(3)
+        _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
+        rec(4)
         _lib.check(L.mot3d_exclusive_scan_i32(_ptr(self.row_count), n, _ptr(self.row_ptr), _ptr(self.scan_ws),
                                               self.scan_ws_bytes, st))
-        rec(4)
+        rec(5)
         _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_ptr),
                                      self.edge_capacity, _ptr(self.col), _ptr(self.cost), None, _ptr(self.overflow),
                                      st))
-        rec(5)
+        rec(6)
         _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), self.edge_capacity,
                                        _ptr(self.row_ptr),
                                        _ptr(self.col), _ptr(self.cost), _ptr(self.entry_cost), _ptr(self.node_cost),
                                        _ptr(self.exit_cost), _ptr(self.next), _ptr(self.prev), _ptr(self.n_paths),
                                        _ptr(self.total_cost), None, _ptr(self.stats), _ptr(self.solve_ws),
                                        self.solve_ws_bytes, st))
-        rec(6)
+        rec(7)
         _lib.check(L.mot3d_extract_tracks(G, _ptr(batch.graph_ptr), _ptr(self.next), _ptr(self.prev),
                                           _ptr(self.track_count), _ptr(self.track_ptr), _ptr(self.track_det), st))
-        rec(7)
+        rec(8)
         self._n, self._G = n, G
 
     def check_overflow(self):

@@ -45,8 +45,9 @@ def _golden_transitions(d):
     return np.cumsum(row_ptr), (head[m] - 2) // 2, d["w_float"][m], d["cost"][m]
 
 
+@pytest.mark.parametrize("pruned", [True, False], ids=["xwindow", "allpairs"])
 @pytest.mark.parametrize("name", gu.DETECTION_CASES)
-def test_edge_build_matches_reference(name):
+def test_edge_build_matches_reference(name, pruned):
     import mot3d_b200 as mot3d
     from mot3d_b200 import _lib
     torch = _torch()
@@ -54,7 +55,7 @@ def test_edge_build_matches_reference(name):
     spec = _spec_from(d["spec"], mot3d)
     b = _batch_from(d, mot3d).to("cuda")
     row_ptr, col, w, cost = _golden_transitions(d)
-    out = mot3d.build_graphs(b, spec, direction=_lib.DIR_OUT, with_weights=True)
+    out = mot3d.build_graphs(b, spec, direction=_lib.DIR_OUT, with_weights=True, pruned=pruned)
     assert out.n_edges == len(col)
     assert (out.row_ptr.cpu().numpy() == row_ptr).all()
     e = out.n_edges
@@ -62,7 +63,7 @@ def test_edge_build_matches_reference(name):
     np.testing.assert_allclose(out.weight[:e].cpu().numpy(), w, rtol=RTOL, atol=0)
     gu.assert_costs_match(out.cost[:e].cpu().numpy(), cost, w)
     # the solver's orientation is the transpose of the same arc set
-    inn = mot3d.build_graphs(b, spec, direction=_lib.DIR_IN, with_weights=True)
+    inn = mot3d.build_graphs(b, spec, direction=_lib.DIR_IN, with_weights=True, pruned=pruned)
     assert inn.n_edges == e
     rp = inn.row_ptr.cpu().numpy().astype(np.int64)
     dst = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
