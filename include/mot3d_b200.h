@@ -175,6 +175,19 @@ int32_t mot3d_tracklet_edge_fill(const mot3d_tracklets *trk, const mot3d_trackle
                                  int64_t edge_capacity, int32_t *col_out, int64_t *cost_out, double *weight_out,
                                  int32_t *overflow_flag, void *stream);
 
+/* ---- connected components: every graph is split into groups of detections no arc connects; the solver treats each
+ *      group as an independent small graph (same optimum: S and T are the only coupling). No reference counterpart.
+ *   comp_perm_out[q]   detection at regrouped position q (graph g keeps the positions [graph_ptr[g], graph_ptr[g+1]))
+ *   comp_inv_out[d]    regrouped position of detection d
+ *   cgraph_ptr_out     [n_total + n_graphs] component c = positions [cgraph_ptr[c], cgraph_ptr[c+1])
+ *   cgraph_graph_out   [n_total] graph of component c;  graph_cbase_out [n_graphs] first component of graph g
+ *   n_cgraphs_out      device int32[4]: [0] = number of components, [1] = 0 (work-queue cursor of the solver) */
+size_t mot3d_components_workspace_bytes(int64_t n_total, int32_t n_graphs);
+int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, const int32_t *in_ptr,
+                         const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out, int32_t *comp_inv_out,
+                         int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out, int32_t *graph_cbase_out,
+                         int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- solve: replaces wrapper.solve (wrapper.cpp:171-317) and the muSSP core it drives ------------------------ */
 
 size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t arc_capacity);
@@ -186,7 +199,8 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
  *   next_out[i]  : successor of detection i on its track (global index), -2 if the track ends at i, -1 if i is unused
  *   prev_out[i]  : predecessor, -2 if a track starts at i, -1 if unused
  *   n_paths_out[g], total_cost_out[g] : K and the sum of accepted path costs
- *   path_cost_out : optional [n_total]; graph g's k-th path cost at graph_ptr[g]+k
+ *   path_cost_out : optional [n_total]; the accepted path costs of graph g are the entries < MOT3D_INF_COST of its slice
+ *                   [graph_ptr[g], graph_ptr[g+1]) (grouped by connected component, ascending inside a component)
  *   stats_out     : optional int64 [n_graphs][MOT3D_SOLVE_STATS]: [0..3] = ascending sweeps, descending sweeps, node
  *                   pulls, arc pulls (what bench.py's roofline accounting needs); [4..10] = SM cycles spent in:
  *                   sink arg-min, branch collection, staging, path walk, re-labelling sweeps, write-back, first tree

@@ -83,6 +83,8 @@ SIGNATURES = {
     "mot3d_tracklet_edge_count": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _vp]),
     "mot3d_tracklet_edge_fill": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _i64, _vp, _vp,
                                         _vp, _vp, _vp]),
+    "mot3d_components_workspace_bytes": (_sz, [_i64, _i32]),
+    "mot3d_components": (_i32, [_i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),

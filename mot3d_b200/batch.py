@@ -221,6 +221,14 @@ def solve_graphs(gb, want_path_costs=True):
                                    _ptr(gb.cost), _ptr(gb.entry_cost), _ptr(gb.node_cost), _ptr(gb.exit_cost),
                                    _ptr(sol.next), _ptr(sol.prev), _ptr(sol.n_paths), _ptr(sol.total_cost),
                                    _ptr(sol.path_cost), _ptr(sol.stats), _ptr(ws), ws_bytes, st))
+    if want_path_costs and n:
+        # the kernel leaves the accepted path costs grouped by connected component inside every graph's slice
+        # (MOT3D_INF_COST elsewhere); present them per graph in the order the reference finds them (ascending)
+        gp = b.graph_ptr.to(torch.int64)
+        gid = torch.repeat_interleave(torch.arange(G, device=dev), gp[1:] - gp[:-1])
+        v, o = torch.sort(sol.path_cost[:n], stable=True)
+        _, o2 = torch.sort(gid[o], stable=True)
+        sol.path_cost = torch.cat([v[o2], sol.path_cost[n:]])
     return sol
 
 

@@ -68,6 +68,7 @@ struct SolveParams {
     int32_t rec_cap;  // records / arcs of the shared-memory staging area
     int32_t arc_cap;
     int32_t pad;
+    int64_t n_total;
     const int32_t *graph_ptr;
     const int32_t *tkey;
     const int32_t *in_ptr;
@@ -76,28 +77,39 @@ struct SolveParams {
     const int64_t *en;
     const int64_t *cn;
     const int64_t *ex;
-    int32_t *next_out;  // also the solver's next[] (local indices while solving, globalised at the end)
+    int32_t *next_out;
     int32_t *prev_out;
     int32_t *n_paths;
     int64_t *total;
-    int64_t *path_cost;
+    int64_t *path_cost;    // optional [n_total], indexed like the regrouped order (component's k-th path at c0 + k)
     int64_t *stats;        // optional [n_graphs][MOT3D_SOLVE_STATS], see include/mot3d_b200.h
     int64_t arc_capacity;  // arcs actually present in in_src/in_cost (graphs reaching beyond it are skipped)
-    // global workspace: per-node state (exact distances, parent, branch labels) ...
-    int64_t *ws_dpre;
+    // component graphs (csrc/components.cu): detections regrouped by connected component
+    const int32_t *comp_perm;   // [n_total] detection at every regrouped position
+    const int32_t *comp_inv;    // [n_total] regrouped position of every detection
+    const int32_t *cgraph_ptr;  // [n_cgraphs + 1] regrouped positions
+    const int32_t *cgraph_win;  // [n_cgraphs] graph of every component
+    const int32_t *win_cbase;   // [n_graphs] first component of every graph
+    int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
+    int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
+    int32_t *first_sink;        // [n_total] ... and the position where it ends
+    // per-node state in the regrouped order, values are regrouped positions too:
+    int64_t *ws_dpre;   // exact distances from S (the invariant the incremental update relies on)
     int64_t *ws_dpost;
-    int64_t *ws_mcost;
-    int32_t *ws_par;
-    int32_t *ws_anc_pre;
-    int32_t *ws_anc_post;
+    int64_t *ws_mcost;  // cost of the matched in-arc prev -> this
+    int32_t *ws_par;    // parent of the pre node: PAR_S / PAR_POST / PAR_NONE / position of the source detection
+    int32_t *ws_anc_pre;   // branch = position of the detection whose S->pre arc starts the node's tree path
+    int32_t *ws_anc_post;  // (muSSP's ancestor_node_id, Graph.cpp:160-161)
+    int32_t *ws_nxt;    // flow: successor position / TERM / NONE
+    int32_t *ws_prv;
     int32_t *ws_slot_of;
     int32_t *ws_dl;
     int32_t *ws_dla0;
-    int32_t *ws_lvl;  // [n_total + n_graphs]
-    // ... and the fallback staging area for branches that do not fit in shared memory
+    int32_t *ws_lvl;  // [n_total + n_graphs] frame layers (first tree)
+    // fallback staging area for branches that do not fit in shared memory
     Rec *ws_rec;      // n_total
     int32_t *ws_tk;   // n_total
-    StArc *ws_arc;    // arc_capacity
+    StArc *ws_arc;    // arc_capacity + n_total + 8
 };
 
 __device__ __forceinline__ KeyIdx group_min(KeyIdx best, unsigned mask) {
@@ -130,14 +142,15 @@ __device__ __forceinline__ int block_excl_scan1(int v, int *scratch, int phase, 
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-// Everything the per-augmentation work needs (pointers are already offset to the graph).
+// Everything the per-augmentation work needs. Per-node arrays are indexed by regrouped position (global), and the
+// values they hold (parents, branches, next/prev) are regrouped positions as well.
 struct Ctx {
     const SolveParams *p;
-    int g0, n, arc0;
+    int c0, n;  // the component graph = positions [c0, c0 + n)
     int64_t *dpre, *dpost, *mcost;
-    int32_t *par, *anc_pre, *anc_post, *slot_of, *dl, *dla0, *nxt, *prv;
-    const int32_t *tkey, *in_ptr;
-    const int64_t *en, *cn;
+    int32_t *par, *anc_pre, *anc_post, *slot_of, *nxt, *prv;
+    int32_t *dl, *dla0;  // scratch lists of this component (offset by c0)
+    const int32_t *perm, *inv;
 };
 
 struct Counters {
@@ -168,30 +181,31 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
         st.arc = (StArc *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec));
         st.tk = (int32_t *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec) + (size_t)(p.arc_cap + 8) * sizeof(StArc));
     } else {
-        st.rec = p.ws_rec + c.g0;
-        st.arc = p.ws_arc + c.arc0 + c.g0 + 8 * (size_t)blockIdx.x;  // all in-arcs + a marker per detection + pad
-        st.tk = p.ws_tk + c.g0;
+        st.rec = p.ws_rec + c.c0;
+        st.arc = p.ws_arc;  // a record's arcs sit at in_ptr[d] + d: room for its in-degree + the end marker
+        st.tk = p.ws_tk + c.c0;
     }
     // ---- stage the branch: one lane group per record
     for (int sb = 0; sb < nd; sb += ngrp) {
         const int s = sb + grp;
         const bool valid = s < nd;
         const int ent = valid ? c.dl[s] : 0;
-        const int j = ent & DL_MASK;
+        const int j = ent & DL_MASK;            // regrouped position
+        const int dj = valid ? c.perm[j] : 0;   // detection
         KeyIdx cbest;  // best in-arc from outside the branch
         cbest.key = INF;
         cbest.idx = PAR_NONE;
         int nda = 0, a0 = 0;
         if (valid && (ent & DL_PRE)) {
-            a0 = c.dla0[s];
-            const int e0 = c.in_ptr[j], deg = c.in_ptr[j + 1] - e0;
+            const int e0 = p.in_ptr[dj], deg = p.in_ptr[dj + 1] - e0;
+            a0 = SM ? c.dla0[s] : e0 + dj;
             for (int k0 = 0; k0 < deg; k0 += LPN) {
                 const int k = k0 + sub;
                 const bool has = k < deg;
                 int i = -1, a = -2;
                 int64_t w = 0, di = INF;
                 if (has) {
-                    i = p.in_src[e0 + k] - c.g0;
+                    i = c.inv[p.in_src[e0 + k]];
                     w = p.in_cost[e0 + k];
                     a = c.anc_post[i];
                     di = c.dpost[i];
@@ -216,7 +230,7 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
         }
         cbest = group_min(cbest, gmask);
         if (valid && sub == 0) {
-            const int64_t dpre_j = c.dpre[j], dpost_j = c.dpost[j], cn_j = c.cn[j];
+            const int64_t dpre_j = c.dpre[j], dpost_j = c.dpost[j], cn_j = p.cn[dj];
             const int prv_j = c.prv[j], nxt_j = c.nxt[j], par_j = c.par[j];
             const int apost_j = c.anc_post[j];
             int64_t bkey = cbest.key;
@@ -241,12 +255,12 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
             }
             r.B = make_int4(((ent & DL_POST) && nxt_j >= 0) ? c.slot_of[nxt_j] : -1,
                             ((ent & DL_PRE) && par_j >= 0) ? c.slot_of[par_j] : -1, bpar, banc);
-            r.C = make_longlong2(bkey, c.en[j]);
+            r.C = make_longlong2(bkey, p.en[dj]);
             r.D = make_longlong2(cn_j, c.mcost[j]);
             r.E = make_longlong2(dpre_j, dpost_j);
             r.F = make_int4(par_j, c.anc_pre[j], apost_j, nxt_j);
             st.rec[s] = r;
-            st.tk[s] = c.tkey[j];
+            st.tk[s] = p.tkey[dj];
         }
     }
     __syncthreads();
@@ -553,35 +567,124 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
     return true;
 }
 
-__global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
-    __shared__ int s_scan[64];
-    __shared__ KeyIdx s_red[33];
-    __shared__ int s_ok[2], s_sweep_warp;
-    __shared__ long long s_work[4];  // ascending sweeps, descending sweeps, node pulls, arc pulls (sweep warp)
-
+// ---- first shortest-path tree of every graph (before it is split into components): no flow yet, the network is a
+//      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
+//      State is written in the regrouped order; branch label = position of the detection whose S arc starts the path.
+__global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
+    __shared__ int s_scan[33];
     const int g = blockIdx.x;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
-    const int T = blockDim.x;
-    const int tid = threadIdx.x;
-    int32_t *nxt = p.next_out + g0, *prv = p.prev_out + g0;
-    if (n <= 0 || (int64_t)p.in_ptr[g0 + n] > p.arc_capacity) {
-        // empty graph, or the arc buffer overflowed during the build (reported by the fill kernel's flag)
-        if (tid == 0) {
-            p.n_paths[g] = n <= 0 ? 0 : -1;
-            p.total[g] = 0;
-        }
+    const int T = blockDim.x, tid = threadIdx.x;
+    if (tid == 0) {
+        p.n_paths[g] = 0;
+        p.total[g] = 0;
+        if (p.stats)
+            for (int k = 0; k < MOT3D_SOLVE_STATS; k++) p.stats[(size_t)MOT3D_SOLVE_STATS * g + k] = 0;
+    }
+    if (n <= 0) return;
+    const int32_t *tkey = p.tkey + g0;
+    const int32_t *in_ptr = p.in_ptr + g0;
+    const int32_t *inv = p.comp_inv + g0;
+    if ((int64_t)in_ptr[n] > p.arc_capacity) {  // arc buffer overflow (reported by the fill kernel): skipped
+        if (tid == 0) p.n_paths[g] = -1;
         for (int i = tid; i < n; i += T) {
-            nxt[i] = NONE;
-            prv[i] = NONE;
+            p.next_out[g0 + i] = NONE;
+            p.prev_out[g0 + i] = NONE;
         }
         return;
     }
+    for (int i = tid; i < n; i += T) {  // regrouped positions of this graph are [g0, g0 + n) as well
+        const int q = g0 + i;
+        p.ws_nxt[q] = NONE;
+        p.ws_prv[q] = NONE;
+        p.ws_dpre[q] = INF;
+        p.ws_dpost[q] = INF;
+        p.ws_par[q] = PAR_NONE;
+        p.ws_anc_pre[q] = -1;
+        p.ws_anc_post[q] = -1;
+        p.ws_mcost[q] = 0;
+        p.first_cost[q] = INF;
+        p.first_sink[q] = -1;
+        if (p.path_cost) p.path_cost[q] = INF;
+    }
+    int32_t *lvl = p.ws_lvl + g0 + g;
+    int L = 0;
+    for (int base = 0; base < n; base += T) {
+        const int i = base + tid;
+        const int f = (i < n && (i == 0 || tkey[i] != tkey[i - 1])) ? 1 : 0;
+        int tot;
+        const int ex_ = block_excl_scan(f, s_scan, &tot);
+        if (f) lvl[L + ex_] = i;
+        L += tot;
+    }
+    if (tid == 0) lvl[L] = n;
+    __syncthreads();
+    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
+    for (int l = 0; l < L; l++) {
+        const int a = lvl[l], b = lvl[l + 1];
+        for (int jb = a; jb < b; jb += ngrp) {
+            const int j = jb + grp;  // detection (local)
+            const bool valid = j < b;
+            KeyIdx best;
+            best.key = INF;
+            best.idx = PAR_NONE;
+            if (valid) {
+                const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
+                for (int k = sub; k < deg; k += LPN) {
+                    const int qi = p.comp_inv[p.in_src[e0 + k]];  // position of the source
+                    const int64_t di = p.ws_dpost[qi];
+                    if (di < INF_CUT) {
+                        const int64_t cand = di + p.in_cost[e0 + k];
+                        if (cand < best.key || (cand == best.key && qi < best.idx)) {
+                            best.key = cand;
+                            best.idx = qi;
+                        }
+                    }
+                }
+            }
+            best = group_min(best, 0xffffffffu);
+            if (valid && sub == 0) {
+                const int q = inv[j];
+                int anc = best.idx >= 0 ? p.ws_anc_post[best.idx] : -1;
+                const int64_t e_ = p.en[g0 + j];
+                if (e_ < best.key) {
+                    best.key = e_;
+                    best.idx = PAR_S;
+                    anc = q;
+                }
+                if (best.key < INF_CUT) {
+                    p.ws_dpre[q] = best.key;
+                    p.ws_par[q] = best.idx;
+                    p.ws_anc_pre[q] = anc;
+                    p.ws_dpost[q] = best.key + p.cn[g0 + j];
+                    p.ws_anc_post[q] = anc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.stats && tid == 0) {
+        int64_t *o = p.stats + (size_t)MOT3D_SOLVE_STATS * g;
+        o[0] = 1;
+        o[2] = 2 * (int64_t)n;
+        o[3] = in_ptr[n] - in_ptr[0];
+    }
+}
+
+// ---- successive shortest paths on every component graph. Blocks fetch components from a work queue.
+__global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
+    __shared__ int s_scan[64];
+    __shared__ KeyIdx s_red[33];
+    __shared__ int s_ok[2], s_sweep_warp, s_job;
+    __shared__ long long s_work[4];  // ascending sweeps, descending sweeps, node pulls, arc pulls (sweep warp)
+
+    const int T = blockDim.x;
+    const int tid = threadIdx.x;
     // Which warp runs the sequential sweeps: blocks sharing an SM should use different SM sub-partitions (warp
     // schedulers), otherwise their sweep warps fight for one issue port. %warpid is the hardware warp slot; slots
     // of a block are consecutive, slot % 4 = sub-partition. Pick the warp whose sub-partition equals the block's
     // slot group.
-    if (tid < 4) s_work[tid] = 0;
     if (tid % 32 == 0) {
         unsigned hw;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
@@ -600,222 +703,207 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
     }
     __syncthreads();
     const int sweep_warp = s_sweep_warp;
-    Ctx c;
-    c.p = &p;
-    c.g0 = g0;
-    c.n = n;
-    c.dpre = p.ws_dpre + g0;
-    c.dpost = p.ws_dpost + g0;
-    c.mcost = p.ws_mcost + g0;
-    c.par = p.ws_par + g0;
-    c.anc_pre = p.ws_anc_pre + g0;
-    c.anc_post = p.ws_anc_post + g0;
-    c.slot_of = p.ws_slot_of + g0;
-    c.dl = p.ws_dl + g0;
-    c.dla0 = p.ws_dla0 + g0;
-    c.nxt = nxt;
-    c.prv = prv;
-    c.tkey = p.tkey + g0;
-    c.in_ptr = p.in_ptr + g0;
-    c.en = p.en + g0;
-    c.cn = p.cn + g0;
-    c.arc0 = c.in_ptr[0];
-    int64_t *dpre = c.dpre, *dpost = c.dpost;
-    int32_t *par = c.par, *anc_pre = c.anc_pre, *anc_post = c.anc_post;
-    int32_t *lvl = p.ws_lvl + g0 + g;
-    const int32_t *tkey = c.tkey, *in_ptr = c.in_ptr;
-    const int64_t *en = c.en, *cn = c.cn, *ex = p.ex + g0;
-    const int n_arcs_graph = in_ptr[n] - c.arc0;
+    const int n_jobs = p.n_cgraphs[0];
 
-    // ---- prologue: empty flow, nothing labelled, frame layers
-    for (int i = tid; i < n; i += T) {
-        nxt[i] = NONE;
-        prv[i] = NONE;
-        dpre[i] = INF;
-        dpost[i] = INF;
-        par[i] = PAR_NONE;
-        anc_pre[i] = -1;
-        anc_post[i] = -1;
-        c.mcost[i] = 0;
-    }
-    int L = 0;
-    for (int base = 0; base < n; base += T) {
-        const int i = base + tid;
-        const int f = (i < n && (i == 0 || tkey[i] != tkey[i - 1])) ? 1 : 0;
-        int tot;
-        const int ex_ = block_excl_scan(f, s_scan, &tot);
-        if (f) lvl[L + ex_] = i;
-        L += tot;
-    }
-    if (tid == 0) lvl[L] = n;
-    __syncthreads();
+    for (;;) {
+        if (tid == 0) s_job = atomicAdd(&p.n_cgraphs[1], 1);
+        if (tid < 4) s_work[tid] = 0;
+        __syncthreads();
+        const int cg = s_job;
+        __syncthreads();
+        if (cg >= n_jobs) break;
+        const int c0 = p.cgraph_ptr[cg];
+        const int n = p.cgraph_ptr[cg + 1] - c0;
+        const int g = p.cgraph_win[cg];
+        if (n <= 0 || p.n_paths[g] < 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
+        Ctx c;
+        c.p = &p;
+        c.c0 = c0;
+        c.n = n;
+        c.dpre = p.ws_dpre;
+        c.dpost = p.ws_dpost;
+        c.mcost = p.ws_mcost;
+        c.par = p.ws_par;
+        c.anc_pre = p.ws_anc_pre;
+        c.anc_post = p.ws_anc_post;
+        c.slot_of = p.ws_slot_of;
+        c.nxt = p.ws_nxt;
+        c.prv = p.ws_prv;
+        c.dl = p.ws_dl + c0;
+        c.dla0 = p.ws_dla0 + c0;
+        c.perm = p.comp_perm;
+        c.inv = p.comp_inv;
+        const int64_t *dpost = p.ws_dpost + c0;
+        const int32_t *nxt = p.ws_nxt + c0, *anc_pre = p.ws_anc_pre + c0, *anc_post = p.ws_anc_post + c0;
+        const int32_t *perm = p.comp_perm + c0;
 
-    int K = 0;
-    int64_t total = 0;
-    Counters cnt;
-    cnt.n_asc = 1;
-    cnt.n_desc = 0;
-    cnt.n_node = 2 * (int64_t)n;
-    cnt.n_arc = 0;
-    for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
-    cnt.t_mark = clock64();
-    const int sub = tid % LPN;
-    const int grp = tid / LPN;
-    const int ngrp = T / LPN;
+        int K = 0;
+        int64_t total = 0;
+        Counters cnt;
+        cnt.n_asc = 0;
+        cnt.n_desc = 0;
+        cnt.n_node = 0;
+        cnt.n_arc = 0;
+        for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
+        cnt.t_mark = clock64();
 
-    // ---- first tree: no flow yet, the network is a DAG: one pull sweep over the frame layers with the whole block
-    //      (Graph::shortest_path_dag, Graph.cpp:139-187); branch label = the detection whose S arc starts the path
-    for (int l = 0; l < L; l++) {
-        const int a = lvl[l], b = lvl[l + 1];
-        for (int jb = a; jb < b; jb += ngrp) {
-            const int j = jb + grp;
-            const bool valid = j < b;
+        for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+            // ---- cheapest way into T (Graph::update_sink_info's job, Graph.cpp:508-541; here a block-wide arg-min)
             KeyIdx best;
             best.key = INF;
-            best.idx = PAR_NONE;
-            if (valid) {
-                const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
-                for (int k = sub; k < deg; k += LPN) {
-                    const int i = p.in_src[e0 + k] - g0;
-                    const int64_t di = dpost[i];
-                    if (di < INF_CUT) {
-                        const int64_t cand = di + p.in_cost[e0 + k];
-                        if (cand < best.key) {  // sources ascend: the first minimum has the lowest index
-                            best.key = cand;
-                            best.idx = i;
+            best.idx = -1;
+#pragma unroll 4
+            for (int i = tid; i < n; i += T) {
+                const int64_t d = dpost[i], x = p.ex[perm[i]];
+                const int nx = nxt[i];
+                if (nx != TERM && d < INF_CUT && x < INF_CUT) {
+                    KeyIdx v;
+                    v.key = d + x;
+                    v.idx = c0 + i;
+                    best = min_ki(best, v);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                KeyIdx o = shfl_xor_ki(best, d);
+                if (o.idx >= 0 && (best.idx < 0 || o.key < best.key || (o.key == best.key && o.idx < best.idx)))
+                    best = o;
+            }
+            if (lane_id() == 0) s_red[warp_id()] = best;
+            __syncthreads();
+            KeyIdx sink;
+            {
+                const int nw = (T + 31) >> 5;
+                sink.key = INF;
+                sink.idx = -1;
+                for (int k = 0; k < nw; k++) {
+                    const KeyIdx o = s_red[k];
+                    if (o.idx >= 0 && (sink.idx < 0 || o.key < sink.key || (o.key == sink.key && o.idx < sink.idx)))
+                        sink = o;
+                }
+            }
+            __syncthreads();  // s_red is rewritten next iteration
+            cnt.tick(0);
+            if (sink.idx < 0) break;  // T unreachable
+            if (sink.key >= 0) {
+                // wrapper.cpp:263-267: stop when the next path does not pay. The reference keeps the very first path
+                // of a graph whatever it costs (wrapper.cpp:205,220); with components that decision belongs to the
+                // whole graph: remember this component's first path, k_first_path_rule applies the rule afterwards.
+                if (K == 0 && tid == 0) {
+                    p.first_cost[cg] = sink.key;
+                    p.first_sink[cg] = sink.idx;
+                }
+                break;
+            }
+            const int root = p.ws_anc_post[sink.idx];
+            if (root < 0) break;  // cannot happen: a labelled node always has a branch
+            // ---- the path lies in the branch hanging from S -> pre_root, and that branch is exactly what loses its
+            //      labels when the path is flipped (Graph::find_node_set4update, Graph.cpp:341-343): collect it in
+            //      layer order (= ascending position). Every thread owns a contiguous chunk: one block scan suffices.
+            int nd = 0, atot = 0;
+            {
+                const int chunk = (n + T - 1) / T;
+                const int i0 = tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
+                int my_nd = 0, my_arcs = 0;
+                for (int i = i0; i < i1; i++) {
+                    const bool fp = anc_pre[i] == root, fo = anc_post[i] == root;
+                    my_nd += (fp || fo) ? 1 : 0;
+                    if (fp) {
+                        const int d = perm[i];
+                        my_arcs += p.in_ptr[d + 1] - p.in_ptr[d] + 1;  // + 1: end-of-list marker
+                    }
+                }
+                int tot_nd, tot_arcs;
+                int slot = block_excl_scan1(my_nd, s_scan, 0, &tot_nd);
+                int a0 = block_excl_scan1(my_arcs, s_scan, 1, &tot_arcs);
+                nd = tot_nd;
+                atot = tot_arcs;
+                if (my_nd)
+                    for (int i = i0; i < i1; i++) {
+                        int f = 0;
+                        if (anc_pre[i] == root) f |= DL_PRE;
+                        if (anc_post[i] == root) f |= DL_POST;
+                        if (f) {
+                            c.dl[slot] = (c0 + i) | f;
+                            c.dla0[slot] = a0;
+                            c.slot_of[c0 + i] = slot;
+                            slot++;
+                            if (f & DL_PRE) {
+                                const int d = perm[i];
+                                a0 += p.in_ptr[d + 1] - p.in_ptr[d] + 1;
+                            }
                         }
                     }
-                }
             }
-            best = group_min(best, 0xffffffffu);
-            if (valid && sub == 0) {
-                int anc = best.idx >= 0 ? anc_post[best.idx] : -1;
-                const int64_t e_ = en[j];
-                if (e_ < best.key) {
-                    best.key = e_;
-                    best.idx = PAR_S;
-                    anc = j;
-                }
-                if (best.key < INF_CUT) {
-                    dpre[j] = best.key;
-                    par[j] = best.idx;
-                    anc_pre[j] = anc;
-                    dpost[j] = best.key + cn[j];
-                    anc_post[j] = anc;
-                }
-            }
+            __syncthreads();
+            cnt.tick(1);
+            if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
+            const bool in_smem = nd <= p.rec_cap && atot <= p.arc_cap;
+            const bool ok = in_smem ? relabel_branch<true>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt)
+                                    : relabel_branch<false>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt);
+            if (!ok) break;  // defensive: inconsistent state, stop with what we have
+            K++;
+            total += sink.key;
         }
+        // ---- results of this component: flow in detection indices, totals added to its graph
         __syncthreads();
-    }
-    cnt.n_arc = (tid == 0) ? n_arcs_graph : 0;
-    cnt.tick(6);
-
-    for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
-        // ---- cheapest way into T (Graph::update_sink_info's job, Graph.cpp:508-541; here a block-wide arg-min)
-        KeyIdx best;
-        best.key = INF;
-        best.idx = -1;
-#pragma unroll 4
-        for (int i = tid; i < n; i += T) {
-            const int64_t d = dpost[i], x = ex[i];
-            const int nx = nxt[i];
-            if (nx != TERM && d < INF_CUT && x < INF_CUT) {
-                KeyIdx v;
-                v.key = d + x;
-                v.idx = i;
-                best = min_ki(best, v);
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            KeyIdx o = shfl_xor_ki(best, d);
-            if (o.idx >= 0 && (best.idx < 0 || o.key < best.key || (o.key == best.key && o.idx < best.idx))) best = o;
-        }
-        if (lane_id() == 0) s_red[warp_id()] = best;
-        __syncthreads();
-        KeyIdx sink;
-        {
-            const int nw = (T + 31) >> 5;
-            sink.key = INF;
-            sink.idx = -1;
-            for (int k = 0; k < nw; k++) {
-                const KeyIdx o = s_red[k];
-                if (o.idx >= 0 && (sink.idx < 0 || o.key < sink.key || (o.key == sink.key && o.idx < sink.idx)))
-                    sink = o;
-            }
-        }
-        __syncthreads();  // s_red is rewritten next iteration
-        cnt.tick(0);
-        if (sink.idx < 0) break;             // T unreachable
-        if (K >= 1 && sink.key >= 0) break;  // wrapper.cpp:263-267: stop when the next path does not pay
-        const int root = anc_post[sink.idx];
-        if (root < 0) break;  // cannot happen: a labelled node always has a branch
-        // ---- the path lies in the branch hanging from S -> pre_root, and that branch is exactly what loses its
-        //      labels when the path is flipped (Graph::find_node_set4update, Graph.cpp:341-343): collect it in
-        //      layer order (= ascending detection index). One scan carries both counts: records and their in-arcs.
-        // Every thread owns a contiguous chunk of detections, so one block scan suffices.
-        int nd = 0, atot = 0;
-        {
-            const int chunk = (n + T - 1) / T;
-            const int i0 = tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
-            int my_nd = 0, my_arcs = 0;
-            for (int i = i0; i < i1; i++) {
-                const bool fp = anc_pre[i] == root, fo = anc_post[i] == root;
-                my_nd += (fp || fo) ? 1 : 0;
-                if (fp) my_arcs += in_ptr[i + 1] - in_ptr[i] + 1;  // + 1: end-of-list marker
-            }
-            int tot_nd, tot_arcs;
-            int slot = block_excl_scan1(my_nd, s_scan, 0, &tot_nd);
-            int a0 = block_excl_scan1(my_arcs, s_scan, 1, &tot_arcs);
-            nd = tot_nd;
-            atot = tot_arcs;
-            if (my_nd)
-                for (int i = i0; i < i1; i++) {
-                    int f = 0;
-                    if (anc_pre[i] == root) f |= DL_PRE;
-                    if (anc_post[i] == root) f |= DL_POST;
-                    if (f) {
-                        c.dl[slot] = i | f;
-                        c.dla0[slot] = a0;
-                        c.slot_of[i] = slot;
-                        slot++;
-                        if (f & DL_PRE) a0 += in_ptr[i + 1] - in_ptr[i] + 1;
-                    }
-                }
-        }
-        __syncthreads();
-        cnt.tick(1);
-        if (tid == 0 && p.path_cost) p.path_cost[g0 + K] = sink.key;
-        const bool in_smem = nd <= p.rec_cap && atot <= p.arc_cap;
-        const bool ok = in_smem ? relabel_branch<true>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt)
-                                : relabel_branch<false>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt);
-        if (!ok) break;  // defensive: inconsistent state, stop with what we have
-        K++;
-        total += sink.key;
-    }
-    // ---- results
-    __syncthreads();
-    if (p.stats) {
         if (tid == 0) {
-            int64_t *o = p.stats + (size_t)MOT3D_SOLVE_STATS * g;
-            o[0] = cnt.n_asc + s_work[0];
-            o[1] = cnt.n_desc + s_work[1];
-            o[2] = cnt.n_node + s_work[2];
-            o[3] = cnt.n_arc + s_work[3];
-            for (int k = 0; k < 7; k++) o[4 + k] = cnt.t_phase[k];
-            o[11] = 0;
+            if (K) {
+                atomicAdd(&p.n_paths[g], K);
+                atomicAdd((unsigned long long *)&p.total[g], (unsigned long long)total);
+            }
+            if (p.stats) {
+                unsigned long long *o = (unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g);
+                atomicAdd(&o[0], (unsigned long long)(cnt.n_asc + s_work[0]));
+                atomicAdd(&o[1], (unsigned long long)(cnt.n_desc + s_work[1]));
+                atomicAdd(&o[2], (unsigned long long)(cnt.n_node + s_work[2]));
+                atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
+                for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
+            }
         }
+        for (int i = tid; i < n; i += T) {
+            const int a = p.ws_nxt[c0 + i], b = p.ws_prv[c0 + i];
+            const int d = perm[i];
+            p.next_out[d] = a >= 0 ? p.comp_perm[a] : a;
+            p.prev_out[d] = b >= 0 ? p.comp_perm[b] : b;
+        }
+        __syncthreads();
     }
-    if (tid == 0) {
-        p.n_paths[g] = K;
-        p.total[g] = total;
+}
+
+// ---- the reference keeps the first path of a graph even when its cost is >= 0 (wrapper.cpp:205,220). Components
+//      only keep paths that pay; a graph that ended with no path at all gets the cheapest "first path" among its
+//      components (none of them was touched, so the path is a plain chain of unused detections in the first tree).
+__global__ void k_first_path_rule(const SolveParams p) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n_graphs) return;
+    if (p.n_paths[g] != 0) return;
+    const int c_begin = p.win_cbase[g];
+    const int c_end = (g + 1 < p.n_graphs) ? p.win_cbase[g + 1] : p.n_cgraphs[0];
+    int64_t best = INF;
+    int q = -1;
+    for (int c = c_begin; c < c_end; c++)
+        if (p.first_sink[c] >= 0 && p.first_cost[c] < best) {
+            best = p.first_cost[c];
+            q = p.first_sink[c];
+        }
+    if (q < 0) return;  // no source->sink path at all: K stays 0 (build_graph returns None for such graphs)
+    int nx = TERM;
+    for (int step = 0; step < p.n_total; step++) {
+        const int d = p.comp_perm[q];
+        p.next_out[d] = nx;
+        const int pq = p.ws_par[q];
+        if (pq < 0) {
+            p.prev_out[d] = TERM;
+            break;
+        }
+        p.prev_out[d] = p.comp_perm[pq];
+        nx = d;
+        q = pq;
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += T) {
-        const int a = nxt[i], b = prv[i];
-        nxt[i] = a >= 0 ? a + g0 : a;
-        prv[i] = b >= 0 ? b + g0 : b;
-    }
+    p.n_paths[g] = 1;
+    p.total[g] = best;
+    if (p.path_cost) p.path_cost[p.cgraph_ptr[c_begin]] = best;
 }
 
 // Tracks of each graph, ordered by first detection (the reference enumerates S's successors in node order,
@@ -876,8 +964,8 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
-    return a256(n * 8) * 3 + a256(n * 4) * 6 + a256((n + g) * 4) + a256(n * sizeof(Rec)) + a256(n * 4) +
-           a256((e + n + 8 * g + 8) * sizeof(StArc)) + 256;
+    return a256(n * 8) * 4 + a256(n * 4) * 13 + a256((n + g) * 4) * 2 + a256(g * 4) + a256(n * sizeof(Rec)) +
+           a256((e + n + 8) * sizeof(StArc)) + a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
 }
 
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
@@ -891,7 +979,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     M3_CHECK_ARG(graph_ptr && tkey && in_ptr && entry_cost && node_cost && exit_cost, "NULL input");
     M3_CHECK_ARG(next_out && prev_out && n_paths_out && total_cost_out && ws, "NULL output/workspace");
     M3_CHECK_ARG(n_total >= max_graph_nodes, "n_total < max_graph_nodes");
-    M3_CHECK_ARG(max_graph_nodes < DL_FIRST, "graph too large");
+    M3_CHECK_ARG(n_total < DL_FIRST, "batch too large");
     if (ws_bytes < mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity)) {
         set_error("solve workspace too small: %zu < %zu", ws_bytes,
                   mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity));
@@ -901,9 +989,15 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     const size_t n_cap = (size_t)(n_total > 0 ? n_total : 1);
     const size_t e_cap = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     char *w = (char *)ws;
+    auto take = [&](size_t bytes) {
+        char *r = w;
+        w += a256(bytes);
+        return r;
+    };
     SolveParams p;
     p.n_graphs = n_graphs;
     p.pad = 0;
+    p.n_total = (int64_t)n_total;
     p.graph_ptr = graph_ptr;
     p.tkey = tkey;
     p.in_ptr = in_ptr;
@@ -919,36 +1013,49 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.path_cost = path_cost_out;
     p.stats = stats_out;
     p.arc_capacity = arc_capacity;
-    p.ws_dpre = (int64_t *)w;
-    w += a256(n_cap * 8);
-    p.ws_dpost = (int64_t *)w;
-    w += a256(n_cap * 8);
-    p.ws_mcost = (int64_t *)w;
-    w += a256(n_cap * 8);
-    p.ws_par = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_anc_pre = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_anc_post = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_slot_of = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_dl = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_dla0 = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_lvl = (int32_t *)w;
-    w += a256((n_cap + g) * 4);
-    p.ws_rec = (Rec *)w;
-    w += a256(n_cap * sizeof(Rec));
-    p.ws_tk = (int32_t *)w;
-    w += a256(n_cap * 4);
-    p.ws_arc = (StArc *)w;
+    p.ws_dpre = (int64_t *)take(n_cap * 8);
+    p.ws_dpost = (int64_t *)take(n_cap * 8);
+    p.ws_mcost = (int64_t *)take(n_cap * 8);
+    p.first_cost = (int64_t *)take(n_cap * 8);
+    p.ws_par = (int32_t *)take(n_cap * 4);
+    p.ws_anc_pre = (int32_t *)take(n_cap * 4);
+    p.ws_anc_post = (int32_t *)take(n_cap * 4);
+    p.ws_nxt = (int32_t *)take(n_cap * 4);
+    p.ws_prv = (int32_t *)take(n_cap * 4);
+    p.ws_slot_of = (int32_t *)take(n_cap * 4);
+    p.ws_dl = (int32_t *)take(n_cap * 4);
+    p.ws_dla0 = (int32_t *)take(n_cap * 4);
+    p.first_sink = (int32_t *)take(n_cap * 4);
+    int32_t *comp_perm = (int32_t *)take(n_cap * 4);
+    int32_t *comp_inv = (int32_t *)take(n_cap * 4);
+    int32_t *cgraph_win = (int32_t *)take(n_cap * 4);
+    p.ws_tk = (int32_t *)take(n_cap * 4);
+    p.ws_lvl = (int32_t *)take((n_cap + g) * 4);
+    int32_t *cgraph_ptr = (int32_t *)take((n_cap + g) * 4);
+    int32_t *win_cbase = (int32_t *)take(g * 4);
+    p.ws_rec = (Rec *)take(n_cap * sizeof(Rec));
+    p.ws_arc = (StArc *)take((e_cap + n_cap + 8) * sizeof(StArc));
+    const size_t cws_bytes = mot3d_components_workspace_bytes(n_total, n_graphs);
+    void *cws = take(cws_bytes);
+    int32_t *n_cgraphs = (int32_t *)take(16);
+    p.comp_perm = comp_perm;
+    p.comp_inv = comp_inv;
+    p.cgraph_ptr = cgraph_ptr;
+    p.cgraph_win = cgraph_win;
+    p.win_cbase = win_cbase;
+    p.n_cgraphs = n_cgraphs;
 
-    // Shared memory per block: only the staging area for one branch. Sized so that several blocks (graphs) share
-    // an SM: per-node state lives in global memory (L2), the sequential re-labelling never leaves shared memory.
-    // tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / MOT3D_SOLVE_THREADS override the plan below
-    size_t rec_target = 320;
+    cudaStream_t st = (cudaStream_t)stream;
+    // 1. connected components of every graph, detections regrouped by component
+    int32_t rc = mot3d_components(n_graphs, n_total, graph_ptr, in_ptr, in_src, arc_capacity, comp_perm, comp_inv,
+                                  cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
+    if (rc) return rc;
+    // 2. first shortest-path tree per graph
+    k_first_tree<<<n_graphs, 256, 0, st>>>(p);
+    M3_LAUNCH_CHECK("k_first_tree");
+    // 3. successive shortest paths per component. Shared memory per block: the staging area for one branch, sized so
+    //    that several blocks share an SM; blocks pull components from a work queue.
+    size_t rec_target = 320;  // tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / _THREADS / _BLOCKS_PER_SM
     if (const char *e = getenv("MOT3D_SOLVE_RECCAP")) rec_target = (size_t)atoi(e) > 31 ? (size_t)atoi(e) : 32;
     size_t rec_cap = (size_t)max_graph_nodes < rec_target ? (size_t)max_graph_nodes : rec_target;
     if (rec_cap < 32) rec_cap = 32;
@@ -962,11 +1069,24 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         const int t = atoi(e);
         if (t == 64 || t == 128 || t == 192 || t == 256) threads = t;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ssp_solve<<<n_graphs, threads, smem, st>>>(p);
+    int dev = 0, n_sm = 148, per_sm = 4;
+    M3_CUDA(cudaGetDevice(&dev));
+    M3_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    M3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ssp_solve, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("MOT3D_SOLVE_BLOCKS_PER_SM")) {
+        const int b = atoi(e);
+        if (b >= 1 && b < per_sm) per_sm = b;
+    }
+    long long grid = (long long)n_sm * per_sm;
+    if (grid > n_total) grid = n_total > 0 ? n_total : 1;  // never more blocks than possible components
+    k_ssp_solve<<<(unsigned)grid, threads, smem, st>>>(p);
     M3_LAUNCH_CHECK("k_ssp_solve");
+    // 4. the reference's "first path is always kept" rule, per graph
+    k_first_path_rule<<<(n_graphs + 127) / 128, 128, 0, st>>>(p);
+    M3_LAUNCH_CHECK("k_first_path_rule");
     return MOT3D_OK;
 }
 
