@@ -330,14 +330,34 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
             ent |= DL_FIRST;
             st.rec[s].A.x = ent;
         }
+        // New labels start from what cannot change during the fix-point (the best arc from outside the branch, the
+        // S arc) instead of "unreachable": that is exactly what a first ascending sweep would find for the records
+        // on tracks, so the sweeps below start with a descending one.
+        int64_t key = INF;
+        int par = PAR_NONE, anc = -1;
         if (ent & DL_PRE) {
-            st.rec[s].E.x = INF;
-            st.rec[s].F.x = PAR_NONE;
-            st.rec[s].F.y = -1;
+            const Rec *r = st.rec + s;
+            key = r->C.x;
+            par = r->B.z;
+            anc = r->B.w;
+            if (r->A.w != TERM && r->C.y < key) {
+                key = r->C.y;
+                par = PAR_S;
+                anc = ent & DL_MASK;
+            }
+            if (key >= INF_CUT) {
+                key = INF;
+                par = PAR_NONE;
+                anc = -1;
+            }
+            st.rec[s].E.x = key;
+            st.rec[s].F.x = par;
+            st.rec[s].F.y = anc;
         }
         if (ent & DL_POST) {
-            st.rec[s].E.y = INF;
-            st.rec[s].F.z = -1;
+            const bool unused_labelled = (ent & DL_PRE) && st.rec[s].A.w == NONE && key < INF_CUT;
+            st.rec[s].E.y = unused_labelled ? key + st.rec[s].D.x : INF;
+            st.rec[s].F.z = unused_labelled ? anc : -1;
         }
     }
     __syncthreads();
@@ -351,9 +371,9 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
         // previous descending sweep changed, the descending sweep at the highest record the ascending one changed.
         int asc_from = 0;
         for (int round = 0; round < 2 * nd + 4; round++) {
-            int hi_ch = -1;
-            n_asc32++;
-            for (int q = asc_from; q < nd;) {
+            int hi_ch = (round == 0) ? nd - 1 : -1;  // round 0: the initial labels stand in for the ascending sweep
+            if (round > 0) n_asc32++;
+            for (int q = (round == 0) ? nd : asc_from; q < nd;) {
                 // one step = the records of one layer, at most 4 at a time, 8 lanes per record (one per in-arc)
                 const int r8 = lane >> 3, a8 = lane & 7;
                 const int s = q + r8;
@@ -528,8 +548,8 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) lo_ch = min(lo_ch, __shfl_xor_sync(0xffffffffu, lo_ch, d));
-            if (lo_ch >= nd) break;  // nothing moved: fix-point
-            asc_from = lo_ch;
+            if (lo_ch >= nd && round > 0) break;  // nothing moved: fix-point
+            asc_from = (round == 0) ? 0 : lo_ch;   // the initial labels ignored arcs inside the branch: full sweep
         }
         // work counters of this branch (the leaders of the lane groups counted the arcs)
 #pragma unroll
@@ -1055,7 +1075,10 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     M3_LAUNCH_CHECK("k_first_tree");
     // 3. successive shortest paths per component. Shared memory per block: the staging area for one branch, sized so
     //    that several blocks share an SM; blocks pull components from a work queue.
-    size_t rec_target = 320;  // tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / _THREADS / _BLOCKS_PER_SM
+    // Graphs of up to 8192 detections are split into components (typically a few tracks each): small staging area
+    // and small blocks so that ~8 blocks share an SM. Small graphs (<= 1024) are usually one dense component: keep
+    // room for a whole branch. Tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / _THREADS / _BLOCKS_PER_SM.
+    size_t rec_target = max_graph_nodes <= 1024 ? 320 : 128;
     if (const char *e = getenv("MOT3D_SOLVE_RECCAP")) rec_target = (size_t)atoi(e) > 31 ? (size_t)atoi(e) : 32;
     size_t rec_cap = (size_t)max_graph_nodes < rec_target ? (size_t)max_graph_nodes : rec_target;
     if (rec_cap < 32) rec_cap = 32;
@@ -1064,10 +1087,10 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.rec_cap = (int32_t)rec_cap;
     p.arc_cap = (int32_t)arc_cap;
     const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
-    int threads = max_graph_nodes <= 512 ? 128 : 256;
+    int threads = 128;
     if (const char *e = getenv("MOT3D_SOLVE_THREADS")) {
         const int t = atoi(e);
-        if (t == 64 || t == 128 || t == 192 || t == 256) threads = t;
+        if (t == 32 || t == 64 || t == 128 || t == 192 || t == 256) threads = t;
     }
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,4 +1,4 @@
-for cfg in "256 320" "128 320" "128 160" "192 256" "128 224" "64 160"; do
+for cfg in "128 128" "32 128" "32 96" "32 64" "32 48" "64 64"; do
   set -- $cfg
   MOT3D_SOLVE_THREADS=$1 MOT3D_SOLVE_RECCAP=$2 timeout 300 python bench.py --steps 3 --warmup 3 --seqs 60 --no-cpu > gpurun_out/b.log 2>&1
   python -c "
