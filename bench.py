@@ -75,7 +75,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -318,8 +318,15 @@ def run_ours(args):
     build_ms = (stage_ms[STAGES.index("frame_sort")] + stage_ms[STAGES.index("edge_count")] +
                 stage_ms[STAGES.index("edge_fill")])
     build_gbs = build_bytes / (build_ms * 1e-3) / 1e9
+    # measured DRAM traffic per launch: from the committed ncu capture of this very configuration, else null
+    traffic_solve = traffic_build = None
+    tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tf):
+        t = json.load(open(tf))
+        if t.get("seqs") == S:
+            traffic_solve, traffic_build = t.get("k_ssp_solve"), t.get("edge_build")
     roofline = {"bound": "hbm", "kernel": "k_ssp_solve", "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
-                "frac": solve_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": solve_gbs / peak, "traffic": traffic_solve, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": float(stage_ms[i_solve]),
                 "ascending_sweeps_per_graph_mean": float(stats[:, 0].mean()),
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
@@ -327,7 +334,7 @@ def run_ours(args):
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(
                     ["sink_argmin", "collect_branch", "stage", "walk", "sweeps", "write_back", "first_tree"])}}
     roofline_build = {"bound": "hbm", "kernel": "k_frame_sort + k_edge_build_pruned<count> + <fill> + k_edge_cost", "achieved": build_gbs, "peak": peak,
-                      "unit": "GB/s", "frac": build_gbs / peak, "traffic": None,
+                      "unit": "GB/s", "frac": build_gbs / peak, "traffic": traffic_build,
                       "algorithmic_bytes_per_launch": build_bytes, "launch_ms": float(build_ms)}
 
     # ---- CPU baseline on this box (rank 0, N=1 only), bounded sample
@@ -371,7 +378,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=60, help="sequences (of 20 windows) per GPU and step")

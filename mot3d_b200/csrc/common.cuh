@@ -122,6 +122,28 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  : "memory");
 }
 
+// Stage g[c0 .. c0+cnt) into shared memory so that element e sits at s[e - c0 + shift]; the 16-byte aligned body
+// goes through the TMA unit (cp.async.bulk -> UBLKCP), the ragged head/tail through ordinary loads.
+// Returns shift. *bulk_bytes (thread 0 only) accumulates the bytes the mbarrier has to expect.
+template <typename T>
+__device__ __forceinline__ int stage_slice(const T *__restrict__ g, T *s, int64_t c0, int cnt, uint64_t *bar,
+                                           uint32_t *bulk_bytes) {
+    constexpr int Q = 16 / (int)sizeof(T);
+    const uintptr_t first = (uintptr_t)(g + c0) / sizeof(T);
+    const int shift = (int)(first % Q);
+    int head = (Q - shift) % Q;
+    if (head > cnt) head = cnt;
+    int body = ((cnt - head) / Q) * Q;
+    int tail = cnt - head - body;
+    if (threadIdx.x == 0 && body > 0) {
+        tma_load_1d(s + shift + head, g + c0 + head, (uint32_t)(body * sizeof(T)), bar);
+        *bulk_bytes += (uint32_t)(body * sizeof(T));
+    }
+    if ((int)threadIdx.x < head) s[shift + threadIdx.x] = g[c0 + threadIdx.x];
+    if ((int)threadIdx.x < tail) s[shift + head + body + threadIdx.x] = g[c0 + head + body + threadIdx.x];
+    return shift;
+}
+
 // ---------------------------------------------------------------------------------------- exact quantisation
 // Nearest integer to w * 1e7 evaluated exactly (ties to even) = what "{:0.7f}".format(w) prints
 // (mot3d/mot3d.py:224), without the double rounding of llrint(w * 1e7).

@@ -73,28 +73,6 @@ __device__ __forceinline__ int64_t warp_bound(const int32_t *__restrict__ a, int
     return lo;
 }
 
-// Stage g[c0 .. c0+cnt) into shared memory so that element e sits at s[e - c0 + shift]; the 16-byte aligned body
-// goes through the TMA unit (cp.async.bulk -> UBLKCP), the ragged head/tail through ordinary loads.
-// Returns shift. *bulk_bytes (thread 0 only) accumulates the bytes the mbarrier has to expect.
-template <typename T>
-__device__ __forceinline__ int stage_slice(const T *__restrict__ g, T *s, int64_t c0, int cnt, uint64_t *bar,
-                                           uint32_t *bulk_bytes) {
-    constexpr int Q = 16 / (int)sizeof(T);
-    const uintptr_t first = (uintptr_t)(g + c0) / sizeof(T);
-    const int shift = (int)(first % Q);
-    int head = (Q - shift) % Q;
-    if (head > cnt) head = cnt;
-    int body = ((cnt - head) / Q) * Q;
-    int tail = cnt - head - body;
-    if (threadIdx.x == 0 && body > 0) {
-        tma_load_1d(s + shift + head, g + c0 + head, (uint32_t)(body * sizeof(T)), bar);
-        *bulk_bytes += (uint32_t)(body * sizeof(T));
-    }
-    if ((int)threadIdx.x < head) s[shift + threadIdx.x] = g[c0 + threadIdx.x];
-    if ((int)threadIdx.x < tail) s[shift + head + body + threadIdx.x] = g[c0 + head + body + threadIdx.x];
-    return shift;
-}
-
 __device__ __forceinline__ double bbox_similarity(const double *__restrict__ bb, int64_t n, int64_t a, int64_t b) {
     // size = (ymax-ymin, xmax-xmin); 1 - (|h1-h2|/(max(h1,h2)+1e-12) + |w1-w2|/(max(w1,w2)+1e-12))/2
     double h1 = bb[3 * n + a] - bb[1 * n + a];

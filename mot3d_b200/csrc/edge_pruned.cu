@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(EP_TPB) k_edge_build_pruned(const PrunedParams
     extern __shared__ __align__(16) unsigned char ep_smem[];
     __shared__ int64_t s_range[2];
     __shared__ int s_seg_lo[EP_TABLE], s_seg_hi[EP_TABLE];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int64_t n = p.n;
     const int64_t r0 = (int64_t)blockIdx.x * EP_TPB;
@@ -88,6 +89,8 @@ __global__ void __launch_bounds__(EP_TPB) k_edge_build_pruned(const PrunedParams
     if (threadIdx.x == 0) {
         s_range[0] = bound_i32<false>(p.tkey, 0, n, kmin);
         s_range[1] = bound_i32<true>(p.tkey, 0, n, kmax);
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
     }
     for (int t = threadIdx.x; t < EP_TABLE; t += EP_TPB) {
         s_seg_lo[t] = 0;
@@ -98,19 +101,25 @@ __global__ void __launch_bounds__(EP_TPB) k_edge_build_pruned(const PrunedParams
     const int m = (int)(hi - lo);
     const bool staged = m <= EP_CAP;
     const bool tabled = (kmax - kmin) < EP_TABLE;
-    double *s_x = (double *)ep_smem;
-    double *s_y = s_x + EP_CAP;
-    double *s_z = s_y + EP_CAP;  // only touched when has_z (the launch sizes the buffer accordingly)
-    int32_t *s_perm = (int32_t *)(s_y + EP_CAP + (has_z ? EP_CAP : 0));
-    int32_t *s_key = s_perm + EP_CAP;
-    if (staged) {
-        for (int c = threadIdx.x; c < m; c += EP_TPB) {
-            s_x[c] = p.spos[lo + c];
-            s_y[c] = p.spos[n + lo + c];
-            if (has_z) s_z[c] = p.spos[2 * n + lo + c];
-            s_perm[c] = p.sperm[lo + c];
-            s_key[c] = p.tkey[lo + c];
-        }
+    // staging buffers: every array keeps 4 spare slots so that the 16-byte aligned body of its slice can go through
+    // the TMA unit (cp.async.bulk, SASS UBLKCP) with the element alignment of the global address preserved
+    double *b_x = (double *)ep_smem;
+    double *b_y = b_x + EP_CAP + 4;
+    double *b_z = b_y + EP_CAP + 4;  // only touched when has_z (the launch sizes the buffer accordingly)
+    int32_t *b_perm = (int32_t *)(b_y + EP_CAP + 4 + (has_z ? EP_CAP + 4 : 0));
+    int32_t *b_key = b_perm + EP_CAP + 4;
+    const double *s_x = b_x, *s_y = b_y, *s_z = b_z;
+    const int32_t *s_perm = b_perm, *s_key = b_key;
+    if (staged && m > 0) {
+        uint32_t bulk = 0;
+        s_x = b_x + stage_slice(p.spos, b_x, lo, m, &s_bar, &bulk);
+        s_y = b_y + stage_slice(p.spos + n, b_y, lo, m, &s_bar, &bulk);
+        if (has_z) s_z = b_z + stage_slice(p.spos + 2 * n, b_z, lo, m, &s_bar, &bulk);
+        s_perm = b_perm + stage_slice(p.sperm, b_perm, lo, m, &s_bar, &bulk);
+        s_key = b_key + stage_slice(p.tkey, b_key, lo, m, &s_bar, &bulk);
+        if (threadIdx.x == 0) mbar_expect_tx(&s_bar, bulk);
+        __syncthreads();  // ragged head/tail stores visible
+        mbar_wait(&s_bar, 0);
     }
     __syncthreads();
     // frame segments of the candidate range, indexed by key - kmin
@@ -230,7 +239,7 @@ int32_t launch_pruned(const mot3d_dets *d, const mot3d_cost_spec *s, int directi
     p.col = col;
     p.cost = cost;
     p.overflow = overflow;
-    const size_t smem = (size_t)EP_CAP * (8 + 8 + (d->dim == 3 ? 8 : 0) + 4 + 4);
+    const size_t smem = (size_t)(EP_CAP + 4) * (8 + 8 + (d->dim == 3 ? 8 : 0) + 4 + 4) + 16;
     const unsigned grid = (unsigned)((d->n + EP_TPB - 1) / EP_TPB);
 #define M3_EP_LAUNCH(DIRV, FILLV)                                                                                  \
     do {                                                                                                           \
