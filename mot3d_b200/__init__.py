@@ -9,6 +9,8 @@ from .types import *            # noqa: F401,F403
 from .weight_functions import *  # noqa: F401,F403
 from .distance_functions import *  # noqa: F401,F403
 from .mot3d import *            # noqa: F401,F403
+from .utils.trajectory import *  # noqa: F401,F403
+from . import utils  # noqa: F401
 from .mot3d import TrackingGraph, TrackletGraph  # noqa: F401
 from . import weight_functions, distance_functions, types  # noqa: F401
 from .spec import CostSpec, TrackletCostSpec  # noqa: F401

@@ -1,0 +1,2 @@
+"""Glue between the two passes of the reference pipelines."""
+from . import trajectory  # noqa: F401

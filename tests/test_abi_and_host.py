@@ -191,3 +191,13 @@ def test_gather_tracks_gloo_world2(built, tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_trajectory_glue(built):
+    import mot3d_b200 as mot3d
+    traj = [mot3d.Detection2D(i, (i, 0)) for i in [3, 4, 5, 6, 9, 10, 11, 14, 15, 21]]
+    pieces = mot3d.split_trajectory_modulo(traj, length=5)
+    assert [[d.index for d in p] for p in pieces] == [[3, 4], [5, 6, 9], [10, 11, 14], [15, 21]]  # only a wrap of index % length cuts
+    assert [[d.index for d in p] for p in mot3d.remove_short_trajectories(pieces, th_length=2)] == [[5, 6, 9], [10, 11, 14]]
+    assert [d.index for d in mot3d.concat_tracklets(pieces)] == [d.index for d in traj]
+    assert mot3d.split_trajectory_modulo([], length=5) == []

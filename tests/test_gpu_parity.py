@@ -429,3 +429,106 @@ def test_tracklet_public_api_drop_in(name):
     gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
     assert got == gold
     assert g.total_cost == gu.ref_total_units(d)
+
+
+# ------------------------------------------------------------------------------------------------------ fuzzing
+def test_random_graphs_against_oracle():
+    """300 random small windows in ONE batch (ragged sizes incl. empty and single-detection graphs, missing frames,
+    dense and sparse scenes, entry costs that make the first path unprofitable) vs the integer oracle: K, total cost
+    and a feasible flow of exactly that cost for every graph. Exercises the component split, the first-path rule and
+    the work queue on shapes the golden vectors do not cover."""
+    import mot3d_b200 as mot3d
+    from oracle import oracle
+    rng = np.random.RandomState(123)
+    G = 300
+    frames, poss, confs, sizes = [], [], [], []
+    for g in range(G):
+        n = int(rng.choice([0, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144]))
+        F = int(rng.randint(1, 30))
+        extent = float(rng.choice([20.0, 60.0, 200.0]))
+        f = np.sort(rng.randint(0, F, size=n))
+        frames.append(f)
+        poss.append(rng.rand(n, 2) * extent)
+        confs.append(rng.rand(n))
+        sizes.append(n)
+    gp = np.cumsum([0] + sizes)
+    kw = dict(sigma_jump=0.5, sigma_distance=8, max_distance=25, use_color_histogram=False, use_bbox=False)
+    for wss, mul, bias in [(0.3, 1, 0), (2.5, 1, 0.1), (0.05, 0.5, 0)]:
+        spec = mot3d.CostSpec(kind="detections_2d", distance=kw, confidence=dict(mul=mul, bias=bias),
+                              weight_source_sink=wss, max_jump=3)
+        b, order = mot3d.DetectionBatch.from_arrays(gp, np.concatenate(frames), np.concatenate(poss),
+                                                    np.concatenate(confs))
+        gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+        K = sol.n_paths.cpu().numpy()
+        total = sol.total_cost.cpu().numpy()
+        tracks = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                       sol.track_det.cpu().numpy())
+        ospec = oracle.CostSpec(weight_source_sink=wss, max_jump=3, mul=mul, bias=bias, **kw)
+        for g in range(G):
+            n = sizes[g]
+            if n == 0:
+                assert K[g] == 0 and total[g] == 0 and tracks[g] == []
+                continue
+            fr, xy, cf = b.frame[gp[g]:gp[g + 1]], b.pos[:, gp[g]:gp[g + 1]].T, b.conf[gp[g]:gp[g + 1]]
+            row_ptr, col, w = oracle.build_transitions(fr, xy, ospec)
+            tail, head, ww = oracle.graph_arcs(n, float(wss), oracle.node_weights(cf, ospec), 0.0, row_ptr, col, w)
+            cost = oracle.quantise(ww)
+            ref = oracle.ssp_solve(2 * n + 2, tail, head, cost)
+            assert K[g] == ref["K"], (g, n, K[g], ref["K"])
+            assert total[g] == ref["total"], (g, n, total[g], ref["total"])
+            # our tracks form a feasible flow of exactly that cost
+            arc = {(int(t), int(h)): int(c) for t, h, c in zip(tail, head, cost)}
+            got = 0
+            used = set()
+            for t in tracks[g]:
+                got += arc[(1, 2 + 2 * t[0])] + arc[(3 + 2 * t[-1], 2 * n + 2)]
+                for a_, b_ in zip(t[:-1], t[1:]):
+                    got += arc[(3 + 2 * a_, 2 + 2 * b_)]
+                for d_ in t:
+                    assert d_ not in used
+                    used.add(d_)
+                    got += arc[(2 + 2 * d_, 3 + 2 * d_)]
+            assert got == total[g] and len(tracks[g]) == K[g]
+            assert [t[0] for t in tracks[g]] == sorted(t[0] for t in tracks[g])
+
+
+def test_two_pass_pipeline_drop_in():
+    """examples/simple_2d_tracklets/example.py end to end through the drop-in surface: detections -> build_graph ->
+    solve_graph -> split_trajectory_modulo / remove_short_trajectories -> DetectionTracklet2D -> build_graph ->
+    solve_graph. Both passes must reproduce the reference's graphs (sha of graph_to_text) and trajectories."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    from oracle import oracle
+    d1, d2 = gu.load("c1_simple_2d"), gu.load("c2_tracklets_pass2")
+    n = len(d1["frame"])
+    hist = d1["hist"]
+    dets = [mot3d.Detection2D(int(d1["frame"][i]), d1["pos"][i], confidence=float(d1["conf"][i]),
+                              color_histogram=[hist[i, 0], hist[i, 1], hist[i, 2]], bbox=list(d1["bbox"][i]))
+            for i in range(n)]
+    g = mot3d.build_graph(dets, weight_source_sink=0.1, max_jump=4, verbose=False,
+                          weight_confidence=lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0),
+                          weight_distance=lambda a, b: wf.weight_distance_detections_2d(
+                              a, b, sigma_jump=1, sigma_distance=10, sigma_color_histogram=0.3, sigma_box_size=0.3,
+                              max_distance=15, use_color_histogram=True, use_bbox=True))
+    trajectories = mot3d.solve_graph(g, verbose=False)
+    tracklets = []
+    for traj in trajectories:
+        tracklets += mot3d.split_trajectory_modulo(traj, length=5)
+    tracklets = mot3d.remove_short_trajectories(tracklets, th_length=2)
+    dts = [mot3d.DetectionTracklet2D(t) for t in tracklets]
+    assert len(dts) == len(d2["t_conf"])
+    g2 = mot3d.build_graph(dts, weight_source_sink=0.1, max_jump=20, verbose=False,
+                           weight_confidence=lambda t: wf.weight_confidence_tracklets_2d(t, mul=1, bias=0),
+                           weight_distance=lambda a, b: wf.weight_distance_tracklets_2d(
+                               a, b, max_distance=None, sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7,
+                               cutoff_motion=0.1, cutoff_appearance=0.1, use_color_histogram=True))
+    assert oracle.text_sha(mot3d.graph_to_text(g2)) == str(d2["sha"])
+    final = mot3d.solve_graph(g2, verbose=False)
+    got = [[dts.index(t) for t in tr] for tr in final]
+    gold = [d2["track_det"][d2["track_ptr"][k]:d2["track_ptr"][k + 1]].tolist()
+            for k in range(len(d2["track_ptr"]) - 1)]
+    assert got == gold
+    joined = [mot3d.concat_tracklets([t.tracklet for t in tr]) for tr in final]
+    assert [len(j) for j in joined] == [13, 13]
+    for j in joined:
+        assert [d.index for d in j] == sorted(d.index for d in j)
