@@ -32,6 +32,12 @@ int32_t cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return m3::cuda_fail(e__, name);  \
     } while (0)
 
+// csrc/components.cu: mot3d_components with the shared-memory footprint sized by the largest graph of the batch
+int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
+                       const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
+                       int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
+                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream);
+
 constexpr int64_t INF = MOT3D_INF_COST;
 constexpr int64_t INF_CUT = MOT3D_INF_COST / 2;  // anything >= this is "unreachable"
 

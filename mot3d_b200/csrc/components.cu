@@ -7,11 +7,13 @@
 // window into ~60 independent chains of 1-3, and the per-augmentation scans shrink from the window to the group.
 // The reference has no counterpart (muSSP handles one graph sequentially); results are identical.
 //
-// One block per graph: min-label propagation with pointer jumping over the transition arcs (labels in global memory),
-// then a bitonic sort of (component rank, detection) keys in shared memory gives the detections grouped by component,
-// ascending detection index inside a component (= frame order, which the solver's layer sweeps need). Graphs larger
-// than CC_MAX_SORT detections are kept whole.
+// One block per graph: a lock-free union-find over the transition arcs in shared memory (roots hook under smaller
+// roots, so the root of a component is its smallest detection), then a stable counting sort by component rank gives
+// the detections grouped by component, ascending detection index inside a component (= frame order, which the solver's
+// layer sweeps need). Graphs larger than CC_MAX_SORT detections are kept whole.
 #include "common.cuh"
+
+extern "C" size_t mot3d_components_workspace_bytes(int64_t n_total, int32_t n_graphs);
 
 namespace m3 {
 
@@ -20,21 +22,48 @@ constexpr int CC_MAX_SORT = 8192;
 
 struct CompParams {
     int32_t n_graphs;
+    int32_t cap;           // shared-memory capacity in detections (<= CC_MAX_SORT); larger graphs are kept whole
     const int32_t *graph_ptr;
     const int32_t *in_ptr;
     const int32_t *in_src;
     int64_t arc_capacity;
-    int32_t *label;        // [n_total] scratch: component root (local index) per detection
     int32_t *comp_perm;    // [n_total] out: detection (global index) at every regrouped position
     int32_t *comp_inv;     // [n_total] out: regrouped position (global) of every detection
     int32_t *win_ncomp;    // [n_graphs] out: components per graph
     int32_t *win_cstart;   // [n_total] out: graph g's component c starts at regrouped position win_cstart[g0 + c]
 };
 
+// Union-find on shared memory, safe under concurrent hooks: parents only ever decrease, so any value read is an
+// ancestor and the racing path-halving writes are benign.
+__device__ __forceinline__ int cc_find(volatile int *par, int x) {
+    int q = par[x];
+    while (q != x) {
+        const int gq = par[q];
+        if (gq != q) par[x] = gq;
+        x = q;
+        q = gq;
+    }
+    return x;
+}
+__device__ __forceinline__ int cc_unite(int *par, int ra, int rb) {  // returns a representative of the merged set
+    while (ra != rb) {
+        if (ra < rb) {
+            const int t = ra;
+            ra = rb;
+            rb = t;
+        }
+        const int old = atomicCAS(&par[ra], ra, rb);  // hook the larger root under the smaller one
+        if (old == ra) return rb;
+        ra = cc_find(par, old);  // ra was hooked by somebody else meanwhile
+    }
+    return rb;
+}
+
 __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
-    __shared__ int s_keys[CC_MAX_SORT];
+    extern __shared__ int s_dyn[];
     __shared__ int s_scan[33];
-    __shared__ int s_changed;
+    int *s_par = s_dyn;          // [cap] parent -> root -> component rank -> regrouped position
+    int *s_cnt = s_dyn + p.cap;  // [cap] rank of a root -> detections per component -> placement cursor
     const int g = blockIdx.x;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
@@ -43,10 +72,9 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
         if (tid == 0) p.win_ncomp[g] = 0;
         return;
     }
-    int32_t *label = p.label + g0;
     const int32_t *in_ptr = p.in_ptr + g0;
     const bool overflow = (int64_t)in_ptr[n] > p.arc_capacity;  // arc buffer overflow: reported by the fill kernel
-    const bool split = n <= CC_MAX_SORT && !overflow;
+    const bool split = n <= p.cap && !overflow;
     if (!split) {  // kept whole: one component, identity order
         for (int i = tid; i < n; i += T) {
             p.comp_perm[g0 + i] = g0 + i;
@@ -58,89 +86,83 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
         }
         return;
     }
-    for (int i = tid; i < n; i += T) label[i] = i;
+    for (int i = tid; i < n; i += T) s_par[i] = i;
     __syncthreads();
-    // ---- min-label propagation over the arcs + pointer jumping, until nothing changes
-    for (int iter = 0; iter < n + 2; iter++) {
-        if (tid == 0) s_changed = 0;
-        __syncthreads();
-        int ch = 0;
-        for (int j = tid; j < n; j += T) {
-            const int e1 = in_ptr[j + 1];
-            int lj = label[j];
-            for (int e = in_ptr[j]; e < e1; e++) {
-                const int i = p.in_src[e] - g0;
-                const int li = label[i];
-                if (li < lj) {
-                    lj = li;
-                } else if (lj < li) {
-                    atomicMin(&label[i], lj);
-                    ch = 1;
-                }
-            }
-            if (lj < label[j]) {
-                atomicMin(&label[j], lj);
-                ch = 1;
-            }
+    // ---- one pass over the arcs: unite every detection with the sources of its incoming transitions
+    for (int j = tid; j < n; j += T) {
+        const int e0 = in_ptr[j], e1 = in_ptr[j + 1];
+        if (e0 == e1) continue;
+        int rj = cc_find(s_par, j);
+        for (int e = e0; e < e1; e++) {
+            const int ri = cc_find(s_par, p.in_src[e] - g0);
+            rj = cc_unite(s_par, ri, rj);
         }
-        __syncthreads();
-        for (int i = tid; i < n; i += T) {  // jump to the label's label until a fixed point
-            int l = label[i];
-            int ll = label[l];
-            while (ll != l) {
-                l = ll;
-                ll = label[l];
-            }
-            if (l != label[i]) {
-                label[i] = l;
-                ch = 1;
-            }
-        }
-        if (ch) s_changed = 1;
-        __syncthreads();
-        if (!s_changed) break;
-        __syncthreads();
     }
-    // ---- rank the roots (ascending root index) and sort (rank, detection) keys
-    int32_t *root_rank = p.win_cstart + g0;  // scratch until the final loop below rewrites it
+    __syncthreads();
+    // flatten: every detection points at its root. Read-only chase (no path halving here: a halving write landing
+    // after the owner's final write would leave a non-root behind); only the owner writes an entry.
+    for (int i = tid; i < n; i += T) {
+        volatile int *par = s_par;
+        int r = par[i], q = par[r];
+        while (q != r) {
+            r = q;
+            q = par[r];
+        }
+        par[i] = r;
+    }
+    __syncthreads();
+    // ---- rank the roots (ascending root index = ascending first detection of the component)
     int ncomp = 0;
     for (int base = 0; base < n; base += T) {
         const int i = base + tid;
-        const int f = (i < n && label[i] == i) ? 1 : 0;
+        const int f = (i < n && s_par[i] == i) ? 1 : 0;
         int tot;
         const int ex = block_excl_scan(f, s_scan, &tot);
-        if (f) root_rank[i] = ncomp + ex;
+        if (f) s_cnt[i] = ncomp + ex;
         ncomp += tot;
     }
     __syncthreads();
-    int npow = 1;
-    while (npow < n) npow <<= 1;
-    for (int i = tid; i < npow; i += T)  // key = rank << 13 | detection (n <= 8192); padding sorts last
-        s_keys[i] = (i < n) ? ((root_rank[label[i]] << 13) | i) : 0x7fffffff;
+    for (int i = tid; i < n; i += T) s_par[i] = s_cnt[s_par[i]];  // own entry only: nobody else reads s_par[i] here
     __syncthreads();
-    for (int k = 2; k <= npow; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npow; i += T) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int a = s_keys[i], b = s_keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        s_keys[i] = b;
-                        s_keys[ixj] = a;
-                    }
-                }
+    for (int c = tid; c < ncomp; c += T) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) atomicAdd(&s_cnt[s_par[i]], 1);
+    __syncthreads();
+    int run = 0;
+    for (int base = 0; base < ncomp; base += T) {  // exclusive scan of the component sizes -> component starts
+        const int c = base + tid;
+        const int v = c < ncomp ? s_cnt[c] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, s_scan, &tot);
+        if (c < ncomp) {
+            s_cnt[c] = run + ex;
+            p.win_cstart[g0 + c] = g0 + run + ex;
+        }
+        run += tot;
+    }
+    __syncthreads();
+    // ---- stable placement: one warp walks the detections in order, lanes of the same component share a cursor bump
+    if (tid < 32) {
+        const unsigned lt = (1u << tid) - 1u;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + tid;
+            const int r = i < n ? s_par[i] : -1;
+            const unsigned m = __match_any_sync(0xffffffffu, r);
+            const int leader = __ffs(m) - 1;
+            int start = 0;
+            if (tid == leader && r >= 0) {
+                start = s_cnt[r];
+                s_cnt[r] = start + __popc(m);
             }
-            __syncthreads();
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (i < n) s_par[i] = start + __popc(m & lt);
         }
     }
-    for (int q = tid; q < n; q += T) {
-        const int key = s_keys[q];
-        const int i = key & 8191;
-        p.comp_perm[g0 + q] = g0 + i;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        const int q = s_par[i];
         p.comp_inv[g0 + i] = g0 + q;
-        const int rank = key >> 13;
-        if (q == 0 || (s_keys[q - 1] >> 13) != rank) p.win_cstart[g0 + rank] = g0 + q;
+        p.comp_perm[g0 + q] = g0 + i;
     }
     if (tid == 0) p.win_ncomp[g] = ncomp;
 }
@@ -183,22 +205,12 @@ __global__ void k_comp_fill(int n_graphs, const int32_t *__restrict__ graph_ptr,
     if (g == n_graphs - 1 && threadIdx.x == 0) cgraph_ptr[cb + nc] = graph_ptr[n_graphs];
 }
 
-}  // namespace m3
-
-using namespace m3;
-
-extern "C" {
-
-size_t mot3d_components_workspace_bytes(int64_t n_total, int32_t n_graphs) {
-    size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
-    return ((n * 4 + 255) & ~(size_t)255) * 2 + ((g * 4 + 255) & ~(size_t)255) + 256;
-}
-
-int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, const int32_t *in_ptr,
-                         const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out, int32_t *comp_inv_out,
-                         int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out, int32_t *graph_cbase_out,
-                         int32_t *n_cgraphs_out, void *ws,
-                         size_t ws_bytes, void *stream) {
+// max_graph_nodes sizes the shared memory of k_components (8 bytes per detection of the largest graph); the exported
+// entry point does not know it and asks for the CC_MAX_SORT worst case.
+int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
+                       const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
+                       int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
+                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream) {
     M3_CHECK_ARG(n_graphs >= 0 && n_total >= 0, "negative sizes");
     M3_CHECK_ARG(n_cgraphs_out, "n_cgraphs_out is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -217,12 +229,15 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
     char *w = (char *)ws;
     CompParams p;
     p.n_graphs = n_graphs;
+    int64_t cap = max_graph_nodes;
+    if (cap > n_total) cap = n_total;
+    if (cap > CC_MAX_SORT) cap = CC_MAX_SORT;
+    if (cap < 32) cap = 32;
+    p.cap = (int32_t)cap;
     p.graph_ptr = graph_ptr;
     p.in_ptr = in_ptr;
     p.in_src = in_src;
     p.arc_capacity = arc_capacity;
-    p.label = (int32_t *)w;
-    w += (n * 4 + 255) & ~(size_t)255;
     p.win_cstart = (int32_t *)w;
     w += (n * 4 + 255) & ~(size_t)255;
     p.win_ncomp = (int32_t *)w;
@@ -230,7 +245,10 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
     int32_t *win_cbase = graph_cbase_out;
     p.comp_perm = comp_perm_out;
     p.comp_inv = comp_inv_out;
-    k_components<<<n_graphs, CC_TPB, 0, st>>>(p);
+    const size_t smem = (size_t)cap * 2 * sizeof(int);
+    if (smem > 48 * 1024)
+        M3_CUDA(cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_components<<<n_graphs, CC_TPB, smem, st>>>(p);
     M3_LAUNCH_CHECK("k_components");
     k_comp_offsets<<<1, 1024, 0, st>>>(n_graphs, graph_ptr, p.win_ncomp, win_cbase, n_cgraphs_out);
     M3_LAUNCH_CHECK("k_comp_offsets");
@@ -238,6 +256,27 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
                                          cgraph_graph_out);
     M3_LAUNCH_CHECK("k_comp_fill");
     return MOT3D_OK;
+}
+
+}  // namespace m3
+
+using namespace m3;
+
+extern "C" {
+
+size_t mot3d_components_workspace_bytes(int64_t n_total, int32_t n_graphs) {
+    size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
+    return ((n * 4 + 255) & ~(size_t)255) + ((g * 4 + 255) & ~(size_t)255) + 256;
+}
+
+int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, const int32_t *in_ptr,
+                         const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out, int32_t *comp_inv_out,
+                         int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out, int32_t *graph_cbase_out,
+                         int32_t *n_cgraphs_out, void *ws,
+                         size_t ws_bytes, void *stream) {
+    return components_run(n_graphs, n_total, graph_ptr, CC_MAX_SORT, in_ptr, in_src, arc_capacity, comp_perm_out,
+                          comp_inv_out, cgraph_ptr_out, cgraph_graph_out, graph_cbase_out, n_cgraphs_out, ws, ws_bytes,
+                          stream);
 }
 
 }  // extern "C"

@@ -1067,8 +1067,8 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 
     cudaStream_t st = (cudaStream_t)stream;
     // 1. connected components of every graph, detections regrouped by component
-    int32_t rc = mot3d_components(n_graphs, n_total, graph_ptr, in_ptr, in_src, arc_capacity, comp_perm, comp_inv,
-                                  cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
+    int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
+                                comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
     if (rc) return rc;
     // 2. first shortest-path tree per graph
     k_first_tree<<<n_graphs, 256, 0, st>>>(p);

@@ -532,3 +532,70 @@ def test_two_pass_pipeline_drop_in():
     assert [len(j) for j in joined] == [13, 13]
     for j in joined:
         assert [d.index for d in j] == sorted(d.index for d in j)
+
+
+def test_components_against_scipy():
+    """mot3d_components (csrc/components.cu): the regrouping of every graph by connected component of its transition
+    arcs, checked against scipy on a ragged batch; repeated, because the union-find runs lock-free."""
+    import ctypes
+    import torch
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    rng = np.random.RandomState(5)
+    sizes = [0, 1, 37, 3000, 5000, 800, 8192, 2, 9000, 4999] + [int(s) for s in rng.randint(1, 4000, size=40)]
+    frames, poss = [], []
+    for s in sizes:
+        f = np.sort(rng.randint(0, 40, size=s))
+        frames.append(f)
+        poss.append(rng.rand(s, 2) * (300.0 + 5.0 * np.sqrt(s)))
+    gp = np.cumsum([0] + sizes).astype(np.int32)
+    frame, pos = np.concatenate(frames), np.concatenate(poss)
+    spec = mot3d.CostSpec(kind="detections_2d", max_jump=3, weight_source_sink=1,
+                          distance=dict(sigma_jump=1, sigma_distance=10, max_distance=25, use_color_histogram=False,
+                                        use_bbox=False))
+    b, _ = mot3d.DetectionBatch.from_arrays(gp, frame, pos, np.full(len(frame), 0.9))
+    gb = mot3d.build_graphs(b.to("cuda"), spec)
+    n, G, E = len(frame), len(sizes), gb.n_edges
+    L = _lib.lib()
+    dev = gb.row_ptr.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    row_ptr, col = gb.row_ptr.cpu().numpy(), gb.col.cpu().numpy()[:E]
+    rows = np.repeat(np.arange(n), np.diff(row_ptr))
+    ws_bytes = L.mot3d_components_workspace_bytes(n, G)
+    for rep in range(8):
+        perm, inv = torch.full((n,), -1, **i32), torch.full((n,), -1, **i32)
+        cptr, cgraph = torch.full((n + 1,), -1, **i32), torch.full((n,), -1, **i32)
+        cbase, ncg = torch.full((G,), -1, **i32), torch.full((4,), -1, **i32)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.mot3d_components(G, n, ptr(gb.dets.graph_ptr), ptr(gb.row_ptr), ptr(gb.col), E, ptr(perm),
+                                      ptr(inv), ptr(cptr), ptr(cgraph), ptr(cbase), ptr(ncg), ptr(ws), ws_bytes,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        perm, inv, cptr, cgraph, cbase = [t.cpu().numpy() for t in (perm, inv, cptr, cgraph, cbase)]
+        n_cg = int(ncg[0].item())
+        assert (perm[inv] == np.arange(n)).all() and cptr[n_cg] == n
+        c = 0
+        for g, s in enumerate(sizes):
+            g0 = gp[g]
+            if s == 0:
+                continue
+            assert cbase[g] == c
+            if s > 8192:  # kept whole
+                assert cgraph[c] == g and cptr[c] == g0 and (perm[g0:g0 + s] == np.arange(g0, g0 + s)).all()
+                c += 1
+                continue
+            m = (rows >= g0) & (rows < g0 + s)
+            A = sp.coo_matrix((np.ones(m.sum()), (rows[m] - g0, col[m] - g0)), shape=(s, s))
+            k, lab = connected_components(A, directed=False)
+            first = np.full(k, s)
+            np.minimum.at(first, lab, np.arange(s))
+            rank = np.argsort(np.argsort(first))[lab]        # components ordered by their first detection
+            order = np.lexsort((np.arange(s), rank))         # grouped by component, ascending detection inside
+            assert (perm[g0:g0 + s] == g0 + order).all()
+            starts = g0 + np.concatenate([[0], np.cumsum(np.bincount(rank, minlength=k))[:-1]])
+            assert (cptr[c:c + k] == starts).all() and (cgraph[c:c + k] == g).all()
+            c += k
+        assert c == n_cg
