@@ -307,7 +307,7 @@ def run_ours(args):
         peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    stats = pipe.stats.cpu().numpy().reshape(-1, 12)[:G]
+    stats = pipe.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)[:G]
     # relaxation work actually done (k_ssp_solve only touches the branch it has to re-label):
     # every arc pull reads 4 B source + 8 B cost, every node pull moves 8 B dist + 8 B dist + 4 B parent
     solve_bytes = float(np.sum(stats[:, 3] * 12 + stats[:, 2] * 20))
@@ -329,6 +329,13 @@ def run_ours(args):
                 "frac": solve_gbs / peak, "traffic": traffic_solve, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": float(stage_ms[i_solve]),
                 "ascending_sweeps_per_graph_mean": float(stats[:, 0].mean()),
+                "descending_sweeps_per_graph_mean": float(stats[:, 1].mean()),
+                "branches_relabelled_per_graph_mean": float(stats[:, 11].mean()),
+                "records_staged_per_graph_mean": float(stats[:, 12].mean()),
+                "sweep_warp_cycles_per_step": {"ascending": float(stats[:, 13].sum() / max(stats[:, 15].sum(), 1)),
+                                               "descending": float(stats[:, 14].sum() / max(stats[:, 16].sum(), 1))},
+                "sweep_steps_per_graph_mean": {"ascending": float(stats[:, 15].mean()),
+                                               "descending": float(stats[:, 16].mean())},
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
                 "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(

@@ -210,7 +210,7 @@ def solve_graphs(gb, want_path_costs=True):
     sol.n_paths = torch.zeros(max(G, 1), **i32)
     sol.total_cost = torch.zeros(max(G, 1), **i64)
     sol.path_cost = torch.zeros(max(n, 1), **i64) if want_path_costs else None
-    sol.stats = torch.zeros(max(G, 1) * 12, **i64)
+    sol.stats = torch.zeros(max(G, 1) * _lib.SOLVE_STATS, **i64)
     ws_bytes = L.mot3d_solve_workspace_bytes(n, G, max(gb.n_edges, 0))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     max_nodes = getattr(b, "_max_nodes", None)

@@ -54,13 +54,30 @@ struct __align__(16) StArc {
     int src;  // slot of the source record
     int pad;
 };
+// Shared-memory flavour of a staged arc, half the size: used when every transition cost of the graph fits 32 bits
+// (always the case for the built-in cost functions: weights in [-1, 0] -> [-1e7, 0]); graphs with wider costs take
+// the global staging area. src / pad of the first arc of a list = length of the list, like StArc.
+struct __align__(8) PArc {
+    int cost;
+    unsigned short src;
+    unsigned short pad;
+};
+template <bool SM>
+struct ArcOf {
+    typedef StArc type;
+};
+template <>
+struct ArcOf<true> {
+    typedef PArc type;
+};
+template <bool SM>
 struct Stage {
     Rec *rec;
-    StArc *arc;
+    typename ArcOf<SM>::type *arc;
     int32_t *tk;  // frame-layer key per record (only used to flag the first record of every layer)
 };
 constexpr int REC_BYTES = sizeof(Rec) + 4;
-constexpr int ARC_BYTES = sizeof(StArc);
+constexpr int ARC_BYTES = sizeof(PArc);
 static_assert(sizeof(Rec) == 96, "record layout");
 
 struct SolveParams {
@@ -90,6 +107,7 @@ struct SolveParams {
     const int32_t *cgraph_ptr;  // [n_cgraphs + 1] regrouped positions
     const int32_t *cgraph_win;  // [n_cgraphs] graph of every component
     const int32_t *win_cbase;   // [n_graphs] first component of every graph
+    int32_t *win_wide;          // [n_graphs] 1 = some transition cost does not fit 32 bits (k_first_tree)
     int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
@@ -155,6 +173,7 @@ struct Ctx {
 
 struct Counters {
     int64_t n_asc, n_desc, n_node, n_arc;
+    int64_t n_branch, n_rec;  // branches re-labelled, records staged
     long long t_phase[7];  // cycles (thread 0): arg-min, collect, stage, walk, sweeps, write-back, first tree
     long long t_mark;
     __device__ __forceinline__ void tick(int k) {
@@ -175,16 +194,21 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
     const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);  // the lanes of this thread's group
     const int gshift = (tid & 31) / LPN * LPN;
-    Stage st;
+    typedef typename ArcOf<SM>::type Arc;
+    Stage<SM> st;
     if (SM) {
         st.rec = (Rec *)smem_raw;
-        st.arc = (StArc *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec));
-        st.tk = (int32_t *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec) + (size_t)(p.arc_cap + 8) * sizeof(StArc));
+        st.arc = (Arc *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec));
+        st.tk = (int32_t *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec) + (size_t)(p.arc_cap + 8) * sizeof(Arc));
     } else {
         st.rec = p.ws_rec + c.c0;
-        st.arc = p.ws_arc;  // a record's arcs sit at in_ptr[d] + d: room for its in-degree + the end marker
+        st.arc = (Arc *)p.ws_arc;  // a record's arcs sit at in_ptr[d] + d: room for its in-degree + the end marker
         st.tk = p.ws_tk + c.c0;
     }
+    // arc list of a record: A.y >= 0 = offset in the staging area, < 0 = ~offset in the global area. The global area
+    // is addressed in StArc units whatever the arc type, so that the lists of different detections never overlap
+    // (other blocks may be using it with the wide arcs at the same time).
+    auto arcs_of = [&](int ay) -> Arc * { return (SM && ay < 0) ? (Arc *)(p.ws_arc + ~ay) : st.arc + ay; };
     // ---- stage the branch: one lane group per record
     for (int sb = 0; sb < nd; sb += ngrp) {
         const int s = sb + grp;
@@ -199,6 +223,9 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
         if (valid && (ent & DL_PRE)) {
             const int e0 = p.in_ptr[dj], deg = p.in_ptr[dj + 1] - e0;
             a0 = SM ? c.dla0[s] : e0 + dj;
+            // shared arc area full: this record's list goes to the global area (the records stay in shared memory)
+            if (SM && a0 + deg + 1 > p.arc_cap) a0 = ~(e0 + dj);
+            Arc *const ap = arcs_of(a0);
             for (int k0 = 0; k0 < deg; k0 += LPN) {
                 const int k = k0 + sub;
                 const bool has = k < deg;
@@ -213,11 +240,11 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                 const bool inside = has && a == root;
                 const unsigned m = (__ballot_sync(gmask, inside) >> gshift) & 0xFu;
                 if (inside) {
-                    StArc x;
-                    x.cost = w;
-                    x.src = c.slot_of[i];
+                    Arc x;
+                    x.cost = (decltype(x.cost))w;
+                    x.src = (decltype(x.src))c.slot_of[i];
                     x.pad = 0;
-                    st.arc[a0 + nda + __popc(m & ((1u << sub) - 1u))] = x;
+                    ap[nda + __popc(m & ((1u << sub) - 1u))] = x;
                 } else if (has && di < INF_CUT) {
                     const int64_t cand = di + w;
                     if (cand < cbest.key) {
@@ -246,12 +273,13 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
             Rec r;
             r.A = make_int4(ent, a0, ((ent & DL_PRE) && prv_j >= 0) ? c.slot_of[prv_j] : -1, prv_j);
             if (ent & DL_PRE) {
-                StArc x;
+                Arc x;
                 x.cost = 0;
-                x.src = -1;  // end of this record's arc list
+                x.src = 0;
                 x.pad = 0;
-                st.arc[a0 + nda] = x;
-                st.arc[a0].pad = nda;  // the first slot also carries the length of the list
+                Arc *const ap = arcs_of(a0);
+                ap[nda] = x;  // one spare slot, so that a record without staged arcs still has a length
+                ap[0].pad = (decltype(x.pad))nda;  // the first slot also carries the length of the list
             }
             r.B = make_int4(((ent & DL_POST) && nxt_j >= 0) ? c.slot_of[nxt_j] : -1,
                             ((ent & DL_PRE) && par_j >= 0) ? c.slot_of[par_j] : -1, bpar, banc);
@@ -313,11 +341,12 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
     if (!*s_ok) return false;
     for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
         const int m = c.dla0[h];
-        const int qs = st.rec[m].A.z, b0 = st.rec[m].A.y;
-        const int deg = st.arc[b0].pad;
+        const int qs = st.rec[m].A.z;
+        const Arc *const ap = arcs_of(st.rec[m].A.y);
+        const int deg = ap[0].pad;
         for (int k = 0; k < deg; k++) {
-            const StArc x = st.arc[b0 + k];
-            if (x.src == qs) {
+            const Arc x = ap[k];
+            if ((int)x.src == qs) {
                 st.rec[m].D.y = x.cost;
                 break;
             }
@@ -361,53 +390,67 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
         }
     }
     __syncthreads();
-    // ---- re-label it: exact Bellman-Ford fix-point in pull mode by ONE warp, one lane per record of the current
-    //      layer. Ascending layer order settles forward arcs, descending order the reversed arcs (they run
-    //      backwards in time along tracks); alternate until nothing moves.
+    // ---- re-label it: exact Bellman-Ford fix-point in pull mode by ONE warp. Ascending order settles the forward
+    //      arcs, a descending pass settles the reversed arcs (they run backwards in time along tracks); the two
+    //      alternate until nothing moves.
     if (warp_id() == sweep_warp) {
         const int lane = lane_id();
-        int n_node32 = 0, n_arc32 = 0, n_asc32 = 0, n_desc32 = 0;
-        // A sweep only has to revisit what can still change: the ascending sweep starts at the lowest record the
-        // previous descending sweep changed, the descending sweep at the highest record the ascending one changed.
+        int n_node32 = 0, n_arc32 = 0, n_asc32 = 0, n_desc32 = 0, n_astep = 0, n_dstep = 0;
+        long long t_asc = 0, t_desc = 0, t0 = clock64();
+        // The ascending sweep only has to revisit what can still change: it starts at the lowest record whose post
+        // label the previous descending pass changed.
         int asc_from = 0;
         for (int round = 0; round < 2 * nd + 4; round++) {
             int hi_ch = (round == 0) ? nd - 1 : -1;  // round 0: the initial labels stand in for the ascending sweep
             if (round > 0) n_asc32++;
             for (int q = (round == 0) ? nd : asc_from; q < nd;) {
-                // one step = the records of one layer, at most 4 at a time, 8 lanes per record (one per in-arc)
+                // One step = up to 4 records, 8 lanes per record (one per in-arc). Forward arcs only leave post
+                // nodes, and during an ascending sweep the post label of a record on a track does not depend on
+                // lower layers (it hangs from its successor's pre node): only UNUSED records pass a freshly computed
+                // label on. So a step may run across layer boundaries until it has taken such a record.
                 const int r8 = lane >> 3, a8 = lane & 7;
                 const int s = q + r8;
                 const bool in_range = s < nd;
                 const Rec *rp = st.rec + (in_range ? s : nd - 1);
                 int4 A = rp->A, B = rp->B, F = rp->F;
                 const longlong2 C = rp->C, D = rp->D, E = rp->E;
-                const unsigned brk =
-                    __ballot_sync(0xffffffffu, lane >= 8 && a8 == 0 && (!in_range || (A.x & DL_FIRST)));
-                const int cn_t = brk ? (__ffs(brk) - 1) >> 3 : 4;
+                // one ballot, three questions: lane 8r = "record r passes a new label on", lane 8r + 1 = "record r
+                // starts a layer", lane 8r + 2 = "record r is out of range"
+                const bool q0 = in_range && (A.x & DL_POST) && A.w == NONE;
+                const bool q1 = (A.x & DL_FIRST) != 0;
+                const unsigned vt = __ballot_sync(0xffffffffu, a8 == 0 ? q0 : (a8 == 1 ? q1 : (a8 == 2 && !in_range)));
+                int cn_t = 4;
+                {
+                    unsigned prod = vt & 1u;
+                    if (((vt >> 26) & 1u) | (((vt >> 25) & 1u) & (prod | ((vt >> 8) & 1u) | ((vt >> 16) & 1u)))) cn_t = 3;
+                    if (((vt >> 18) & 1u) | (((vt >> 17) & 1u) & (prod | ((vt >> 8) & 1u)))) cn_t = 2;
+                    if (((vt >> 10) & 1u) | (((vt >> 9) & 1u) & prod)) cn_t = 1;
+                }
                 const bool valid = r8 < cn_t;
                 const int ent = valid ? A.x : 0;
-                // next record on the track (higher layer, not in this step) and this record's in-arcs from inside
-                // the branch: all loads are issued before anything is decided
+                // next record on the track (higher layer) and this record's in-arcs from inside the branch: all
+                // loads are issued before anything is decided
                 int64_t nx_dpre = INF, nx_mc = 0;
                 int nx_apre = -1;
-                KeyIdx best;
+                KeyIdx best;  // idx = slot of the source; "none" = INF with the largest unsigned idx
                 best.key = INF;
                 best.idx = -1;
                 int deg = 0;
                 if (ent & DL_PRE) {
-                    const StArc x0 = st.arc[A.y + a8];  // speculative: issued together with the list length
-                    deg = st.arc[A.y].pad;
+                    const Arc *const ap = arcs_of(A.y);
+                    const Arc x0 = ap[a8];  // speculative: issued together with the list length
+                    deg = ap[0].pad;
                     if (a8 < deg) {
                         const int64_t d = st.rec[x0.src].E.y;
-                        if (x0.src != A.z && d < INF_CUT) {
+                        if ((int)x0.src != A.z && d < INF_CUT) {
                             best.key = d + x0.cost;
                             best.idx = x0.src;
                         }
                     }
                     for (int k = a8 + 8; k < deg; k += 8) {
-                        const StArc x = st.arc[A.y + k];
+                        const Arc x = ap[k];
                         const int64_t d = st.rec[x.src].E.y;
-                        if (x.src != A.z && d < INF_CUT && d + x.cost < best.key) {
+                        if ((int)x.src != A.z && d < INF_CUT && d + x.cost < best.key) {
                             best.key = d + x.cost;
                             best.idx = x.src;
                         }
@@ -422,12 +465,13 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
 #pragma unroll
                 for (int d = 1; d < 8; d <<= 1) {  // slots ascend with the detection index: lowest slot wins ties
                     const KeyIdx o = shfl_xor_ki(best, d);
-                    if (o.idx >= 0 && (best.idx < 0 || o.key < best.key || (o.key == best.key && o.idx < best.idx)))
-                        best = o;
+                    const bool take = o.key < best.key || (o.key == best.key && (unsigned)o.idx < (unsigned)best.idx);
+                    best.key = take ? o.key : best.key;
+                    best.idx = take ? o.idx : best.idx;
                 }
                 if (valid && a8 == 0) {
                     int64_t dpre_s = E.x, dpost_s = E.y;
-                    bool upd = false;
+                    bool upd = false, down = false;  // down: the change can travel along a reversed arc
                     if (ent & DL_PRE) {
                         int64_t key = INF;
                         int par = PAR_NONE, anc = -1;
@@ -456,6 +500,7 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                             F.x = par;
                             F.y = anc;
                             upd = true;
+                            down = A.z >= 0;  // pre_s feeds the post node of its predecessor on the track
                         }
                         n_arc32 += deg;
                     }
@@ -475,90 +520,113 @@ __device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, i
                             dpost_s = v;
                             F.z = a;
                             upd = true;
+                            down = down || A.w != NONE;  // post_s feeds its own pre node (reversed node arc)
                         }
                     }
                     if (upd) {
                         st.rec[s].E = make_longlong2(dpre_s, dpost_s);
                         st.rec[s].F = F;
-                        hi_ch = s;
+                        if (down) hi_ch = s;
                     }
                 }
                 n_node32 += cn_t;
+                n_astep++;
                 q += cn_t;
                 __syncwarp();
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) hi_ch = max(hi_ch, __shfl_xor_sync(0xffffffffu, hi_ch, d));
+            {
+                const long long t1 = clock64();
+                t_asc += t1 - t0;
+                t0 = t1;
+            }
             if (hi_ch < 0) break;  // nothing moved: fix-point
+            // Descending pass. Reversed arcs only connect a record with its successor on the track (post_s hangs
+            // from pre_next) and the two nodes of a record on a track (pre_s hangs from post_s): the pass falls apart
+            // into independent chains, one per track segment inside the branch. Every lane looks at its share of the
+            // records; the lane that finds the last record of a segment walks the segment down on its own, no
+            // warp-wide step per layer. Unused records only forward pre -> post.
             int lo_ch = nd;
             n_desc32++;
-            for (int q = hi_ch + 1; q > 0;) {
-                // walking down: the records of one layer (until the one flagged DL_FIRST), one lane each
-                const int s = q - 1 - lane;
-                const bool in_range = s >= 0;
-                const Rec *rp = st.rec + (in_range ? s : 0);
-                int4 A = rp->A, F = rp->F;
-                const int ns = rp->B.x;
-                const longlong2 D = rp->D, E = rp->E;
-                const unsigned fst = __ballot_sync(0xffffffffu, !in_range || (A.x & DL_FIRST) != 0);
-                const int cn_t = fst ? __ffs(fst) : 32;  // lanes 0 .. ffs-1 (the layer's first record included)
-                if (lane < cn_t && in_range) {
+            for (int sb = 0; sb < nd; sb += 32) {
+                int cur = sb + lane;
+                bool head = false;
+                if (cur < nd) {
+                    const int4 A = st.rec[cur].A;
+                    if (A.w == NONE) {
+                        if (A.x & DL_POST) {
+                            const longlong2 E = st.rec[cur].E;
+                            if (E.x < INF_CUT && E.x + st.rec[cur].D.x < E.y) {
+                                st.rec[cur].E.y = E.x + st.rec[cur].D.x;
+                                st.rec[cur].F.z = st.rec[cur].F.y;
+                                lo_ch = min(lo_ch, cur);
+                            }
+                        }
+                    } else {
+                        head = st.rec[cur].B.x < 0;  // on a track, successor not in the branch
+                    }
+                }
+                int64_t nx_dpre = INF, nx_mc = 0;
+                int nx_apre = -1;
+                if (!head) cur = -1;
+                while (cur >= 0) {
+                    const Rec *rp = st.rec + cur;
+                    const int4 A = rp->A;
+                    int4 F = rp->F;
+                    const longlong2 D = rp->D, E = rp->E;
                     const int ent = A.x;
                     int64_t dpre_s = E.x, dpost_s = E.y;
                     bool upd = false;
-                    if (ent & DL_POST) {
-                        int64_t v = INF;
-                        int a = -1;
-                        if (A.w == NONE) {
-                            if (dpre_s < INF_CUT) {
-                                v = dpre_s + D.x;
-                                a = F.y;
-                            }
-                        } else if (ns >= 0) {
-                            const Rec *r = st.rec + ns;
-                            const int64_t d = r->E.x;
-                            if (d < INF_CUT) {
-                                v = d - r->D.y;
-                                a = r->F.y;
-                            }
-                        }
-                        if (v < dpost_s) {
-                            dpost_s = v;
-                            F.z = a;
-                            upd = true;
-                        }
+                    if ((ent & DL_POST) && nx_dpre < INF_CUT && nx_dpre - nx_mc < dpost_s) {
+                        dpost_s = nx_dpre - nx_mc;
+                        F.z = nx_apre;
+                        upd = true;
+                        lo_ch = min(lo_ch, cur);  // forward arcs leave post_s: the ascending sweep has to come back
                     }
-                    if ((ent & DL_PRE) && (ent & DL_POST) && A.w != NONE && dpost_s < INF_CUT &&
-                        dpost_s - D.x < dpre_s) {
+                    if ((ent & DL_PRE) && (ent & DL_POST) && dpost_s < INF_CUT && dpost_s - D.x < dpre_s) {
                         dpre_s = dpost_s - D.x;
                         F.x = PAR_POST;
                         F.y = F.z;
                         upd = true;
                     }
                     if (upd) {
-                        st.rec[s].E = make_longlong2(dpre_s, dpost_s);
-                        st.rec[s].F = F;
-                        lo_ch = s;
+                        st.rec[cur].E = make_longlong2(dpre_s, dpost_s);
+                        st.rec[cur].F = F;
                     }
+                    nx_dpre = (ent & DL_PRE) ? dpre_s : INF;
+                    nx_mc = D.y;
+                    nx_apre = F.y;
+                    cur = A.z;  // predecessor on the track (its post node hangs from pre_cur), -1 = segment ends
+                    n_dstep++;
                 }
-                const int done = cn_t < q ? cn_t : q;
-                n_node32 += done;
-                q -= done;
-                __syncwarp();
             }
+            __syncwarp();
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) lo_ch = min(lo_ch, __shfl_xor_sync(0xffffffffu, lo_ch, d));
+            {
+                const long long t1 = clock64();
+                t_desc += t1 - t0;
+                t0 = t1;
+            }
             if (lo_ch >= nd && round > 0) break;  // nothing moved: fix-point
             asc_from = (round == 0) ? 0 : lo_ch;   // the initial labels ignored arcs inside the branch: full sweep
         }
         // work counters of this branch (the leaders of the lane groups counted the arcs)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) n_arc32 += __shfl_xor_sync(0xffffffffu, n_arc32, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            n_arc32 += __shfl_xor_sync(0xffffffffu, n_arc32, d);
+            n_dstep += __shfl_xor_sync(0xffffffffu, n_dstep, d);
+        }
         if (lane == 0) {
             s_work[0] += n_asc32;
             s_work[1] += n_desc32;
-            s_work[2] += n_node32;
+            s_work[2] += n_node32 + n_dstep;  // records visited: ascending steps + hops of the descending chains
             s_work[3] += n_arc32;
+            s_work[4] += t_asc;
+            s_work[5] += t_desc;
+            s_work[6] += n_astep;
+            s_work[7] += n_dstep;
         }
     }
     __syncthreads();
@@ -641,6 +709,7 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     if (tid == 0) lvl[L] = n;
     __syncthreads();
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
+    int wide = 0;  // some transition cost needs more than 32 bits: the packed staging of k_ssp_solve is off
     for (int l = 0; l < L; l++) {
         const int a = lvl[l], b = lvl[l + 1];
         for (int jb = a; jb < b; jb += ngrp) {
@@ -654,8 +723,10 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
                 for (int k = sub; k < deg; k += LPN) {
                     const int qi = p.comp_inv[p.in_src[e0 + k]];  // position of the source
                     const int64_t di = p.ws_dpost[qi];
+                    const int64_t w = p.in_cost[e0 + k];
+                    wide |= (w != (int64_t)(int)w) ? 1 : 0;
                     if (di < INF_CUT) {
-                        const int64_t cand = di + p.in_cost[e0 + k];
+                        const int64_t cand = di + w;
                         if (cand < best.key || (cand == best.key && qi < best.idx)) {
                             best.key = cand;
                             best.idx = qi;
@@ -684,6 +755,8 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
         }
         __syncthreads();
     }
+    wide = __syncthreads_or(wide);
+    if (tid == 0) p.win_wide[g] = wide;
     if (p.stats && tid == 0) {
         int64_t *o = p.stats + (size_t)MOT3D_SOLVE_STATS * g;
         o[0] = 1;
@@ -697,7 +770,9 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
     __shared__ int s_scan[64];
     __shared__ KeyIdx s_red[33];
     __shared__ int s_ok[2], s_sweep_warp, s_job;
-    __shared__ long long s_work[4];  // ascending sweeps, descending sweeps, node pulls, arc pulls (sweep warp)
+    // sweep warp's counters: ascending sweeps, descending sweeps, node pulls, arc pulls, cycles in ascending /
+    // descending sweeps, ascending / descending steps
+    __shared__ long long s_work[8];
 
     const int T = blockDim.x;
     const int tid = threadIdx.x;
@@ -727,7 +802,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
 
     for (;;) {
         if (tid == 0) s_job = atomicAdd(&p.n_cgraphs[1], 1);
-        if (tid < 4) s_work[tid] = 0;
+        if (tid < 8) s_work[tid] = 0;
         __syncthreads();
         const int cg = s_job;
         __syncthreads();
@@ -736,6 +811,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
         const int n = p.cgraph_ptr[cg + 1] - c0;
         const int g = p.cgraph_win[cg];
         if (n <= 0 || p.n_paths[g] < 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
+        const bool wide = p.win_wide[g] != 0;
         Ctx c;
         c.p = &p;
         c.c0 = c0;
@@ -764,6 +840,8 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
         cnt.n_desc = 0;
         cnt.n_node = 0;
         cnt.n_arc = 0;
+        cnt.n_branch = 0;
+        cnt.n_rec = 0;
         for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
         cnt.t_mark = clock64();
 
@@ -858,7 +936,9 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
             __syncthreads();
             cnt.tick(1);
             if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
-            const bool in_smem = nd <= p.rec_cap && atot <= p.arc_cap;
+            const bool in_smem = nd <= p.rec_cap && !wide;  // arc lists beyond the shared area spill one by one
+            cnt.n_branch++;
+            cnt.n_rec += nd;
             const bool ok = in_smem ? relabel_branch<true>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt)
                                     : relabel_branch<false>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt);
             if (!ok) break;  // defensive: inconsistent state, stop with what we have
@@ -879,6 +959,9 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
                 atomicAdd(&o[2], (unsigned long long)(cnt.n_node + s_work[2]));
                 atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
                 for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
+                atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
+                atomicAdd(&o[12], (unsigned long long)cnt.n_rec);
+                for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
             }
         }
         for (int i = tid; i < n; i += T) {
@@ -984,7 +1067,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
-    return a256(n * 8) * 4 + a256(n * 4) * 13 + a256((n + g) * 4) * 2 + a256(g * 4) + a256(n * sizeof(Rec)) +
+    return a256(n * 8) * 4 + a256(n * 4) * 13 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 + a256(n * sizeof(Rec)) +
            a256((e + n + 8) * sizeof(StArc)) + a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
 }
 
@@ -1053,6 +1136,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.ws_lvl = (int32_t *)take((n_cap + g) * 4);
     int32_t *cgraph_ptr = (int32_t *)take((n_cap + g) * 4);
     int32_t *win_cbase = (int32_t *)take(g * 4);
+    p.win_wide = (int32_t *)take(g * 4);
     p.ws_rec = (Rec *)take(n_cap * sizeof(Rec));
     p.ws_arc = (StArc *)take((e_cap + n_cap + 8) * sizeof(StArc));
     const size_t cws_bytes = mot3d_components_workspace_bytes(n_total, n_graphs);
@@ -1078,12 +1162,24 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     // Graphs of up to 8192 detections are split into components (typically a few tracks each): small staging area
     // and small blocks so that ~8 blocks share an SM. Small graphs (<= 1024) are usually one dense component: keep
     // room for a whole branch. Tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / _THREADS / _BLOCKS_PER_SM.
-    size_t rec_target = max_graph_nodes <= 1024 ? 320 : 128;
+    size_t rec_target = max_graph_nodes <= 1024 ? 320 : 192;
     if (const char *e = getenv("MOT3D_SOLVE_RECCAP")) rec_target = (size_t)atoi(e) > 31 ? (size_t)atoi(e) : 32;
     size_t rec_cap = (size_t)max_graph_nodes < rec_target ? (size_t)max_graph_nodes : rec_target;
     if (rec_cap < 32) rec_cap = 32;
-    size_t arc_cap = rec_cap * 9 / 2 + 32;  // room reserved by in-degree (+1) of the branch's pre nodes
-    if (arc_cap > 1400) arc_cap = 1400;
+    size_t arc_cap = rec_cap * 9 + 32;  // room is reserved by in-degree (+1) of the branch's pre nodes
+    if (arc_cap > 2800) arc_cap = 2800;
+    int dev = 0, n_sm = 148, per_sm = 4, smem_sm = 228 * 1024;
+    M3_CUDA(cudaGetDevice(&dev));
+    M3_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    M3_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    if (max_graph_nodes > 1024) {
+        // 8 blocks per SM: the arc area takes what is left of an eighth of the SM's shared memory (1 KB per block
+        // is reserved by the system, ~1 KB is static)
+        const size_t budget = (size_t)smem_sm / 8 - 1024 - 1024;
+        const size_t fixed = rec_cap * REC_BYTES + 8 * ARC_BYTES + 16;
+        if (budget > fixed + 64 * ARC_BYTES && arc_cap > (budget - fixed) / ARC_BYTES) arc_cap = (budget - fixed) / ARC_BYTES;
+    }
+    if (const char *e = getenv("MOT3D_SOLVE_ARCCAP")) arc_cap = (size_t)atoi(e) > 63 ? (size_t)atoi(e) : 64;
     p.rec_cap = (int32_t)rec_cap;
     p.arc_cap = (int32_t)arc_cap;
     const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
@@ -1094,9 +1190,6 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     }
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, n_sm = 148, per_sm = 4;
-    M3_CUDA(cudaGetDevice(&dev));
-    M3_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     M3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ssp_solve, threads, smem));
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("MOT3D_SOLVE_BLOCKS_PER_SM")) {

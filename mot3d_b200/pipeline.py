@@ -42,7 +42,7 @@ class TrackPipeline(object):
         self.prev = torch.empty(n, **i32)
         self.n_paths = torch.empty(G, **i32)
         self.total_cost = torch.empty(G, **i64)
-        self.stats = torch.zeros(12 * G, **i64)
+        self.stats = torch.zeros(_lib.SOLVE_STATS * G, **i64)
         self.solve_ws_bytes = L.mot3d_solve_workspace_bytes(n, G, E)
         self.solve_ws = torch.empty(self.solve_ws_bytes, dtype=torch.uint8, device=dev)
         self.track_count = torch.empty(G, **i32)

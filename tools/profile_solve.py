@@ -26,4 +26,4 @@ sc = spec.to_c()
 for _ in range(2):
     pipe.run(db, spec, sc)
 torch.cuda.synchronize()
-print("ok", pipe.n_paths.cpu().numpy()[:n_graphs], pipe.stats.cpu().numpy().reshape(-1, 12)[:n_graphs])
+print("ok", pipe.n_paths.cpu().numpy()[:n_graphs], pipe.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)[:n_graphs])
