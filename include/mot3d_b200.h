@@ -205,7 +205,8 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
  *                   pulls, arc pulls (what bench.py's roofline accounting needs); [4..10] = SM cycles spent in:
  *                   sink arg-min, branch collection, staging, path walk, re-labelling sweeps, write-back, first tree;
  *                   [11] = branches re-labelled, [12] = records staged for them, [13..14] = SM cycles of the sweep
- *                   warp in ascending / descending sweeps, [15..16] = ascending / descending steps, [17] = reserved
+ *                   warp in ascending / descending sweeps, [15..16] = ascending / descending steps, [17] (first graph of the
+ *                   batch only) = cycles all solver blocks were busy, summed
  * Acceptance rule of wrapper.cpp:199-267 on integers: path 1 always, then while cost < 0. */
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                           const int32_t *tkey, int64_t arc_capacity,

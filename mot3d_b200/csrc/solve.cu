@@ -108,6 +108,7 @@ struct SolveParams {
     const int32_t *cgraph_win;  // [n_cgraphs] graph of every component
     const int32_t *win_cbase;   // [n_graphs] first component of every graph
     int32_t *win_wide;          // [n_graphs] 1 = some transition cost does not fit 32 bits (k_first_tree)
+    int32_t *job_order;         // [n_cgraphs] component graphs, largest first (k_job_order)
     int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
@@ -765,6 +766,35 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     }
 }
 
+// ---- work queue order: largest components first (longest-processing-time-first keeps the tail of the solver short:
+//      a component is solved by one block, path after path). One block: counting sort by size class, 4 classes per
+//      power of two; the order inside a class does not matter.
+constexpr int JOB_CLASSES = 64;
+__device__ __forceinline__ int job_class(int n) {
+    if (n < 4) return n;
+    const int lg = 31 - __clz(n);
+    return 4 * (lg - 1) + ((n >> (lg - 2)) & 3);  // 4 -> 4, 8 -> 8, ..., 8192 -> 48
+}
+__global__ void __launch_bounds__(1024) k_job_order(const SolveParams p) {
+    __shared__ int s_cnt[JOB_CLASSES], s_start[JOB_CLASSES];
+    const int n_jobs = p.n_cgraphs[0];
+    if (threadIdx.x < JOB_CLASSES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
+        atomicAdd(&s_cnt[job_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = JOB_CLASSES - 1; b >= 0; b--) {
+            s_start[b] = run;
+            run += s_cnt[b];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
+        p.job_order[atomicAdd(&s_start[job_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1)] = c;
+}
+
 // ---- successive shortest paths on every component graph. Blocks fetch components from a work queue.
 __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
     __shared__ int s_scan[64];
@@ -799,14 +829,21 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
     __syncthreads();
     const int sweep_warp = s_sweep_warp;
     const int n_jobs = p.n_cgraphs[0];
+    const long long t_block0 = clock64();
 
     for (;;) {
         if (tid == 0) s_job = atomicAdd(&p.n_cgraphs[1], 1);
         if (tid < 8) s_work[tid] = 0;
         __syncthreads();
-        const int cg = s_job;
+        const int job = s_job;
         __syncthreads();
-        if (cg >= n_jobs) break;
+        const int cg = job < n_jobs ? p.job_order[job] : n_jobs;
+        if (cg >= n_jobs) {
+            // [17] of the batch's first graph: cycles the blocks spent between their first and their last job
+            if (tid == 0 && p.stats)
+                atomicAdd((unsigned long long *)(p.stats + 17), (unsigned long long)(clock64() - t_block0));
+            break;
+        }
         const int c0 = p.cgraph_ptr[cg];
         const int n = p.cgraph_ptr[cg + 1] - c0;
         const int g = p.cgraph_win[cg];
@@ -1067,7 +1104,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
-    return a256(n * 8) * 4 + a256(n * 4) * 13 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 + a256(n * sizeof(Rec)) +
+    return a256(n * 8) * 4 + a256(n * 4) * 14 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 + a256(n * sizeof(Rec)) +
            a256((e + n + 8) * sizeof(StArc)) + a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
 }
 
@@ -1137,6 +1174,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     int32_t *cgraph_ptr = (int32_t *)take((n_cap + g) * 4);
     int32_t *win_cbase = (int32_t *)take(g * 4);
     p.win_wide = (int32_t *)take(g * 4);
+    p.job_order = (int32_t *)take(n_cap * 4);
     p.ws_rec = (Rec *)take(n_cap * sizeof(Rec));
     p.ws_arc = (StArc *)take((e_cap + n_cap + 8) * sizeof(StArc));
     const size_t cws_bytes = mot3d_components_workspace_bytes(n_total, n_graphs);
@@ -1154,9 +1192,11 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
                                 comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
     if (rc) return rc;
-    // 2. first shortest-path tree per graph
+    // 2. first shortest-path tree per graph; work queue order of the components
     k_first_tree<<<n_graphs, 256, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_tree");
+    k_job_order<<<1, 1024, 0, st>>>(p);
+    M3_LAUNCH_CHECK("k_job_order");
     // 3. successive shortest paths per component. Shared memory per block: the staging area for one branch, sized so
     //    that several blocks share an SM; blocks pull components from a work queue.
     // Graphs of up to 8192 detections are split into components (typically a few tracks each): small staging area

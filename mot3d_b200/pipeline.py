@@ -11,7 +11,9 @@ from . import _lib
 from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
 
 STAGES = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
-LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 3 + 2 + 1 + 1  # kernels launched by one run(): see the entry points in csrc/
+# kernels launched by one run() (see the entry points in csrc/): keys 2, node costs 1, frame sort 1, edge count 1,
+# scan 3, edge fill + cost 2, solve 7 (components 3, first tree, job order, solver, first-path rule), extract 1
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 3 + 2 + 7 + 1
 
 
 class TrackPipeline(object):
