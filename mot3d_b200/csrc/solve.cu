@@ -84,7 +84,8 @@ struct SolveParams {
     int32_t n_graphs;
     int32_t rec_cap;  // records / arcs of the shared-memory staging area
     int32_t arc_cap;
-    int32_t pad;
+    int32_t rcap;   // resident mode (solve_resident): records / arcs of a whole component, 0 = off
+    int32_t racap;
     int64_t n_total;
     const int32_t *graph_ptr;
     const int32_t *tkey;
@@ -160,6 +161,13 @@ __device__ __forceinline__ int block_excl_scan1(int v, int *scratch, int phase, 
 }
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
+
+// 32-bit costs of the packed / resident staging: NO_ARC32 stands for "no such arc" (cost >= INF_CUT)
+constexpr int NO_ARC32 = 0x7fffffff;
+__device__ __forceinline__ bool fits_narrow(int64_t v) {
+    return v >= INF_CUT || (v == (int64_t)(int)v && (int)v != NO_ARC32);
+}
+__device__ __forceinline__ int to_narrow(int64_t v) { return v >= INF_CUT ? NO_ARC32 : (int)v; }
 
 // Everything the per-augmentation work needs. Per-node arrays are indexed by regrouped position (global), and the
 // values they hold (parents, branches, next/prev) are regrouped positions as well.
@@ -740,6 +748,8 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
                 const int q = inv[j];
                 int anc = best.idx >= 0 ? p.ws_anc_post[best.idx] : -1;
                 const int64_t e_ = p.en[g0 + j];
+                const int64_t c_ = p.cn[g0 + j];
+                wide |= (fits_narrow(e_) && fits_narrow(p.ex[g0 + j]) && c_ == (int64_t)(int)c_) ? 0 : 1;
                 if (e_ < best.key) {
                     best.key = e_;
                     best.idx = PAR_S;
@@ -764,6 +774,576 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
         o[2] = 2 * (int64_t)n;
         o[3] = in_ptr[n] - in_ptr[0];
     }
+}
+
+// ===================================================================================================================
+// Resident mode: a component that fits the block's shared memory (the common case: one to five tracks) is staged
+// ONCE, solved path after path without touching global memory, and only its flow is written back. Same algorithm as
+// relabel_branch; what changes is where the state lives: records are the component's detections (slot = position in
+// the component, so every label -- parent, branch, next, prev -- is a slot), a record's arc list holds all its in-arcs
+// (their sources are in the component by construction), and the branch to re-label is a list of slots.
+// Costs are stored in 32 bits (k_first_tree checked that they fit; NO_ARC32 = no such arc), distances in 64.
+// ===================================================================================================================
+struct __align__(16) RRec {
+    int4 A;       // x = DL_PRE | DL_POST | DL_FIRST of the current branch, y = arc list (arcs_of), z = prev, w = next
+    int4 F;       // x = parent of the pre node (slot / PAR_*), y = branch of pre, z = branch of post, w = unused
+    longlong2 E;  // distance of pre, of post
+    int4 W;       // costs: S -> pre, pre -> post, post -> T, matched arc prev -> this
+};
+static_assert(sizeof(RRec) == 64, "resident record layout");
+constexpr int RES_BYTES_PER_REC = sizeof(RRec) + 4 + 3 * 2;  // + layer key + entries of the branch / hop / producer lists
+
+__device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, const int c0, const int n, const int g,
+                                            int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work,
+                                            const int sweep_warp) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
+    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
+    RRec *const rec = (RRec *)smem_raw;
+    PArc *const arc = (PArc *)(smem_raw + (size_t)p.rcap * sizeof(RRec));
+    int32_t *const tk = (int32_t *)(smem_raw + (size_t)p.rcap * sizeof(RRec) + (size_t)(p.racap + 8) * sizeof(PArc));
+    unsigned short *const bl = (unsigned short *)(tk + p.rcap);
+    unsigned short *const hop = bl + p.rcap;
+    unsigned short *const pl = hop + p.rcap;  // the branch's unused records with a post node to re-label, in order
+    auto arcs_of = [&](int ay) -> PArc * { return ay < 0 ? (PArc *)(p.ws_arc + ~ay) : arc + ay; };
+    const int32_t *perm = p.comp_perm + c0;
+
+    Counters cnt;
+    cnt.n_asc = cnt.n_desc = cnt.n_node = cnt.n_arc = cnt.n_branch = cnt.n_rec = 0;
+    for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
+    cnt.t_mark = clock64();
+
+    // ---- stage the component: records, then arc lists (offsets by a block scan over contiguous chunks)
+    const int chunk = (n + T - 1) / T;
+    const int i0 = min(tid * chunk, n), i1 = min(i0 + chunk, n);
+    {
+        int my_arcs = 0;
+        for (int i = i0; i < i1; i++) {
+            const int d = perm[i];
+            my_arcs += p.in_ptr[d + 1] - p.in_ptr[d] + 1;  // + 1: a list without arcs still carries its length
+        }
+        int tot;
+        int a0 = block_excl_scan1(my_arcs, s_scan, 0, &tot);
+        for (int i = i0; i < i1; i++) {
+            const int q = c0 + i, d = perm[i];
+            const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
+            int off = a0;
+            a0 += deg + 1;
+            if (off + deg + 1 > p.racap) off = ~(e0 + d);  // shared arc area full: this list lives in global memory
+            const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
+            RRec r;
+            r.A = make_int4(0, off, NONE, NONE);
+            r.F = make_int4(par >= 0 ? par - c0 : par, ap_ >= 0 ? ap_ - c0 : -1, ao_ >= 0 ? ao_ - c0 : -1, 0);
+            r.E = make_longlong2(p.ws_dpre[q], p.ws_dpost[q]);
+            r.W = make_int4(to_narrow(p.en[d]), (int)p.cn[d], to_narrow(p.ex[d]), 0);
+            rec[i] = r;
+            tk[i] = p.tkey[d];
+        }
+        if (tid == 0) cnt.n_arc += tot - n;
+    }
+    __syncthreads();
+    for (int ib = 0; ib < n; ib += ngrp) {
+        const int i = ib + grp;
+        if (i < n) {
+            const int d = perm[i];
+            const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
+            PArc *const ap = arcs_of(rec[i].A.y);
+            for (int k = sub; k < deg; k += LPN) {
+                PArc x;
+                x.cost = (int)p.in_cost[e0 + k];
+                x.src = (unsigned short)(p.comp_inv[p.in_src[e0 + k]] - c0);
+                x.pad = (unsigned short)deg;  // only read from the first arc of the list
+                ap[k] = x;
+            }
+            if (deg == 0 && sub == 0) {
+                PArc x;
+                x.cost = 0;
+                x.src = 0;
+                x.pad = 0;
+                ap[0] = x;
+            }
+        }
+    }
+    __syncthreads();
+    cnt.tick(2);
+
+    int K = 0;
+    int64_t total = 0;
+    for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+        // ---- cheapest way into T
+        KeyIdx best;
+        best.key = INF;
+        best.idx = -1;
+        for (int i = tid; i < n; i += T) {
+            const int64_t d = rec[i].E.y;
+            const int x = rec[i].W.z;
+            if (rec[i].A.w != TERM && d < INF_CUT && x != NO_ARC32) {
+                KeyIdx v;
+                v.key = d + x;
+                v.idx = i;
+                best = min_ki(best, v);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const KeyIdx o = shfl_xor_ki(best, d);
+            const bool take = o.key < best.key || (o.key == best.key && (unsigned)o.idx < (unsigned)best.idx);
+            best.key = take ? o.key : best.key;
+            best.idx = take ? o.idx : best.idx;
+        }
+        if (lane_id() == 0) s_red[warp_id()] = best;
+        __syncthreads();
+        KeyIdx sink;
+        sink.key = INF;
+        sink.idx = -1;
+        for (int k = 0; k < (T + 31) >> 5; k++) {
+            const KeyIdx o = s_red[k];
+            if (o.key < sink.key || (o.key == sink.key && (unsigned)o.idx < (unsigned)sink.idx)) sink = o;
+        }
+        __syncthreads();  // s_red is rewritten next iteration
+        cnt.tick(0);
+        if (sink.idx < 0) break;  // T unreachable
+        if (sink.key >= 0) {      // see k_ssp_solve: the first-path rule belongs to the whole graph
+            if (K == 0 && tid == 0) {
+                p.first_cost[cg] = sink.key;
+                p.first_sink[cg] = c0 + sink.idx;
+            }
+            break;
+        }
+        const int root = rec[sink.idx].F.z;
+        if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        __syncthreads();      // everybody has read the root before the flags are rewritten
+        // ---- the branch hanging from S -> pre_root, as a list of slots in layer order
+        int nd;
+        {
+            int my_nd = 0;
+            for (int i = i0; i < i1; i++) {
+                const int4 F = rec[i].F;
+                const int f = (F.y == root ? DL_PRE : 0) | (F.z == root ? DL_POST : 0);
+                rec[i].A.x = f;
+                my_nd += f ? 1 : 0;
+            }
+            int lp = block_excl_scan1(my_nd, s_scan, 1, &nd);
+            if (my_nd)
+                for (int i = i0; i < i1; i++)
+                    if (rec[i].A.x) bl[lp++] = (unsigned short)i;
+        }
+        __syncthreads();
+        for (int lp = tid; lp < nd; lp += T)
+            if (lp == 0 || tk[bl[lp]] != tk[bl[lp - 1]]) rec[bl[lp]].A.x |= DL_FIRST;
+        if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
+        cnt.n_branch++;
+        cnt.n_rec += nd;
+        cnt.tick(1);
+        // ---- augment: walk the path back from T and rewrite next/prev (Graph::flip_path, Graph.cpp:266-335)
+        if (tid == 0) {
+            int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx;
+            for (int step = 0; step <= n; step++) {
+                const int cur_prv = rec[cur].A.z, cur_nxt = rec[cur].A.w;
+                rec[cur].A.w = nxt_new;
+                int m;
+                if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
+                    m = cur;
+                } else {  // post_cur came from pre_m, m = its old successor: the arc cur -> m is cancelled
+                    m = cur_nxt;
+                    while (m >= 0 && rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
+                        const int m2 = rec[m].A.w;
+                        rec[m].A.w = NONE;
+                        rec[m].A.z = NONE;
+                        m = m2;
+                    }
+                }
+                if (m < 0) break;  // cannot happen on a consistent residual state
+                const int q = rec[m].F.x;
+                if (q < 0) {  // PAR_S: the path starts here
+                    rec[m].A.z = TERM;
+                    ok = 1;
+                    break;
+                }
+                rec[m].A.z = q;
+                hop[nhop++] = (unsigned short)m;  // the cost of the newly matched arc q -> m is looked up below
+                nxt_new = m;
+                cur = q;
+            }
+            s_ok[0] = ok;
+            s_ok[1] = nhop;
+        }
+        __syncthreads();
+        cnt.tick(3);
+        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        {  // the "producers" of the ascending sweeps (see below): every thread looks at two list entries
+            const int lp0 = min(2 * tid, nd), lp1 = min(lp0 + 2, nd);
+            int mine = 0;
+            for (int lp = lp0; lp < lp1; lp++) {
+                const int4 A = rec[bl[lp]].A;
+                mine += ((A.x & DL_POST) && A.z == NONE) ? 1 : 0;
+            }
+            int np;
+            int k = block_excl_scan1(mine, s_scan, 0, &np);
+            if (mine)
+                for (int lp = lp0; lp < lp1; lp++) {
+                    const int4 A = rec[bl[lp]].A;
+                    if ((A.x & DL_POST) && A.z == NONE) pl[k++] = bl[lp];
+                }
+            if (tid == 0) {
+                s_ok[6] = np;
+                s_ok[2] = s_ok[3] = s_ok[4] = s_ok[5] = 0;  // flags of the fix-point rounds
+            }
+        }
+        for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
+            const int m = hop[h], q = rec[m].A.z;
+            const PArc *const ap = arcs_of(rec[m].A.y);
+            const int deg = ap[0].pad;
+            for (int k = 0; k < deg; k++) {
+                const PArc x = ap[k];
+                if ((int)x.src == q) {
+                    rec[m].W.w = x.cost;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- new labels of the branch start from what cannot change during the fix-point: in-arcs from outside the
+        //      branch, the S arc, the own post node when it is outside. One lane group per record.
+        for (int sb = 0; sb < nd; sb += ngrp) {
+            const int lp = sb + grp;
+            const bool valid = lp < nd;
+            const int s = valid ? bl[lp] : 0;
+            const int4 A = rec[s].A;
+            KeyIdx cb;
+            cb.key = INF;
+            cb.idx = -1;
+            if (valid && (A.x & DL_PRE)) {
+                const PArc *const ap = arcs_of(A.y);
+                const int deg = ap[0].pad;
+                for (int k = sub; k < deg; k += LPN) {
+                    const PArc x = ap[k];
+                    const int64_t d = rec[x.src].E.y;
+                    if (!(rec[x.src].A.x & DL_POST) && (int)x.src != A.z && d < INF_CUT) {
+                        const int64_t cand = d + x.cost;
+                        if (cand < cb.key || (cand == cb.key && (unsigned)x.src < (unsigned)cb.idx)) {
+                            cb.key = cand;
+                            cb.idx = x.src;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 1; d < LPN; d <<= 1) {
+                const KeyIdx o = shfl_xor_ki(cb, d, gmask);
+                const bool take = o.key < cb.key || (o.key == cb.key && (unsigned)o.idx < (unsigned)cb.idx);
+                cb.key = take ? o.key : cb.key;
+                cb.idx = take ? o.idx : cb.idx;
+            }
+            // every lane of every group has finished reading its sources' post labels before any of them is reset
+            // (a record with DL_POST is never a source here, but its E/F words are rewritten as a whole)
+            __syncwarp();
+            if (valid && sub == 0) {
+                int4 F = rec[s].F;
+                const longlong2 E = rec[s].E;
+                const int4 W = rec[s].W;
+                int64_t key = INF, dpost_new = E.y;
+                int par = PAR_NONE, anc = -1;
+                if (A.x & DL_PRE) {
+                    if (cb.idx >= 0) {
+                        key = cb.key;
+                        par = cb.idx;
+                        anc = rec[cb.idx].F.z;
+                    }
+                    if (!(A.x & DL_POST) && A.z != NONE && E.y < INF_CUT && E.y - W.y < key) {
+                        key = E.y - W.y;  // own post node is outside the branch: a constant candidate
+                        par = PAR_POST;
+                        anc = F.z;
+                    }
+                    if (A.z != TERM && W.x != NO_ARC32 && W.x < key) {
+                        key = W.x;
+                        par = PAR_S;
+                        anc = s;
+                    }
+                    if (key >= INF_CUT) {
+                        key = INF;
+                        par = PAR_NONE;
+                        anc = -1;
+                    }
+                    F.x = par;
+                    F.y = anc;
+                }
+                if (A.x & DL_POST) {
+                    const bool unused_labelled = (A.x & DL_PRE) && A.z == NONE && key < INF_CUT;
+                    dpost_new = unused_labelled ? key + W.y : INF;
+                    F.z = unused_labelled ? anc : -1;
+                }
+                rec[s].E = make_longlong2((A.x & DL_PRE) ? key : E.x, dpost_new);
+                rec[s].F = F;
+            }
+        }
+        __syncthreads();
+        cnt.tick(2);
+        // ---- fix-point (see relabel_branch). Ascending sweep in two phases: (A) the unused records whose post label
+        //      is recomputed from their pre label are the only ones that pass a new label on to higher layers, they
+        //      go first, layer by layer, by one warp; (B) every other record only reads post labels that are final
+        //      for this sweep, so all of them are relaxed at once by the whole block, 8 lanes per record.
+        //      Descending pass: independent chain walks, one thread per track segment.
+        {
+            const int lane = lane_id(), wid = warp_id(), nw = (T + 31) >> 5;
+            const int r8 = lane >> 3, a8 = lane & 7;
+            int n_node32 = 0, n_arc32 = 0, n_astep = 0, n_dstep = 0;
+            long long t_asc = 0, t_desc = 0, t0 = clock64();
+            const int np = s_ok[6];  // producers (list pl)
+            // relax the pre node of record s over its in-arcs, S and its own post node, then its post node; 8 lanes.
+            // Returns true if a change can travel along a reversed arc (to lower layers).
+            auto relax = [&](const int s, const bool valid) -> bool {
+                const RRec *rp = rec + s;
+                const int4 A = rp->A, W = rp->W;
+                int4 F = rp->F;
+                const longlong2 E = rp->E;
+                const int ent = valid ? A.x : 0;
+                KeyIdx best;
+                best.key = INF;
+                best.idx = -1;
+                int deg = 0;
+                if (ent & DL_PRE) {
+                    const PArc *const ap = arcs_of(A.y);
+                    const PArc x0 = ap[a8];  // speculative: the first arc also carries the list length
+                    deg = ap[0].pad;
+                    if (a8 < deg) {
+                        const int64_t d = rec[x0.src].E.y;
+                        if ((int)x0.src != A.z && d < INF_CUT) {
+                            best.key = d + x0.cost;
+                            best.idx = x0.src;
+                        }
+                    }
+                    for (int k = a8 + 8; k < deg; k += 8) {
+                        const PArc x = ap[k];
+                        const int64_t d = rec[x.src].E.y;
+                        if ((int)x.src != A.z && d < INF_CUT &&
+                            (d + x.cost < best.key || (d + x.cost == best.key && (unsigned)x.src < (unsigned)best.idx))) {
+                            best.key = d + x.cost;
+                            best.idx = x.src;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {  // lowest slot wins ties
+                    const KeyIdx o = shfl_xor_ki(best, d);
+                    const bool take = o.key < best.key || (o.key == best.key && (unsigned)o.idx < (unsigned)best.idx);
+                    best.key = take ? o.key : best.key;
+                    best.idx = take ? o.idx : best.idx;
+                }
+                bool down = false;
+                if (ent != 0 && a8 == 0) {
+                    int64_t dpre_s = E.x, dpost_s = E.y;
+                    bool upd = false;
+                    if (ent & DL_PRE) {
+                        int64_t key = INF;
+                        int par = PAR_NONE, anc = -1;
+                        if (best.idx >= 0) {
+                            key = best.key;
+                            par = best.idx;
+                            anc = rec[best.idx].F.z;
+                        }
+                        if (A.z != TERM && W.x != NO_ARC32 && W.x < key) {
+                            key = W.x;
+                            par = PAR_S;
+                            anc = s;
+                        }
+                        if (A.z != NONE && dpost_s < INF_CUT && dpost_s - W.y < key) {
+                            key = dpost_s - W.y;
+                            par = PAR_POST;
+                            anc = F.z;
+                        }
+                        if (key < dpre_s) {
+                            dpre_s = key;
+                            F.x = par;
+                            F.y = anc;
+                            upd = true;
+                            down = A.z >= 0;  // pre_s feeds the post node of its predecessor on the track
+                        }
+                        n_arc32 += deg;
+                    }
+                    // The post node of a record on a track hangs from its successor's pre node: that is the descending
+                    // pass's business, and it keeps every post label read during phase (B) stable.
+                    if ((ent & DL_POST) && A.z == NONE && dpre_s < INF_CUT && dpre_s + W.y < dpost_s) {
+                        dpost_s = dpre_s + W.y;
+                        F.z = F.y;
+                        upd = true;
+                    }
+                    if (upd) {
+                        rec[s].E = make_longlong2(dpre_s, dpost_s);
+                        rec[s].F = F;
+                    }
+                }
+                return down;
+            };
+            for (int round = 0; round < 2 * nd + 4; round++) {
+                const int pb = round & 1;
+                if (round > 0) {  // round 0: the initial labels stand in for the ascending sweep
+                    bool down = false;
+                    if (wid == sweep_warp) {  // (A) producers, one layer at a time
+                        for (int q = 0; q < np;) {
+                            const int k = q + r8;
+                            const bool in_range = k < np;
+                            const int s = pl[in_range ? k : np - 1];
+                            const bool same = in_range && tk[s] == tk[pl[q]];
+                            const unsigned m = __ballot_sync(0xffffffffu, a8 == 0 && !same) & 0x01010100u;
+                            const int cn_t = m ? (__ffs(m) - 1) >> 3 : 4;
+                            down |= relax(s, r8 < cn_t);
+                            n_node32 += cn_t;
+                            n_astep++;
+                            q += cn_t;
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                    for (int base = 0; base < nd; base += 4 * nw) {  // (B) everything else, all at once
+                        const int lp = base + 4 * wid + r8;
+                        const bool in_range = lp < nd;
+                        const int s = bl[in_range ? lp : nd - 1];
+                        const int f = rec[s].A.x;
+                        const bool producer = (f & DL_POST) && rec[s].A.z == NONE;
+                        down |= relax(s, in_range && !producer);
+                        n_astep++;
+                    }
+                    if (wid == 0) n_node32 += nd - np;
+                    if (__any_sync(0xffffffffu, down) && lane == 0) s_ok[2 + pb] = 1;
+                    if (wid == sweep_warp && lane == 0) s_work[0] += 1;
+                    __syncthreads();
+                    {
+                        const long long t1 = clock64();
+                        t_asc += t1 - t0;
+                        t0 = t1;
+                    }
+                    if (!s_ok[2 + pb]) break;  // nothing can travel down: fix-point
+                }
+                // descending pass: every thread looks at its share of the list
+                bool up = false;
+                for (int lp = tid; lp < nd; lp += T) {
+                    const int s0 = bl[lp];
+                    int4 A = rec[s0].A;
+                    if (A.z == NONE) {
+                        if (A.x & DL_POST) {
+                            const longlong2 E = rec[s0].E;
+                            const int cn = rec[s0].W.y;
+                            if (E.x < INF_CUT && E.x + cn < E.y) {
+                                rec[s0].E.y = E.x + cn;
+                                rec[s0].F.z = rec[s0].F.y;
+                                up = true;
+                            }
+                        }
+                        continue;
+                    }
+                    if ((A.x & DL_POST) && A.w >= 0) continue;  // reached from its successor's walk
+                    // on a track, successor not in the branch: a segment starts here; walk it down
+                    int cur = s0;
+                    int4 W = rec[cur].W, F = rec[cur].F;
+                    longlong2 E = rec[cur].E;
+                    int64_t nx_dpre = INF;
+                    int nx_mc = 0, nx_apre = -1;
+                    for (;;) {
+                        // the predecessor's post node hangs from pre_cur: it is in the branch when pre_cur is
+                        const int prv = ((A.x & DL_PRE) && A.z >= 0) ? A.z : -1;
+                        int4 An = A, Wn = W, Fn = F;
+                        longlong2 En = E;
+                        if (prv >= 0) {  // fetch the next record of the walk before working on this one
+                            const RRec *rn = rec + prv;
+                            An = rn->A;
+                            Wn = rn->W;
+                            Fn = rn->F;
+                            En = rn->E;
+                        }
+                        const int ent = A.x;
+                        int64_t dpre_s = E.x, dpost_s = E.y;
+                        bool upd = false;
+                        if ((ent & DL_POST) && nx_dpre < INF_CUT && nx_dpre - nx_mc < dpost_s) {
+                            dpost_s = nx_dpre - nx_mc;
+                            F.z = nx_apre;
+                            upd = true;
+                            up = true;  // forward arcs leave post_s: the ascending sweep has to come back
+                        }
+                        if ((ent & DL_PRE) && (ent & DL_POST) && dpost_s < INF_CUT && dpost_s - W.y < dpre_s) {
+                            dpre_s = dpost_s - W.y;
+                            F.x = PAR_POST;
+                            F.y = F.z;
+                            upd = true;
+                        }
+                        if (upd) {
+                            rec[cur].E = make_longlong2(dpre_s, dpost_s);
+                            rec[cur].F = F;
+                        }
+                        n_dstep++;
+                        if (prv < 0) break;
+                        nx_dpre = dpre_s;
+                        nx_mc = W.w;
+                        nx_apre = F.y;
+                        cur = prv;
+                        A = An;
+                        W = Wn;
+                        F = Fn;
+                        E = En;
+                    }
+                }
+                if (__any_sync(0xffffffffu, up) && lane == 0) s_ok[4 + pb] = 1;
+                if (tid == 0) {
+                    s_ok[2 + (pb ^ 1)] = 0;  // the next round's flags
+                    s_ok[4 + (pb ^ 1)] = 0;
+                    s_work[1] += 1;
+                }
+                __syncthreads();
+                {
+                    const long long t1 = clock64();
+                    t_desc += t1 - t0;
+                    t0 = t1;
+                }
+                if (!s_ok[4 + pb] && round > 0) break;  // nothing can travel up: fix-point
+            }
+            // work counters of this branch
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                n_arc32 += __shfl_xor_sync(0xffffffffu, n_arc32, d);
+                n_dstep += __shfl_xor_sync(0xffffffffu, n_dstep, d);
+            }
+            if (lane == 0) {
+                atomicAdd((unsigned long long *)&s_work[2], (unsigned long long)(n_node32 + n_dstep));
+                atomicAdd((unsigned long long *)&s_work[3], (unsigned long long)n_arc32);
+                atomicAdd((unsigned long long *)&s_work[7], (unsigned long long)n_dstep);
+                if (wid == sweep_warp) {
+                    s_work[4] += t_asc;
+                    s_work[5] += t_desc;
+                    atomicAdd((unsigned long long *)&s_work[6], (unsigned long long)n_astep);
+                }
+            }
+        }
+        __syncthreads();
+        cnt.tick(4);
+        K++;
+        total += sink.key;
+    }
+    // ---- results of this component: flow in detection indices, totals added to its graph
+    __syncthreads();
+    if (tid == 0) {
+        if (K) {
+            atomicAdd(&p.n_paths[g], K);
+            atomicAdd((unsigned long long *)&p.total[g], (unsigned long long)total);
+        }
+        if (p.stats) {
+            unsigned long long *o = (unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g);
+            atomicAdd(&o[0], (unsigned long long)(cnt.n_asc + s_work[0]));
+            atomicAdd(&o[1], (unsigned long long)(cnt.n_desc + s_work[1]));
+            atomicAdd(&o[2], (unsigned long long)(cnt.n_node + s_work[2]));
+            atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
+            for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
+            atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
+            atomicAdd(&o[12], (unsigned long long)cnt.n_rec);
+            for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
+        }
+    }
+    for (int i = tid; i < n; i += T) {
+        const int a = rec[i].A.w, b = rec[i].A.z;
+        const int d = perm[i];
+        p.next_out[d] = a >= 0 ? perm[a] : a;
+        p.prev_out[d] = b >= 0 ? perm[b] : b;
+    }
+    __syncthreads();
 }
 
 // ---- work queue order: largest components first (longest-processing-time-first keeps the tail of the solver short:
@@ -796,10 +1376,10 @@ __global__ void __launch_bounds__(1024) k_job_order(const SolveParams p) {
 }
 
 // ---- successive shortest paths on every component graph. Blocks fetch components from a work queue.
-__global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
+__global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ SolveParams p) {
     __shared__ int s_scan[64];
     __shared__ KeyIdx s_red[33];
-    __shared__ int s_ok[2], s_sweep_warp, s_job;
+    __shared__ int s_ok[8], s_sweep_warp, s_job;
     // sweep warp's counters: ascending sweeps, descending sweeps, node pulls, arc pulls, cycles in ascending /
     // descending sweeps, ascending / descending steps
     __shared__ long long s_work[8];
@@ -838,6 +1418,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
         const int job = s_job;
         __syncthreads();
         const int cg = job < n_jobs ? p.job_order[job] : n_jobs;
+        const long long t_job0 = clock64();  // DEBUG
         if (cg >= n_jobs) {
             // [17] of the batch's first graph: cycles the blocks spent between their first and their last job
             if (tid == 0 && p.stats)
@@ -849,6 +1430,11 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
         const int g = p.cgraph_win[cg];
         if (n <= 0 || p.n_paths[g] < 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
         const bool wide = p.win_wide[g] != 0;
+        if (n <= p.rcap && !wide) {  // the whole component fits: solve it without leaving shared memory
+            solve_resident(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
+            if (tid == 0 && p.stats && p.n_graphs > 2) atomicMax((unsigned long long *)(p.stats + 17 + MOT3D_SOLVE_STATS), (unsigned long long)(clock64() - t_job0));  // DEBUG
+            continue;
+        }
         Ctx c;
         c.p = &p;
         c.c0 = c0;
@@ -1001,6 +1587,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const SolveParams p) {
                 for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
             }
         }
+        if (tid == 0 && p.stats && p.n_graphs > 2) atomicMax((unsigned long long *)(p.stats + 17 + 2 * MOT3D_SOLVE_STATS), (unsigned long long)(clock64() - t_job0));  // DEBUG
         for (int i = tid; i < n; i += T) {
             const int a = p.ws_nxt[c0 + i], b = p.ws_prv[c0 + i];
             const int d = perm[i];
@@ -1136,7 +1723,8 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     };
     SolveParams p;
     p.n_graphs = n_graphs;
-    p.pad = 0;
+    p.rcap = 0;
+    p.racap = 0;
     p.n_total = (int64_t)n_total;
     p.graph_ptr = graph_ptr;
     p.tkey = tkey;
@@ -1223,6 +1811,17 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.rec_cap = (int32_t)rec_cap;
     p.arc_cap = (int32_t)arc_cap;
     const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
+    {
+        // resident mode shares the same shared memory: as many records as the largest graph can need, the rest arcs
+        size_t rcap = max_graph_nodes <= 1024 ? 448 : 256;
+        if (rcap > (size_t)((max_graph_nodes + 7) & ~7)) rcap = (size_t)((max_graph_nodes + 7) & ~7);
+        if (rcap < 32) rcap = 32;
+        if (const char *e = getenv("MOT3D_SOLVE_RESIDENT")) rcap = (size_t)atoi(e) & ~(size_t)7;
+        if (rcap && smem >= 16 + rcap * RES_BYTES_PER_REC + (64 + 8) * ARC_BYTES) {
+            p.rcap = (int32_t)rcap;
+            p.racap = (int32_t)((smem - 16 - rcap * RES_BYTES_PER_REC) / ARC_BYTES - 8);
+        }
+    }
     int threads = 128;
     if (const char *e = getenv("MOT3D_SOLVE_THREADS")) {
         const int t = atoi(e);
