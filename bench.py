@@ -337,7 +337,6 @@ def run_ours(args):
                 "sweep_steps_per_graph_mean": {"ascending": float(stats[:, 15].mean()),
                                                "descending": float(stats[:, 16].mean())},
                 "solver_block_busy_cycles": float(stats[0, 17]),
-                "dbg_max_job_cycles_resident": float(stats[1, 17]), "dbg_max_job_cycles_general": float(stats[2, 17]),
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
                 "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(

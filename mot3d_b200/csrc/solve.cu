@@ -1,91 +1,105 @@
-// Min-cost-flow solve: successive shortest paths on the residual network, one thread block per graph.
+// Min-cost-flow solve: successive shortest paths on the residual network, one thread block per connected component.
 //
 // Replaces wrapper.solve (reference mot3d/solvers/wrappers/muSSP/wrapper.cpp:171-317) and the muSSP core it drives
 // (zip!/muSSP-master/muSSP/Graph.cpp).  Same network, same path-update rule, same acceptance rule, exact int64:
 //   network        S -> pre_i (entry), pre_i -> post_i (node cost), post_i -> T (exit), post_i -> pre_j (transition);
 //                  unit capacities                                   (mot3d/mot3d.py:75-141)
 //   first tree     one relaxation pass over the frame layers         (Graph::shortest_path_dag, Graph.cpp:139-187)
+//   components     a graph falls apart into connected components (csrc/components.cu); each one is a job of the work
+//                  queue, staged ONCE into the block's shared memory (records = its detections, arc lists = their
+//                  in-arcs; every label -- parent, branch, next, prev -- is a slot of that staging area), solved path
+//                  after path without global traffic, and only its flow is written back. Components that do not fit
+//                  (or whose costs need more than 32 bits) run the same code on a staging area in global memory.
 //   next paths     muSSP's observation (Graph.cpp:341-343, 394-503): after a path through S -> pre_a is flipped,
 //                  only the branch of the shortest-path tree that hung from that arc loses its labels; every
-//                  other node keeps its exact distance.  The branch is collected (in frame-layer order) into
-//                  shared memory together with its in-arcs and re-labelled by an exact Bellman-Ford fix-point in
-//                  pull mode: ascending layer order settles the forward arcs, descending order settles the
-//                  reversed arcs (they only run backwards in time along tracks); the two alternate until nothing
-//                  moves.  No tolerances, no heap.
+//                  other node keeps its exact distance.  The branch is listed in frame-layer order and re-labelled
+//                  by an exact Bellman-Ford fix-point in pull mode: ascending layer order settles the forward arcs,
+//                  a descending pass settles the reversed arcs (they only run backwards in time along tracks); the
+//                  two alternate until nothing moves.  No tolerances, no heap.
 //   path update    reverse the arcs of the path                      (Graph::flip_path, Graph.cpp:266-335); with unit
-//                  capacities the residual state is just next[]/prev[] per detection
+//                  capacities the residual state is just next/prev per detection
 //   acceptance     path 1 always; path k >= 2 while its cost < 0     (wrapper.cpp:199-267 on integers)
-// Flow read-out (make_output2, wrapper.cpp:139-169) is unnecessary: next[]/prev[] are the flow.
+// Flow read-out (make_output2, wrapper.cpp:139-169) is unnecessary: next/prev are the flow.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace m3 {
 
-constexpr int LPN = 4;  // lanes cooperating on one node's in-arcs
+constexpr int LPN = 4;  // lanes cooperating on one node's in-arcs (first tree, initial labels)
 
-// state markers (local indices are >= 0)
+// state markers (slots / positions are >= 0)
 constexpr int NONE = -1;  // detection unused
 constexpr int TERM = -2;  // next: track ends here (post->T saturated); prev: track starts here (S->pre saturated)
 constexpr int PAR_S = -1;     // pre reached from S
 constexpr int PAR_POST = -2;  // pre reached from its own post (reversed node arc)
 constexpr int PAR_NONE = -3;
-constexpr int DL_PRE = 1 << 29;  // work-record flags: the detection's pre / post node is to be re-labelled
+constexpr int DL_PRE = 1 << 29;  // branch flags of a record: its pre / post node is being re-labelled
 constexpr int DL_POST = 1 << 30;
-constexpr int DL_FIRST = 1 << 28;  // first record of its frame layer (set while staging)
-constexpr int DL_MASK = DL_FIRST - 1;
+constexpr int DL_FIRST = 1 << 28;  // first record of its frame layer in the branch list
 
-// Staging area for the branch being re-labelled: nd records + their in-arcs from inside the branch. It lives in
-// shared memory when the branch fits (the common case: ~150 of 10 000 nodes on a C5 window) and in the global
-// workspace otherwise. A record = one detection of the branch with everything the path walk and the sweeps need,
-// packed in 16-byte groups so that a step is a handful of 128-bit shared-memory loads:
-//   A  node | flags, (a0 << 16 | adeg) = its staged in-arcs, pslot = slot of prev, prv = prev (node id / marker)
-//   B  nslot = slot of next, parslot = slot of the parent, bpar / banc = parent and branch of the best candidate
-//      that cannot change during the fix-point (in-arcs from outside the branch, own post node outside the branch)
-//   C  bkey = that candidate's distance, en = S->pre cost        D  cn = pre->post cost, mc = cost of prev->this
-//   E  dpre, dpost (the labels being recomputed)                 F  par, apre, apost (labels), nxt (node id / marker)
-struct __align__(16) Rec {
-    int4 A, B;
-    longlong2 C, D, E;
-    int4 F;
+// ---- staging area of a component, two flavours:
+//   SM = true   shared memory; costs in 32 bits (k_first_tree checked that they fit; NO_ARC32 = no such arc), slots
+//               in 16 bits. 64-byte records, 8-byte arcs.
+//   SM = false  global workspace; 64-bit costs, 32-bit slots: any size, any cost. 80-byte records, 16-byte arcs.
+// A record, in 16-byte groups so that a relaxation is a handful of 128-bit loads:
+//   A  x = DL_* flags of the current branch, y = arc list (see arcs_of), z = prev, w = next (slots / NONE / TERM)
+//   F  x = parent of the pre node (slot / PAR_*), y = branch of pre, z = branch of post (slot of the detection whose
+//      S -> pre arc starts the node's tree path; muSSP's ancestor_node_id, Graph.cpp:160-161)
+//   E  exact distances from S of pre and post (the invariant the incremental update relies on)
+//   W  costs: S -> pre, pre -> post, post -> T, matched arc prev -> this
+constexpr int NO_ARC32 = 0x7fffffff;
+__device__ __forceinline__ bool fits_narrow(int64_t v) {
+    return v >= INF_CUT || (v == (int64_t)(int)v && (int)v != NO_ARC32);
+}
+struct __align__(16) Cost4 {
+    int64_t x, y, z, w;
 };
-struct __align__(16) StArc {
-    long long cost;
-    int src;  // slot of the source record
-    int pad;
-};
-// Shared-memory flavour of a staged arc, half the size: used when every transition cost of the graph fits 32 bits
-// (always the case for the built-in cost functions: weights in [-1, 0] -> [-1e7, 0]); graphs with wider costs take
-// the global staging area. src / pad of the first arc of a list = length of the list, like StArc.
-struct __align__(8) PArc {
+struct __align__(8) PArc {  // the first arc of a list also carries the length of the list in pad
     int cost;
     unsigned short src;
     unsigned short pad;
 };
+struct __align__(16) StArc {
+    long long cost;
+    int src;
+    int pad;
+};
 template <bool SM>
-struct ArcOf {
-    typedef StArc type;
+struct Staging;
+template <>
+struct Staging<true> {
+    typedef int4 costs_t;
+    typedef int cost_t;
+    typedef PArc arc_t;
+    typedef unsigned short slot_t;
+    static __device__ __forceinline__ int conv(int64_t v) { return v >= INF_CUT ? NO_ARC32 : (int)v; }
+    static __device__ __forceinline__ bool has(int v) { return v != NO_ARC32; }
 };
 template <>
-struct ArcOf<true> {
-    typedef PArc type;
+struct Staging<false> {
+    typedef Cost4 costs_t;
+    typedef int64_t cost_t;
+    typedef StArc arc_t;
+    typedef int slot_t;
+    static __device__ __forceinline__ int64_t conv(int64_t v) { return v; }
+    static __device__ __forceinline__ bool has(int64_t v) { return v < INF_CUT; }
 };
 template <bool SM>
-struct Stage {
-    Rec *rec;
-    typename ArcOf<SM>::type *arc;
-    int32_t *tk;  // frame-layer key per record (only used to flag the first record of every layer)
+struct __align__(16) RecT {
+    int4 A, F;
+    longlong2 E;
+    typename Staging<SM>::costs_t W;
 };
-constexpr int REC_BYTES = sizeof(Rec) + 4;
-constexpr int ARC_BYTES = sizeof(PArc);
-static_assert(sizeof(Rec) == 96, "record layout");
+static_assert(sizeof(RecT<true>) == 64 && sizeof(RecT<false>) == 80, "record layout");
+constexpr int SM_BYTES_PER_REC = sizeof(RecT<true>) + 4 + 3 * 2;  // + layer key + entries of the three slot lists
+constexpr int SM_ARC_BYTES = sizeof(PArc);
 
 struct SolveParams {
     int32_t n_graphs;
-    int32_t rec_cap;  // records / arcs of the shared-memory staging area
-    int32_t arc_cap;
-    int32_t rcap;   // resident mode (solve_resident): records / arcs of a whole component, 0 = off
+    int32_t rcap;   // shared-memory staging area: records / arcs (0 = off)
     int32_t racap;
+    int32_t pad;
     int64_t n_total;
     const int32_t *graph_ptr;
     const int32_t *tkey;
@@ -108,28 +122,25 @@ struct SolveParams {
     const int32_t *cgraph_ptr;  // [n_cgraphs + 1] regrouped positions
     const int32_t *cgraph_win;  // [n_cgraphs] graph of every component
     const int32_t *win_cbase;   // [n_graphs] first component of every graph
-    int32_t *win_wide;          // [n_graphs] 1 = some transition cost does not fit 32 bits (k_first_tree)
+    int32_t *win_wide;          // [n_graphs] 1 = some cost does not fit 32 bits (k_first_tree)
     int32_t *job_order;         // [n_cgraphs] component graphs, largest first (k_job_order)
     int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
-    // per-node state in the regrouped order, values are regrouped positions too:
-    int64_t *ws_dpre;   // exact distances from S (the invariant the incremental update relies on)
+    // first shortest-path tree (k_first_tree), per regrouped position; values are regrouped positions too
+    int64_t *ws_dpre;
     int64_t *ws_dpost;
-    int64_t *ws_mcost;  // cost of the matched in-arc prev -> this
-    int32_t *ws_par;    // parent of the pre node: PAR_S / PAR_POST / PAR_NONE / position of the source detection
+    int32_t *ws_par;       // parent of the pre node: PAR_S / PAR_NONE / position of the source detection
     int32_t *ws_anc_pre;   // branch = position of the detection whose S->pre arc starts the node's tree path
-    int32_t *ws_anc_post;  // (muSSP's ancestor_node_id, Graph.cpp:160-161)
-    int32_t *ws_nxt;    // flow: successor position / TERM / NONE
-    int32_t *ws_prv;
-    int32_t *ws_slot_of;
-    int32_t *ws_dl;
-    int32_t *ws_dla0;
-    int32_t *ws_lvl;  // [n_total + n_graphs] frame layers (first tree)
-    // fallback staging area for branches that do not fit in shared memory
-    Rec *ws_rec;      // n_total
-    int32_t *ws_tk;   // n_total
-    StArc *ws_arc;    // arc_capacity + n_total + 8
+    int32_t *ws_anc_post;
+    int32_t *ws_lvl;       // [n_total + n_graphs] frame layers
+    // global staging area (components that do not fit shared memory; spilled arc lists of those that do)
+    RecT<false> *ws_rec;   // [n_total]
+    int32_t *ws_tk;        // [n_total] layer keys
+    int32_t *ws_bl;        // [n_total] x 3 slot lists
+    int32_t *ws_hop;
+    int32_t *ws_pl;
+    StArc *ws_arc;         // [arc_capacity + n_total + 8]: the list of detection d starts at in_ptr[d] + d
 };
 
 __device__ __forceinline__ KeyIdx group_min(KeyIdx best, unsigned mask) {
@@ -162,28 +173,10 @@ __device__ __forceinline__ int block_excl_scan1(int v, int *scratch, int phase, 
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-// 32-bit costs of the packed / resident staging: NO_ARC32 stands for "no such arc" (cost >= INF_CUT)
-constexpr int NO_ARC32 = 0x7fffffff;
-__device__ __forceinline__ bool fits_narrow(int64_t v) {
-    return v >= INF_CUT || (v == (int64_t)(int)v && (int)v != NO_ARC32);
-}
-__device__ __forceinline__ int to_narrow(int64_t v) { return v >= INF_CUT ? NO_ARC32 : (int)v; }
-
-// Everything the per-augmentation work needs. Per-node arrays are indexed by regrouped position (global), and the
-// values they hold (parents, branches, next/prev) are regrouped positions as well.
-struct Ctx {
-    const SolveParams *p;
-    int c0, n;  // the component graph = positions [c0, c0 + n)
-    int64_t *dpre, *dpost, *mcost;
-    int32_t *par, *anc_pre, *anc_post, *slot_of, *nxt, *prv;
-    int32_t *dl, *dla0;  // scratch lists of this component (offset by c0)
-    const int32_t *perm, *inv;
-};
-
 struct Counters {
-    int64_t n_asc, n_desc, n_node, n_arc;
-    int64_t n_branch, n_rec;  // branches re-labelled, records staged
-    long long t_phase[7];  // cycles (thread 0): arg-min, collect, stage, walk, sweeps, write-back, first tree
+    int64_t n_arc;            // arcs read while staging
+    int64_t n_branch, n_rec;  // branches re-labelled, records listed for them
+    long long t_phase[7];  // cycles (thread 0): arg-min, branch list, staging + initial labels, walk, fix-point, -, -
     long long t_mark;
     __device__ __forceinline__ void tick(int k) {
         const long long now = clock64();
@@ -191,478 +184,6 @@ struct Counters {
         t_mark = now;
     }
 };
-
-// Stage the branch (nd records, listed in dl[]), flip the path that ends in `sink_node`, re-label the branch,
-// write it back. SM = the staging area is in shared memory (the compiler then emits LDS/STS), otherwise in the
-// global workspace. Returns false if the walk found an inconsistent state (cannot happen).
-template <bool SM>
-__device__ __forceinline__ bool relabel_branch(const Ctx &c, int nd, int atot, int root, int sink_node, int *s_ok,
-                                               long long *s_work, int sweep_warp, Counters &cnt) {
-    const SolveParams &p = *c.p;
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
-    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);  // the lanes of this thread's group
-    const int gshift = (tid & 31) / LPN * LPN;
-    typedef typename ArcOf<SM>::type Arc;
-    Stage<SM> st;
-    if (SM) {
-        st.rec = (Rec *)smem_raw;
-        st.arc = (Arc *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec));
-        st.tk = (int32_t *)(smem_raw + (size_t)p.rec_cap * sizeof(Rec) + (size_t)(p.arc_cap + 8) * sizeof(Arc));
-    } else {
-        st.rec = p.ws_rec + c.c0;
-        st.arc = (Arc *)p.ws_arc;  // a record's arcs sit at in_ptr[d] + d: room for its in-degree + the end marker
-        st.tk = p.ws_tk + c.c0;
-    }
-    // arc list of a record: A.y >= 0 = offset in the staging area, < 0 = ~offset in the global area. The global area
-    // is addressed in StArc units whatever the arc type, so that the lists of different detections never overlap
-    // (other blocks may be using it with the wide arcs at the same time).
-    auto arcs_of = [&](int ay) -> Arc * { return (SM && ay < 0) ? (Arc *)(p.ws_arc + ~ay) : st.arc + ay; };
-    // ---- stage the branch: one lane group per record
-    for (int sb = 0; sb < nd; sb += ngrp) {
-        const int s = sb + grp;
-        const bool valid = s < nd;
-        const int ent = valid ? c.dl[s] : 0;
-        const int j = ent & DL_MASK;            // regrouped position
-        const int dj = valid ? c.perm[j] : 0;   // detection
-        KeyIdx cbest;  // best in-arc from outside the branch
-        cbest.key = INF;
-        cbest.idx = PAR_NONE;
-        int nda = 0, a0 = 0;
-        if (valid && (ent & DL_PRE)) {
-            const int e0 = p.in_ptr[dj], deg = p.in_ptr[dj + 1] - e0;
-            a0 = SM ? c.dla0[s] : e0 + dj;
-            // shared arc area full: this record's list goes to the global area (the records stay in shared memory)
-            if (SM && a0 + deg + 1 > p.arc_cap) a0 = ~(e0 + dj);
-            Arc *const ap = arcs_of(a0);
-            for (int k0 = 0; k0 < deg; k0 += LPN) {
-                const int k = k0 + sub;
-                const bool has = k < deg;
-                int i = -1, a = -2;
-                int64_t w = 0, di = INF;
-                if (has) {
-                    i = c.inv[p.in_src[e0 + k]];
-                    w = p.in_cost[e0 + k];
-                    a = c.anc_post[i];
-                    di = c.dpost[i];
-                }
-                const bool inside = has && a == root;
-                const unsigned m = (__ballot_sync(gmask, inside) >> gshift) & 0xFu;
-                if (inside) {
-                    Arc x;
-                    x.cost = (decltype(x.cost))w;
-                    x.src = (decltype(x.src))c.slot_of[i];
-                    x.pad = 0;
-                    ap[nda + __popc(m & ((1u << sub) - 1u))] = x;
-                } else if (has && di < INF_CUT) {
-                    const int64_t cand = di + w;
-                    if (cand < cbest.key) {
-                        cbest.key = cand;
-                        cbest.idx = i;
-                    }
-                }
-                nda += __popc(m);
-            }
-        }
-        cbest = group_min(cbest, gmask);
-        if (valid && sub == 0) {
-            const int64_t dpre_j = c.dpre[j], dpost_j = c.dpost[j], cn_j = p.cn[dj];
-            const int prv_j = c.prv[j], nxt_j = c.nxt[j], par_j = c.par[j];
-            const int apost_j = c.anc_post[j];
-            int64_t bkey = cbest.key;
-            int bpar = cbest.idx, banc = cbest.idx >= 0 ? c.anc_post[cbest.idx] : -1;
-            if ((ent & DL_PRE) && !(ent & DL_POST) && prv_j != NONE && dpost_j < INF_CUT) {
-                const int64_t v = dpost_j - cn_j;  // own post node is outside the branch: a constant candidate
-                if (v < bkey) {
-                    bkey = v;
-                    bpar = PAR_POST;
-                    banc = apost_j;
-                }
-            }
-            Rec r;
-            r.A = make_int4(ent, a0, ((ent & DL_PRE) && prv_j >= 0) ? c.slot_of[prv_j] : -1, prv_j);
-            if (ent & DL_PRE) {
-                Arc x;
-                x.cost = 0;
-                x.src = 0;
-                x.pad = 0;
-                Arc *const ap = arcs_of(a0);
-                ap[nda] = x;  // one spare slot, so that a record without staged arcs still has a length
-                ap[0].pad = (decltype(x.pad))nda;  // the first slot also carries the length of the list
-            }
-            r.B = make_int4(((ent & DL_POST) && nxt_j >= 0) ? c.slot_of[nxt_j] : -1,
-                            ((ent & DL_PRE) && par_j >= 0) ? c.slot_of[par_j] : -1, bpar, banc);
-            r.C = make_longlong2(bkey, p.en[dj]);
-            r.D = make_longlong2(cn_j, c.mcost[j]);
-            r.E = make_longlong2(dpre_j, dpost_j);
-            r.F = make_int4(par_j, c.anc_pre[j], apost_j, nxt_j);
-            st.rec[s] = r;
-            st.tk[s] = p.tkey[dj];
-        }
-    }
-    __syncthreads();
-    cnt.tick(2);
-    // ---- augment: walk the path back from T inside the staged branch and rewrite next/prev
-    //      (Graph::flip_path, Graph.cpp:266-335). One thread.
-    if (tid == 0) {
-        int ok = 0, nhop = 0;
-        int nxt_new = TERM, nxt_new_slot = -1;
-        int cur = c.slot_of[sink_node];
-        for (int step = 0; step <= nd; step++) {
-            int m;
-            const int cur_prv = st.rec[cur].A.w, cur_ns = st.rec[cur].B.x;
-            st.rec[cur].F.w = nxt_new;
-            st.rec[cur].B.x = nxt_new_slot;
-            if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
-                m = cur;
-            } else {  // post_cur came from pre_m, m = its old successor: the arc cur->m is cancelled
-                m = cur_ns;
-                while (m >= 0 && st.rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
-                    const int m2 = st.rec[m].B.x;
-                    st.rec[m].F.w = NONE;
-                    st.rec[m].B.x = -1;
-                    st.rec[m].A.w = NONE;
-                    st.rec[m].A.z = -1;
-                    m = m2;
-                }
-            }
-            if (m < 0) break;  // cannot happen on a consistent residual state
-            const int4 mA = st.rec[m].A;
-            const int q = st.rec[m].F.x, qs = st.rec[m].B.y;
-            if (q < 0) {  // PAR_S: the path starts here
-                st.rec[m].A.w = TERM;
-                st.rec[m].A.z = -1;
-                ok = 1;
-                break;
-            }
-            st.rec[m].A.w = q;
-            st.rec[m].A.z = qs;
-            c.dla0[nhop++] = m;  // the cost of the newly matched arc q -> m is looked up in parallel below
-            nxt_new = mA.x & DL_MASK;
-            nxt_new_slot = m;
-            cur = qs;
-        }
-        *s_ok = ok;
-        s_ok[1] = nhop;
-    }
-    __syncthreads();
-    cnt.tick(3);
-    if (!*s_ok) return false;
-    for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
-        const int m = c.dla0[h];
-        const int qs = st.rec[m].A.z;
-        const Arc *const ap = arcs_of(st.rec[m].A.y);
-        const int deg = ap[0].pad;
-        for (int k = 0; k < deg; k++) {
-            const Arc x = ap[k];
-            if ((int)x.src == qs) {
-                st.rec[m].D.y = x.cost;
-                break;
-            }
-        }
-    }
-    // ---- un-label the branch; flag the first record of every layer (DL_FIRST) for the sweeps
-    for (int s = tid; s < nd; s += T) {
-        int ent = st.rec[s].A.x;
-        if (s == 0 || st.tk[s] != st.tk[s - 1]) {
-            ent |= DL_FIRST;
-            st.rec[s].A.x = ent;
-        }
-        // New labels start from what cannot change during the fix-point (the best arc from outside the branch, the
-        // S arc) instead of "unreachable": that is exactly what a first ascending sweep would find for the records
-        // on tracks, so the sweeps below start with a descending one.
-        int64_t key = INF;
-        int par = PAR_NONE, anc = -1;
-        if (ent & DL_PRE) {
-            const Rec *r = st.rec + s;
-            key = r->C.x;
-            par = r->B.z;
-            anc = r->B.w;
-            if (r->A.w != TERM && r->C.y < key) {
-                key = r->C.y;
-                par = PAR_S;
-                anc = ent & DL_MASK;
-            }
-            if (key >= INF_CUT) {
-                key = INF;
-                par = PAR_NONE;
-                anc = -1;
-            }
-            st.rec[s].E.x = key;
-            st.rec[s].F.x = par;
-            st.rec[s].F.y = anc;
-        }
-        if (ent & DL_POST) {
-            const bool unused_labelled = (ent & DL_PRE) && st.rec[s].A.w == NONE && key < INF_CUT;
-            st.rec[s].E.y = unused_labelled ? key + st.rec[s].D.x : INF;
-            st.rec[s].F.z = unused_labelled ? anc : -1;
-        }
-    }
-    __syncthreads();
-    // ---- re-label it: exact Bellman-Ford fix-point in pull mode by ONE warp. Ascending order settles the forward
-    //      arcs, a descending pass settles the reversed arcs (they run backwards in time along tracks); the two
-    //      alternate until nothing moves.
-    if (warp_id() == sweep_warp) {
-        const int lane = lane_id();
-        int n_node32 = 0, n_arc32 = 0, n_asc32 = 0, n_desc32 = 0, n_astep = 0, n_dstep = 0;
-        long long t_asc = 0, t_desc = 0, t0 = clock64();
-        // The ascending sweep only has to revisit what can still change: it starts at the lowest record whose post
-        // label the previous descending pass changed.
-        int asc_from = 0;
-        for (int round = 0; round < 2 * nd + 4; round++) {
-            int hi_ch = (round == 0) ? nd - 1 : -1;  // round 0: the initial labels stand in for the ascending sweep
-            if (round > 0) n_asc32++;
-            for (int q = (round == 0) ? nd : asc_from; q < nd;) {
-                // One step = up to 4 records, 8 lanes per record (one per in-arc). Forward arcs only leave post
-                // nodes, and during an ascending sweep the post label of a record on a track does not depend on
-                // lower layers (it hangs from its successor's pre node): only UNUSED records pass a freshly computed
-                // label on. So a step may run across layer boundaries until it has taken such a record.
-                const int r8 = lane >> 3, a8 = lane & 7;
-                const int s = q + r8;
-                const bool in_range = s < nd;
-                const Rec *rp = st.rec + (in_range ? s : nd - 1);
-                int4 A = rp->A, B = rp->B, F = rp->F;
-                const longlong2 C = rp->C, D = rp->D, E = rp->E;
-                // one ballot, three questions: lane 8r = "record r passes a new label on", lane 8r + 1 = "record r
-                // starts a layer", lane 8r + 2 = "record r is out of range"
-                const bool q0 = in_range && (A.x & DL_POST) && A.w == NONE;
-                const bool q1 = (A.x & DL_FIRST) != 0;
-                const unsigned vt = __ballot_sync(0xffffffffu, a8 == 0 ? q0 : (a8 == 1 ? q1 : (a8 == 2 && !in_range)));
-                int cn_t = 4;
-                {
-                    unsigned prod = vt & 1u;
-                    if (((vt >> 26) & 1u) | (((vt >> 25) & 1u) & (prod | ((vt >> 8) & 1u) | ((vt >> 16) & 1u)))) cn_t = 3;
-                    if (((vt >> 18) & 1u) | (((vt >> 17) & 1u) & (prod | ((vt >> 8) & 1u)))) cn_t = 2;
-                    if (((vt >> 10) & 1u) | (((vt >> 9) & 1u) & prod)) cn_t = 1;
-                }
-                const bool valid = r8 < cn_t;
-                const int ent = valid ? A.x : 0;
-                // next record on the track (higher layer) and this record's in-arcs from inside the branch: all
-                // loads are issued before anything is decided
-                int64_t nx_dpre = INF, nx_mc = 0;
-                int nx_apre = -1;
-                KeyIdx best;  // idx = slot of the source; "none" = INF with the largest unsigned idx
-                best.key = INF;
-                best.idx = -1;
-                int deg = 0;
-                if (ent & DL_PRE) {
-                    const Arc *const ap = arcs_of(A.y);
-                    const Arc x0 = ap[a8];  // speculative: issued together with the list length
-                    deg = ap[0].pad;
-                    if (a8 < deg) {
-                        const int64_t d = st.rec[x0.src].E.y;
-                        if ((int)x0.src != A.z && d < INF_CUT) {
-                            best.key = d + x0.cost;
-                            best.idx = x0.src;
-                        }
-                    }
-                    for (int k = a8 + 8; k < deg; k += 8) {
-                        const Arc x = ap[k];
-                        const int64_t d = st.rec[x.src].E.y;
-                        if ((int)x.src != A.z && d < INF_CUT && d + x.cost < best.key) {
-                            best.key = d + x.cost;
-                            best.idx = x.src;
-                        }
-                    }
-                }
-                if (valid && B.x >= 0 && a8 == 0) {
-                    const Rec *r = st.rec + B.x;
-                    nx_dpre = r->E.x;
-                    nx_mc = r->D.y;
-                    nx_apre = r->F.y;
-                }
-#pragma unroll
-                for (int d = 1; d < 8; d <<= 1) {  // slots ascend with the detection index: lowest slot wins ties
-                    const KeyIdx o = shfl_xor_ki(best, d);
-                    const bool take = o.key < best.key || (o.key == best.key && (unsigned)o.idx < (unsigned)best.idx);
-                    best.key = take ? o.key : best.key;
-                    best.idx = take ? o.idx : best.idx;
-                }
-                if (valid && a8 == 0) {
-                    int64_t dpre_s = E.x, dpost_s = E.y;
-                    bool upd = false, down = false;  // down: the change can travel along a reversed arc
-                    if (ent & DL_PRE) {
-                        int64_t key = INF;
-                        int par = PAR_NONE, anc = -1;
-                        if (best.idx >= 0) {
-                            key = best.key;
-                            par = st.rec[best.idx].A.x & DL_MASK;
-                            anc = st.rec[best.idx].F.z;
-                        }
-                        if (C.x < key || (C.x == key && B.z >= 0 && B.z < par)) {
-                            key = C.x;
-                            par = B.z;
-                            anc = B.w;
-                        }
-                        if (A.w != TERM && C.y < key) {
-                            key = C.y;
-                            par = PAR_S;
-                            anc = ent & DL_MASK;
-                        }
-                        if ((ent & DL_POST) && A.w != NONE && dpost_s < INF_CUT && dpost_s - D.x < key) {
-                            key = dpost_s - D.x;
-                            par = PAR_POST;
-                            anc = F.z;
-                        }
-                        if (key < dpre_s) {
-                            dpre_s = key;
-                            F.x = par;
-                            F.y = anc;
-                            upd = true;
-                            down = A.z >= 0;  // pre_s feeds the post node of its predecessor on the track
-                        }
-                        n_arc32 += deg;
-                    }
-                    if (ent & DL_POST) {
-                        int64_t v = INF;
-                        int a = -1;
-                        if (A.w == NONE) {
-                            if (dpre_s < INF_CUT) {
-                                v = dpre_s + D.x;
-                                a = F.y;
-                            }
-                        } else if (nx_dpre < INF_CUT) {
-                            v = nx_dpre - nx_mc;
-                            a = nx_apre;
-                        }
-                        if (v < dpost_s) {
-                            dpost_s = v;
-                            F.z = a;
-                            upd = true;
-                            down = down || A.w != NONE;  // post_s feeds its own pre node (reversed node arc)
-                        }
-                    }
-                    if (upd) {
-                        st.rec[s].E = make_longlong2(dpre_s, dpost_s);
-                        st.rec[s].F = F;
-                        if (down) hi_ch = s;
-                    }
-                }
-                n_node32 += cn_t;
-                n_astep++;
-                q += cn_t;
-                __syncwarp();
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) hi_ch = max(hi_ch, __shfl_xor_sync(0xffffffffu, hi_ch, d));
-            {
-                const long long t1 = clock64();
-                t_asc += t1 - t0;
-                t0 = t1;
-            }
-            if (hi_ch < 0) break;  // nothing moved: fix-point
-            // Descending pass. Reversed arcs only connect a record with its successor on the track (post_s hangs
-            // from pre_next) and the two nodes of a record on a track (pre_s hangs from post_s): the pass falls apart
-            // into independent chains, one per track segment inside the branch. Every lane looks at its share of the
-            // records; the lane that finds the last record of a segment walks the segment down on its own, no
-            // warp-wide step per layer. Unused records only forward pre -> post.
-            int lo_ch = nd;
-            n_desc32++;
-            for (int sb = 0; sb < nd; sb += 32) {
-                int cur = sb + lane;
-                bool head = false;
-                if (cur < nd) {
-                    const int4 A = st.rec[cur].A;
-                    if (A.w == NONE) {
-                        if (A.x & DL_POST) {
-                            const longlong2 E = st.rec[cur].E;
-                            if (E.x < INF_CUT && E.x + st.rec[cur].D.x < E.y) {
-                                st.rec[cur].E.y = E.x + st.rec[cur].D.x;
-                                st.rec[cur].F.z = st.rec[cur].F.y;
-                                lo_ch = min(lo_ch, cur);
-                            }
-                        }
-                    } else {
-                        head = st.rec[cur].B.x < 0;  // on a track, successor not in the branch
-                    }
-                }
-                int64_t nx_dpre = INF, nx_mc = 0;
-                int nx_apre = -1;
-                if (!head) cur = -1;
-                while (cur >= 0) {
-                    const Rec *rp = st.rec + cur;
-                    const int4 A = rp->A;
-                    int4 F = rp->F;
-                    const longlong2 D = rp->D, E = rp->E;
-                    const int ent = A.x;
-                    int64_t dpre_s = E.x, dpost_s = E.y;
-                    bool upd = false;
-                    if ((ent & DL_POST) && nx_dpre < INF_CUT && nx_dpre - nx_mc < dpost_s) {
-                        dpost_s = nx_dpre - nx_mc;
-                        F.z = nx_apre;
-                        upd = true;
-                        lo_ch = min(lo_ch, cur);  // forward arcs leave post_s: the ascending sweep has to come back
-                    }
-                    if ((ent & DL_PRE) && (ent & DL_POST) && dpost_s < INF_CUT && dpost_s - D.x < dpre_s) {
-                        dpre_s = dpost_s - D.x;
-                        F.x = PAR_POST;
-                        F.y = F.z;
-                        upd = true;
-                    }
-                    if (upd) {
-                        st.rec[cur].E = make_longlong2(dpre_s, dpost_s);
-                        st.rec[cur].F = F;
-                    }
-                    nx_dpre = (ent & DL_PRE) ? dpre_s : INF;
-                    nx_mc = D.y;
-                    nx_apre = F.y;
-                    cur = A.z;  // predecessor on the track (its post node hangs from pre_cur), -1 = segment ends
-                    n_dstep++;
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) lo_ch = min(lo_ch, __shfl_xor_sync(0xffffffffu, lo_ch, d));
-            {
-                const long long t1 = clock64();
-                t_desc += t1 - t0;
-                t0 = t1;
-            }
-            if (lo_ch >= nd && round > 0) break;  // nothing moved: fix-point
-            asc_from = (round == 0) ? 0 : lo_ch;   // the initial labels ignored arcs inside the branch: full sweep
-        }
-        // work counters of this branch (the leaders of the lane groups counted the arcs)
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            n_arc32 += __shfl_xor_sync(0xffffffffu, n_arc32, d);
-            n_dstep += __shfl_xor_sync(0xffffffffu, n_dstep, d);
-        }
-        if (lane == 0) {
-            s_work[0] += n_asc32;
-            s_work[1] += n_desc32;
-            s_work[2] += n_node32 + n_dstep;  // records visited: ascending steps + hops of the descending chains
-            s_work[3] += n_arc32;
-            s_work[4] += t_asc;
-            s_work[5] += t_desc;
-            s_work[6] += n_astep;
-            s_work[7] += n_dstep;
-        }
-    }
-    __syncthreads();
-    cnt.tick(4);
-    // ---- write the branch back
-    for (int s = tid; s < nd; s += T) {
-        const Rec r = st.rec[s];
-        const int ent = r.A.x;
-        const int j = ent & DL_MASK;
-        if (ent & DL_PRE) {
-            c.dpre[j] = r.E.x;
-            c.par[j] = r.F.x;
-            c.anc_pre[j] = r.F.y;
-        }
-        if (ent & DL_POST) {
-            c.dpost[j] = r.E.y;
-            c.anc_post[j] = r.F.z;
-        }
-        c.nxt[j] = r.F.w;
-        c.prv[j] = r.A.w;
-        c.mcost[j] = r.D.y;
-    }
-    if (tid == 0) cnt.n_arc += atot;  // arcs read while staging
-    __syncthreads();
-    cnt.tick(5);
-    return true;
-}
 
 // ---- first shortest-path tree of every graph (before it is split into components): no flow yet, the network is a
 //      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
@@ -693,14 +214,11 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     }
     for (int i = tid; i < n; i += T) {  // regrouped positions of this graph are [g0, g0 + n) as well
         const int q = g0 + i;
-        p.ws_nxt[q] = NONE;
-        p.ws_prv[q] = NONE;
         p.ws_dpre[q] = INF;
         p.ws_dpost[q] = INF;
         p.ws_par[q] = PAR_NONE;
         p.ws_anc_pre[q] = -1;
         p.ws_anc_post[q] = -1;
-        p.ws_mcost[q] = 0;
         p.first_cost[q] = INF;
         p.first_sink[q] = -1;
         if (p.path_cost) p.path_cost[q] = INF;
@@ -776,40 +294,48 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     }
 }
 
-// ===================================================================================================================
-// Resident mode: a component that fits the block's shared memory (the common case: one to five tracks) is staged
-// ONCE, solved path after path without touching global memory, and only its flow is written back. Same algorithm as
-// relabel_branch; what changes is where the state lives: records are the component's detections (slot = position in
-// the component, so every label -- parent, branch, next, prev -- is a slot), a record's arc list holds all its in-arcs
-// (their sources are in the component by construction), and the branch to re-label is a list of slots.
-// Costs are stored in 32 bits (k_first_tree checked that they fit; NO_ARC32 = no such arc), distances in 64.
-// ===================================================================================================================
-struct __align__(16) RRec {
-    int4 A;       // x = DL_PRE | DL_POST | DL_FIRST of the current branch, y = arc list (arcs_of), z = prev, w = next
-    int4 F;       // x = parent of the pre node (slot / PAR_*), y = branch of pre, z = branch of post, w = unused
-    longlong2 E;  // distance of pre, of post
-    int4 W;       // costs: S -> pre, pre -> post, post -> T, matched arc prev -> this
-};
-static_assert(sizeof(RRec) == 64, "resident record layout");
-constexpr int RES_BYTES_PER_REC = sizeof(RRec) + 4 + 3 * 2;  // + layer key + entries of the branch / hop / producer lists
-
-__device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, const int c0, const int n, const int g,
-                                            int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work,
-                                            const int sweep_warp) {
+// Solve one component: positions [c0, c0 + n) of graph g. SM = staging area in shared memory (see Staging).
+template <bool SM>
+__device__ __noinline__ void solve_component(const SolveParams &p, const int cg, const int c0, const int n, const int g,
+                                             int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work,
+                                             const int sweep_warp) {
+    typedef Staging<SM> S;
+    typedef RecT<SM> Rec;
+    typedef typename S::arc_t Arc;
+    typedef typename S::costs_t Costs;
+    typedef typename S::cost_t Cost;
+    typedef typename S::slot_t Slot;
     const int T = blockDim.x, tid = threadIdx.x;
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
     const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
-    RRec *const rec = (RRec *)smem_raw;
-    PArc *const arc = (PArc *)(smem_raw + (size_t)p.rcap * sizeof(RRec));
-    int32_t *const tk = (int32_t *)(smem_raw + (size_t)p.rcap * sizeof(RRec) + (size_t)(p.racap + 8) * sizeof(PArc));
-    unsigned short *const bl = (unsigned short *)(tk + p.rcap);
-    unsigned short *const hop = bl + p.rcap;
-    unsigned short *const pl = hop + p.rcap;  // the branch's unused records with a post node to re-label, in order
-    auto arcs_of = [&](int ay) -> PArc * { return ay < 0 ? (PArc *)(p.ws_arc + ~ay) : arc + ay; };
+    // slot lists: bl = the branch in layer order, hop = detections whose matched in-arc changed, pl = the branch's
+    // unused records with a post node to re-label ("producers" of the ascending sweep)
+    Rec *rec;
+    Arc *arc;
+    int32_t *tk;
+    Slot *bl, *hop, *pl;
+    if (SM) {
+        rec = (Rec *)smem_raw;
+        arc = (Arc *)(smem_raw + (size_t)p.rcap * sizeof(Rec));
+        tk = (int32_t *)(smem_raw + (size_t)p.rcap * sizeof(Rec) + (size_t)(p.racap + 8) * sizeof(Arc));
+        bl = (Slot *)(tk + p.rcap);
+        hop = bl + p.rcap;
+        pl = hop + p.rcap;
+    } else {
+        rec = (Rec *)(p.ws_rec + c0);
+        arc = nullptr;
+        tk = p.ws_tk + c0;
+        bl = (Slot *)(p.ws_bl + c0);
+        hop = (Slot *)(p.ws_hop + c0);
+        pl = (Slot *)(p.ws_pl + c0);
+    }
+    // arc list of a record: A.y >= 0 = offset in the shared arc area, < 0 = ~offset in the global area. The global
+    // area is addressed in StArc units whatever the arc type, so that lists of different detections never overlap.
+    auto arcs_of = [&](int ay) -> Arc * { return (!SM || ay < 0) ? (Arc *)(p.ws_arc + ~ay) : arc + ay; };
     const int32_t *perm = p.comp_perm + c0;
 
     Counters cnt;
-    cnt.n_asc = cnt.n_desc = cnt.n_node = cnt.n_arc = cnt.n_branch = cnt.n_rec = 0;
+    cnt.n_arc = cnt.n_branch = cnt.n_rec = 0;
     for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
     cnt.t_mark = clock64();
 
@@ -829,13 +355,16 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
             const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
             int off = a0;
             a0 += deg + 1;
-            if (off + deg + 1 > p.racap) off = ~(e0 + d);  // shared arc area full: this list lives in global memory
+            if (!SM || off + deg + 1 > p.racap) off = ~(e0 + d);  // (shared arc area full:) the list lives in global memory
             const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
-            RRec r;
+            Rec r;
             r.A = make_int4(0, off, NONE, NONE);
             r.F = make_int4(par >= 0 ? par - c0 : par, ap_ >= 0 ? ap_ - c0 : -1, ao_ >= 0 ? ao_ - c0 : -1, 0);
             r.E = make_longlong2(p.ws_dpre[q], p.ws_dpost[q]);
-            r.W = make_int4(to_narrow(p.en[d]), (int)p.cn[d], to_narrow(p.ex[d]), 0);
+            r.W.x = S::conv(p.en[d]);
+            r.W.y = S::conv(p.cn[d]);
+            r.W.z = S::conv(p.ex[d]);
+            r.W.w = 0;
             rec[i] = r;
             tk[i] = p.tkey[d];
         }
@@ -847,16 +376,16 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
         if (i < n) {
             const int d = perm[i];
             const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
-            PArc *const ap = arcs_of(rec[i].A.y);
+            Arc *const ap = arcs_of(rec[i].A.y);
             for (int k = sub; k < deg; k += LPN) {
-                PArc x;
-                x.cost = (int)p.in_cost[e0 + k];
-                x.src = (unsigned short)(p.comp_inv[p.in_src[e0 + k]] - c0);
-                x.pad = (unsigned short)deg;  // only read from the first arc of the list
+                Arc x;
+                x.cost = (decltype(x.cost))p.in_cost[e0 + k];
+                x.src = (decltype(x.src))(p.comp_inv[p.in_src[e0 + k]] - c0);
+                x.pad = (decltype(x.pad))deg;  // only read from the first arc of the list
                 ap[k] = x;
             }
             if (deg == 0 && sub == 0) {
-                PArc x;
+                Arc x;
                 x.cost = 0;
                 x.src = 0;
                 x.pad = 0;
@@ -876,8 +405,8 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
         best.idx = -1;
         for (int i = tid; i < n; i += T) {
             const int64_t d = rec[i].E.y;
-            const int x = rec[i].W.z;
-            if (rec[i].A.w != TERM && d < INF_CUT && x != NO_ARC32) {
+            const Cost x = rec[i].W.z;
+            if (rec[i].A.w != TERM && d < INF_CUT && S::has(x)) {
                 KeyIdx v;
                 v.key = d + x;
                 v.idx = i;
@@ -926,7 +455,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
             int lp = block_excl_scan1(my_nd, s_scan, 1, &nd);
             if (my_nd)
                 for (int i = i0; i < i1; i++)
-                    if (rec[i].A.x) bl[lp++] = (unsigned short)i;
+                    if (rec[i].A.x) bl[lp++] = (Slot)i;
         }
         __syncthreads();
         for (int lp = tid; lp < nd; lp += T)
@@ -961,7 +490,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                     break;
                 }
                 rec[m].A.z = q;
-                hop[nhop++] = (unsigned short)m;  // the cost of the newly matched arc q -> m is looked up below
+                hop[nhop++] = (Slot)m;  // the cost of the newly matched arc q -> m is looked up below
                 nxt_new = m;
                 cur = q;
             }
@@ -971,8 +500,9 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
         __syncthreads();
         cnt.tick(3);
         if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
-        {  // the "producers" of the ascending sweeps (see below): every thread looks at two list entries
-            const int lp0 = min(2 * tid, nd), lp1 = min(lp0 + 2, nd);
+        {  // the "producers" of the ascending sweeps (see below): every thread looks at a chunk of the list
+            const int lchunk = (nd + T - 1) / T;
+            const int lp0 = min(tid * lchunk, nd), lp1 = min(lp0 + lchunk, nd);
             int mine = 0;
             for (int lp = lp0; lp < lp1; lp++) {
                 const int4 A = rec[bl[lp]].A;
@@ -992,10 +522,10 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
         }
         for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
             const int m = hop[h], q = rec[m].A.z;
-            const PArc *const ap = arcs_of(rec[m].A.y);
+            const Arc *const ap = arcs_of(rec[m].A.y);
             const int deg = ap[0].pad;
             for (int k = 0; k < deg; k++) {
-                const PArc x = ap[k];
+                const Arc x = ap[k];
                 if ((int)x.src == q) {
                     rec[m].W.w = x.cost;
                     break;
@@ -1014,10 +544,10 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
             cb.key = INF;
             cb.idx = -1;
             if (valid && (A.x & DL_PRE)) {
-                const PArc *const ap = arcs_of(A.y);
+                const Arc *const ap = arcs_of(A.y);
                 const int deg = ap[0].pad;
                 for (int k = sub; k < deg; k += LPN) {
-                    const PArc x = ap[k];
+                    const Arc x = ap[k];
                     const int64_t d = rec[x.src].E.y;
                     if (!(rec[x.src].A.x & DL_POST) && (int)x.src != A.z && d < INF_CUT) {
                         const int64_t cand = d + x.cost;
@@ -1041,7 +571,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
             if (valid && sub == 0) {
                 int4 F = rec[s].F;
                 const longlong2 E = rec[s].E;
-                const int4 W = rec[s].W;
+                const Costs W = rec[s].W;
                 int64_t key = INF, dpost_new = E.y;
                 int par = PAR_NONE, anc = -1;
                 if (A.x & DL_PRE) {
@@ -1055,7 +585,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                         par = PAR_POST;
                         anc = F.z;
                     }
-                    if (A.z != TERM && W.x != NO_ARC32 && W.x < key) {
+                    if (A.z != TERM && S::has(W.x) && W.x < key) {
                         key = W.x;
                         par = PAR_S;
                         anc = s;
@@ -1093,8 +623,9 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
             // relax the pre node of record s over its in-arcs, S and its own post node, then its post node; 8 lanes.
             // Returns true if a change can travel along a reversed arc (to lower layers).
             auto relax = [&](const int s, const bool valid) -> bool {
-                const RRec *rp = rec + s;
-                const int4 A = rp->A, W = rp->W;
+                const Rec *rp = rec + s;
+                const int4 A = rp->A;
+                const Costs W = rp->W;
                 int4 F = rp->F;
                 const longlong2 E = rp->E;
                 const int ent = valid ? A.x : 0;
@@ -1103,8 +634,8 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                 best.idx = -1;
                 int deg = 0;
                 if (ent & DL_PRE) {
-                    const PArc *const ap = arcs_of(A.y);
-                    const PArc x0 = ap[a8];  // speculative: the first arc also carries the list length
+                    const Arc *const ap = arcs_of(A.y);
+                    const Arc x0 = ap[a8];  // speculative: the first arc also carries the list length
                     deg = ap[0].pad;
                     if (a8 < deg) {
                         const int64_t d = rec[x0.src].E.y;
@@ -1114,7 +645,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                         }
                     }
                     for (int k = a8 + 8; k < deg; k += 8) {
-                        const PArc x = ap[k];
+                        const Arc x = ap[k];
                         const int64_t d = rec[x.src].E.y;
                         if ((int)x.src != A.z && d < INF_CUT &&
                             (d + x.cost < best.key || (d + x.cost == best.key && (unsigned)x.src < (unsigned)best.idx))) {
@@ -1142,7 +673,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                             par = best.idx;
                             anc = rec[best.idx].F.z;
                         }
-                        if (A.z != TERM && W.x != NO_ARC32 && W.x < key) {
+                        if (A.z != TERM && S::has(W.x) && W.x < key) {
                             key = W.x;
                             par = PAR_S;
                             anc = s;
@@ -1223,7 +754,7 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                     if (A.z == NONE) {
                         if (A.x & DL_POST) {
                             const longlong2 E = rec[s0].E;
-                            const int cn = rec[s0].W.y;
+                            const Cost cn = rec[s0].W.y;
                             if (E.x < INF_CUT && E.x + cn < E.y) {
                                 rec[s0].E.y = E.x + cn;
                                 rec[s0].F.z = rec[s0].F.y;
@@ -1235,17 +766,19 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
                     if ((A.x & DL_POST) && A.w >= 0) continue;  // reached from its successor's walk
                     // on a track, successor not in the branch: a segment starts here; walk it down
                     int cur = s0;
-                    int4 W = rec[cur].W, F = rec[cur].F;
+                    Costs W = rec[cur].W;
+                    int4 F = rec[cur].F;
                     longlong2 E = rec[cur].E;
-                    int64_t nx_dpre = INF;
-                    int nx_mc = 0, nx_apre = -1;
+                    int64_t nx_dpre = INF, nx_mc = 0;
+                    int nx_apre = -1;
                     for (;;) {
                         // the predecessor's post node hangs from pre_cur: it is in the branch when pre_cur is
                         const int prv = ((A.x & DL_PRE) && A.z >= 0) ? A.z : -1;
-                        int4 An = A, Wn = W, Fn = F;
+                        int4 An = A, Fn = F;
+                        Costs Wn = W;
                         longlong2 En = E;
                         if (prv >= 0) {  // fetch the next record of the walk before working on this one
-                            const RRec *rn = rec + prv;
+                            const Rec *rn = rec + prv;
                             An = rn->A;
                             Wn = rn->W;
                             Fn = rn->F;
@@ -1327,9 +860,9 @@ __device__ __noinline__ void solve_resident(const SolveParams &p, const int cg, 
         }
         if (p.stats) {
             unsigned long long *o = (unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g);
-            atomicAdd(&o[0], (unsigned long long)(cnt.n_asc + s_work[0]));
-            atomicAdd(&o[1], (unsigned long long)(cnt.n_desc + s_work[1]));
-            atomicAdd(&o[2], (unsigned long long)(cnt.n_node + s_work[2]));
+            atomicAdd(&o[0], (unsigned long long)s_work[0]);
+            atomicAdd(&o[1], (unsigned long long)s_work[1]);
+            atomicAdd(&o[2], (unsigned long long)s_work[2]);
             atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
             for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
             atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
@@ -1380,16 +913,16 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
     __shared__ int s_scan[64];
     __shared__ KeyIdx s_red[33];
     __shared__ int s_ok[8], s_sweep_warp, s_job;
-    // sweep warp's counters: ascending sweeps, descending sweeps, node pulls, arc pulls, cycles in ascending /
-    // descending sweeps, ascending / descending steps
+    // counters of the fix-point rounds: ascending sweeps, descending passes, node pulls, arc pulls, cycles in ascending
+    // sweeps / descending passes, ascending steps / descending hops
     __shared__ long long s_work[8];
 
     const int T = blockDim.x;
     const int tid = threadIdx.x;
-    // Which warp runs the sequential sweeps: blocks sharing an SM should use different SM sub-partitions (warp
-    // schedulers), otherwise their sweep warps fight for one issue port. %warpid is the hardware warp slot; slots
-    // of a block are consecutive, slot % 4 = sub-partition. Pick the warp whose sub-partition equals the block's
-    // slot group.
+    // Which warp runs the sequential part of the ascending sweeps: blocks sharing an SM should use different SM
+    // sub-partitions (warp schedulers), otherwise those warps fight for one issue port. %warpid is the hardware warp
+    // slot; slots of a block are consecutive, slot % 4 = sub-partition. Pick the warp whose sub-partition equals the
+    // block's slot group.
     if (tid % 32 == 0) {
         unsigned hw;
         asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
@@ -1417,184 +950,21 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
         __syncthreads();
         const int job = s_job;
         __syncthreads();
-        const int cg = job < n_jobs ? p.job_order[job] : n_jobs;
-        const long long t_job0 = clock64();  // DEBUG
-        if (cg >= n_jobs) {
+        if (job >= n_jobs) {
             // [17] of the batch's first graph: cycles the blocks spent between their first and their last job
             if (tid == 0 && p.stats)
                 atomicAdd((unsigned long long *)(p.stats + 17), (unsigned long long)(clock64() - t_block0));
             break;
         }
+        const int cg = p.job_order[job];
         const int c0 = p.cgraph_ptr[cg];
         const int n = p.cgraph_ptr[cg + 1] - c0;
         const int g = p.cgraph_win[cg];
         if (n <= 0 || p.n_paths[g] < 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
-        const bool wide = p.win_wide[g] != 0;
-        if (n <= p.rcap && !wide) {  // the whole component fits: solve it without leaving shared memory
-            solve_resident(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
-            if (tid == 0 && p.stats && p.n_graphs > 2) atomicMax((unsigned long long *)(p.stats + 17 + MOT3D_SOLVE_STATS), (unsigned long long)(clock64() - t_job0));  // DEBUG
-            continue;
-        }
-        Ctx c;
-        c.p = &p;
-        c.c0 = c0;
-        c.n = n;
-        c.dpre = p.ws_dpre;
-        c.dpost = p.ws_dpost;
-        c.mcost = p.ws_mcost;
-        c.par = p.ws_par;
-        c.anc_pre = p.ws_anc_pre;
-        c.anc_post = p.ws_anc_post;
-        c.slot_of = p.ws_slot_of;
-        c.nxt = p.ws_nxt;
-        c.prv = p.ws_prv;
-        c.dl = p.ws_dl + c0;
-        c.dla0 = p.ws_dla0 + c0;
-        c.perm = p.comp_perm;
-        c.inv = p.comp_inv;
-        const int64_t *dpost = p.ws_dpost + c0;
-        const int32_t *nxt = p.ws_nxt + c0, *anc_pre = p.ws_anc_pre + c0, *anc_post = p.ws_anc_post + c0;
-        const int32_t *perm = p.comp_perm + c0;
-
-        int K = 0;
-        int64_t total = 0;
-        Counters cnt;
-        cnt.n_asc = 0;
-        cnt.n_desc = 0;
-        cnt.n_node = 0;
-        cnt.n_arc = 0;
-        cnt.n_branch = 0;
-        cnt.n_rec = 0;
-        for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
-        cnt.t_mark = clock64();
-
-        for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
-            // ---- cheapest way into T (Graph::update_sink_info's job, Graph.cpp:508-541; here a block-wide arg-min)
-            KeyIdx best;
-            best.key = INF;
-            best.idx = -1;
-#pragma unroll 4
-            for (int i = tid; i < n; i += T) {
-                const int64_t d = dpost[i], x = p.ex[perm[i]];
-                const int nx = nxt[i];
-                if (nx != TERM && d < INF_CUT && x < INF_CUT) {
-                    KeyIdx v;
-                    v.key = d + x;
-                    v.idx = c0 + i;
-                    best = min_ki(best, v);
-                }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                KeyIdx o = shfl_xor_ki(best, d);
-                if (o.idx >= 0 && (best.idx < 0 || o.key < best.key || (o.key == best.key && o.idx < best.idx)))
-                    best = o;
-            }
-            if (lane_id() == 0) s_red[warp_id()] = best;
-            __syncthreads();
-            KeyIdx sink;
-            {
-                const int nw = (T + 31) >> 5;
-                sink.key = INF;
-                sink.idx = -1;
-                for (int k = 0; k < nw; k++) {
-                    const KeyIdx o = s_red[k];
-                    if (o.idx >= 0 && (sink.idx < 0 || o.key < sink.key || (o.key == sink.key && o.idx < sink.idx)))
-                        sink = o;
-                }
-            }
-            __syncthreads();  // s_red is rewritten next iteration
-            cnt.tick(0);
-            if (sink.idx < 0) break;  // T unreachable
-            if (sink.key >= 0) {
-                // wrapper.cpp:263-267: stop when the next path does not pay. The reference keeps the very first path
-                // of a graph whatever it costs (wrapper.cpp:205,220); with components that decision belongs to the
-                // whole graph: remember this component's first path, k_first_path_rule applies the rule afterwards.
-                if (K == 0 && tid == 0) {
-                    p.first_cost[cg] = sink.key;
-                    p.first_sink[cg] = sink.idx;
-                }
-                break;
-            }
-            const int root = p.ws_anc_post[sink.idx];
-            if (root < 0) break;  // cannot happen: a labelled node always has a branch
-            // ---- the path lies in the branch hanging from S -> pre_root, and that branch is exactly what loses its
-            //      labels when the path is flipped (Graph::find_node_set4update, Graph.cpp:341-343): collect it in
-            //      layer order (= ascending position). Every thread owns a contiguous chunk: one block scan suffices.
-            int nd = 0, atot = 0;
-            {
-                const int chunk = (n + T - 1) / T;
-                const int i0 = tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
-                int my_nd = 0, my_arcs = 0;
-                for (int i = i0; i < i1; i++) {
-                    const bool fp = anc_pre[i] == root, fo = anc_post[i] == root;
-                    my_nd += (fp || fo) ? 1 : 0;
-                    if (fp) {
-                        const int d = perm[i];
-                        my_arcs += p.in_ptr[d + 1] - p.in_ptr[d] + 1;  // + 1: end-of-list marker
-                    }
-                }
-                int tot_nd, tot_arcs;
-                int slot = block_excl_scan1(my_nd, s_scan, 0, &tot_nd);
-                int a0 = block_excl_scan1(my_arcs, s_scan, 1, &tot_arcs);
-                nd = tot_nd;
-                atot = tot_arcs;
-                if (my_nd)
-                    for (int i = i0; i < i1; i++) {
-                        int f = 0;
-                        if (anc_pre[i] == root) f |= DL_PRE;
-                        if (anc_post[i] == root) f |= DL_POST;
-                        if (f) {
-                            c.dl[slot] = (c0 + i) | f;
-                            c.dla0[slot] = a0;
-                            c.slot_of[c0 + i] = slot;
-                            slot++;
-                            if (f & DL_PRE) {
-                                const int d = perm[i];
-                                a0 += p.in_ptr[d + 1] - p.in_ptr[d] + 1;
-                            }
-                        }
-                    }
-            }
-            __syncthreads();
-            cnt.tick(1);
-            if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
-            const bool in_smem = nd <= p.rec_cap && !wide;  // arc lists beyond the shared area spill one by one
-            cnt.n_branch++;
-            cnt.n_rec += nd;
-            const bool ok = in_smem ? relabel_branch<true>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt)
-                                    : relabel_branch<false>(c, nd, atot, root, sink.idx, s_ok, s_work, sweep_warp, cnt);
-            if (!ok) break;  // defensive: inconsistent state, stop with what we have
-            K++;
-            total += sink.key;
-        }
-        // ---- results of this component: flow in detection indices, totals added to its graph
-        __syncthreads();
-        if (tid == 0) {
-            if (K) {
-                atomicAdd(&p.n_paths[g], K);
-                atomicAdd((unsigned long long *)&p.total[g], (unsigned long long)total);
-            }
-            if (p.stats) {
-                unsigned long long *o = (unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g);
-                atomicAdd(&o[0], (unsigned long long)(cnt.n_asc + s_work[0]));
-                atomicAdd(&o[1], (unsigned long long)(cnt.n_desc + s_work[1]));
-                atomicAdd(&o[2], (unsigned long long)(cnt.n_node + s_work[2]));
-                atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
-                for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
-                atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
-                atomicAdd(&o[12], (unsigned long long)cnt.n_rec);
-                for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
-            }
-        }
-        if (tid == 0 && p.stats && p.n_graphs > 2) atomicMax((unsigned long long *)(p.stats + 17 + 2 * MOT3D_SOLVE_STATS), (unsigned long long)(clock64() - t_job0));  // DEBUG
-        for (int i = tid; i < n; i += T) {
-            const int a = p.ws_nxt[c0 + i], b = p.ws_prv[c0 + i];
-            const int d = perm[i];
-            p.next_out[d] = a >= 0 ? p.comp_perm[a] : a;
-            p.prev_out[d] = b >= 0 ? p.comp_perm[b] : b;
-        }
-        __syncthreads();
+        if (n <= p.rcap && !p.win_wide[g])
+            solve_component<true>(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
+        else
+            solve_component<false>(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
     }
 }
 
@@ -1691,24 +1061,24 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
-    return a256(n * 8) * 4 + a256(n * 4) * 14 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 + a256(n * sizeof(Rec)) +
-           a256((e + n + 8) * sizeof(StArc)) + a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
+    return a256(n * 8) * 3 + a256(n * 4) * 12 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
+           a256(n * sizeof(RecT<false>)) + a256((e + n + 8) * sizeof(StArc)) +
+           a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
 }
 
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                           const int32_t *tkey, int64_t arc_capacity, const int32_t *in_ptr, const int32_t *in_src,
                           const int64_t *in_cost, const int64_t *entry_cost, const int64_t *node_cost,
                           const int64_t *exit_cost, int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out,
-                          int64_t *total_cost_out, int64_t *path_cost_out, int64_t *stats_out, void *ws,
-                          size_t ws_bytes, void *stream) {
+                          int64_t *total_cost_out, int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes,
+                          void *stream) {
     M3_CHECK_ARG(n_graphs >= 0 && max_graph_nodes >= 0 && arc_capacity >= 0, "negative sizes");
     if (n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(graph_ptr && tkey && in_ptr && entry_cost && node_cost && exit_cost, "NULL input");
-    M3_CHECK_ARG(next_out && prev_out && n_paths_out && total_cost_out && ws, "NULL output/workspace");
+    M3_CHECK_ARG(next_out && prev_out && n_paths_out && total_cost_out && ws, "NULL output");
     M3_CHECK_ARG(n_total >= max_graph_nodes, "n_total < max_graph_nodes");
-    M3_CHECK_ARG(n_total < DL_FIRST, "batch too large");
     if (ws_bytes < mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity)) {
-        set_error("solve workspace too small: %zu < %zu", ws_bytes,
+        set_error("solve workspace too small: %zu < %zu bytes", ws_bytes,
                   mot3d_solve_workspace_bytes(n_total, n_graphs, arc_capacity));
         return MOT3D_E_CAPACITY;
     }
@@ -1725,6 +1095,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.n_graphs = n_graphs;
     p.rcap = 0;
     p.racap = 0;
+    p.pad = 0;
     p.n_total = (int64_t)n_total;
     p.graph_ptr = graph_ptr;
     p.tkey = tkey;
@@ -1743,27 +1114,24 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.arc_capacity = arc_capacity;
     p.ws_dpre = (int64_t *)take(n_cap * 8);
     p.ws_dpost = (int64_t *)take(n_cap * 8);
-    p.ws_mcost = (int64_t *)take(n_cap * 8);
     p.first_cost = (int64_t *)take(n_cap * 8);
     p.ws_par = (int32_t *)take(n_cap * 4);
     p.ws_anc_pre = (int32_t *)take(n_cap * 4);
     p.ws_anc_post = (int32_t *)take(n_cap * 4);
-    p.ws_nxt = (int32_t *)take(n_cap * 4);
-    p.ws_prv = (int32_t *)take(n_cap * 4);
-    p.ws_slot_of = (int32_t *)take(n_cap * 4);
-    p.ws_dl = (int32_t *)take(n_cap * 4);
-    p.ws_dla0 = (int32_t *)take(n_cap * 4);
+    p.ws_tk = (int32_t *)take(n_cap * 4);
+    p.ws_bl = (int32_t *)take(n_cap * 4);
+    p.ws_hop = (int32_t *)take(n_cap * 4);
+    p.ws_pl = (int32_t *)take(n_cap * 4);
     p.first_sink = (int32_t *)take(n_cap * 4);
+    p.job_order = (int32_t *)take(n_cap * 4);
     int32_t *comp_perm = (int32_t *)take(n_cap * 4);
     int32_t *comp_inv = (int32_t *)take(n_cap * 4);
     int32_t *cgraph_win = (int32_t *)take(n_cap * 4);
-    p.ws_tk = (int32_t *)take(n_cap * 4);
     p.ws_lvl = (int32_t *)take((n_cap + g) * 4);
     int32_t *cgraph_ptr = (int32_t *)take((n_cap + g) * 4);
     int32_t *win_cbase = (int32_t *)take(g * 4);
     p.win_wide = (int32_t *)take(g * 4);
-    p.job_order = (int32_t *)take(n_cap * 4);
-    p.ws_rec = (Rec *)take(n_cap * sizeof(Rec));
+    p.ws_rec = (RecT<false> *)take(n_cap * sizeof(RecT<false>));
     p.ws_arc = (StArc *)take((e_cap + n_cap + 8) * sizeof(StArc));
     const size_t cws_bytes = mot3d_components_workspace_bytes(n_total, n_graphs);
     void *cws = take(cws_bytes);
@@ -1785,42 +1153,31 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     M3_LAUNCH_CHECK("k_first_tree");
     k_job_order<<<1, 1024, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_job_order");
-    // 3. successive shortest paths per component. Shared memory per block: the staging area for one branch, sized so
-    //    that several blocks share an SM; blocks pull components from a work queue.
-    // Graphs of up to 8192 detections are split into components (typically a few tracks each): small staging area
-    // and small blocks so that ~8 blocks share an SM. Small graphs (<= 1024) are usually one dense component: keep
-    // room for a whole branch. Tuning knobs (bench experiments): MOT3D_SOLVE_RECCAP / _THREADS / _BLOCKS_PER_SM.
-    size_t rec_target = max_graph_nodes <= 1024 ? 320 : 192;
-    if (const char *e = getenv("MOT3D_SOLVE_RECCAP")) rec_target = (size_t)atoi(e) > 31 ? (size_t)atoi(e) : 32;
-    size_t rec_cap = (size_t)max_graph_nodes < rec_target ? (size_t)max_graph_nodes : rec_target;
-    if (rec_cap < 32) rec_cap = 32;
-    size_t arc_cap = rec_cap * 9 + 32;  // room is reserved by in-degree (+1) of the branch's pre nodes
-    if (arc_cap > 2800) arc_cap = 2800;
+    // 3. successive shortest paths per component. Shared memory per block = the staging area of one component; blocks
+    //    pull components from the work queue. Graphs of more than 1024 detections fall apart into components of a
+    //    few tracks each: room for 256 records, 8 blocks per SM. Small graphs are usually one dense component: room
+    //    for the whole graph, fewer blocks. Tuning knobs (bench experiments): MOT3D_SOLVE_RESIDENT (records),
+    //    MOT3D_SOLVE_SMEM (bytes per block), MOT3D_SOLVE_THREADS, MOT3D_SOLVE_BLOCKS_PER_SM.
     int dev = 0, n_sm = 148, per_sm = 4, smem_sm = 228 * 1024;
     M3_CUDA(cudaGetDevice(&dev));
     M3_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     M3_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    if (max_graph_nodes > 1024) {
-        // 8 blocks per SM: the arc area takes what is left of an eighth of the SM's shared memory (1 KB per block
-        // is reserved by the system, ~1 KB is static)
-        const size_t budget = (size_t)smem_sm / 8 - 1024 - 1024;
-        const size_t fixed = rec_cap * REC_BYTES + 8 * ARC_BYTES + 16;
-        if (budget > fixed + 64 * ARC_BYTES && arc_cap > (budget - fixed) / ARC_BYTES) arc_cap = (budget - fixed) / ARC_BYTES;
-    }
-    if (const char *e = getenv("MOT3D_SOLVE_ARCCAP")) arc_cap = (size_t)atoi(e) > 63 ? (size_t)atoi(e) : 64;
-    p.rec_cap = (int32_t)rec_cap;
-    p.arc_cap = (int32_t)arc_cap;
-    const size_t smem = rec_cap * REC_BYTES + (arc_cap + 8) * ARC_BYTES + 16;  // + 8: speculative arc loads
-    {
-        // resident mode shares the same shared memory: as many records as the largest graph can need, the rest arcs
-        size_t rcap = max_graph_nodes <= 1024 ? 448 : 256;
-        if (rcap > (size_t)((max_graph_nodes + 7) & ~7)) rcap = (size_t)((max_graph_nodes + 7) & ~7);
-        if (rcap < 32) rcap = 32;
-        if (const char *e = getenv("MOT3D_SOLVE_RESIDENT")) rcap = (size_t)atoi(e) & ~(size_t)7;
-        if (rcap && smem >= 16 + rcap * RES_BYTES_PER_REC + (64 + 8) * ARC_BYTES) {
-            p.rcap = (int32_t)rcap;
-            p.racap = (int32_t)((smem - 16 - rcap * RES_BYTES_PER_REC) / ARC_BYTES - 8);
-        }
+    size_t rcap = max_graph_nodes <= 1024 ? 448 : 256;
+    if (rcap > (size_t)((max_graph_nodes + 7) & ~7)) rcap = (size_t)((max_graph_nodes + 7) & ~7);
+    if (rcap < 32) rcap = 32;
+    if (const char *e = getenv("MOT3D_SOLVE_RESIDENT")) rcap = (size_t)atoi(e) & ~(size_t)7;
+    // an eighth (big graphs) / a quarter (small graphs) of the SM's shared memory; 1 KB per block is reserved by the
+    // system, ~1 KB is static
+    size_t smem = (size_t)smem_sm / (max_graph_nodes <= 1024 ? 4 : 8) - 2048;
+    const size_t want = 16 + rcap * SM_BYTES_PER_REC + (rcap * 10 + 8) * SM_ARC_BYTES;  // ~9 in-arcs per detection + 1
+    if (smem > want) smem = want;
+    if (const char *e = getenv("MOT3D_SOLVE_SMEM")) smem = (size_t)atoi(e);
+    smem &= ~(size_t)15;
+    if (rcap && smem >= 16 + rcap * SM_BYTES_PER_REC + (64 + 8) * SM_ARC_BYTES) {
+        p.rcap = (int32_t)rcap;
+        p.racap = (int32_t)((smem - 16 - rcap * SM_BYTES_PER_REC) / SM_ARC_BYTES - 8);
+    } else {
+        smem = 0;  // everything on the global staging area
     }
     int threads = 128;
     if (const char *e = getenv("MOT3D_SOLVE_THREADS")) {
