@@ -337,6 +337,12 @@ def run_ours(args):
                 "sweep_steps_per_graph_mean": {"ascending": float(stats[:, 15].mean()),
                                                "descending": float(stats[:, 16].mean())},
                 "solver_block_busy_cycles": float(stats[0, 17]),
+                "global_staging": {"components_per_graph_mean": float(stats[:, 22].mean()),
+                                   "cycles_per_graph_mean": float(stats[:, 23].mean()),
+                                   "ascending_cycles_per_step": float(stats[:, 18].sum() / max(stats[:, 20].sum(), 1)),
+                                   "ascending_steps_per_graph_mean": float(stats[:, 20].mean()),
+                                   "descending_cycles_per_hop": float(stats[:, 19].sum() / max(stats[:, 21].sum(), 1)),
+                                   "descending_hops_per_graph_mean": float(stats[:, 21].mean())},
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
                 "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(

@@ -177,7 +177,7 @@ struct Counters {
     int64_t n_arc;            // arcs read while staging
     int64_t n_branch, n_rec;  // branches re-labelled, records listed for them
     long long t_phase[7];  // cycles (thread 0): arg-min, branch list, staging + initial labels, walk, fix-point, -, -
-    long long t_mark;
+    long long t_mark, t_start;
     __device__ __forceinline__ void tick(int k) {
         const long long now = clock64();
         t_phase[k] += now - t_mark;
@@ -337,7 +337,7 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
     Counters cnt;
     cnt.n_arc = cnt.n_branch = cnt.n_rec = 0;
     for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
-    cnt.t_mark = clock64();
+    cnt.t_mark = cnt.t_start = clock64();
 
     // ---- stage the component: records, then arc lists (offsets by a block scan over contiguous chunks)
     const int chunk = (n + T - 1) / T;
@@ -868,6 +868,11 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
             atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
             atomicAdd(&o[12], (unsigned long long)cnt.n_rec);
             for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
+            if (!SM) {  // the same four for the components on the global staging area alone, and how many they were
+                for (int k = 0; k < 4; k++) atomicAdd(&o[18 + k], (unsigned long long)s_work[4 + k]);
+                atomicAdd(&o[22], 1ull);
+                atomicAdd(&o[23], (unsigned long long)(clock64() - cnt.t_start));
+            }
         }
     }
     for (int i = tid; i < n; i += T) {
