@@ -88,14 +88,30 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
     }
     for (int i = tid; i < n; i += T) s_par[i] = i;
     __syncthreads();
-    // ---- one pass over the arcs: unite every detection with the sources of its incoming transitions
-    for (int j = tid; j < n; j += T) {
-        const int e0 = in_ptr[j], e1 = in_ptr[j + 1];
-        if (e0 == e1) continue;
-        int rj = cc_find(s_par, j);
-        for (int e = e0; e < e1; e++) {
-            const int ri = cc_find(s_par, p.in_src[e] - g0);
-            rj = cc_unite(s_par, ri, rj);
+    // ---- one pass over the arcs: unite every detection with the sources of its incoming transitions. A warp takes
+    //      32 consecutive rows: their arcs are one contiguous range, read with coalesced, independent loads; the row of
+    //      an arc is found by a binary search over the 32 row starts held by the lanes.
+    {
+        const int lane = lane_id(), nwarp = T >> 5;
+        for (int j0 = warp_id() * 32; j0 < n; j0 += nwarp * 32) {
+            const int jl = j0 + lane;
+            const int start = in_ptr[jl < n ? jl : n];  // rows beyond the graph: empty
+            const int a0 = __shfl_sync(0xffffffffu, start, 0);
+            const int a1 = in_ptr[j0 + 32 < n ? j0 + 32 : n];
+            for (int eb = a0; eb < a1; eb += 32) {
+                const int e = eb + lane;
+                int lo = 0;  // the last row whose arcs start at or before e
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int s = __shfl_sync(0xffffffffu, start, (lo + step) & 31);
+                    if (s <= e) lo += step;
+                }
+                if (e < a1) {
+                    const int ri = cc_find(s_par, p.in_src[e] - g0);
+                    const int rj = cc_find(s_par, j0 + lo);
+                    cc_unite(s_par, ri, rj);
+                }
+            }
         }
     }
     __syncthreads();

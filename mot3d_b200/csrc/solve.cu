@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     }
     if (tid == 0) lvl[L] = n;
     __syncthreads();
-    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
-    int wide = 0;  // some transition cost needs more than 32 bits: the packed staging of k_ssp_solve is off
+    // FT_LPN lanes per node, every lane keeps FT_U independent arc loads in flight: a layer of ~100 nodes with ~8
+    // in-arcs each is one pass of the block and four dependent memory levels (row, source, position, label).
+    constexpr int FT_LPN = 2, FT_U = 4;
+    const int sub = tid % FT_LPN, grp = tid / FT_LPN, ngrp = T / FT_LPN;
+    int wide = 0;  // some cost needs more than 32 bits: the packed staging of k_ssp_solve is off
     for (int l = 0; l < L; l++) {
         const int a = lvl[l], b = lvl[l + 1];
         for (int jb = a; jb < b; jb += ngrp) {
@@ -245,29 +248,50 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
             KeyIdx best;
             best.key = INF;
             best.idx = PAR_NONE;
+            int q = 0;
+            int64_t e_ = INF, c_ = 0, x_ = INF;
             if (valid) {
                 const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
-                for (int k = sub; k < deg; k += LPN) {
-                    const int qi = p.comp_inv[p.in_src[e0 + k]];  // position of the source
-                    const int64_t di = p.ws_dpost[qi];
-                    const int64_t w = p.in_cost[e0 + k];
-                    wide |= (w != (int64_t)(int)w) ? 1 : 0;
-                    if (di < INF_CUT) {
-                        const int64_t cand = di + w;
-                        if (cand < best.key || (cand == best.key && qi < best.idx)) {
-                            best.key = cand;
-                            best.idx = qi;
+                if (sub == 0) {  // the node's own costs: in flight together with the arc loads
+                    q = inv[j];
+                    e_ = p.en[g0 + j];
+                    c_ = p.cn[g0 + j];
+                    x_ = p.ex[g0 + j];
+                }
+                for (int kb = 0; kb < deg; kb += FT_LPN * FT_U) {
+                    int src[FT_U], qi[FT_U];
+                    int64_t w[FT_U], di[FT_U];
+#pragma unroll
+                    for (int u = 0; u < FT_U; u++) {
+                        const int k = kb + u * FT_LPN + sub;
+                        src[u] = k < deg ? p.in_src[e0 + k] : -1;
+                        w[u] = k < deg ? p.in_cost[e0 + k] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < FT_U; u++) qi[u] = src[u] >= 0 ? p.comp_inv[src[u]] : -1;  // position of the source
+#pragma unroll
+                    for (int u = 0; u < FT_U; u++) di[u] = qi[u] >= 0 ? p.ws_dpost[qi[u]] : INF;
+#pragma unroll
+                    for (int u = 0; u < FT_U; u++) {
+                        wide |= (w[u] != (int64_t)(int)w[u]) ? 1 : 0;
+                        if (di[u] < INF_CUT) {
+                            const int64_t cand = di[u] + w[u];
+                            if (cand < best.key || (cand == best.key && qi[u] < best.idx)) {
+                                best.key = cand;
+                                best.idx = qi[u];
+                            }
                         }
                     }
                 }
             }
-            best = group_min(best, 0xffffffffu);
+#pragma unroll
+            for (int d = 1; d < FT_LPN; d <<= 1) {  // lowest source position wins ties
+                const KeyIdx o = shfl_xor_ki(best, d);
+                if (o.key < best.key || (o.key == best.key && o.idx >= 0 && (best.idx < 0 || o.idx < best.idx))) best = o;
+            }
             if (valid && sub == 0) {
-                const int q = inv[j];
                 int anc = best.idx >= 0 ? p.ws_anc_post[best.idx] : -1;
-                const int64_t e_ = p.en[g0 + j];
-                const int64_t c_ = p.cn[g0 + j];
-                wide |= (fits_narrow(e_) && fits_narrow(p.ex[g0 + j]) && c_ == (int64_t)(int)c_) ? 0 : 1;
+                wide |= (fits_narrow(e_) && fits_narrow(x_) && c_ == (int64_t)(int)c_) ? 0 : 1;
                 if (e_ < best.key) {
                     best.key = e_;
                     best.idx = PAR_S;
@@ -277,7 +301,7 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
                     p.ws_dpre[q] = best.key;
                     p.ws_par[q] = best.idx;
                     p.ws_anc_pre[q] = anc;
-                    p.ws_dpost[q] = best.key + p.cn[g0 + j];
+                    p.ws_dpost[q] = best.key + c_;
                     p.ws_anc_post[q] = anc;
                 }
             }

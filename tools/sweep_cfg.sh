@@ -1,8 +1,17 @@
-for cfg in "128 128" "32 128" "32 96" "32 64" "32 48" "64 64"; do
-  set -- $cfg
-  MOT3D_SOLVE_THREADS=$1 MOT3D_SOLVE_RECCAP=$2 timeout 300 python bench.py --steps 3 --warmup 3 --seqs 60 --no-cpu > gpurun_out/b.log 2>&1
-  python -c "
-import json
-d=json.loads(open('gpurun_out/b.log').read().strip().splitlines()[-1]); print('$cfg', round(d['value']/1e6,1), 'Mdet/s solve_ms', round(d['stage_ms']['solve'],2), {k:int(v/1e5)/10 for k,v in d['roofline']['phase_cycles_per_graph_mean'].items()})
-" 2>&1 | tail -1
-done
+#!/bin/bash
+# solver launch-configuration sweep (bench experiments): prints solve ms per config
+run() {
+  echo "== $*"
+  env "$@" timeout 200 python bench.py --no-cpu --steps 4 --warmup 3 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.1f M/s  step %.2f ms  solve %.2f ms' % (d['value'] / 1e6, d['ms_per_step'], d['stage_ms']['solve']))"
+}
+run MOT3D_X=0
+run MOT3D_SOLVE_THREADS=64
+run MOT3D_SOLVE_THREADS=32
+run MOT3D_SOLVE_THREADS=64 MOT3D_SOLVE_SMEM=13312 MOT3D_SOLVE_RESIDENT=128
+run MOT3D_SOLVE_THREADS=32 MOT3D_SOLVE_SMEM=13312 MOT3D_SOLVE_RESIDENT=128
+run MOT3D_SOLVE_THREADS=32 MOT3D_SOLVE_SMEM=6144 MOT3D_SOLVE_RESIDENT=64
+run MOT3D_SOLVE_THREADS=64 MOT3D_SOLVE_SMEM=18432 MOT3D_SOLVE_RESIDENT=160
+run MOT3D_SOLVE_THREADS=256
