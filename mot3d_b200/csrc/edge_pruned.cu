@@ -47,15 +47,56 @@ __device__ __forceinline__ int64_t bound_i32(const int32_t *a, int64_t lo, int64
     return lo;
 }
 
-// rank of every detection inside its frame by (x, index): sorted copies of the positions + permutation
+// The same bound found by one warp: 32 probes per step shrink the range 33-fold, so a batch of millions of keys takes
+// 5 dependent loads instead of 23. All 32 lanes must call; every lane returns the result.
+template <bool UPPER>
+__device__ __forceinline__ int64_t warp_bound_i32(const int32_t *a, int64_t lo, int64_t hi, int64_t key) {
+    const int lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        const int64_t span = hi - lo;
+        const int64_t pos = lo + (span * (lane + 1)) / 33;  // lo < pos < hi, non-decreasing in lane
+        const int64_t v = a[pos];
+        const bool below = UPPER ? (v <= key) : (v < key);  // the bound lies beyond pos
+        const unsigned m = __ballot_sync(0xffffffffu, below);
+        const int c = __popc(m);  // probes 0 .. c-1 are below (the keys are sorted)
+        const int64_t new_lo = c > 0 ? __shfl_sync(0xffffffffu, pos, c - 1) + 1 : lo;
+        const int64_t new_hi = c < 32 ? __shfl_sync(0xffffffffu, pos, c < 32 ? c : 31) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    const int64_t pos = lo + lane;
+    const bool below = pos < hi && (UPPER ? (a[pos] <= key) : (a[pos] < key));
+    return lo + __popc(__ballot_sync(0xffffffffu, below));
+}
+
+// rank of every detection inside its frame by (x, index): sorted copies of the positions + permutation.
+// One block = 128 consecutive detections; only the frames that stick out of the block need a search.
 __global__ void __launch_bounds__(128) k_frame_sort(int64_t n, int dim, const int32_t *__restrict__ tkey,
                                                     const double *__restrict__ pos, double *__restrict__ spos,
                                                     int32_t *__restrict__ sperm) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int k = tkey[i];
-    const int64_t lo = bound_i32<false>(tkey, 0, i + 1, k);
-    const int64_t hi = bound_i32<true>(tkey, i, n, k);
+    __shared__ int s_key[128];
+    __shared__ int64_t s_edge[2];  // start of the block's first frame, end of its last frame
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t b1 = (b0 + blockDim.x < n) ? b0 + blockDim.x : n;
+    const int64_t i = b0 + threadIdx.x;
+    const bool active = i < n;
+    const int k = active ? tkey[i] : 0;
+    s_key[threadIdx.x] = k;
+    if (threadIdx.x < 32) {
+        const int64_t lo = warp_bound_i32<false>(tkey, 0, b0 + 1, tkey[b0]);
+        if (threadIdx.x == 0) s_edge[0] = lo;
+    } else if (threadIdx.x < 64) {
+        const int64_t hi = warp_bound_i32<true>(tkey, b1 - 1, n, tkey[b1 - 1]);
+        if (threadIdx.x == 32) s_edge[1] = hi;
+    }
+    __syncthreads();
+    if (!active) return;
+    const int nb = (int)(b1 - b0);
+    int l = threadIdx.x, h = threadIdx.x + 1;  // the detection's frame inside the block: [l, h)
+    while (l > 0 && s_key[l - 1] == k) l--;
+    while (h < nb && s_key[h] == k) h++;
+    const int64_t lo = (l == 0 && s_key[0] == k) ? s_edge[0] : b0 + l;
+    const int64_t hi = (h == nb && s_key[nb - 1] == k) ? s_edge[1] : b0 + h;
     const double x = pos[i];
     int rank = 0;
     for (int64_t j = lo; j < hi; j++) {
@@ -65,6 +106,159 @@ __global__ void __launch_bounds__(128) k_frame_sort(int64_t n, int dim, const in
     const int64_t o = lo + rank;
     sperm[o] = (int32_t)i;
     for (int d = 0; d < dim; d++) spos[(size_t)d * n + o] = pos[(size_t)d * n + i];
+}
+
+// the arcs of one row: x-window search in each of the <= max_jump frames it may link to. cx/cy/cz/cperm/ckey = the
+// tile's candidate range (shared memory copies when STAGED, the global arrays otherwise), m entries.
+template <int DIR, bool FILL, bool STAGED>
+__device__ __forceinline__ int row_arcs(const PrunedParams &p, const int64_t r, const int64_t kmin, const bool tabled,
+                                        const int *s_seg_lo, const int *s_seg_hi, const double *cx, const double *cy,
+                                        const double *cz, const int32_t *cperm, const int32_t *ckey, const int m) {
+    const int64_t n = p.n;
+    const int J = p.max_jump;
+    const bool has_z = p.dim == 3;
+    const int key_r = p.tkey[r];
+    const double xr = p.pos[r], yr = p.pos[n + r];
+    const double zr = has_z ? p.pos[2 * n + r] : 0.0;
+    const double xlo = xr - p.x_window, xhi = xr + p.x_window;
+    int cnt = 0;
+    const int64_t out_base = FILL ? p.row_ptr[r] : 0;
+    for (int jj = 1; jj <= J; jj++) {
+        // frames in ascending time order, so that the arcs of a row ascend by detection index
+        const int kt = (DIR == MOT3D_DIR_OUT) ? key_r + jj : key_r - (J + 1 - jj);
+        int a, b;
+        if (tabled) {
+            const int t = kt - (int)kmin;
+            a = s_seg_lo[t];
+            b = s_seg_hi[t];
+        } else {
+            a = (int)bound_i32<false>(ckey, 0, m, kt);
+            b = (int)bound_i32<true>(ckey, a, m, kt);
+        }
+        if (b <= a) continue;
+        // first candidate with x >= xr - window
+        int l = a, h = b;
+        while (l < h) {
+            const int mid = (l + h) >> 1;
+            if (cx[mid] < xlo)
+                l = mid + 1;
+            else
+                h = mid;
+        }
+        // The survivors of this frame come out in x order; the reference emits them in detection order
+        // (mot3d/mot3d.py:111-127). Up to 4 are sorted in registers, a longer run falls back to an insertion into the
+        // output arrays.
+        int nf = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int c = l; c < b; c++) {
+            const double xc = cx[c];
+            if (xc > xhi) break;
+            const double dx = xr - xc;
+            const double dy = yr - cy[c];
+            double s = dx * dx;  // sum([dx^2, dy^2, dz^2]) left to right, as the reference's euclidean()
+            s = s + dy * dy;
+            if (has_z) {
+                const double dz = zr - cz[c];
+                s = s + dz * dz;
+            }
+            if (s <= p.sq_dist_max) {
+                if (FILL) {
+                    const int other = cperm[c];
+                    if (nf == 0) {
+                        o0 = other;
+                        s0 = s;
+                    } else if (nf == 1) {
+                        o1 = other;
+                        s1 = s;
+                    } else if (nf == 2) {
+                        o2 = other;
+                        s2 = s;
+                    } else if (nf == 3) {
+                        o3 = other;
+                        s3 = s;
+                    } else {
+                        if (nf == 4) {  // spill the four held back, in x order; the insertion below sorts them
+                            const int oo[4] = {o0, o1, o2, o3};
+                            const double ss[4] = {s0, s1, s2, s3};
+                            for (int t = 0; t < 4; t++) {
+                                int64_t e = out_base + cnt + t;
+                                if (e < p.edge_capacity) {
+                                    while (e > out_base + cnt && p.col[e - 1] > oo[t]) {
+                                        p.col[e] = p.col[e - 1];
+                                        p.cost[e] = p.cost[e - 1];
+                                        e--;
+                                    }
+                                    p.col[e] = oo[t];
+                                    p.cost[e] = __double_as_longlong(ss[t]);
+                                } else if (p.overflow) {
+                                    *p.overflow = 1;
+                                }
+                            }
+                        }
+                        int64_t e = out_base + cnt + nf;
+                        if (e < p.edge_capacity) {
+                            while (e > out_base + cnt && p.col[e - 1] > other) {
+                                p.col[e] = p.col[e - 1];
+                                p.cost[e] = p.cost[e - 1];
+                                e--;
+                            }
+                            p.col[e] = other;
+                            p.cost[e] = __double_as_longlong(s);
+                        } else if (p.overflow) {
+                            *p.overflow = 1;
+                        }
+                    }
+                }
+                nf++;
+            }
+        }
+        if (FILL && nf > 0 && nf <= 4) {
+            // sorting network on (detection, squared distance) pairs; unused slots sort last
+            if (nf < 2) o1 = 0x7fffffff;
+            if (nf < 3) o2 = 0x7fffffff;
+            if (nf < 4) o3 = 0x7fffffff;
+#define M3_CSWAP(oa, sa, ob, sb)      \
+    if (oa > ob) {                    \
+        const int to_ = oa;           \
+        oa = ob;                      \
+        ob = to_;                     \
+        const double ts_ = sa;        \
+        sa = sb;                      \
+        sb = ts_;                     \
+    }
+            if (nf > 1) {
+                M3_CSWAP(o0, s0, o1, s1);
+                if (nf > 2) {
+                    M3_CSWAP(o2, s2, o3, s3);
+                    M3_CSWAP(o0, s0, o2, s2);
+                    M3_CSWAP(o1, s1, o3, s3);
+                    M3_CSWAP(o1, s1, o2, s2);
+                }
+            }
+#undef M3_CSWAP
+            const int64_t e = out_base + cnt;
+            if (e + nf <= p.edge_capacity) {
+                p.col[e] = o0;
+                p.cost[e] = __double_as_longlong(s0);
+                if (nf > 1) {
+                    p.col[e + 1] = o1;
+                    p.cost[e + 1] = __double_as_longlong(s1);
+                }
+                if (nf > 2) {
+                    p.col[e + 2] = o2;
+                    p.cost[e + 2] = __double_as_longlong(s2);
+                }
+                if (nf > 3) {
+                    p.col[e + 3] = o3;
+                    p.cost[e + 3] = __double_as_longlong(s3);
+                }
+            } else if (p.overflow) {
+                *p.overflow = 1;
+            }
+        }
+        cnt += nf;
+    }
+    return cnt;
 }
 
 template <int DIR, bool FILL>
@@ -82,22 +276,28 @@ __global__ void __launch_bounds__(EP_TPB) k_edge_build_pruned(const PrunedParams
     const int J = p.max_jump;
     const bool has_z = p.dim == 3;
 
-    // candidate index range of the tile (the sorted copies permute detections inside frames only)
+    // candidate index range of the tile (the sorted copies permute detections inside frames only): two warps search
+    // the two ends; the keys are sorted, so the range lies before (DIR_IN) / after (DIR_OUT) the tile
     const int64_t k_first = p.tkey[r0], k_last = p.tkey[r1 - 1];
     const int64_t kmin = (DIR == MOT3D_DIR_OUT) ? k_first + 1 : k_first - J;
     const int64_t kmax = (DIR == MOT3D_DIR_OUT) ? k_last + J : k_last - 1;
-    if (threadIdx.x == 0) {
-        s_range[0] = bound_i32<false>(p.tkey, 0, n, kmin);
-        s_range[1] = bound_i32<true>(p.tkey, 0, n, kmax);
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
+    if (threadIdx.x < 32) {
+        const int64_t v = warp_bound_i32<false>(p.tkey, (DIR == MOT3D_DIR_OUT) ? r0 : 0, (DIR == MOT3D_DIR_OUT) ? n : r1, kmin);
+        if (threadIdx.x == 0) {
+            s_range[0] = v;
+            mbar_init(&s_bar, 1);
+            fence_mbar_init();
+        }
+    } else if (threadIdx.x < 64) {
+        const int64_t v = warp_bound_i32<true>(p.tkey, (DIR == MOT3D_DIR_OUT) ? r0 : 0, (DIR == MOT3D_DIR_OUT) ? n : r1, kmax);
+        if (threadIdx.x == 32) s_range[1] = v;
     }
     for (int t = threadIdx.x; t < EP_TABLE; t += EP_TPB) {
         s_seg_lo[t] = 0;
         s_seg_hi[t] = 0;
     }
     __syncthreads();
-    const int64_t lo = s_range[0], hi = s_range[1];
+    const int64_t lo = s_range[0], hi = s_range[1] > s_range[0] ? s_range[1] : s_range[0];
     const int m = (int)(hi - lo);
     const bool staged = m <= EP_CAP;
     const bool tabled = (kmax - kmin) < EP_TABLE;
@@ -134,73 +334,12 @@ __global__ void __launch_bounds__(EP_TPB) k_edge_build_pruned(const PrunedParams
     }
     __syncthreads();
     if (!active) return;
-
-    const int key_r = p.tkey[r];
-    const double xr = p.pos[r], yr = p.pos[n + r];
-    const double zr = has_z ? p.pos[2 * n + r] : 0.0;
-    const double xlo = xr - p.x_window, xhi = xr + p.x_window;
-    const double *gx = p.spos + lo, *gy = p.spos + n + lo, *gz = p.spos + 2 * n + lo;
-    const int32_t *gperm = p.sperm + lo, *gkey = p.tkey + lo;
-    int cnt = 0;
-    const int64_t out_base = FILL ? p.row_ptr[r] : 0;
-
-    for (int jj = 1; jj <= J; jj++) {
-        // frames in ascending time order, so that the arcs of a row ascend by detection index
-        const int kt = (DIR == MOT3D_DIR_OUT) ? key_r + jj : key_r - (J + 1 - jj);
-        int a, b;
-        if (tabled) {
-            const int t = kt - (int)kmin;
-            a = s_seg_lo[t];
-            b = s_seg_hi[t];
-        } else {
-            a = (int)bound_i32<false>(gkey, 0, m, kt);
-            b = (int)bound_i32<true>(gkey, a, m, kt);
-        }
-        if (b <= a) continue;
-        // first candidate with x >= xr - window
-        int l = a, h = b;
-        while (l < h) {
-            const int mid = (l + h) >> 1;
-            const double v = staged ? s_x[mid] : gx[mid];
-            if (v < xlo)
-                l = mid + 1;
-            else
-                h = mid;
-        }
-        const int first = cnt;
-        for (int c = l; c < b; c++) {
-            const double xc = staged ? s_x[c] : gx[c];
-            if (xc > xhi) break;
-            const double dx = xr - xc;
-            const double dy = yr - (staged ? s_y[c] : gy[c]);
-            double s = dx * dx;  // sum([dx^2, dy^2, dz^2]) left to right, as the reference's euclidean()
-            s = s + dy * dy;
-            if (has_z) {
-                const double dz = zr - (staged ? s_z[c] : gz[c]);
-                s = s + dz * dz;
-            }
-            if (s <= p.sq_dist_max) {
-                if (FILL) {
-                    const int other = staged ? s_perm[c] : gperm[c];
-                    int64_t e = out_base + cnt;
-                    if (e < p.edge_capacity) {
-                        // insertion into the (short) run of this frame's arcs, ascending detection index
-                        const int64_t e_first = out_base + first;
-                        while (e > e_first && p.col[e - 1] > other) {
-                            p.col[e] = p.col[e - 1];
-                            p.cost[e] = p.cost[e - 1];
-                            e--;
-                        }
-                        p.col[e] = other;
-                        p.cost[e] = __double_as_longlong(s);
-                    } else if (p.overflow) {
-                        *p.overflow = 1;
-                    }
-                }
-                cnt++;
-            }
-        }
-    }
+    int cnt;
+    if (staged)
+        cnt = row_arcs<DIR, FILL, true>(p, r, kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z, s_perm, s_key, m);
+    else
+        cnt = row_arcs<DIR, FILL, false>(p, r, kmin, tabled, s_seg_lo, s_seg_hi, p.spos + lo, p.spos + n + lo,
+                                         p.spos + 2 * n + lo, p.sperm + lo, p.tkey + lo, m);
     if (!FILL) p.row_count[r] = cnt;
 }
 
