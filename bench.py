@@ -346,7 +346,8 @@ def run_ours(args):
                 "node_pulls_per_graph_mean": float(stats[:, 2].mean()),
                 "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(
-                    ["sink_argmin", "collect_branch", "stage", "walk", "sweeps", "write_back", "first_tree"])}}
+                    ["sink_argmin", "list_branch", "stage_and_initial_labels", "walk", "fix_point", "certificate"])},
+                "components_finished_by_certificate_per_graph_mean": float(stats[:, 10].mean())}
     roofline_build = {"bound": "hbm", "kernel": "k_frame_sort + k_edge_build_pruned<count> + <fill> + k_edge_cost", "achieved": build_gbs, "peak": peak,
                       "unit": "GB/s", "frac": build_gbs / peak, "traffic": traffic_build,
                       "algorithmic_bytes_per_launch": build_bytes, "launch_ms": float(build_ms)}

@@ -202,9 +202,10 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
  *   path_cost_out : optional [n_total]; the accepted path costs of graph g are the entries < MOT3D_INF_COST of its slice
  *                   [graph_ptr[g], graph_ptr[g+1]) (grouped by connected component, ascending inside a component)
  *   stats_out     : optional int64 [n_graphs][MOT3D_SOLVE_STATS]: [0..3] = ascending sweeps, descending sweeps, node
- *                   pulls, arc pulls (what bench.py's roofline accounting needs); [4..10] = SM cycles spent in:
- *                   sink arg-min, branch collection, staging, path walk, re-labelling sweeps, write-back, first tree;
- *                   [11] = branches re-labelled, [12] = records staged for them, [13..14] = SM cycles of the sweep
+ *                   pulls, arc pulls (what bench.py's roofline accounting needs); [4..9] = SM cycles spent in:
+ *                   sink arg-min, branch listing, staging + initial labels, path walk, fix-point rounds, optimality
+ *                   certificate; [10] = components finished by the certificate;
+ *                   [11] = branches re-labelled, [12] = records listed for them, [13..14] = SM cycles of the sweep
  *                   warp in ascending / descending sweeps, [15..16] = ascending / descending steps, [17] (first graph of the
  *                   batch only) = cycles all solver blocks were busy, summed; [18..21] = [13..16] of the
  *                   components solved on the global staging area alone, [22] = how many, [23] = their cycles

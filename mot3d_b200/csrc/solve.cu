@@ -176,7 +176,9 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 struct Counters {
     int64_t n_arc;            // arcs read while staging
     int64_t n_branch, n_rec;  // branches re-labelled, records listed for them
-    long long t_phase[7];  // cycles (thread 0): arg-min, branch list, staging + initial labels, walk, fix-point, -, -
+    int64_t n_cert;           // components finished by the optimality certificate instead of a last re-labelling
+    long long t_phase[7];  // cycles (thread 0): arg-min, branch list, staging + initial labels, walk, fix-point, -,
+                           // optimality certificate
     long long t_mark, t_start;
     __device__ __forceinline__ void tick(int k) {
         const long long now = clock64();
@@ -359,7 +361,7 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
     const int32_t *perm = p.comp_perm + c0;
 
     Counters cnt;
-    cnt.n_arc = cnt.n_branch = cnt.n_rec = 0;
+    cnt.n_arc = cnt.n_branch = cnt.n_rec = cnt.n_cert = 0;
     for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
     cnt.t_mark = cnt.t_start = clock64();
 
@@ -420,7 +422,7 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
     __syncthreads();
     cnt.tick(2);
 
-    int K = 0;
+    int K = 0, n_used = 0;
     int64_t total = 0;
     for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
         // ---- cheapest way into T
@@ -465,7 +467,96 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
         }
         const int root = rec[sink.idx].F.z;
         if (root < 0) break;  // cannot happen: a labelled node always has a branch
-        __syncthreads();      // everybody has read the root before the flags are rewritten
+        // ---- augment: walk the path back from T and rewrite next/prev (Graph::flip_path, Graph.cpp:266-335)
+        if (tid == 0) {
+            int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
+            for (int step = 0; step <= n; step++) {
+                const int cur_prv = rec[cur].A.z, cur_nxt = rec[cur].A.w;
+                rec[cur].A.w = nxt_new;
+                int m;
+                if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
+                    m = cur;
+                    joined++;
+                } else {  // post_cur came from pre_m, m = its old successor: the arc cur -> m is cancelled
+                    m = cur_nxt;
+                    while (m >= 0 && rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
+                        const int m2 = rec[m].A.w;
+                        rec[m].A.w = NONE;
+                        rec[m].A.z = NONE;
+                        m = m2;
+                        joined--;
+                    }
+                }
+                if (m < 0) break;  // cannot happen on a consistent residual state
+                const int q = rec[m].F.x;
+                if (q < 0) {  // PAR_S: the path starts here
+                    rec[m].A.z = TERM;
+                    ok = 1;
+                    break;
+                }
+                rec[m].A.z = q;
+                hop[nhop++] = (Slot)m;  // the cost of the newly matched arc q -> m is looked up below
+                nxt_new = m;
+                cur = q;
+            }
+            s_ok[0] = ok;
+            s_ok[1] = nhop;
+            s_ok[7] = joined;
+        }
+        __syncthreads();
+        cnt.tick(3);
+        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        n_used += s_ok[7];
+        for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
+            const int m = hop[h], q = rec[m].A.z;
+            const Arc *const ap = arcs_of(rec[m].A.y);
+            const int deg = ap[0].pad;
+            for (int k = 0; k < deg; k++) {
+                const Arc x = ap[k];
+                if ((int)x.src == q) {
+                    rec[m].W.w = x.cost;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- Is this component finished? Once every detection is on a track, a further S -> T path in the residual
+        //      network has the shape  S -> pre_i, (pre -> post of the predecessor: cancels a matched arc, -mc), then
+        //      any number of hops post_a -> pre_b -> post_prev(b) (an unused arc and the cancellation of b's matched
+        //      arc: w_ab - mc_b) or post_a -> pre_a -> post_prev(a) (-cn_a - mc_a), then post -> T. If every matched arc
+        //      is the cheapest in-arc of its head (w_ab >= mc_b), mc <= 0, cn + mc <= 0 and no entry / exit cost is
+        //      negative, every piece is >= 0: no path can pay, exactly what the re-labelling + arg-min below would
+        //      find out. One pass over the arcs instead.
+        if (n_used == n) {
+            bool good = true;
+            for (int ib = 0; ib < n; ib += ngrp) {
+                const int i = ib + grp;
+                if (i < n) {
+                    const int4 A = rec[i].A;
+                    const Costs W = rec[i].W;
+                    if ((S::has(W.x) && W.x < 0) || (S::has(W.z) && W.z < 0)) good = false;
+                    if (A.z >= 0) {
+                        const int64_t mc = W.w;
+                        if (mc > 0 || (int64_t)W.y + mc > 0) good = false;
+                        const Arc *const ap = arcs_of(A.y);
+                        const int deg = ap[0].pad;
+                        for (int k = sub; k < deg; k += LPN) {
+                            const Arc x = ap[k];
+                            if ((int)x.src != A.z && (int64_t)x.cost < mc) good = false;
+                        }
+                    }
+                }
+            }
+            if (__syncthreads_and(good)) {
+                if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
+                K++;
+                total += sink.key;
+                cnt.n_cert++;
+                cnt.tick(6);
+                break;
+            }
+            cnt.tick(6);
+        }
         // ---- the branch hanging from S -> pre_root, as a list of slots in layer order
         int nd;
         {
@@ -488,42 +579,6 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
         cnt.n_branch++;
         cnt.n_rec += nd;
         cnt.tick(1);
-        // ---- augment: walk the path back from T and rewrite next/prev (Graph::flip_path, Graph.cpp:266-335)
-        if (tid == 0) {
-            int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx;
-            for (int step = 0; step <= n; step++) {
-                const int cur_prv = rec[cur].A.z, cur_nxt = rec[cur].A.w;
-                rec[cur].A.w = nxt_new;
-                int m;
-                if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
-                    m = cur;
-                } else {  // post_cur came from pre_m, m = its old successor: the arc cur -> m is cancelled
-                    m = cur_nxt;
-                    while (m >= 0 && rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
-                        const int m2 = rec[m].A.w;
-                        rec[m].A.w = NONE;
-                        rec[m].A.z = NONE;
-                        m = m2;
-                    }
-                }
-                if (m < 0) break;  // cannot happen on a consistent residual state
-                const int q = rec[m].F.x;
-                if (q < 0) {  // PAR_S: the path starts here
-                    rec[m].A.z = TERM;
-                    ok = 1;
-                    break;
-                }
-                rec[m].A.z = q;
-                hop[nhop++] = (Slot)m;  // the cost of the newly matched arc q -> m is looked up below
-                nxt_new = m;
-                cur = q;
-            }
-            s_ok[0] = ok;
-            s_ok[1] = nhop;
-        }
-        __syncthreads();
-        cnt.tick(3);
-        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
         {  // the "producers" of the ascending sweeps (see below): every thread looks at a chunk of the list
             const int lchunk = (nd + T - 1) / T;
             const int lp0 = min(tid * lchunk, nd), lp1 = min(lp0 + lchunk, nd);
@@ -542,18 +597,6 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
             if (tid == 0) {
                 s_ok[6] = np;
                 s_ok[2] = s_ok[3] = s_ok[4] = s_ok[5] = 0;  // flags of the fix-point rounds
-            }
-        }
-        for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
-            const int m = hop[h], q = rec[m].A.z;
-            const Arc *const ap = arcs_of(rec[m].A.y);
-            const int deg = ap[0].pad;
-            for (int k = 0; k < deg; k++) {
-                const Arc x = ap[k];
-                if ((int)x.src == q) {
-                    rec[m].W.w = x.cost;
-                    break;
-                }
             }
         }
         __syncthreads();
@@ -889,6 +932,8 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
             atomicAdd(&o[2], (unsigned long long)s_work[2]);
             atomicAdd(&o[3], (unsigned long long)(cnt.n_arc + s_work[3]));
             for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)cnt.t_phase[k]);
+            atomicAdd(&o[9], (unsigned long long)cnt.t_phase[6]);
+            atomicAdd(&o[10], (unsigned long long)cnt.n_cert);
             atomicAdd(&o[11], (unsigned long long)cnt.n_branch);
             atomicAdd(&o[12], (unsigned long long)cnt.n_rec);
             for (int k = 0; k < 4; k++) atomicAdd(&o[13 + k], (unsigned long long)s_work[4 + k]);
