@@ -21,6 +21,7 @@
 //   acceptance     path 1 always; path k >= 2 while its cost < 0     (wrapper.cpp:199-267 on integers)
 // Flow read-out (make_output2, wrapper.cpp:139-169) is unnecessary: next/prev are the flow.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -99,7 +100,7 @@ struct SolveParams {
     int32_t n_graphs;
     int32_t rcap;   // shared-memory staging area: records / arcs (0 = off)
     int32_t racap;
-    int32_t pad;
+    int32_t role;   // 0 = the whole queue; 1 = the giants' launch (front of the queue); 2 = the main launch (the rest)
     int64_t n_total;
     const int32_t *graph_ptr;
     const int32_t *tkey;
@@ -963,23 +964,30 @@ __device__ __forceinline__ int job_class(int n) {
     return 4 * (lg - 1) + ((n >> (lg - 2)) & 3);  // 4 -> 4, 8 -> 8, ..., 8192 -> 48
 }
 __global__ void __launch_bounds__(1024) k_job_order(const SolveParams p) {
-    __shared__ int s_cnt[JOB_CLASSES], s_start[JOB_CLASSES];
+    // two bands of size classes: components that do not fit the main kernel's staging area ("giants", solved by a
+    // launch of their own with a large staging area, see mot3d_solve_batch) come first
+    __shared__ int s_cnt[2 * JOB_CLASSES], s_start[2 * JOB_CLASSES];
     const int n_jobs = p.n_cgraphs[0];
-    if (threadIdx.x < JOB_CLASSES) s_cnt[threadIdx.x] = 0;
+    auto band_class = [&](int n) { return job_class(n) + (n > p.rcap ? JOB_CLASSES : 0); };
+    if (threadIdx.x < 2 * JOB_CLASSES) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
-        atomicAdd(&s_cnt[job_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1);
+        atomicAdd(&s_cnt[band_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        for (int b = JOB_CLASSES - 1; b >= 0; b--) {
+        for (int b = 2 * JOB_CLASSES - 1; b >= 0; b--) {
             s_start[b] = run;
             run += s_cnt[b];
+            if (b == JOB_CLASSES) {
+                p.n_cgraphs[2] = run;  // cursor of the main kernel's part of the queue
+                p.n_cgraphs[3] = run;  // number of giants = where that part starts
+            }
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
-        p.job_order[atomicAdd(&s_start[job_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1)] = c;
+        p.job_order[atomicAdd(&s_start[band_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1)] = c;
 }
 
 // ---- successive shortest paths on every component graph. Blocks fetch components from a work queue.
@@ -1015,11 +1023,16 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
     }
     __syncthreads();
     const int sweep_warp = s_sweep_warp;
-    const int n_jobs = p.n_cgraphs[0];
+    // The giants' launch lets the main launch start right away (programmatic dependent launch: the two have no data
+    // dependency, they drain disjoint parts of the queue and only meet in integer atomics); the main launch waits for
+    // the giants' grid before it exits, so that whatever follows in the stream sees both finished.
+    if (p.role == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int n_jobs = (p.role == 1) ? p.n_cgraphs[3] : p.n_cgraphs[0];
+    int *const cursor = p.n_cgraphs + (p.role == 2 ? 2 : 1);
     const long long t_block0 = clock64();
 
     for (;;) {
-        if (tid == 0) s_job = atomicAdd(&p.n_cgraphs[1], 1);
+        if (tid == 0) s_job = atomicAdd(cursor, 1);
         if (tid < 8) s_work[tid] = 0;
         __syncthreads();
         const int job = s_job;
@@ -1028,6 +1041,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
             // [17] of the batch's first graph: cycles the blocks spent between their first and their last job
             if (tid == 0 && p.stats)
                 atomicAdd((unsigned long long *)(p.stats + 17), (unsigned long long)(clock64() - t_block0));
+            if (p.role == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
             break;
         }
         const int cg = p.job_order[job];
@@ -1169,7 +1183,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.n_graphs = n_graphs;
     p.rcap = 0;
     p.racap = 0;
-    p.pad = 0;
+    p.role = 0;
     p.n_total = (int64_t)n_total;
     p.graph_ptr = graph_ptr;
     p.tkey = tkey;
@@ -1225,8 +1239,6 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     // 2. first shortest-path tree per graph; work queue order of the components
     k_first_tree<<<n_graphs, 256, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_tree");
-    k_job_order<<<1, 1024, 0, st>>>(p);
-    M3_LAUNCH_CHECK("k_job_order");
     // 3. successive shortest paths per component. Shared memory per block = the staging area of one component; blocks
     //    pull components from the work queue. Graphs of more than 1024 detections fall apart into components of a
     //    few tracks each: room for 256 records, 8 blocks per SM. Small graphs are usually one dense component: room
@@ -1258,8 +1270,22 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         const int t = atoi(e);
         if (t == 32 || t == 64 || t == 128 || t == 192 || t == 256) threads = t;
     }
-    if (smem > 48 * 1024)
-        M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_job_order<<<1, 1024, 0, st>>>(p);  // after p.rcap is known: it splits the queue at that size
+    M3_LAUNCH_CHECK("k_job_order");
+    // Giants: components beyond the main staging area (C5: 0.2 % of them, several hundred detections, 6-9 tracks) are
+    // sequential work for one block and would set the length of the whole solve if they ran on the global staging
+    // area. They get a launch of their own - one 256-thread block per SM, room for 1024 records - which the main
+    // launch overlaps (programmatic dependent launch, see k_ssp_solve).
+    const bool split = p.rcap > 0 && (size_t)max_graph_nodes > rcap && !getenv("MOT3D_SOLVE_NO_GIANTS");
+    size_t g_rcap = 1024, g_smem = 0;
+    if (split) {
+        if (g_rcap > (size_t)((max_graph_nodes + 7) & ~7)) g_rcap = (size_t)((max_graph_nodes + 7) & ~7);
+        g_smem = (16 + g_rcap * SM_BYTES_PER_REC + (g_rcap * 10 + 8) * SM_ARC_BYTES) & ~(size_t)15;
+        if (g_smem > (size_t)smem_sm - 4096) g_smem = ((size_t)smem_sm - 4096) & ~(size_t)15;
+    }
+    const size_t smem_max = g_smem > smem ? g_smem : smem;
+    if (smem_max > 48 * 1024)
+        M3_CUDA(cudaFuncSetAttribute(k_ssp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     M3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ssp_solve, threads, smem));
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("MOT3D_SOLVE_BLOCKS_PER_SM")) {
@@ -1268,7 +1294,31 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     }
     long long grid = (long long)n_sm * per_sm;
     if (grid > n_total) grid = n_total > 0 ? n_total : 1;  // never more blocks than possible components
-    k_ssp_solve<<<(unsigned)grid, threads, smem, st>>>(p);
+    if (split) {
+        SolveParams pg = p;
+        pg.role = 1;
+        pg.rcap = (int32_t)g_rcap;
+        pg.racap = (int32_t)((g_smem - 16 - g_rcap * SM_BYTES_PER_REC) / SM_ARC_BYTES - 8);
+        long long g_grid = n_sm;
+        if (g_grid > n_total / (long long)rcap + 1) g_grid = n_total / (long long)rcap + 1;  // giants are > rcap each
+        k_ssp_solve<<<(unsigned)g_grid, 256, g_smem, st>>>(pg);
+        M3_LAUNCH_CHECK("k_ssp_solve (giants)");
+        p.role = 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve, p));
+    } else {
+        k_ssp_solve<<<(unsigned)grid, threads, smem, st>>>(p);
+    }
     M3_LAUNCH_CHECK("k_ssp_solve");
     // 4. the reference's "first path is always kept" rule, per graph
     k_first_path_rule<<<(n_graphs + 127) / 128, 128, 0, st>>>(p);
