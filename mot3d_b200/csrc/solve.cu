@@ -124,7 +124,8 @@ struct SolveParams {
     const int32_t *cgraph_win;  // [n_cgraphs] graph of every component
     const int32_t *win_cbase;   // [n_graphs] first component of every graph
     int32_t *win_wide;          // [n_graphs] 1 = some cost does not fit 32 bits (k_first_tree)
-    int32_t *job_order;         // [n_cgraphs] component graphs, largest first (k_job_order)
+    int4 *job_tab;              // [n_cgraphs] the work queue, largest components first (k_job_order): x = first
+                                // position, y = detections (0 = nothing to do), z = graph, w = 1 if the costs are wide
     int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
@@ -366,50 +367,69 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
     for (int k = 0; k < 7; k++) cnt.t_phase[k] = 0;
     cnt.t_mark = cnt.t_start = clock64();
 
-    // ---- stage the component: records, then arc lists (offsets by a block scan over contiguous chunks)
+    // ---- stage the component. Records first: every load of a record is issued before any is used (one memory level
+    //      after the permutation); its in-degree and first arc wait in A.x / F.w for the arc pass. Arc-list offsets by
+    //      a block scan over contiguous chunks.
     const int chunk = (n + T - 1) / T;
     const int i0 = min(tid * chunk, n), i1 = min(i0 + chunk, n);
     {
         int my_arcs = 0;
         for (int i = i0; i < i1; i++) {
-            const int d = perm[i];
-            my_arcs += p.in_ptr[d + 1] - p.in_ptr[d] + 1;  // + 1: a list without arcs still carries its length
+            const int q = c0 + i, d = perm[i];
+            const int e0 = p.in_ptr[d], e1 = p.in_ptr[d + 1];
+            const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
+            const int64_t dpre = p.ws_dpre[q], dpost = p.ws_dpost[q];
+            const int64_t en = p.en[d], cn = p.cn[d], ex = p.ex[d];
+            const int key = p.tkey[d];
+            Rec r;
+            r.A = make_int4(e1 - e0, 0, NONE, NONE);
+            r.F = make_int4(par >= 0 ? par - c0 : par, ap_ >= 0 ? ap_ - c0 : -1, ao_ >= 0 ? ao_ - c0 : -1, e0);
+            r.E = make_longlong2(dpre, dpost);
+            r.W.x = S::conv(en);
+            r.W.y = S::conv(cn);
+            r.W.z = S::conv(ex);
+            r.W.w = 0;
+            rec[i] = r;
+            tk[i] = key;
+            my_arcs += e1 - e0 + 1;  // + 1: a list without arcs still carries its length
         }
         int tot;
         int a0 = block_excl_scan1(my_arcs, s_scan, 0, &tot);
         for (int i = i0; i < i1; i++) {
-            const int q = c0 + i, d = perm[i];
-            const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
+            const int deg = rec[i].A.x;
             int off = a0;
             a0 += deg + 1;
-            if (!SM || off + deg + 1 > p.racap) off = ~(e0 + d);  // (shared arc area full:) the list lives in global memory
-            const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
-            Rec r;
-            r.A = make_int4(0, off, NONE, NONE);
-            r.F = make_int4(par >= 0 ? par - c0 : par, ap_ >= 0 ? ap_ - c0 : -1, ao_ >= 0 ? ao_ - c0 : -1, 0);
-            r.E = make_longlong2(p.ws_dpre[q], p.ws_dpost[q]);
-            r.W.x = S::conv(p.en[d]);
-            r.W.y = S::conv(p.cn[d]);
-            r.W.z = S::conv(p.ex[d]);
-            r.W.w = 0;
-            rec[i] = r;
-            tk[i] = p.tkey[d];
+            // (shared arc area full:) the list lives in global memory, at the detection's own place
+            if (!SM || off + deg + 1 > p.racap) off = ~(rec[i].F.w + perm[i]);
+            rec[i].A.y = off;
         }
         if (tid == 0) cnt.n_arc += tot - n;
     }
     __syncthreads();
-    for (int ib = 0; ib < n; ib += ngrp) {
+    for (int ib = 0; ib < n; ib += ngrp) {  // arc lists: one lane group per record, two independent arcs per lane
         const int i = ib + grp;
         if (i < n) {
-            const int d = perm[i];
-            const int e0 = p.in_ptr[d], deg = p.in_ptr[d + 1] - e0;
+            const int e0 = rec[i].F.w, deg = rec[i].A.x;
             Arc *const ap = arcs_of(rec[i].A.y);
-            for (int k = sub; k < deg; k += LPN) {
-                Arc x;
-                x.cost = (decltype(x.cost))p.in_cost[e0 + k];
-                x.src = (decltype(x.src))(p.comp_inv[p.in_src[e0 + k]] - c0);
-                x.pad = (decltype(x.pad))deg;  // only read from the first arc of the list
-                ap[k] = x;
+            for (int kb = 0; kb < deg; kb += 2 * LPN) {
+                const int k0 = kb + sub, k1 = kb + LPN + sub;
+                const int src0 = k0 < deg ? p.in_src[e0 + k0] : 0, src1 = k1 < deg ? p.in_src[e0 + k1] : 0;
+                const int64_t w0 = k0 < deg ? p.in_cost[e0 + k0] : 0, w1 = k1 < deg ? p.in_cost[e0 + k1] : 0;
+                const int q0 = p.comp_inv[src0], q1 = p.comp_inv[src1];
+                if (k0 < deg) {
+                    Arc x;
+                    x.cost = (decltype(x.cost))w0;
+                    x.src = (decltype(x.src))(q0 - c0);
+                    x.pad = (decltype(x.pad))deg;  // only read from the first arc of the list
+                    ap[k0] = x;
+                }
+                if (k1 < deg) {
+                    Arc x;
+                    x.cost = (decltype(x.cost))w1;
+                    x.src = (decltype(x.src))(q1 - c0);
+                    x.pad = (decltype(x.pad))deg;
+                    ap[k1] = x;
+                }
             }
             if (deg == 0 && sub == 0) {
                 Arc x;
@@ -472,16 +492,21 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
         if (tid == 0) {
             int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
             for (int step = 0; step <= n; step++) {
-                const int cur_prv = rec[cur].A.z, cur_nxt = rec[cur].A.w;
+                const int4 A = rec[cur].A;         // z = prev, w = next
+                const int par_cur = rec[cur].F.x;  // in flight together: the parent of pre_cur (used when cur joins)
                 rec[cur].A.w = nxt_new;
-                int m;
-                if (cur_prv == NONE) {  // post_cur came from pre_cur: detection cur joins a track
+                int m, q;
+                if (A.z == NONE) {  // post_cur came from pre_cur: detection cur joins a track
                     m = cur;
+                    q = par_cur;
                     joined++;
                 } else {  // post_cur came from pre_m, m = its old successor: the arc cur -> m is cancelled
-                    m = cur_nxt;
-                    while (m >= 0 && rec[m].F.x == PAR_POST) {  // pre_m came from post_m: m leaves its track
-                        const int m2 = rec[m].A.w;
+                    m = A.w;
+                    q = PAR_NONE;
+                    while (m >= 0) {
+                        q = rec[m].F.x;
+                        if (q != PAR_POST) break;
+                        const int m2 = rec[m].A.w;  // pre_m came from post_m: m leaves its track
                         rec[m].A.w = NONE;
                         rec[m].A.z = NONE;
                         m = m2;
@@ -489,7 +514,6 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
                     }
                 }
                 if (m < 0) break;  // cannot happen on a consistent residual state
-                const int q = rec[m].F.x;
                 if (q < 0) {  // PAR_S: the path starts here
                     rec[m].A.z = TERM;
                     ok = 1;
@@ -986,8 +1010,11 @@ __global__ void __launch_bounds__(1024) k_job_order(const SolveParams p) {
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
-        p.job_order[atomicAdd(&s_start[band_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1)] = c;
+    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x) {
+        const int c0 = p.cgraph_ptr[c], n = p.cgraph_ptr[c + 1] - c0, g = p.cgraph_win[c];
+        const bool skip = n <= 0 || p.n_paths[g] < 0;  // empty, or the graph was skipped (arc buffer overflow)
+        p.job_tab[atomicAdd(&s_start[band_class(n)], 1)] = make_int4(c0, skip ? 0 : n, g, p.win_wide[g] ? (c | (1 << 31)) : c);
+    }
 }
 
 // ---- successive shortest paths on every component graph. Blocks fetch components from a work queue.
@@ -995,6 +1022,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
     __shared__ int s_scan[64];
     __shared__ KeyIdx s_red[33];
     __shared__ int s_ok[8], s_sweep_warp, s_job;
+    __shared__ int4 s_tab;
     // counters of the fix-point rounds: ascending sweeps, descending passes, node pulls, arc pulls, cycles in ascending
     // sweeps / descending passes, ascending steps / descending hops
     __shared__ long long s_work[8];
@@ -1031,11 +1059,18 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
     int *const cursor = p.n_cgraphs + (p.role == 2 ? 2 : 1);
     const long long t_block0 = clock64();
 
+    // The queue index of the next job is fetched while the current one is being solved.
+    int next_job = 0;
+    if (tid == 0) next_job = atomicAdd(cursor, 1);
     for (;;) {
-        if (tid == 0) s_job = atomicAdd(cursor, 1);
+        if (tid == 0) {
+            s_job = next_job;
+            if (next_job < n_jobs) s_tab = p.job_tab[next_job];
+        }
         if (tid < 8) s_work[tid] = 0;
         __syncthreads();
         const int job = s_job;
+        const int4 jt = s_tab;
         __syncthreads();
         if (job >= n_jobs) {
             // [17] of the batch's first graph: cycles the blocks spent between their first and their last job
@@ -1044,12 +1079,10 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
             if (p.role == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
             break;
         }
-        const int cg = p.job_order[job];
-        const int c0 = p.cgraph_ptr[cg];
-        const int n = p.cgraph_ptr[cg + 1] - c0;
-        const int g = p.cgraph_win[cg];
-        if (n <= 0 || p.n_paths[g] < 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
-        if (n <= p.rcap && !p.win_wide[g])
+        if (tid == 0) next_job = atomicAdd(cursor, 1);
+        const int c0 = jt.x, n = jt.y, g = jt.z, cg = jt.w & 0x7fffffff;
+        if (n <= 0) continue;  // empty, or the graph was skipped (arc buffer overflow)
+        if (n <= p.rcap && jt.w >= 0)
             solve_component<true>(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
         else
             solve_component<false>(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, sweep_warp);
@@ -1149,7 +1182,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     if (n_total < 0 || n_graphs < 0 || arc_capacity < 0) return 0;
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
-    return a256(n * 8) * 3 + a256(n * 4) * 12 + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
+    return a256(n * 8) * 3 + a256(n * 4) * 11 + a256(n * 16) + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
            a256(n * sizeof(RecT<false>)) + a256((e + n + 8) * sizeof(StArc)) +
            a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
 }
@@ -1211,7 +1244,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.ws_hop = (int32_t *)take(n_cap * 4);
     p.ws_pl = (int32_t *)take(n_cap * 4);
     p.first_sink = (int32_t *)take(n_cap * 4);
-    p.job_order = (int32_t *)take(n_cap * 4);
+    p.job_tab = (int4 *)take(n_cap * 16);
     int32_t *comp_perm = (int32_t *)take(n_cap * 4);
     int32_t *comp_inv = (int32_t *)take(n_cap * 4);
     int32_t *cgraph_win = (int32_t *)take(n_cap * 4);
