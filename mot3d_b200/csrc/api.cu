@@ -1,6 +1,8 @@
 // C-ABI plumbing: version, thread-local error text, and the one-call host-buffer entry point
 // (pack -> H2D -> keys -> count -> scan -> fill -> solve -> tracks -> D2H).
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -51,8 +53,10 @@ extern "C" {
 const char *mot3d_version(void) { return "mot3d_b200 0.1 (sm_100a)"; }
 const char *mot3d_last_error(void) { return g_err; }
 
-size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
-    if (n < 0 || n_graphs < 0 || edge_capacity < 0) return 0;
+}  // extern "C"
+
+// device bytes one pipeline pass over (n, n_graphs, edge_capacity) needs
+static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
     size_t b = 0;
     int64_t n1 = n > 0 ? n : 1, g1 = n_graphs > 0 ? n_graphs : 1, e1 = edge_capacity > 0 ? edge_capacity : 1;
     b += align256((size_t)(g1 + 1) * 4);        // graph_ptr
@@ -77,32 +81,61 @@ size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t ed
     b += align256((size_t)g1 * 4);              // track_count
     b += align256((size_t)(n1 + g1) * 4);       // track_ptr
     b += align256((size_t)n1 * 4);              // track_det
-    return b + 4096;
+    return b;
 }
 
-int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec *spec, mot3d_host_result *res,
-                               void *device_ws, size_t ws_bytes, int64_t edge_capacity, void *stream) {
-    M3_CHECK_ARG(hb && spec && res, "NULL batch/spec/result");
-    M3_CHECK_ARG(hb->n_graphs >= 0 && hb->n >= 0, "negative sizes");
-    M3_CHECK_ARG(!spec->use_hist, "mot3d_track_batch_host: colour histograms go through the device entry points");
-    res->n_edges = 0;
-    if (hb->n == 0 || hb->n_graphs == 0) return MOT3D_OK;
-    M3_CHECK_ARG(hb->graph_ptr && hb->frame && hb->pos && hb->conf, "NULL host input");
-    M3_CHECK_ARG(!spec->use_bbox || hb->bbox, "use_bbox set but bbox is NULL");
-    M3_CHECK_ARG(res->track_count && res->track_ptr && res->track_det && res->total_cost, "NULL host output");
-    M3_CHECK_ARG(device_ws, "device_ws is NULL");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = hb->n;
-    const int32_t G = hb->n_graphs;
-    int32_t max_nodes = 0;
-    for (int g = 0; g < G; g++) {
-        int32_t c = hb->graph_ptr[g + 1] - hb->graph_ptr[g];
-        M3_CHECK_ARG(c >= 0, "graph_ptr must be non-decreasing");
-        if (c > max_nodes) max_nodes = c;
-    }
-    M3_CHECK_ARG(hb->graph_ptr[0] == 0 && hb->graph_ptr[G] == n, "graph_ptr must span [0, n]");
+// ---- software pipeline of mot3d_track_batch_host -----------------------------------------------------------------
+// Whole graphs are independent, so a large batch is cut into chunks of consecutive graphs. Every chunk runs its
+// H2D copies, its 18 kernels and its D2H copies on a stream of its own over its own slice of the workspace: the copy
+// engines move chunk c+1 in and chunk c-1 out while the SMs work on chunk c, and the tail of one chunk's solver
+// (a few long components) overlaps the next chunk's build.
+constexpr int HOST_MAX_CHUNKS = 8;
+constexpr int64_t HOST_CHUNK_MIN_DETS = 400000;  // below this a chunk cannot fill the GPU
 
-    Arena A(device_ws, ws_bytes);
+struct HostCtx {
+    int dev = -1;
+    cudaStream_t s[HOST_MAX_CHUNKS];  // kernels + D2H of chunk c; earlier chunks have the higher priority
+    cudaStream_t copy_in;             // all H2D copies, in chunk order
+    cudaEvent_t start, in[HOST_MAX_CHUNKS], done[HOST_MAX_CHUNKS];
+    int32_t *pinned = nullptr;  // [2 * HOST_MAX_CHUNKS]: overflow flag, arc count per chunk
+    int32_t *pinned_gptr = nullptr;  // chunk-local graph_ptr arrays (H2D source), grown on demand
+    size_t gptr_cap = 0;
+    cudaEvent_t t0 = nullptr, trace[HOST_MAX_CHUNKS][4];  // MOT3D_HOST_TRACE=1: H2D done, build done, solve done, D2H done
+};
+
+// per host thread and device: streams, events and a pinned scratch for the two scalars read back per chunk
+static HostCtx *host_ctx() {
+    static thread_local HostCtx ctx[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    HostCtx *c = &ctx[dev];
+    if (c->dev == dev) return c;
+    int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return nullptr;
+    for (int i = 0; i < HOST_MAX_CHUNKS; i++) {
+        int prio = prio_hi + i;
+        if (prio > prio_lo) prio = prio_lo;
+        if (cudaStreamCreateWithPriority(&c->s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&c->in[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaStreamCreateWithPriority(&c->copy_in, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c->start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc((void **)&c->pinned, sizeof(int32_t) * 2 * HOST_MAX_CHUNKS, cudaHostAllocDefault) != cudaSuccess)
+        return nullptr;
+    c->dev = dev;
+    return c;
+}
+
+// graphs [ga, gb) of the batch = detections [d0, d1): enqueue H2D, kernels and D2H on `st`. h_gptr = chunk-local
+// graph_ptr (host, must stay alive until the stream has consumed it); h_flags[0..1] receive overflow flag, arc count.
+static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *spec, mot3d_host_result *res, Arena &A,
+                             int32_t ga, int32_t gb, const int32_t *h_gptr, int32_t max_nodes, int64_t edge_capacity,
+                             int32_t *h_flags, cudaStream_t st, cudaStream_t cin, cudaEvent_t in_done,
+                             cudaEvent_t *trace) {
+    const int64_t d0 = hb->graph_ptr[ga], d1 = hb->graph_ptr[gb];
+    const int64_t n = d1 - d0, N = hb->n;
+    const int32_t G = gb - ga;
     int32_t *d_gptr = A.take<int32_t>(G + 1);
     int32_t *d_frame = A.take<int32_t>(n);
     int32_t *d_tkey = A.take<int32_t>(n);
@@ -132,18 +165,23 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     int32_t *d_tcount = A.take<int32_t>(G);
     int32_t *d_tptr = A.take<int32_t>(n + G);
     int32_t *d_tdet = A.take<int32_t>(n);
-    if (!A.ok) {
-        set_error("device workspace too small: need %zu bytes", mot3d_track_batch_workspace_bytes(n, G, edge_capacity));
-        return MOT3D_E_CAPACITY;
-    }
+    if (!A.ok) return MOT3D_E_CAPACITY;  // the caller retries with fewer chunks / reports
 
-    M3_CUDA(cudaMemcpyAsync(d_gptr, hb->graph_ptr, (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, st));
-    M3_CUDA(cudaMemcpyAsync(d_frame, hb->frame, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    M3_CUDA(cudaMemcpyAsync(d_pos, hb->pos, (size_t)n * 8 * hb->dim, cudaMemcpyHostToDevice, st));
-    M3_CUDA(cudaMemcpyAsync(d_conf, hb->conf, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (d_flags) M3_CUDA(cudaMemcpyAsync(d_flags, hb->flags, (size_t)n, cudaMemcpyHostToDevice, st));
-    if (d_bbox) M3_CUDA(cudaMemcpyAsync(d_bbox, hb->bbox, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    M3_CUDA(cudaMemcpyAsync(d_gptr, h_gptr, (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, cin));
+    M3_CUDA(cudaMemcpyAsync(d_frame, hb->frame + d0, (size_t)n * 4, cudaMemcpyHostToDevice, cin));
+    for (int k = 0; k < hb->dim; k++)
+        M3_CUDA(cudaMemcpyAsync(d_pos + (size_t)k * n, hb->pos + (size_t)k * N + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
+    M3_CUDA(cudaMemcpyAsync(d_conf, hb->conf + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
+    if (d_flags) M3_CUDA(cudaMemcpyAsync(d_flags, hb->flags + d0, (size_t)n, cudaMemcpyHostToDevice, cin));
+    if (d_bbox)
+        for (int k = 0; k < 4; k++)
+            M3_CUDA(cudaMemcpyAsync(d_bbox + (size_t)k * n, hb->bbox + (size_t)k * N + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
+    if (cin != st) {  // inputs travel on the copy stream (FIFO over the chunks); the chunk's own stream picks up from there
+        M3_CUDA(cudaEventRecord(in_done, cin));
+        M3_CUDA(cudaStreamWaitEvent(st, in_done, 0));
+    }
     M3_CUDA(cudaMemsetAsync(d_over, 0, 4, st));
+    if (trace) M3_CUDA(cudaEventRecord(trace[0], st));
 
     int32_t rc;
     if ((rc = mot3d_make_keys(d_frame, d_gptr, G, spec->max_jump, d_tkey, d_gbase, st))) return rc;
@@ -164,25 +202,170 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     if ((rc = mot3d_exclusive_scan_i32(d_rowcnt, n, d_rowptr, d_scan, scan_b, st))) return rc;
     if ((rc = mot3d_edge_fill(&d, spec, MOT3D_DIR_IN, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over, st)))
         return rc;
+    if (trace) M3_CUDA(cudaEventRecord(trace[1], st));
     if ((rc = mot3d_solve_batch(G, n, d_gptr, max_nodes, d_tkey, edge_capacity, d_rowptr, d_col, d_cost, d_en, d_cn, d_ex, d_next, d_prev,
                                 d_np, d_total, nullptr, nullptr, d_solve, solve_b, st)))
         return rc;
     if ((rc = mot3d_extract_tracks(G, d_gptr, d_next, d_prev, d_tcount, d_tptr, d_tdet, st))) return rc;
+    if (trace) M3_CUDA(cudaEventRecord(trace[2], st));
 
-    int32_t h_over = 0, h_edges = 0;
-    M3_CUDA(cudaMemcpyAsync(res->track_count, d_tcount, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(res->track_ptr, d_tptr, (size_t)(n + G) * 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(res->track_det, d_tdet, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(res->total_cost, d_total, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(&h_edges, d_rowptr + n, 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaStreamSynchronize(st));
-    res->n_edges = h_edges;
-    if (h_over || h_edges > edge_capacity) {
-        set_error("edge capacity %lld too small: the batch has %d transition arcs", (long long)edge_capacity, h_edges);
-        return MOT3D_E_CAPACITY;
-    }
+    // the per-graph slices of the outputs sit at graph_ptr[g] + g / graph_ptr[g] (include/mot3d_b200.h), so a chunk's
+    // outputs are one contiguous slice of the caller's arrays
+    M3_CUDA(cudaMemcpyAsync(res->track_count + ga, d_tcount, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+    M3_CUDA(cudaMemcpyAsync(res->track_ptr + d0 + ga, d_tptr, (size_t)(n + G) * 4, cudaMemcpyDeviceToHost, st));
+    M3_CUDA(cudaMemcpyAsync(res->track_det + d0, d_tdet, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    M3_CUDA(cudaMemcpyAsync(res->total_cost + ga, d_total, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+    M3_CUDA(cudaMemcpyAsync(h_flags, d_over, 4, cudaMemcpyDeviceToHost, st));
+    M3_CUDA(cudaMemcpyAsync(h_flags + 1, d_rowptr + n, 4, cudaMemcpyDeviceToHost, st));
+    if (trace) M3_CUDA(cudaEventRecord(trace[3], st));
     return MOT3D_OK;
+}
+
+extern "C" {
+
+size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
+    if (n < 0 || n_graphs < 0 || edge_capacity < 0) return 0;
+    // every array is linear in (n, n_graphs, edge_capacity) up to its 256-byte alignment and a few constants, so the
+    // chunks of the software pipeline fit into the single-pass size plus a fixed allowance per chunk
+    return pass_bytes(n, n_graphs, edge_capacity) + (size_t)HOST_MAX_CHUNKS * 65536 + 4096;
+}
+
+int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec *spec, mot3d_host_result *res,
+                               void *device_ws, size_t ws_bytes, int64_t edge_capacity, void *stream) {
+    M3_CHECK_ARG(hb && spec && res, "NULL batch/spec/result");
+    M3_CHECK_ARG(hb->n_graphs >= 0 && hb->n >= 0, "negative sizes");
+    M3_CHECK_ARG(!spec->use_hist, "mot3d_track_batch_host: colour histograms go through the device entry points");
+    res->n_edges = 0;
+    if (hb->n == 0 || hb->n_graphs == 0) return MOT3D_OK;
+    M3_CHECK_ARG(hb->graph_ptr && hb->frame && hb->pos && hb->conf, "NULL host input");
+    M3_CHECK_ARG(!spec->use_bbox || hb->bbox, "use_bbox set but bbox is NULL");
+    M3_CHECK_ARG(res->track_count && res->track_ptr && res->track_det && res->total_cost, "NULL host output");
+    M3_CHECK_ARG(device_ws, "device_ws is NULL");
+    M3_CHECK_ARG(edge_capacity >= 0, "negative edge capacity");
+    cudaStream_t user = (cudaStream_t)stream;
+    const int64_t n = hb->n;
+    const int32_t G = hb->n_graphs;
+    for (int g = 0; g < G; g++)
+        M3_CHECK_ARG(hb->graph_ptr[g + 1] >= hb->graph_ptr[g], "graph_ptr must be non-decreasing");
+    M3_CHECK_ARG(hb->graph_ptr[0] == 0 && hb->graph_ptr[G] == n, "graph_ptr must span [0, n]");
+
+    // Number of chunks: MOT3D_HOST_CHUNKS, else two for batches large enough to keep the GPU busy with half of them.
+    // More chunks lose: the solver of a chunk cannot take less than ~2 ms (its largest components are sequential
+    // work, profiles/r01e_summary.md), so the chunks' solvers queue up instead of overlapping.
+    int want = n >= 2 * HOST_CHUNK_MIN_DETS ? 2 : 1;
+    if (const char *e = getenv("MOT3D_HOST_CHUNKS")) want = atoi(e);
+    if (want > HOST_MAX_CHUNKS) want = HOST_MAX_CHUNKS;
+    if (want > G) want = G;
+    if (want < 1) want = 1;
+    double edge_w = 1.0 / 3.0;  // size of the first and the last chunk relative to the inner ones
+    if (const char *e = getenv("MOT3D_HOST_EDGE_WEIGHT")) edge_w = atof(e) > 0 ? atof(e) : edge_w;
+    HostCtx *ctx = host_ctx();
+    if (!ctx) return cuda_fail(cudaGetLastError(), "mot3d_track_batch_host: stream/event/pinned scratch creation");
+
+    // chunk-local graph_ptr arrays: pinned, so that their H2D copies are asynchronous like the rest
+    if (ctx->gptr_cap < (size_t)(G + HOST_MAX_CHUNKS + 1)) {
+        if (ctx->pinned_gptr) cudaFreeHost(ctx->pinned_gptr);
+        ctx->pinned_gptr = nullptr;
+        ctx->gptr_cap = 0;
+        const size_t cap = (size_t)(G + HOST_MAX_CHUNKS + 1) * 2;
+        M3_CUDA(cudaHostAlloc((void **)&ctx->pinned_gptr, cap * sizeof(int32_t), cudaHostAllocDefault));
+        ctx->gptr_cap = cap;
+    }
+    int32_t *h_gptr = ctx->pinned_gptr;
+    const bool tracing = getenv("MOT3D_HOST_TRACE") != nullptr;
+    if (tracing && !ctx->t0) {
+        M3_CUDA(cudaEventCreate(&ctx->t0));
+        for (int c = 0; c < HOST_MAX_CHUNKS; c++)
+            for (int k = 0; k < 4; k++) M3_CUDA(cudaEventCreate(&ctx->trace[c][k]));
+    }
+    int32_t rc = MOT3D_OK;
+    for (int chunks = want;; chunks = 1) {
+        // cut at graph boundaries closest to equal detection counts
+        int32_t cut[HOST_MAX_CHUNKS + 1];
+        cut[0] = 0;
+        int nc = 0;
+        // a short first chunk gets the SMs going early, a short last one keeps the exposed D2H tail short
+        double wsum = 0, wacc = 0, wgt[HOST_MAX_CHUNKS];
+        for (int c = 0; c < chunks; c++) wsum += (wgt[c] = (chunks >= 3 && (c == 0 || c == chunks - 1)) ? edge_w : 1.0);
+        for (int c = 1, g = 0; c <= chunks; c++) {
+            wacc += wgt[c - 1];
+            const int64_t target = (int64_t)((double)n * (wacc / wsum));
+            while (g < G && hb->graph_ptr[g] < target) g++;
+            if (c == chunks) g = G;
+            if (g > cut[nc]) cut[++nc] = g;
+        }
+        Arena A(device_ws, ws_bytes);
+        M3_CUDA(cudaEventRecord(ctx->start, user));
+        if (nc > 1) M3_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->start, 0));
+        if (tracing) M3_CUDA(cudaEventRecord(ctx->t0, user));
+        int64_t edges = 0;
+        bool retry = false;
+        rc = MOT3D_OK;
+        int32_t *hg = h_gptr;
+        for (int c = 0; c < nc && rc == MOT3D_OK; c++) {
+            const int32_t ga = cut[c], gb = cut[c + 1];
+            const int64_t d0 = hb->graph_ptr[ga], nd = hb->graph_ptr[gb] - d0;
+            int32_t max_nodes = 0;
+            for (int g = ga; g <= gb; g++) {
+                hg[g - ga] = (int32_t)(hb->graph_ptr[g] - d0);
+                if (g < gb && hb->graph_ptr[g + 1] - hb->graph_ptr[g] > max_nodes)
+                    max_nodes = hb->graph_ptr[g + 1] - hb->graph_ptr[g];
+            }
+            // the arc buffer is shared out by detection count; a chunk that needs more sends the batch through again
+            // in one piece, so the capacity the caller has to provide does not depend on the chunking
+            const int64_t cap = nc == 1 ? edge_capacity : (int64_t)((double)edge_capacity * ((double)nd / (double)n));
+            cudaStream_t st = nc == 1 ? user : ctx->s[c];
+            if (nc > 1) M3_CUDA(cudaStreamWaitEvent(st, ctx->start, 0));
+            rc = enqueue_chunk(hb, spec, res, A, ga, gb, hg, max_nodes, cap, ctx->pinned + 2 * c, st,
+                               nc == 1 ? user : ctx->copy_in, ctx->in[c], tracing ? ctx->trace[c] : nullptr);
+            if (nc > 1 && rc == MOT3D_OK) {
+                M3_CUDA(cudaEventRecord(ctx->done[c], st));
+                M3_CUDA(cudaStreamWaitEvent(user, ctx->done[c], 0));
+            }
+            hg += gb - ga + 1;
+        }
+        // everything enqueued so far has to drain before the workspace or h_gptr can be reused, error or not
+        cudaError_t se = cudaSuccess;
+        if (nc > 1)
+            for (int c = 0; c < nc; c++) {
+                cudaError_t e1 = cudaStreamSynchronize(ctx->s[c]);
+                if (se == cudaSuccess) se = e1;
+            }
+        cudaError_t e2 = cudaStreamSynchronize(user);
+        if (se == cudaSuccess) se = e2;
+        if (rc == MOT3D_E_CAPACITY && !A.ok) {
+            if (nc > 1) continue;  // the allowance per chunk did not cover this cut: one piece always fits
+            set_error("device workspace too small: need %zu bytes", mot3d_track_batch_workspace_bytes(n, G, edge_capacity));
+            break;
+        }
+        if (rc != MOT3D_OK) break;
+        if (se != cudaSuccess) {
+            rc = cuda_fail(se, "mot3d_track_batch_host");
+            break;
+        }
+        if (tracing)
+            for (int c = 0; c < nc; c++) {
+                float t[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], ctx->t0, ctx->trace[c][k]);
+                fprintf(stderr, "mot3d host pipeline: chunk %d/%d graphs [%d, %d): H2D done %.3f ms, build done %.3f, "
+                                "solve+tracks done %.3f, D2H done %.3f\n", c, nc, cut[c], cut[c + 1], t[0], t[1], t[2], t[3]);
+            }
+        for (int c = 0; c < nc; c++) {
+            const int64_t nd = (int64_t)hb->graph_ptr[cut[c + 1]] - hb->graph_ptr[cut[c]];
+            const int64_t cap = nc == 1 ? edge_capacity : (int64_t)((double)edge_capacity * ((double)nd / (double)n));
+            edges += ctx->pinned[2 * c + 1];
+            if (ctx->pinned[2 * c] || ctx->pinned[2 * c + 1] > cap) retry = true;
+        }
+        res->n_edges = edges;
+        if (retry) {
+            if (nc > 1 && edges <= edge_capacity) continue;  // the whole batch fits: run it in one piece
+            set_error("edge capacity %lld too small: the batch has %lld transition arcs", (long long)edge_capacity,
+                      (long long)edges);
+            rc = MOT3D_E_CAPACITY;
+        }
+        break;
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -265,6 +265,55 @@ def test_host_buffer_entry_point():
     assert e.value.code == -3
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_host_entry_point_chunked_pipeline(chunks, monkeypatch):
+    """The software pipeline inside mot3d_track_batch_host (chunks of whole graphs on streams of their own, copies
+    overlapped with kernels) returns what the device path returns on a ragged batch, whatever the number of chunks;
+    a chunk whose share of the arc buffer is too small sends the batch through again in one piece."""
+    import mot3d_b200 as mot3d
+    rng = np.random.RandomState(11)
+    spec = mot3d.CostSpec(kind="detections_2d", max_jump=4, weight_source_sink=1, confidence=dict(mul=1, bias=0),
+                          distance=dict(sigma_jump=1, sigma_distance=10, max_distance=30, use_color_histogram=False,
+                                        use_bbox=False))
+    frames, poss, gp = [], [], [0]
+    for g in range(11):
+        # ragged: empty graphs, a lone detection, sparse and crowded windows (the crowded ones own most of the arcs)
+        F = [0, 1, 12, 25, 3, 40, 0, 18, 30, 9, 22][g]
+        P = [0, 1, 6, 14, 2, 30, 0, 4, 3, 25, 8][g]
+        extent = 60.0 if g in (5, 9) else 400.0
+        pos = rng.rand(P, 2) * extent
+        for f in range(F):
+            pos = pos + rng.randn(P, 2)
+            keep = rng.rand(P) < 0.9
+            frames.append(np.full(int(keep.sum()), f))
+            poss.append(pos[keep].copy())
+        gp.append(sum(len(x) for x in frames))
+    frame = np.concatenate(frames)
+    pos = np.concatenate(poss)
+    gp = np.array(gp)
+    n = len(frame)
+    conf = 0.5 + 0.5 * rng.rand(n)
+    b, order = mot3d.DetectionBatch.from_arrays(gp, frame, pos, conf)
+    assert (order == np.arange(n)).all()
+    gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+    want_tracks = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                        sol.track_det.cpu().numpy())
+    monkeypatch.setenv("MOT3D_HOST_CHUNKS", str(chunks))
+    for cap in (gb.n_edges + 64, gb.n_edges):  # roomy, then exact: the crowded chunk overflows its share
+        ht = mot3d.HostTracker(n_max=n + 5, g_max=len(gp) + 2, edge_capacity=cap, dim=2)
+        ht.load(b)
+        assert ht.run(spec.to_c()) == gb.n_edges
+        assert ht.tracks() == want_tracks
+        assert ht.h_total[:len(gp) - 1].tolist() == sol.total_cost.cpu().tolist()
+        assert ht.run(spec.to_c()) == gb.n_edges  # the workspace and the streams are reusable
+        assert ht.tracks() == want_tracks
+    small = mot3d.HostTracker(n_max=n, g_max=len(gp), edge_capacity=gb.n_edges - 1, dim=2)
+    small.load(b)
+    with pytest.raises(mot3d.Mot3dError) as e:
+        small.run(spec.to_c())
+    assert e.value.code == -3
+
+
 def test_entry_exit_flags_against_oracle():
     """entry_points / exit_point = False (mot3d/mot3d.py:90-99): muSSP cannot run such graphs (UB), the
     integer oracle can."""
