@@ -191,7 +191,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import mot3d_b200 as mot3d
-    from mot3d_b200.pipeline import TrackPipeline, STAGES, LAUNCHES_PER_RUN
+    from mot3d_b200.pipeline import TrackPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,7 +216,8 @@ def run_ours(args):
     E = gb.n_edges
     cap = int(E * 1.02) + 1024
     del gb
-    pipe = TrackPipeline(n, G, cap, device=dev)
+    pipe = TrackPipeline(n, G, cap, device=dev, fused=not args.unfused)
+    STAGES, LAUNCHES_PER_RUN = pipe.stages, pipe.launches_per_run
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -315,8 +316,8 @@ def run_ours(args):
     solve_gbs = solve_bytes / (stage_ms[i_solve] * 1e-3) / 1e9
     # edge build (count + fill): detections 32 B (frame 4 + pos 16 + conf 8, padded) + row_ptr 4 B + arcs 12 B
     build_bytes = n * 32.0 + 4.0 * (n + 1) + E * 12.0
-    build_ms = (stage_ms[STAGES.index("frame_sort")] + stage_ms[STAGES.index("edge_count")] +
-                stage_ms[STAGES.index("edge_fill")])
+    build_stages = ["frame_sort", "edge_build"] if pipe.fused else ["frame_sort", "edge_count", "row_scan", "edge_fill"]
+    build_ms = sum(stage_ms[STAGES.index(k)] for k in build_stages)
     build_gbs = build_bytes / (build_ms * 1e-3) / 1e9
     # measured DRAM traffic per launch: from the committed ncu capture of this very configuration, else null
     traffic_solve = traffic_build = None
@@ -348,7 +349,9 @@ def run_ours(args):
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(
                     ["sink_argmin", "list_branch", "stage_and_initial_labels", "walk", "fix_point", "certificate"])},
                 "components_finished_by_certificate_per_graph_mean": float(stats[:, 10].mean())}
-    roofline_build = {"bound": "hbm", "kernel": "k_frame_sort + k_edge_build_pruned<count> + <fill> + k_edge_cost", "achieved": build_gbs, "peak": peak,
+    roofline_build = {"bound": "hbm", "kernel": ("k_frame_sort + k_edge_build_fused" if pipe.fused else
+                                 "k_frame_sort + k_edge_build_pruned<count> + scan + <fill> + k_edge_cost"),
+                      "achieved": build_gbs, "peak": peak,
                       "unit": "GB/s", "frac": build_gbs / peak, "traffic": traffic_build,
                       "algorithmic_bytes_per_launch": build_bytes, "launch_ms": float(build_ms)}
 
@@ -399,6 +402,8 @@ def main():
     ap.add_argument("--seqs", type=int, default=60, help="sequences (of 20 windows) per GPU and step")
     ap.add_argument("--cpu-windows", type=int, default=40, help="windows in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="count -> scan -> fill graph build instead of the "
+                    "single-pass kernel (device-resident arm only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -120,6 +120,24 @@ int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int
                         int64_t edge_capacity, int32_t *col_out, int64_t *cost_out, double *weight_out,
                         int32_t *overflow_flag, void *stream);
 
+/* Single-pass build (csrc/edge_fused.cu): rows [row_begin, row_end) of the transition CSR in ONE launch - what
+ * mot3d_edge_count + mot3d_exclusive_scan_i32 + mot3d_edge_fill produce, bit for bit, without the second sweep over
+ * the candidates, the scan kernels and the (column, squared distance) round trip through HBM. Needs the x-sorted
+ * copies (mot3d_frame_sort). Arc offsets come from a decoupled look-back over 256-row tiles:
+ *   row_ptr_out[r] for r in [row_begin, row_end] (absolute offsets into col_out / cost_out / weight_out)
+ *   arc_base_in   device int64 or NULL: offset of the first arc of row_begin (NULL = 0), so that consecutive calls over
+ *                 consecutive row ranges append to one CSR;  arc_total_out: device int64 or NULL, receives the offset
+ *                 after the last arc (may alias arc_base_in)
+ *   overflow_flag device int32: bit 0 set when arcs beyond edge_capacity were dropped (row_ptr_out stays exact), bit 1
+ *                 when a tile's time window holds more than 2^24 detections (not supported)
+ *   ws            mot3d_edge_build_workspace_bytes(row_end - row_begin) bytes of device scratch
+ * weight_out / use_hist as in mot3d_edge_fill. */
+size_t mot3d_edge_build_workspace_bytes(int64_t n_rows);
+int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction, int64_t row_begin,
+                         int64_t row_end, int32_t *row_ptr_out, int64_t edge_capacity, int32_t *col_out,
+                         int64_t *cost_out, double *weight_out, int32_t *overflow_flag, const int64_t *arc_base_in,
+                         int64_t *arc_total_out, void *ws, size_t ws_bytes, void *stream);
+
 /* colour-histogram factor (color_histogram_similarity, mot3d/distance_functions.py:21-34) multiplied in, then the
  * bbox and jump factors, then quantisation. One warp per row. */
 int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction,

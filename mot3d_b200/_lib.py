@@ -80,6 +80,8 @@ SIGNATURES = {
     "mot3d_scan_workspace_bytes": (_sz, [_i64]),
     "mot3d_exclusive_scan_i32": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "mot3d_edge_fill": (_i32, [_PD, _PS, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_edge_build_workspace_bytes": (_sz, [_i64]),
+    "mot3d_edge_build": (_i32, [_PD, _PS, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_tracklet_edge_count": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _vp]),
     "mot3d_tracklet_edge_fill": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _i64, _vp, _vp,

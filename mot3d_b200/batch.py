@@ -130,9 +130,11 @@ def _dets_struct(b, tkey, spec, sorted_pos=None, sorted_perm=None):
     return d
 
 
-def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=None, pruned=True):
+def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=None, pruned=True, fused=True):
     """Graph build on the device. `batch` must already live on a CUDA device (DetectionBatch.to).
-    pruned=True: per-frame x-sorted copies + window search (csrc/edge_pruned.cu); False: test every pair."""
+    pruned=True: per-frame x-sorted copies + window search; fused=True (needs pruned): the single-pass kernel
+    (csrc/edge_fused.cu), else count -> scan -> fill (csrc/edge_pruned.cu). pruned=False: test every pair
+    (csrc/edge_build.cu). All three produce the same arrays bit for bit."""
     L = _lib.lib()
     dev = batch.frame.device
     if dev.type != "cuda":
@@ -164,22 +166,51 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
     gb.exit_cost = torch.empty(max(n, 1), **i64)
     _lib.check(L.mot3d_node_costs(ctypes.byref(d), ctypes.byref(cs), _ptr(gb.entry_cost), _ptr(gb.node_cost),
                                   _ptr(gb.exit_cost), st))
-    row_count = torch.empty(max(n, 1), **i32)
-    _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_count), st))
-    row_ptr = torch.empty(n + 1, **i32)
-    ws_bytes = L.mot3d_scan_workspace_bytes(n)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    _lib.check(L.mot3d_exclusive_scan_i32(_ptr(row_count), n, _ptr(row_ptr), _ptr(ws), ws_bytes, st))
-    n_edges = int(row_ptr[n].item()) if n else 0  # the one host read-back of the build: sizes the arc arrays
-    gb.n_edges = n_edges
-    gb.row_ptr = row_ptr
-    gb.col = torch.empty(max(n_edges, 1), **i32)
-    gb.cost = torch.empty(max(n_edges, 1), **i64)
     need_w = with_weights or spec.use_hist
-    gb.weight = torch.empty(max(n_edges, 1), dtype=torch.float64, device=dev) if need_w else None
-    overflow = torch.zeros(1, **i32)
-    _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), n_edges, _ptr(gb.col),
-                                 _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), st))
+    if fused and pruned and n:
+        # one launch; the arc arrays are sized by a guess and the launch is repeated in the rare case it was too small
+        row_ptr = torch.empty(n + 1, **i32)
+        ws_bytes = L.mot3d_edge_build_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        overflow = torch.zeros(1, **i32)
+        cap = max(16 * n, 1024)
+        while True:
+            gb.col = torch.empty(cap, **i32)
+            gb.cost = torch.empty(cap, **i64)
+            gb.weight = torch.empty(cap, dtype=torch.float64, device=dev) if need_w else None
+            overflow.zero_()
+            _lib.check(L.mot3d_edge_build(ctypes.byref(d), ctypes.byref(cs), direction, 0, n, _ptr(row_ptr), cap,
+                                          _ptr(gb.col), _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), None, None,
+                                          _ptr(ws), ws_bytes, st))
+            n_edges = int(row_ptr[n].item())  # the one host read-back of the build
+            flag = int(overflow.item())
+            if flag & 2:
+                raise _lib.Mot3dError(_lib.E_UNSUPPORTED, "more than 2^24 detections inside one time window")
+            if n_edges <= cap:
+                break
+            cap = n_edges
+        gb.n_edges = n_edges
+        gb.row_ptr = row_ptr
+        gb.col = gb.col[:max(n_edges, 1)]
+        gb.cost = gb.cost[:max(n_edges, 1)]
+        if need_w:
+            gb.weight = gb.weight[:max(n_edges, 1)]
+    else:
+        row_count = torch.empty(max(n, 1), **i32)
+        _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_count), st))
+        row_ptr = torch.empty(n + 1, **i32)
+        ws_bytes = L.mot3d_scan_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.mot3d_exclusive_scan_i32(_ptr(row_count), n, _ptr(row_ptr), _ptr(ws), ws_bytes, st))
+        n_edges = int(row_ptr[n].item()) if n else 0  # the one host read-back of the build: sizes the arc arrays
+        gb.n_edges = n_edges
+        gb.row_ptr = row_ptr
+        gb.col = torch.empty(max(n_edges, 1), **i32)
+        gb.cost = torch.empty(max(n_edges, 1), **i64)
+        gb.weight = torch.empty(max(n_edges, 1), dtype=torch.float64, device=dev) if need_w else None
+        overflow = torch.zeros(1, **i32)
+        _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), n_edges,
+                                     _ptr(gb.col), _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), st))
     if spec.use_hist:
         _lib.check(L.mot3d_edge_appearance(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), _ptr(gb.col),
                                            _ptr(gb.weight), _ptr(gb.cost), st))

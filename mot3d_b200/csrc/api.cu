@@ -1,5 +1,5 @@
 // C-ABI plumbing: version, thread-local error text, and the one-call host-buffer entry point
-// (pack -> H2D -> keys -> count -> scan -> fill -> solve -> tracks -> D2H).
+// (pack -> H2D -> keys -> frame sort -> single-pass arc build -> solve -> tracks -> D2H).
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -68,9 +68,8 @@ static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
     b += align256((size_t)g1 * 8);              // graph base
     b += align256((size_t)n1 * 8 * 3) + align256((size_t)n1 * 4);  // x-sorted copies + permutation
     b += align256((size_t)n1 * 8) * 3;          // entry/node/exit cost
-    b += align256((size_t)n1 * 4);              // row_count
     b += align256((size_t)(n1 + 1) * 4);        // row_ptr
-    b += align256(mot3d_scan_workspace_bytes(n1));
+    b += align256(mot3d_edge_build_workspace_bytes(n1));
     b += align256((size_t)e1 * 4);              // col
     b += align256((size_t)e1 * 8);              // cost
     b += align256(4);                           // overflow flag
@@ -149,10 +148,9 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     int64_t *d_en = A.take<int64_t>(n);
     int64_t *d_cn = A.take<int64_t>(n);
     int64_t *d_ex = A.take<int64_t>(n);
-    int32_t *d_rowcnt = A.take<int32_t>(n);
     int32_t *d_rowptr = A.take<int32_t>(n + 1);
-    size_t scan_b = mot3d_scan_workspace_bytes(n);
-    char *d_scan = A.take<char>((int64_t)scan_b);
+    size_t build_b = mot3d_edge_build_workspace_bytes(n);
+    char *d_build = A.take<char>((int64_t)build_b);
     int32_t *d_col = A.take<int32_t>(edge_capacity);
     int64_t *d_cost = A.take<int64_t>(edge_capacity);
     int32_t *d_over = A.take<int32_t>(1);
@@ -198,9 +196,8 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     d.sorted_perm = d_sperm;
     if ((rc = mot3d_node_costs(&d, spec, d_en, d_cn, d_ex, st))) return rc;
     if ((rc = mot3d_frame_sort(&d, st))) return rc;
-    if ((rc = mot3d_edge_count(&d, spec, MOT3D_DIR_IN, d_rowcnt, st))) return rc;
-    if ((rc = mot3d_exclusive_scan_i32(d_rowcnt, n, d_rowptr, d_scan, scan_b, st))) return rc;
-    if ((rc = mot3d_edge_fill(&d, spec, MOT3D_DIR_IN, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over, st)))
+    if ((rc = mot3d_edge_build(&d, spec, MOT3D_DIR_IN, 0, n, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over,
+                               nullptr, nullptr, d_build, build_b, st)))
         return rc;
     if (trace) M3_CUDA(cudaEventRecord(trace[1], st));
     if ((rc = mot3d_solve_batch(G, n, d_gptr, max_nodes, d_tkey, edge_capacity, d_rowptr, d_col, d_cost, d_en, d_cn, d_ex, d_next, d_prev,

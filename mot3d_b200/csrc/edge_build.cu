@@ -17,10 +17,6 @@ namespace m3 {
 constexpr int EB_TPB = 128;    // one thread per CSR row, 4 warps
 constexpr int EB_CHUNK = 1024; // candidates staged in shared memory per step
 
-struct JumpTable {
-    double v[MOT3D_MAX_JUMP];  // -exp(-(jump-1)*sigma_jump), host-evaluated (mot3d_cost_spec::neg_exp_jump)
-};
-
 struct EdgeParams {
     int64_t n;
     int32_t dim;
@@ -71,24 +67,6 @@ __device__ __forceinline__ int64_t warp_bound(const int32_t *__restrict__ a, int
         }
     }
     return lo;
-}
-
-__device__ __forceinline__ double bbox_similarity(const double *__restrict__ bb, int64_t n, int64_t a, int64_t b) {
-    // size = (ymax-ymin, xmax-xmin); 1 - (|h1-h2|/(max(h1,h2)+1e-12) + |w1-w2|/(max(w1,w2)+1e-12))/2
-    double h1 = bb[3 * n + a] - bb[1 * n + a];
-    double w1 = bb[2 * n + a] - bb[0 * n + a];
-    double h2 = bb[3 * n + b] - bb[1 * n + b];
-    double w2 = bb[2 * n + b] - bb[0 * n + b];
-    double th = fabs(h1 - h2) / (fmax(h1, h2) + 1e-12);
-    double tw = fabs(w1 - w2) / (fmax(w1, w2) + 1e-12);
-    return 1.0 - (th + tw) / 2.0;
-}
-
-// w = (-exp(-(jump-1)*sigma_jump)) * ((exp(-dist^2/sigma_d^2) [* w_hist]) * w_bbox)
-__device__ __forceinline__ double distance_factor(double s, double sigma_distance_sq) {
-    double dist = sqrt(s);
-    double q = dist * dist;  // the reference squares the rounded distance (dist**2)
-    return exp(-q / sigma_distance_sq);
 }
 
 template <int DIR, bool FILL>

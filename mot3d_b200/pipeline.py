@@ -1,5 +1,6 @@
 """TrackPipeline: the whole hot path on the device with preallocated buffers and no host synchronisation between
-stages -- keys -> node costs -> arc count -> row scan -> arc fill -> solve -> tracks. All graphs of a batch go
+stages -- keys -> node costs -> frame sort -> single-pass arc build -> solve -> tracks (fused=False: arc count -> row
+scan -> arc fill instead of the single-pass build). All graphs of a batch go
 through each kernel in one launch (one thread block per graph in the solver). This is what the batch scheduler runs
 per rank; bench.py times it stage by stage with CUDA events on the launching stream."""
 import ctypes
@@ -10,14 +11,17 @@ import torch
 from . import _lib
 from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
 
-STAGES = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
-# kernels launched by one run() (see the entry points in csrc/): keys 2, node costs 1, frame sort 1, edge count 1,
-# scan 3, edge fill + cost 2, solve 7 (components 3, first tree, job order, solver, first-path rule), extract 1
-LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 3 + 2 + 7 + 1
+STAGES = ["make_keys", "node_costs", "frame_sort", "edge_build", "solve", "extract"]
+STAGES_UNFUSED = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
+# kernels launched by one run() (see the entry points in csrc/): keys 2, node costs 1, frame sort 1, single-pass
+# build 1 (unfused: edge count 1, scan 3, edge fill + cost 2), solve 8 (components 3, first tree, job order, solver
+# x2: giants + main, first-path rule), extract 1
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 8 + 1
+LAUNCHES_PER_RUN_UNFUSED = 2 + 1 + 1 + 1 + 3 + 2 + 8 + 1
 
 
 class TrackPipeline(object):
-    def __init__(self, n_max, g_max, edge_capacity, device=None, dim=2, pruned=True):
+    def __init__(self, n_max, g_max, edge_capacity, device=None, dim=2, pruned=True, fused=True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         dev = self.device
         self.n_max, self.g_max, self.edge_capacity = int(n_max), int(g_max), int(edge_capacity)
@@ -32,6 +36,11 @@ class TrackPipeline(object):
         self.exit_cost = torch.empty(n, **i64)
         self.row_count = torch.empty(n, **i32)
         self.pruned = pruned
+        self.fused = bool(fused and pruned)
+        self.stages = STAGES if self.fused else STAGES_UNFUSED
+        self.launches_per_run = LAUNCHES_PER_RUN if self.fused else LAUNCHES_PER_RUN_UNFUSED
+        self.build_ws_bytes = L.mot3d_edge_build_workspace_bytes(n)
+        self.build_ws = torch.empty(self.build_ws_bytes, dtype=torch.uint8, device=dev)
         self.sorted_pos = torch.empty(dim * n, dtype=torch.float64, device=dev) if pruned else None
         self.sorted_perm = torch.empty(n, **i32) if pruned else None
         self.row_ptr = torch.empty(n + 1, **i32)
@@ -52,7 +61,7 @@ class TrackPipeline(object):
         self.track_det = torch.empty(n, **i32)
 
     def run(self, batch, spec, spec_c=None, events=None):
-        """batch: DetectionBatch on self.device. events: optional list of len(STAGES)+1 torch.cuda.Event recorded
+        """batch: DetectionBatch on self.device. events: optional list of len(self.stages)+1 torch.cuda.Event recorded
         around every stage on the current stream. Asynchronous: call check_overflow()/synchronize afterwards."""
         L = _lib.lib()
         dev = self.device
@@ -78,25 +87,33 @@ class TrackPipeline(object):
         if self.pruned:
             _lib.check(L.mot3d_frame_sort(ctypes.byref(d), st))
         rec(3)
-        _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
-        rec(4)
-        _lib.check(L.mot3d_exclusive_scan_i32(_ptr(self.row_count), n, _ptr(self.row_ptr), _ptr(self.scan_ws),
-                                              self.scan_ws_bytes, st))
-        rec(5)
-        _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_ptr),
-                                     self.edge_capacity, _ptr(self.col), _ptr(self.cost), None, _ptr(self.overflow),
-                                     st))
-        rec(6)
+        if self.fused:
+            _lib.check(L.mot3d_edge_build(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, 0, n, _ptr(self.row_ptr),
+                                          self.edge_capacity, _ptr(self.col), _ptr(self.cost), None,
+                                          _ptr(self.overflow), None, None, _ptr(self.build_ws), self.build_ws_bytes,
+                                          st))
+            k = 4
+        else:
+            _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
+            rec(4)
+            _lib.check(L.mot3d_exclusive_scan_i32(_ptr(self.row_count), n, _ptr(self.row_ptr), _ptr(self.scan_ws),
+                                                  self.scan_ws_bytes, st))
+            rec(5)
+            _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_ptr),
+                                         self.edge_capacity, _ptr(self.col), _ptr(self.cost), None,
+                                         _ptr(self.overflow), st))
+            k = 6
+        rec(k)
         _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), self.edge_capacity,
                                        _ptr(self.row_ptr),
                                        _ptr(self.col), _ptr(self.cost), _ptr(self.entry_cost), _ptr(self.node_cost),
                                        _ptr(self.exit_cost), _ptr(self.next), _ptr(self.prev), _ptr(self.n_paths),
                                        _ptr(self.total_cost), None, _ptr(self.stats), _ptr(self.solve_ws),
                                        self.solve_ws_bytes, st))
-        rec(7)
+        rec(k + 1)
         _lib.check(L.mot3d_extract_tracks(G, _ptr(batch.graph_ptr), _ptr(self.next), _ptr(self.prev),
                                           _ptr(self.track_count), _ptr(self.track_ptr), _ptr(self.track_det), st))
-        rec(8)
+        rec(k + 2)
         self._n, self._G = n, G
 
     def check_overflow(self):

@@ -45,9 +45,10 @@ def _golden_transitions(d):
     return np.cumsum(row_ptr), (head[m] - 2) // 2, d["w_float"][m], d["cost"][m]
 
 
-@pytest.mark.parametrize("pruned", [True, False], ids=["xwindow", "allpairs"])
+@pytest.mark.parametrize("pruned,fused", [(True, True), (True, False), (False, False)],
+                         ids=["fused", "xwindow", "allpairs"])
 @pytest.mark.parametrize("name", gu.DETECTION_CASES)
-def test_edge_build_matches_reference(name, pruned):
+def test_edge_build_matches_reference(name, pruned, fused):
     import mot3d_b200 as mot3d
     from mot3d_b200 import _lib
     torch = _torch()
@@ -55,7 +56,7 @@ def test_edge_build_matches_reference(name, pruned):
     spec = _spec_from(d["spec"], mot3d)
     b = _batch_from(d, mot3d).to("cuda")
     row_ptr, col, w, cost = _golden_transitions(d)
-    out = mot3d.build_graphs(b, spec, direction=_lib.DIR_OUT, with_weights=True, pruned=pruned)
+    out = mot3d.build_graphs(b, spec, direction=_lib.DIR_OUT, with_weights=True, pruned=pruned, fused=fused)
     assert out.n_edges == len(col)
     assert (out.row_ptr.cpu().numpy() == row_ptr).all()
     e = out.n_edges
@@ -63,7 +64,7 @@ def test_edge_build_matches_reference(name, pruned):
     np.testing.assert_allclose(out.weight[:e].cpu().numpy(), w, rtol=RTOL, atol=0)
     gu.assert_costs_match(out.cost[:e].cpu().numpy(), cost, w)
     # the solver's orientation is the transpose of the same arc set
-    inn = mot3d.build_graphs(b, spec, direction=_lib.DIR_IN, with_weights=True, pruned=pruned)
+    inn = mot3d.build_graphs(b, spec, direction=_lib.DIR_IN, with_weights=True, pruned=pruned, fused=fused)
     assert inn.n_edges == e
     rp = inn.row_ptr.cpu().numpy().astype(np.int64)
     dst = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
@@ -79,6 +80,85 @@ def test_edge_build_matches_reference(name, pruned):
     assert (out.node_cost[:n].cpu().numpy() == node_ref).all()
     assert (out.entry_cost[:n].cpu().numpy() == d["cost"][tail == 1]).all()
     assert (out.exit_cost[:n].cpu().numpy() == 0).all()
+
+
+def _same_graph(a, b):
+    e = a.n_edges
+    assert b.n_edges == e
+    assert (a.row_ptr.cpu() == b.row_ptr.cpu()).all()
+    assert (a.col[:e].cpu() == b.col[:e].cpu()).all()
+    assert (a.cost[:e].cpu() == b.cost[:e].cpu()).all()
+    if a.weight is not None and b.weight is not None:
+        assert (a.weight[:e].cpu() == b.weight[:e].cpu()).all()   # bit-identical float64
+
+
+@pytest.mark.parametrize("cap,acap", [(None, None), (0, None), (None, 0), (0, 0), (64, 256)],
+                         ids=["staged", "cands-global", "arcs-global", "all-global", "tiny"])
+@pytest.mark.parametrize("name", ["c3_soldiers_pass1", "c4_synth_appearance", "c5_window_f50_p100", "c4_pets_view1_w1"])
+def test_fused_build_equals_two_pass_build(name, cap, acap, monkeypatch):
+    """k_edge_build_fused (one launch: window search, look-back scan, costs) writes what count -> scan -> fill writes,
+    bit for bit, in both orientations - also when a tile's candidates and/or arcs do not fit shared memory and the
+    kernel works on the global arrays (forced here by shrinking the staging areas)."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    d = gu.load(name)
+    spec = _spec_from(d["spec"], mot3d)
+    b = _batch_from(d, mot3d).to("cuda")
+    if cap is not None:
+        monkeypatch.setenv("MOT3D_EDGE_CAP", str(cap))
+    if acap is not None:
+        monkeypatch.setenv("MOT3D_EDGE_ACAP", str(acap))
+    for direction in (_lib.DIR_IN, _lib.DIR_OUT):
+        two = mot3d.build_graphs(b, spec, direction=direction, with_weights=True, fused=False)
+        one = mot3d.build_graphs(b, spec, direction=direction, with_weights=True, fused=True)
+        _same_graph(two, one)
+
+
+def test_fused_build_row_ranges_and_capacity():
+    """Consecutive mot3d_edge_build calls over row ranges append to one CSR through the device-side arc counter;
+    a short arc buffer drops the arcs beyond it, raises the flag and still reports exact row offsets."""
+    import ctypes
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    from mot3d_b200.batch import _dets_struct, _ptr, _stream
+    torch = _torch()
+    L = _lib.lib()
+    d = gu.load("c5_window_f50_p100")
+    spec = _spec_from(d["spec"], mot3d)
+    b = _batch_from(d, mot3d).to("cuda")
+    ref = mot3d.build_graphs(b, spec, fused=False)
+    n, e = b.n, ref.n_edges
+    dev = b.frame.device
+    cs = spec.to_c()
+    spos = torch.empty(b.dim * n, dtype=torch.float64, device=dev)
+    sperm = torch.empty(n, dtype=torch.int32, device=dev)
+    ds = _dets_struct(b, ref.tkey, spec, spos, sperm)
+    _lib.check(L.mot3d_frame_sort(ctypes.byref(ds), _stream(dev)))
+    ws_bytes = L.mot3d_edge_build_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def run(cuts, cap):
+        row_ptr = torch.full((n + 1,), -7, dtype=torch.int32, device=dev)
+        col = torch.full((max(cap, 1),), -1, dtype=torch.int32, device=dev)
+        cost = torch.full((max(cap, 1),), -1, dtype=torch.int64, device=dev)
+        over = torch.zeros(1, dtype=torch.int32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        for k, (a, z) in enumerate(zip(cuts[:-1], cuts[1:])):
+            _lib.check(L.mot3d_edge_build(ctypes.byref(ds), ctypes.byref(cs), _lib.DIR_IN, a, z, _ptr(row_ptr), cap,
+                                          _ptr(col), _ptr(cost), None, _ptr(over), _ptr(counter) if k else None,
+                                          _ptr(counter), _ptr(ws), ws_bytes, _stream(dev)))
+        return row_ptr.cpu(), col.cpu(), cost.cpu(), int(over.item()), int(counter.item())
+
+    for cuts in ([0, n], [0, 1, 257, 257, 3000, n], [0, 256, 512, n]):
+        row_ptr, col, cost, over, total = run(cuts, e)
+        assert over == 0 and total == e
+        assert (row_ptr == ref.row_ptr.cpu()).all()
+        assert (col[:e] == ref.col[:e].cpu()).all() and (cost[:e] == ref.cost[:e].cpu()).all()
+    short = e - 1000
+    row_ptr, col, cost, over, total = run([0, n], short)
+    assert over == 1 and total == e
+    assert (row_ptr == ref.row_ptr.cpu()).all()
+    assert (col[:short] == ref.col[:short].cpu()).all() and (cost[:short] == ref.cost[:short].cpu()).all()
 
 
 def _solve_checks(name, d, sol, n, perm=None):
