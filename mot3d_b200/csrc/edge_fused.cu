@@ -13,12 +13,13 @@
 //      reference's exact FP64 expression and keeps (window start, survivor bit mask) per (row, frame) in shared
 //      memory; block scan of the row counts;
 //   3. the tile's arc count goes into a decoupled look-back (one 64-bit status word per tile: flag | running
-//      total): warp 0 publishes the aggregate and walks back over its predecessors 32 tiles at a time while the other
-//      warps already run pass 2, which only needs tile-local offsets;
-//   4. pass 2: the survivors are replayed from the masks into a tile-local arc list in shared memory
-//      (packed candidate slot + jump, squared distance), each (row, frame) run put back into detection order;
-//   5. cost pass: one thread per arc, no divergence: distance / bbox / jump factors, exact quantisation, and fully
-//      coalesced stores of col[], cost[] (and weight[]) at the tile's global offset.
+//      total): the aggregate is published at once, warp 0 walks back over its predecessors 32 tiles at a time
+//      after its share of pass 2, which only needs tile-local offsets;
+//   4. pass 2: the survivors are replayed from the masks into a tile-local arc list in shared memory (4 bytes per
+//      arc: candidate slot, jump, row), each (row, frame) run put back into detection order;
+//   5. cost pass: one thread per arc, no divergence: squared distance recomputed from the staged positions (same
+//      expression, same bits), distance / bbox / jump factors, exact quantisation, and fully coalesced stores of
+//      col[], cost[] (and weight[]) at the tile's global offset.
 // Tiles that do not fit the staging areas (very dense frames) run the same code on the global arrays.
 // The arc offset of the first tile can continue a device-side counter, so consecutive launches over row ranges
 // append to one CSR (software pipeline of mot3d_track_batch_host).
@@ -76,6 +77,39 @@ __device__ __forceinline__ int64_t ef_warp_bound(const int32_t *a, int64_t lo, i
     return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
+// The same bound when it is known to lie close to `start`: one round of 32 probes 64 entries apart, one round over the
+// 64 entries between two probes - two dependent loads instead of five for a batch of millions of keys; ranges the
+// probes do not cover fall back to ef_warp_bound. FORWARD: bound in [start, hi0]; else: bound in [lo0, start].
+template <bool UPPER, bool FORWARD>
+__device__ __forceinline__ int64_t ef_gallop(const int32_t *a, int64_t lo0, int64_t hi0, int64_t start, int64_t key) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = FORWARD ? start + (int64_t)(lane + 1) * 64 : start - (int64_t)(lane + 1) * 64;
+    bool below;
+    if (FORWARD)
+        below = q < hi0 && (UPPER ? (a[q] <= key) : (a[q] < key));
+    else
+        below = q < lo0 || (UPPER ? (a[q] <= key) : (a[q] < key));
+    const unsigned m = __ballot_sync(0xffffffffu, below);
+    int64_t rlo, rhi;  // the bound lies in [rlo, rhi]
+    if (FORWARD) {
+        const int c = __popc(m);  // probes 0 .. c-1 are below
+        if (c == 32) return ef_warp_bound<UPPER>(a, start + 32 * 64 + 1, hi0, key);
+        rlo = start + (int64_t)c * 64 + (c > 0 ? 1 : 0);
+        rhi = start + (int64_t)(c + 1) * 64;
+        if (rhi > hi0) rhi = hi0;
+    } else {
+        const int f = m ? __ffs(m) - 1 : 32;  // first probe that is below
+        if (f == 32) return ef_warp_bound<UPPER>(a, lo0, start - 32 * 64, key);
+        rlo = start - (int64_t)(f + 1) * 64 + 1;
+        if (rlo < lo0) rlo = lo0;
+        rhi = start - (int64_t)f * 64;
+    }
+    const int64_t p0 = rlo + lane, p1 = rlo + 32 + lane;
+    const bool b0 = p0 < rhi && (UPPER ? (a[p0] <= key) : (a[p0] < key));
+    const bool b1 = p1 < rhi && (UPPER ? (a[p1] <= key) : (a[p1] < key));
+    return rlo + __popc(__ballot_sync(0xffffffffu, b0)) + __popc(__ballot_sync(0xffffffffu, b1));
+}
+
 template <bool UPPER>
 __device__ __forceinline__ int ef_bound(const int32_t *a, int lo, int hi, int key) {
     while (lo < hi) {
@@ -92,7 +126,7 @@ __device__ __forceinline__ int ef_bound(const int32_t *a, int lo, int hi, int ke
 // One row against the frames it may link to. FILL = false: count, and remember (window start, survivor mask) per
 // frame when `cache` is set. FILL = true: write the row's arcs to pk[]/sv[] starting at `out` (replayed from the
 // cache where possible), each frame's run in detection order.
-template <int DIR, bool FILL, bool STAGED>
+template <int DIR, bool FILL, bool STAGED, bool A32>
 __device__ __forceinline__ int ef_row(const FusedParams &p, const int key_r, const double xr, const double yr,
                                       const double zr, const int kmin, const bool tabled, const int *s_seg_lo,
                                       const int *s_seg_hi, const double *cx, const double *cy, const double *cz,
@@ -107,29 +141,23 @@ __device__ __forceinline__ int ef_row(const FusedParams &p, const int key_r, con
         // frames in ascending time order, so that the arcs of a row ascend by detection index
         const int kt = (DIR == MOT3D_DIR_OUT) ? key_r + jj : key_r - (J + 1 - jj);
         const uint32_t jm1 = (uint32_t)((DIR == MOT3D_DIR_OUT) ? jj - 1 : J - jj);
+        // arc word: candidate slot | jump-1 | (A32: row of the tile); A32 arcs carry no squared distance, the cost pass
+        // recomputes it from the staged positions
+        const uint32_t tag = A32 ? ((jm1 << 16) | ((uint32_t)threadIdx.x << 24)) : (jm1 << 24);
+        constexpr uint32_t SLOT = A32 ? 0xffffu : 0xffffffu;
         const int start = out + cnt;
-        int nf = 0;
-        uint32_t cw = EF_REDO;
-        if (FILL && cache) cw = cache[(jj - 1) * EF_TPB + threadIdx.x];
-        if (FILL && cw != EF_REDO) {
-            const int l = (int)(cw & 0xffffu);
-            uint32_t mask = cw >> 16;
-            while (mask) {
-                const int c = l + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const double dx = xr - cx[c];
-                const double dy = yr - cy[c];
-                double s = dx * dx;
-                s = s + dy * dy;
-                if (has_z) {
-                    const double dz = zr - cz[c];
-                    s = s + dz * dz;
-                }
-                pk[start + nf] = (uint32_t)c | (jm1 << 24);
-                sv[start + nf] = s;
-                nf++;
+        int nf = 0, l = 0;
+        uint32_t mask = 0;
+        bool replay = false;
+        if (FILL && cache) {
+            const uint32_t cw = cache[(jj - 1) * EF_TPB + threadIdx.x];
+            if (cw != EF_REDO) {
+                l = (int)(cw & 0xffffu);
+                mask = cw >> 16;
+                replay = true;
             }
-        } else {
+        }
+        if (!replay) {
             int a, b;
             if (tabled) {
                 const int t = kt - kmin;
@@ -144,54 +172,126 @@ __device__ __forceinline__ int ef_row(const FusedParams &p, const int key_r, con
                 continue;
             }
             // first candidate with x >= xr - window
-            int l = a, len = b - a;
+            int len = b - a;
+            l = a;
             while (len > 0) {
                 const int half = len >> 1;
                 const bool lt = cx[l + half] < xlo;
                 l = lt ? l + half + 1 : l;
                 len = lt ? len - half - 1 : half;
             }
-            uint32_t mask = 0;
-            int i = 0;
-            for (int c = l; c < b; c++, i++) {
-                const double xc = cx[c];
-                if (xc > xhi) break;
-                const double dx = xr - xc;
-                const double dy = yr - cy[c];
+            // The first 8 candidates of the window are tested without a branch (independent loads and FP64 chains; the
+            // exact test alone decides, the x-window only bounds the search): the average window holds 6.
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = l + k;
+                const int cc = c < b ? c : b - 1;
+                const double dx = xr - cx[cc];
+                const double dy = yr - cy[cc];
                 double s = dx * dx;  // sum([dx^2, dy^2, dz^2]) left to right, as the reference's euclidean()
                 s = s + dy * dy;
                 if (has_z) {
-                    const double dz = zr - cz[c];
+                    const double dz = zr - cz[cc];
                     s = s + dz * dz;
                 }
-                if (s <= smax) {  // <=> not (sqrt(s) > max_distance), see spec.sq_dist_max
-                    if (FILL) {
-                        pk[start + nf] = (uint32_t)c | (jm1 << 24);
-                        sv[start + nf] = s;
-                    } else if (i < 16) {
-                        mask |= 1u << i;
-                    }
-                    nf++;
-                }
+                // s <= smax <=> not (sqrt(s) > max_distance), see spec.sq_dist_max
+                mask |= (c < b && s <= smax) ? (1u << k) : 0u;
             }
-            if (!FILL && cache)
-                cache[(jj - 1) * EF_TPB + threadIdx.x] = (i > 16 || l >= 0xffff) ? EF_REDO : ((uint32_t)l | (mask << 16));
+            nf = __popc(mask);
+            bool big = false;
+            if (l + 8 < b && cx[l + 8] <= xhi) {  // a longer window: the rest one by one
+                int i = 8;
+                for (int c = l + 8; c < b; c++, i++) {
+                    const double xc = cx[c];
+                    if (xc > xhi) break;
+                    const double dx = xr - xc;
+                    const double dy = yr - cy[c];
+                    double s = dx * dx;
+                    s = s + dy * dy;
+                    if (has_z) {
+                        const double dz = zr - cz[c];
+                        s = s + dz * dz;
+                    }
+                    if (s <= smax) {
+                        if (i < 16) mask |= 1u << i;
+                        nf++;
+                    }
+                }
+                big = i > 16;
+            }
+            if (!FILL) {
+                if (cache) cache[(jj - 1) * EF_TPB + threadIdx.x] = (big || l >= 0xffff) ? EF_REDO : ((uint32_t)l | (mask << 16));
+                cnt += nf;
+                continue;
+            }
+            if (big) {  // more than 16 candidates in the window: the mask does not hold them all
+                nf = 0;
+                for (int c = l; c < b; c++) {
+                    const double xc = cx[c];
+                    if (xc > xhi) break;
+                    const double dx = xr - xc;
+                    const double dy = yr - cy[c];
+                    double s = dx * dx;
+                    s = s + dy * dy;
+                    if (has_z) {
+                        const double dz = zr - cz[c];
+                        s = s + dz * dz;
+                    }
+                    if (s <= smax) {
+                        pk[start + nf] = (uint32_t)c | tag;
+                        if (!A32) sv[start + nf] = s;
+                        nf++;
+                    }
+                }
+                mask = 0;
+            }
         }
         if (FILL) {
-            // the survivors of a frame come out in x order; the reference emits them in detection order
-            // (mot3d/mot3d.py:111-127): insertion sort over the 1-3 entries of the run
-            for (int u = 1; u < nf; u++) {
-                const uint32_t w = pk[start + u];
-                const double s = sv[start + u];
-                const int id = cperm[w & 0xffffffu];
-                int v = u;
-                while (v > 0 && cperm[pk[start + v - 1] & 0xffffffu] > id) {
-                    pk[start + v] = pk[start + v - 1];
-                    sv[start + v] = sv[start + v - 1];
-                    v--;
+            if (mask) nf = 0;
+            while (mask) {
+                const int c = l + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (!A32) {
+                    const double dx = xr - cx[c];
+                    const double dy = yr - cy[c];
+                    double s = dx * dx;
+                    s = s + dy * dy;
+                    if (has_z) {
+                        const double dz = zr - cz[c];
+                        s = s + dz * dz;
+                    }
+                    sv[start + nf] = s;
                 }
-                pk[start + v] = w;
-                sv[start + v] = s;
+                pk[start + nf] = (uint32_t)c | tag;
+                nf++;
+            }
+            // the survivors of a frame come out in x order; the reference emits them in detection order
+            // (mot3d/mot3d.py:111-127): a swap for the common pair, insertion sort beyond
+            if (nf == 2) {
+                const uint32_t w0 = pk[start], w1 = pk[start + 1];
+                if (cperm[w0 & SLOT] > cperm[w1 & SLOT]) {
+                    pk[start] = w1;
+                    pk[start + 1] = w0;
+                    if (!A32) {
+                        const double s0 = sv[start], s1 = sv[start + 1];
+                        sv[start] = s1;
+                        sv[start + 1] = s0;
+                    }
+                }
+            } else if (nf > 2) {
+                for (int u = 1; u < nf; u++) {
+                    const uint32_t w = pk[start + u];
+                    const double s = A32 ? 0.0 : sv[start + u];
+                    const int id = cperm[w & SLOT];
+                    int v = u;
+                    while (v > 0 && cperm[pk[start + v - 1] & SLOT] > id) {
+                        pk[start + v] = pk[start + v - 1];
+                        if (!A32) sv[start + v] = sv[start + v - 1];
+                        v--;
+                    }
+                    pk[start + v] = w;
+                    if (!A32) sv[start + v] = s;
+                }
             }
         }
         cnt += nf;
@@ -206,6 +306,34 @@ __device__ __forceinline__ unsigned long long ef_ld_status(const unsigned long l
 }
 __device__ __forceinline__ void ef_st_status(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of tile `tile` (> 0): sum of the aggregates of its predecessors back to the first one that has a
+// prefix. Whole warp 0; lane 0 publishes the tile's own prefix and leaves the exclusive one in *s_base.
+__device__ __forceinline__ void ef_look_back(const FusedParams &p, const int tile, const int total, long long *s_base) {
+    const int tid = threadIdx.x;
+    long long excl = 0;
+    int t = tile - 1;
+    while (true) {
+        const int idx = t - tid;
+        const unsigned long long v = idx >= 0 ? ef_ld_status(p.status + idx) : EF_FLAG_PREFIX;
+        const unsigned flag = (unsigned)(v >> 62);
+        const unsigned bp = __ballot_sync(0xffffffffu, flag == 2);
+        const unsigned bi = __ballot_sync(0xffffffffu, flag == 0);
+        const int first = bp ? __ffs(bp) - 1 : 32;
+        const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1);
+        if (bi & need) continue;  // a predecessor has not published yet
+        long long c = (tid <= first) ? (long long)(v & EF_VALUE) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (first < 32) break;
+        t -= 32;
+    }
+    if (tid == 0) {
+        ef_st_status(p.status + tile, EF_FLAG_PREFIX | (unsigned long long)(excl + total));
+        *s_base = excl;
+    }
 }
 
 template <int DIR>
@@ -238,14 +366,16 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
     const int64_t kmin = (DIR == MOT3D_DIR_OUT) ? k_first + 1 : k_first - J;
     const int64_t kmax = (DIR == MOT3D_DIR_OUT) ? k_last + J : k_last - 1;
     if (tid < 32) {
-        const int64_t v = ef_warp_bound<false>(p.tkey, (DIR == MOT3D_DIR_OUT) ? r0 : 0, (DIR == MOT3D_DIR_OUT) ? n : r1, kmin);
+        const int64_t v = (DIR == MOT3D_DIR_OUT) ? ef_gallop<false, true>(p.tkey, r0, n, r0, kmin)
+                                                 : ef_gallop<false, false>(p.tkey, 0, r1, r0, kmin);
         if (tid == 0) {
             s_range[0] = v;
             mbar_init(&s_bar, 1);
             fence_mbar_init();
         }
     } else if (tid < 64) {
-        const int64_t v = ef_warp_bound<true>(p.tkey, (DIR == MOT3D_DIR_OUT) ? r0 : 0, (DIR == MOT3D_DIR_OUT) ? n : r1, kmax);
+        const int64_t v = (DIR == MOT3D_DIR_OUT) ? ef_gallop<true, true>(p.tkey, r0, n, r1, kmax)
+                                                 : ef_gallop<true, false>(p.tkey, 0, r1, r1 - 1, kmax);
         if (tid == 32) s_range[1] = v;
     }
     for (int t = tid; t < EF_TABLE; t += EF_TPB) {
@@ -266,8 +396,10 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
     double *b_x = (double *)ef_smem;
     double *b_y = b_x + cap4;
     double *b_z = b_y + cap4;  // only there when has_z (the launch sizes the buffer accordingly)
-    double *b_sv = b_y + cap4 + (has_z ? cap4 : 0);
-    int32_t *b_perm = (int32_t *)(b_sv + p.acap);
+    double *b_rx = b_y + cap4 + (has_z ? cap4 : 0);  // the tile's own rows
+    double *b_ry = b_rx + EF_TPB;
+    double *b_rz = b_ry + EF_TPB;
+    int32_t *b_perm = (int32_t *)(b_ry + EF_TPB + (has_z ? EF_TPB : 0));
     uint32_t *b_pk = (uint32_t *)(b_perm + cap4);
     uint32_t *cache = (staged && p.cache_j > 0) ? b_pk + p.acap : nullptr;
     const double *s_x = b_x, *s_y = b_y, *s_z = b_z;
@@ -300,6 +432,9 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
         yr = p.pos[n + r];
         if (has_z) zr = p.pos[2 * n + r];
     }
+    b_rx[tid] = xr;
+    b_ry[tid] = yr;
+    if (has_z) b_rz[tid] = zr;
     __syncthreads();  // table + ragged head/tail stores visible
     if (staged && m > 0) mbar_wait(&s_bar, 0);
 
@@ -307,60 +442,38 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
     int cnt = 0;
     if (active) {
         if (staged)
-            cnt = ef_row<DIR, false, true>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z, s_perm,
-                                           p.tkey + lo, m, cache, nullptr, nullptr, 0);
+            cnt = ef_row<DIR, false, true, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z,
+                                                  s_perm, p.tkey + lo, m, cache, nullptr, nullptr, 0);
         else
-            cnt = ef_row<DIR, false, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, p.spos + lo,
-                                            p.spos + n + lo, p.spos + 2 * n + lo, p.sperm + lo, p.tkey + lo, m, nullptr,
-                                            nullptr, nullptr, 0);
+            cnt = ef_row<DIR, false, false, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, p.spos + lo,
+                                                   p.spos + n + lo, p.spos + 2 * n + lo, p.sperm + lo, p.tkey + lo, m,
+                                                   nullptr, nullptr, nullptr, 0);
     }
     int total;
     const int off = block_excl_scan(cnt, s_scan, &total);
     s_rowoff[tid] = off;
     if (tid == 0) s_rowoff[EF_TPB] = total;
 
-    // ---- decoupled look-back over the tiles' arc counts (warp 0), overlapped with pass 2 of the other warps
-    if (tid < 32) {
+    // ---- decoupled look-back over the tiles' arc counts: the aggregate is published right away, the walk over the
+    //      predecessors (warp 0, 32 tiles per step) waits until the warp has done its share of pass 2 - by then the
+    //      predecessors have usually published their prefix and one step is enough
+    if (tid == 0) {
         if (tile == 0) {
-            if (tid == 0) {
-                const long long b0 = p.arc_base_in ? (long long)*p.arc_base_in : 0;
-                ef_st_status(p.status, EF_FLAG_PREFIX | (unsigned long long)(b0 + total));
-                s_base = b0;
-            }
+            const long long b0 = p.arc_base_in ? (long long)*p.arc_base_in : 0;
+            ef_st_status(p.status, EF_FLAG_PREFIX | (unsigned long long)(b0 + total));
+            s_base = b0;
         } else {
-            if (tid == 0) ef_st_status(p.status + tile, EF_FLAG_AGG | (unsigned long long)total);
-            long long excl = 0;
-            int t = tile - 1;
-            while (true) {
-                const int idx = t - tid;
-                const unsigned long long v = idx >= 0 ? ef_ld_status(p.status + idx) : EF_FLAG_PREFIX;
-                const unsigned flag = (unsigned)(v >> 62);
-                const unsigned bp = __ballot_sync(0xffffffffu, flag == 2);
-                const unsigned bi = __ballot_sync(0xffffffffu, flag == 0);
-                const int first = bp ? __ffs(bp) - 1 : 32;
-                const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1);
-                if (bi & need) continue;  // a predecessor has not published yet
-                long long c = (tid <= first) ? (long long)(v & EF_VALUE) : 0;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                excl += c;
-                if (first < 32) break;
-                t -= 32;
-            }
-            if (tid == 0) {
-                ef_st_status(p.status + tile, EF_FLAG_PREFIX | (unsigned long long)(excl + total));
-                s_base = excl;
-            }
+            ef_st_status(p.status + tile, EF_FLAG_AGG | (unsigned long long)total);
         }
     }
-
-    // ---- pass 2: the tile's arc list
-    const bool arcs_staged = total <= p.acap;
+    // ---- pass 2: the tile's arc list. Staged: 4-byte arcs (slot, jump, row) in shared memory. Else (candidates or
+    //      arcs do not fit): built in place in col[] / cost[] at the tile's final offset (slot | jump, squared distance)
+    const bool arcs_staged = staged && total <= p.acap;
     uint32_t *pk = b_pk;
-    double *sv = b_sv;
+    double *sv = nullptr;
     bool row_ok = true;
     if (!arcs_staged) {
-        // the list does not fit: build it in place in col[] / cost[] at the tile's final offset
+        if (tid < 32 && tile > 0) ef_look_back(p, tile, total, &s_base);
         __syncthreads();
         const long long base = s_base;
         pk = (uint32_t *)(p.col + base);
@@ -369,14 +482,18 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
         if (!row_ok && cnt > 0 && p.overflow) atomicOr(p.overflow, 1);
     }
     if (active && cnt > 0 && row_ok) {
-        if (staged)
-            ef_row<DIR, true, true>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z, s_perm,
-                                    p.tkey + lo, m, cache, pk, sv, off);
+        if (arcs_staged)
+            ef_row<DIR, true, true, true>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z, s_perm,
+                                          p.tkey + lo, m, cache, pk, nullptr, off);
+        else if (staged)
+            ef_row<DIR, true, true, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, s_x, s_y, s_z, s_perm,
+                                           p.tkey + lo, m, cache, pk, sv, off);
         else
-            ef_row<DIR, true, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, p.spos + lo,
-                                     p.spos + n + lo, p.spos + 2 * n + lo, p.sperm + lo, p.tkey + lo, m, nullptr, pk, sv,
-                                     off);
+            ef_row<DIR, true, false, false>(p, key_r, xr, yr, zr, (int)kmin, tabled, s_seg_lo, s_seg_hi, p.spos + lo,
+                                            p.spos + n + lo, p.spos + 2 * n + lo, p.sperm + lo, p.tkey + lo, m, nullptr,
+                                            pk, sv, off);
     }
+    if (arcs_staged && tid < 32 && tile > 0) ef_look_back(p, tile, total, &s_base);
     __syncthreads();
     const long long base = s_base;
     if (active) p.row_ptr[r] = (int32_t)(base + off);
@@ -393,9 +510,26 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
             if (p.overflow) atomicOr(p.overflow, 1);
             break;
         }
-        // row of arc i: last row with offset <= i (needed by the overflow guard of the in-place list and by bbox)
-        int row = 0;
-        if (!arcs_staged || p.use_bbox) {
+        const uint32_t w32 = pk[i];
+        int row, slot;
+        uint32_t jm1;
+        double s;
+        if (arcs_staged) {
+            slot = (int)(w32 & 0xffffu);
+            jm1 = (w32 >> 16) & 0xffu;
+            row = (int)(w32 >> 24);
+            // the expression of the window test, so the same bits
+            const double dx = b_rx[row] - s_x[slot];
+            const double dy = b_ry[row] - s_y[slot];
+            s = dx * dx;
+            s = s + dy * dy;
+            if (has_z) {
+                const double dz = b_rz[row] - s_z[slot];
+                s = s + dz * dz;
+            }
+        } else {
+            // row of arc i: last row with offset <= i; rows of the in-place list that did not fit were never written
+            row = 0;
             int hi_ = EF_TPB;
             while (hi_ - row > 1) {
                 const int mid = (row + hi_) >> 1;
@@ -404,12 +538,12 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
                 else
                     hi_ = mid;
             }
-            // rows of the in-place list that did not fit were never written
-            if (!arcs_staged && base + s_rowoff[row + 1] > p.edge_capacity) continue;
+            if (base + s_rowoff[row + 1] > p.edge_capacity) continue;
+            slot = (int)(w32 & 0xffffffu);
+            jm1 = w32 >> 24;
+            s = sv[i];
         }
-        const uint32_t w32 = pk[i];
-        const double s = sv[i];
-        const int64_t other = cperm[w32 & 0xffffffu];
+        const int64_t other = cperm[slot];
         double prod = distance_factor(s, p.sigma_distance_sq);
         double w;
         if (p.use_hist) {
@@ -422,7 +556,7 @@ __global__ void __launch_bounds__(EF_TPB) k_edge_build_fused(const __grid_consta
                 const double bss = 1.0 - bbox_similarity(p.bbox, n, a, b);
                 prod = prod * exp(-(bss * bss) / p.sigma_bbox_sq);
             }
-            w = p.jt.v[w32 >> 24] * prod;
+            w = p.jt.v[jm1] * prod;
             p.cost[e] = quantise_1e7(w);
         }
         p.col[e] = (int32_t)other;
@@ -517,24 +651,25 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     p.ticket = (int32_t *)((char *)ws + (size_t)tiles * sizeof(unsigned long long));
     p.arc_base_in = arc_base_in;
     p.arc_total_out = arc_total_out;
-    // Shared memory per CTA: three CTAs per SM. Candidates cost 20 (28 in 3-D) bytes each, arcs 12, the pass-1
-    // cache 4 bytes per row and frame. MOT3D_EDGE_CAP / MOT3D_EDGE_ACAP override the split (bench experiments).
+    // Shared memory per CTA, four CTAs per SM: candidates 20 (28 in 3-D) bytes each, the tile's rows 16 (24), arcs 4,
+    // the pass-1 cache 4 bytes per row and frame. MOT3D_EDGE_CAP / MOT3D_EDGE_ACAP override the split (tests, bench).
     p.cache_j = spec->max_jump <= EF_CACHE_J ? spec->max_jump : 0;
     const int per_cand = 8 + 8 + (dets->dim == 3 ? 8 : 0) + 4;
-    const int budget = 72 * 1024 - p.cache_j * EF_TPB * 4;
-    int cap = 1280, acap = 3008;
-    while (cap * per_cand + acap * 12 + 64 > budget && acap > 1024) {
-        acap -= 128;
-        if (cap > 768) cap -= 32;
-    }
+    const int rows_b = EF_TPB * 8 * dets->dim;
+    const int budget = 50 * 1024 - p.cache_j * EF_TPB * 4 - rows_b;
+    int cap = 1280;
+    if (dets->dim == 3) cap = 1024;
+    if ((cap + 4) * per_cand > budget - 8192) cap = ((budget - 8192) / per_cand - 4) & ~3;  // room for 2048 arcs
+    if (cap < 0) cap = 0;
+    int acap = ((budget - (cap + 4) * per_cand - 16) / 4) & ~3;
     if (const char *e = getenv("MOT3D_EDGE_CAP")) cap = atoi(e) & ~3;
     if (const char *e = getenv("MOT3D_EDGE_ACAP")) acap = atoi(e) & ~3;
-    if (cap > 65000) cap = 65000;
+    if (cap > 65000) cap = 65000;  // slots of staged candidates are packed into 16 bits
     if (cap < 0) cap = 0;
     if (acap < 0) acap = 0;
     p.cap = cap;
     p.acap = acap;
-    const size_t smem = (size_t)(cap + 4) * per_cand + (size_t)acap * 12 + (size_t)p.cache_j * EF_TPB * 4 + 16;
+    const size_t smem = (size_t)(cap + 4) * per_cand + (size_t)rows_b + (size_t)acap * 4 + (size_t)p.cache_j * EF_TPB * 4 + 16;
     M3_CUDA(cudaMemsetAsync(ws, 0, need, st));
     if (direction == MOT3D_DIR_IN) {
         M3_CUDA(cudaFuncSetAttribute(k_edge_build_fused<MOT3D_DIR_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -70,14 +70,20 @@ __device__ __forceinline__ int64_t warp_bound_i32(const int32_t *a, int64_t lo, 
 }
 
 // rank of every detection inside its frame by (x, index): sorted copies of the positions + permutation.
-// One block = 128 consecutive detections; only the frames that stick out of the block need a search.
-__global__ void __launch_bounds__(128) k_frame_sort(int64_t n, int dim, const int32_t *__restrict__ tkey,
-                                                    const double *__restrict__ pos, double *__restrict__ spos,
-                                                    int32_t *__restrict__ sperm) {
-    __shared__ int s_key[128];
+// One block = 256 consecutive detections. The x coordinates of the frames the block touches (only the first and the
+// last can stick out of it) are staged in shared memory; a detection's rank is the number of earlier entries of its
+// frame with x <= its own plus the number of later ones with x < its own (stable), counted from shared memory.
+constexpr int FS_TPB = 256;
+constexpr int FS_CAP = 2048;  // staged x values; larger frame spans are read in place
+
+__global__ void __launch_bounds__(FS_TPB) k_frame_sort(int64_t n, int dim, const int32_t *__restrict__ tkey,
+                                                       const double *__restrict__ pos, double *__restrict__ spos,
+                                                       int32_t *__restrict__ sperm) {
+    __shared__ int s_key[FS_TPB];
     __shared__ int64_t s_edge[2];  // start of the block's first frame, end of its last frame
-    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
-    const int64_t b1 = (b0 + blockDim.x < n) ? b0 + blockDim.x : n;
+    __shared__ double s_x[FS_CAP];
+    const int64_t b0 = (int64_t)blockIdx.x * FS_TPB;
+    const int64_t b1 = (b0 + FS_TPB < n) ? b0 + FS_TPB : n;
     const int64_t i = b0 + threadIdx.x;
     const bool active = i < n;
     const int k = active ? tkey[i] : 0;
@@ -90,18 +96,59 @@ __global__ void __launch_bounds__(128) k_frame_sort(int64_t n, int dim, const in
         if (threadIdx.x == 32) s_edge[1] = hi;
     }
     __syncthreads();
+    const int64_t e0 = s_edge[0], e1 = s_edge[1];
+    const bool staged = e1 - e0 <= FS_CAP;
+    if (staged)
+        for (int c = threadIdx.x; c < (int)(e1 - e0); c += FS_TPB) s_x[c] = pos[e0 + c];
+    __syncthreads();
     if (!active) return;
     const int nb = (int)(b1 - b0);
-    int l = threadIdx.x, h = threadIdx.x + 1;  // the detection's frame inside the block: [l, h)
-    while (l > 0 && s_key[l - 1] == k) l--;
-    while (h < nb && s_key[h] == k) h++;
-    const int64_t lo = (l == 0 && s_key[0] == k) ? s_edge[0] : b0 + l;
-    const int64_t hi = (h == nb && s_key[nb - 1] == k) ? s_edge[1] : b0 + h;
-    const double x = pos[i];
+    // the detection's frame inside the block, [l, h): the keys are sorted, two binary searches over the block's keys
+    int l = 0, h = nb;
+    {
+        int a = 0, z = threadIdx.x;  // first index with key == k lies in [0, tid]
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (s_key[mid] < k)
+                a = mid + 1;
+            else
+                z = mid;
+        }
+        l = a;
+        a = threadIdx.x + 1;
+        z = nb;  // first index with key > k lies in [tid + 1, nb]
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (s_key[mid] <= k)
+                a = mid + 1;
+            else
+                z = mid;
+        }
+        h = a;
+    }
+    const int64_t lo = (l == 0 && s_key[0] == k) ? e0 : b0 + l;
+    const int64_t hi = (h == nb && s_key[nb - 1] == k) ? e1 : b0 + h;
     int rank = 0;
-    for (int64_t j = lo; j < hi; j++) {
-        const double xj = pos[j];
-        rank += (xj < x || (xj == x && j < i)) ? 1 : 0;
+    if (staged) {
+        // one loop over the whole frame for all of its detections (same trip count in every lane of a frame):
+        // strictly smaller entries, and how many are equal; ties (rare) are ranked by index in a second pass
+        const int a = (int)(lo - e0), me = (int)(i - e0), z = (int)(hi - e0);
+        const double x = s_x[me];
+        int eq = 0;
+#pragma unroll 4
+        for (int j = a; j < z; j++) {
+            const double xj = s_x[j];
+            rank += (xj < x) ? 1 : 0;
+            eq += (xj == x) ? 1 : 0;
+        }
+        if (eq > 1)
+            for (int j = a; j < me; j++) rank += (s_x[j] == x) ? 1 : 0;
+    } else {
+        const double x = pos[i];
+        for (int64_t j = lo; j < hi; j++) {
+            const double xj = pos[j];
+            rank += (xj < x || (xj == x && j < i)) ? 1 : 0;
+        }
     }
     const int64_t o = lo + rank;
     sperm[o] = (int32_t)i;
@@ -351,8 +398,8 @@ using namespace m3;
 namespace m3 {
 
 int32_t launch_frame_sort(const mot3d_dets *d, cudaStream_t st) {
-    k_frame_sort<<<(unsigned)((d->n + 127) / 128), 128, 0, st>>>(d->n, d->dim, d->tkey, d->pos, d->sorted_pos,
-                                                                 d->sorted_perm);
+    k_frame_sort<<<(unsigned)((d->n + FS_TPB - 1) / FS_TPB), FS_TPB, 0, st>>>(d->n, d->dim, d->tkey, d->pos,
+                                                                               d->sorted_pos, d->sorted_perm);
     M3_LAUNCH_CHECK("k_frame_sort");
     return MOT3D_OK;
 }
