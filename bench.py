@@ -84,11 +84,17 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Samples from now on belong to the timed region (the process is started before the warm-up: nvidia-smi
+        needs a few hundred ms before its first line)."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -97,7 +103,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.03]
+        if not inside and self.rows:  # region shorter than the sampling period: the sample closest to it
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
+        for r in inside:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 9:
                 continue
@@ -225,40 +235,67 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def gather_results():
-        # the only communication of the path: track outputs to every rank (rank 0 consumes them)
-        if world > 1:
-            out_cnt = torch.empty(world * G, dtype=torch.int32, device=dev)
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    if world > 1:
+        out_cnt = torch.empty(world * G, dtype=torch.int32, device=dev)
+        out_det = torch.empty(world * n, dtype=torch.int32, device=dev)
+        out_ptr = torch.empty(world * (n + G + 1), dtype=torch.int32, device=dev)
+
+    def gather_results(after):
+        """The only communication of the path: track outputs to every rank (rank 0 consumes them), three NCCL
+        all-gathers on a stream of their own once `after` (an event on the launching stream) has passed. Returns the
+        event that marks them done: the next step's k_extract_tracks, which overwrites the buffers being sent, waits
+        for it, everything before it overlaps the transfer."""
+        if world == 1:
+            return None
+        comm_stream.wait_event(after)
+        with torch.cuda.stream(comm_stream):
             dist.all_gather_into_tensor(out_cnt, pipe.track_count)
-            out_det = torch.empty(world * n, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(out_det, pipe.track_det)
-            out_ptr = torch.empty(world * (n + G + 1), dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(out_ptr, pipe.track_ptr)
+            done = torch.cuda.Event()
+            done.record(comm_stream)
+        return done
 
     # ---- warm-up
+    stream = torch.cuda.current_stream(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         pipe.run(dbatch, spec, spec_c)
-        gather_results()
+        e = torch.cuda.Event()
+        e.record(stream)
+        done = gather_results(e)
+        if done is not None:
+            stream.wait_event(done)
     barrier()
     pipe.check_overflow()
 
-    # ---- timed: K steps, per-step CUDA events on the launching stream, L2 flushed between steps
-    stream = torch.cuda.current_stream(dev)
-    sampler = ClockSampler(local_rank)
+    # ---- timed: K steps, per-step CUDA events on the launching stream, L2 flushed between steps. The gather of step
+    #      k-1 starts with step k (after the flush, so none of it hides in untimed work) and has to be over before
+    #      step k extracts its tracks; the gather of the last step is waited for inside the last step's interval.
     step_ms = []
     stage_ms = np.zeros(len(STAGES))
     barrier()
-    sampler.start()
+    sampler.mark()
     wall0 = time.time()
+    pending = None  # event after the extract of the previous step
     for k in range(args.steps):
         flush.fill_(k & 0xff)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)]
         e_end = torch.cuda.Event(enable_timing=True)
-        pipe.run(dbatch, spec, spec_c, events=ev)
-        gather_results()
+        e_start = torch.cuda.Event(enable_timing=True)
+        e_start.record(stream)
+        done = gather_results(e_start) if (pending is not None) else None
+        pipe.run(dbatch, spec, spec_c, events=ev, before_extract=done)
+        pending = ev[len(STAGES)]
+        if k == args.steps - 1:
+            done = gather_results(pending)
+            if done is not None:
+                stream.wait_event(done)
         e_end.record(stream)
         e_end.synchronize()
-        step_ms.append(ev[0].elapsed_time(e_end))
+        step_ms.append(e_start.elapsed_time(e_end))
         stage_ms += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(STAGES))])
     barrier()
     wall = time.time() - wall0

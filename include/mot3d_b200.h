@@ -74,7 +74,8 @@ typedef struct mot3d_cost_spec {
     int32_t max_jump;
     int32_t use_bbox;
     int32_t use_hist;
-    int32_t reserved;
+    int32_t defer_cost; /* 1: the build stores the distance factor alone in weight_out and no costs (as with use_hist);
+                           an appearance pass (mot3d_edge_appearance_views) finishes the arcs */
     double sq_dist_max;
     double sigma_distance_sq;
     double sigma_hist_sq;
@@ -143,6 +144,30 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
 int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction,
                               const int32_t *row_ptr, const int32_t *col, double *weight_inout, int64_t *cost_out,
                               void *stream);
+
+/* The 2-D views of 3-D detections (Detection3D.detections_2d, mot3d/types.py:40-45): detection i owns the entries
+ * [view_ptr[i], view_ptr[i+1]) in the iteration order of its dict. */
+typedef struct mot3d_views {
+    int64_t n;                /* detections */
+    int64_t n_entries;        /* view_ptr[n] */
+    int32_t hist_channels;
+    int32_t hist_bins;
+    const int32_t *view_ptr;  /* [n+1] */
+    const int32_t *view_id;   /* [n_entries] camera label */
+    const double *bbox;       /* [4][n_entries] planar xmin,ymin,xmax,ymax of the 2-D detection; NULL unless use_bbox */
+    const double *hist;       /* [n_entries][C][B] its colour histogram; NULL unless use_hist */
+} mot3d_views;
+
+/* Appearance terms of weight_distance_detections_3d (mot3d/weight_functions.py:55-71): (1 - NCC) and (1 - bbox
+ * similarity) averaged over the views both detections were seen in (iterated in the tail detection's dict order, as
+ * the reference does), multiplied into the distance factor left by a build with spec->defer_cost, then the jump
+ * factor and the quantisation. One warp per row.
+ *   spec        the real spec (use_hist / use_bbox as the user gave them)
+ *   error_flag  device int32, set to 1 when two linked detections share no view: the reference's np.mean([]) is nan
+ *               there and the text it feeds muSSP undefined; the arc gets weight nan and cost 0 */
+int32_t mot3d_edge_appearance_views(const mot3d_dets *dets, const mot3d_views *views, const mot3d_cost_spec *spec,
+                                    int32_t direction, const int32_t *row_ptr, const int32_t *col,
+                                    double *weight_inout, int64_t *cost_out, int32_t *error_flag, void *stream);
 
 /* ---- tracklet linking (second pass): replaces build_graph on DetectionTracklet lists (mot3d/mot3d.py:106-141)
  *      with weight_distance_tracklets_2d/_3d (mot3d/weight_functions.py:80-160) and linear_motion

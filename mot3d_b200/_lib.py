@@ -31,11 +31,17 @@ class Dets(ctypes.Structure):
 
 class CostSpecC(ctypes.Structure):
     _fields_ = [("max_jump", ctypes.c_int32), ("use_bbox", ctypes.c_int32), ("use_hist", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("sq_dist_max", ctypes.c_double),
+                ("defer_cost", ctypes.c_int32), ("sq_dist_max", ctypes.c_double),
                 ("sigma_distance_sq", ctypes.c_double), ("sigma_hist_sq", ctypes.c_double),
                 ("sigma_bbox_sq", ctypes.c_double), ("conf_mul", ctypes.c_double), ("conf_bias", ctypes.c_double),
                 ("entry_cost", ctypes.c_int64), ("exit_cost", ctypes.c_int64),
                 ("neg_exp_jump", ctypes.c_double * MAX_JUMP)]
+
+
+class Views(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int64), ("n_entries", ctypes.c_int64), ("hist_channels", ctypes.c_int32),
+                ("hist_bins", ctypes.c_int32), ("view_ptr", ctypes.c_void_p), ("view_id", ctypes.c_void_p),
+                ("bbox", ctypes.c_void_p), ("hist", ctypes.c_void_p)]
 
 
 class Tracklets(ctypes.Structure):
@@ -83,6 +89,7 @@ SIGNATURES = {
     "mot3d_edge_build_workspace_bytes": (_sz, [_i64]),
     "mot3d_edge_build": (_i32, [_PD, _PS, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_edge_appearance_views": (_i32, [_PD, ctypes.POINTER(Views), _PS, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_tracklet_edge_count": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _vp]),
     "mot3d_tracklet_edge_fill": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _i64, _vp, _vp,
                                         _vp, _vp, _vp]),

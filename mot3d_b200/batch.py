@@ -32,7 +32,9 @@ class DetectionBatch(object):
     frame int32[N]; pos float64[dim, N] (planar); conf float64[N]; flags uint8[N] or None;
     bbox float64[4, N] or None; hist float64[N, C, B] or None."""
 
-    def __init__(self, graph_ptr, frame, pos, conf, flags=None, bbox=None, hist=None):
+    def __init__(self, graph_ptr, frame, pos, conf, flags=None, bbox=None, hist=None, views=None):
+        self.views = views  # 3-D detections: dict(view_ptr int32[N+1], view_id int32[E], bbox float64[4, E] or None,
+        #                     hist float64[E, C, B] or None) - Detection3D.detections_2d, entries in dict order
         self.graph_ptr = graph_ptr
         self.frame = frame
         self.pos = pos
@@ -86,8 +88,9 @@ class DetectionBatch(object):
                 return None
             t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
             return t.to(device, non_blocking=True).contiguous()
+        views = None if self.views is None else {k: mv(v) for k, v in self.views.items()}
         b = DetectionBatch(mv(self.graph_ptr), mv(self.frame), mv(self.pos), mv(self.conf), mv(self.flags),
-                           mv(self.bbox), mv(self.hist))
+                           mv(self.bbox), mv(self.hist), views)
         b._max_nodes = self.max_graph_nodes()
         return b
 
@@ -107,6 +110,11 @@ class GraphBatch(object):
         self.n_edges = 0
 
 
+def _views_mode(spec):
+    """3-D detections with appearance terms: averaged over the shared 2-D views by mot3d_edge_appearance_views."""
+    return getattr(spec, "kind", None) == "detections_3d" and (spec.use_hist or spec.use_bbox)
+
+
 def _dets_struct(b, tkey, spec, sorted_pos=None, sorted_perm=None):
     d = _lib.Dets()
     if sorted_pos is not None:
@@ -118,6 +126,10 @@ def _dets_struct(b, tkey, spec, sorted_pos=None, sorted_perm=None):
     d.pos = b.pos.data_ptr()
     d.conf = b.conf.data_ptr()
     d.flags = b.flags.data_ptr() if b.flags is not None else None
+    if _views_mode(spec):
+        if b.views is None:
+            raise ValueError("use_color_histogram / use_bbox on 3-D detections need their detections_2d views")
+        return d
     d.bbox = b.bbox.data_ptr() if (b.bbox is not None and spec.use_bbox) else None
     if spec.use_hist:
         if b.hist is None:
@@ -142,8 +154,14 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
     n, G = batch.n, batch.n_graphs
     st = _stream(dev)
     cs = spec.to_c()
+    cs_real = cs
+    views_mode = _views_mode(spec)
+    if views_mode:
+        # the build leaves the distance factor in weight[]; mot3d_edge_appearance_views finishes the arcs
+        cs = spec.to_c()
+        cs.use_hist, cs.use_bbox, cs.defer_cost = 0, 0, 1
     gb = GraphBatch()
-    gb.dets, gb.spec, gb.cspec, gb.direction = batch, spec, cs, direction
+    gb.dets, gb.spec, gb.cspec, gb.direction = batch, spec, cs_real, direction
     i32 = dict(dtype=torch.int32, device=dev)
     i64 = dict(dtype=torch.int64, device=dev)
     if keys is None:
@@ -166,7 +184,7 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
     gb.exit_cost = torch.empty(max(n, 1), **i64)
     _lib.check(L.mot3d_node_costs(ctypes.byref(d), ctypes.byref(cs), _ptr(gb.entry_cost), _ptr(gb.node_cost),
                                   _ptr(gb.exit_cost), st))
-    need_w = with_weights or spec.use_hist
+    need_w = with_weights or spec.use_hist or views_mode
     if fused and pruned and n:
         # one launch; the arc arrays are sized by a guess and the launch is repeated in the rare case it was too small
         row_ptr = torch.empty(n + 1, **i32)
@@ -211,7 +229,25 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
         overflow = torch.zeros(1, **i32)
         _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), n_edges,
                                      _ptr(gb.col), _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), st))
-    if spec.use_hist:
+    if views_mode:
+        if n:
+            v = batch.views
+            vs = _lib.Views()
+            vs.n, vs.n_entries = n, int(v["view_id"].shape[0])
+            vs.view_ptr, vs.view_id = v["view_ptr"].data_ptr(), v["view_id"].data_ptr()
+            if spec.use_bbox:
+                vs.bbox = v["bbox"].data_ptr()
+            if spec.use_hist:
+                vs.hist = v["hist"].data_ptr()
+                vs.hist_channels, vs.hist_bins = int(v["hist"].shape[1]), int(v["hist"].shape[2])
+            err = torch.zeros(1, **i32)
+            _lib.check(L.mot3d_edge_appearance_views(ctypes.byref(d), ctypes.byref(vs), ctypes.byref(cs_real), direction,
+                                                     _ptr(gb.row_ptr), _ptr(gb.col), _ptr(gb.weight), _ptr(gb.cost),
+                                                     _ptr(err), st))
+            if int(err.item()):
+                raise ValueError("two linked 3-D detections share no 2-D view: weight_distance_detections_3d is nan "
+                                 "for them (np.mean of an empty list, reference mot3d/weight_functions.py:55-71)")
+    elif spec.use_hist:
         _lib.check(L.mot3d_edge_appearance(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), _ptr(gb.col),
                                            _ptr(gb.weight), _ptr(gb.cost), st))
     return gb

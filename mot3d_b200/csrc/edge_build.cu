@@ -434,6 +434,91 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(const int32_t *__restri
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
 }
 
+// Multi-view appearance of 3-D detections (weight_distance_detections_3d, mot3d/weight_functions.py:55-71):
+//   chs_v = 1 - color_histogram_similarity(d1.detections_2d[v].color_histogram, d2.detections_2d[v].color_histogram)
+//   bss_v = 1 - bbox_size_similarity(d1.detections_2d[v].bbox, d2.detections_2d[v].bbox)
+// for every view v of d1 (dict order) that d2 also has; the factors are exp(-mean(chs)^2/sigma_c^2) and
+// exp(-mean(bss)^2/sigma_b^2), multiplied into the distance factor in that order (np.prod), then the jump factor.
+// One warp per row; d1 = arc tail, d2 = arc head. np.mean of < 8 values adds them left to right.
+template <int DIR>
+__global__ void __launch_bounds__(128) k_edge_appearance_views(
+    int64_t n, const int32_t *__restrict__ tkey, const int32_t *__restrict__ view_ptr,
+    const int32_t *__restrict__ view_id, const double *__restrict__ vbbox, int64_t n_entries,
+    const double *__restrict__ vhist, int C, int B, int use_hist, int use_bbox, double sigma_hist_sq,
+    double sigma_bbox_sq, const __grid_constant__ JumpTable jt, const int32_t *__restrict__ row_ptr,
+    const int32_t *__restrict__ col, double *__restrict__ weight, int64_t *__restrict__ cost,
+    int32_t *__restrict__ error_flag) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (r >= n) return;
+    const int l = lane_id();
+    const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    for (int e = e0; e < e1; e++) {
+        const int64_t o = col[e];
+        const int64_t a = (DIR == MOT3D_DIR_OUT) ? r : o;  // d1: the earlier detection
+        const int64_t b = (DIR == MOT3D_DIR_OUT) ? o : r;  // d2
+        const int a0 = view_ptr[a], a1 = view_ptr[a + 1], b0 = view_ptr[b], b1 = view_ptr[b + 1];
+        double sum_c = 0.0, sum_b = 0.0;
+        int shared = 0;
+        for (int u = a0; u < a1; u++) {
+            const int id = view_id[u];
+            int v = -1;
+            for (int t = b0; t < b1; t++)
+                if (view_id[t] == id) {
+                    v = t;
+                    break;
+                }
+            if (v < 0) continue;
+            shared++;
+            if (use_hist) {
+                const double *h1 = vhist + (int64_t)u * C * B;
+                const double *h2 = vhist + (int64_t)v * C * B;
+                double scs = 0.0;
+                for (int c = 0; c < C; c++) {
+                    double ab = 0, aa = 0, bb = 0;
+                    for (int k = l; k < B; k += 32) {
+                        const double x = h1[c * B + k], y = h2[c * B + k];
+                        ab += x * y;
+                        aa += x * x;
+                        bb += y * y;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        ab += __shfl_xor_sync(0xffffffffu, ab, d);
+                        aa += __shfl_xor_sync(0xffffffffu, aa, d);
+                        bb += __shfl_xor_sync(0xffffffffu, bb, d);
+                    }
+                    scs = scs + ab / sqrt(aa * bb);
+                }
+                sum_c = sum_c + (1.0 - scs / (double)C);
+            }
+            if (use_bbox) sum_b = sum_b + (1.0 - bbox_similarity(vbbox, n_entries, u, v));
+        }
+        if (l == 0) {
+            double w;
+            int64_t q = 0;
+            if (shared == 0) {
+                w = __longlong_as_double(0x7ff8000000000000ll);  // nan, as np.mean([]) gives the reference
+                *error_flag = 1;
+            } else {
+                double prod = weight[e];
+                if (use_hist) {
+                    const double mc = sum_c / (double)shared;
+                    prod = prod * exp(-(mc * mc) / sigma_hist_sq);
+                }
+                if (use_bbox) {
+                    const double mb = sum_b / (double)shared;
+                    prod = prod * exp(-(mb * mb) / sigma_bbox_sq);
+                }
+                const int dk = (DIR == MOT3D_DIR_OUT) ? (tkey[o] - tkey[r]) : (tkey[r] - tkey[o]);
+                w = jt.v[dk - 1] * prod;
+                q = quantise_1e7(w);
+            }
+            weight[e] = w;
+            cost[e] = q;
+        }
+    }
+}
+
 static int32_t check_dets(const mot3d_dets *d, const mot3d_cost_spec *s) {
     M3_CHECK_ARG(d && s, "dets/spec is NULL");
     M3_CHECK_ARG(d->n >= 0 && d->n < ((int64_t)1 << 31), "detection count out of range");
@@ -505,7 +590,7 @@ static void fill_params(EdgeParams &p, const mot3d_dets *d, const mot3d_cost_spe
     p.dim = d->dim;
     p.max_jump = s->max_jump;
     p.use_bbox = s->use_bbox;
-    p.use_hist = s->use_hist;
+    p.use_hist = (s->use_hist || s->defer_cost) ? 1 : 0;  // = "distance factor only, an appearance pass finishes"
     p.tkey = d->tkey;
     p.pos = d->pos;
     p.bbox = d->bbox;
@@ -553,7 +638,8 @@ int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int
     if (dets->n == 0) return MOT3D_OK;
     M3_CHECK_ARG(row_ptr && edge_capacity >= 0, "row_ptr is NULL / negative capacity");
     M3_CHECK_ARG(edge_capacity == 0 || (col_out && cost_out), "col_out/cost_out is NULL");
-    M3_CHECK_ARG(!spec->use_hist || weight_out, "use_hist needs weight_out (finished by mot3d_edge_appearance)");
+    M3_CHECK_ARG(!(spec->use_hist || spec->defer_cost) || weight_out,
+                 "use_hist / defer_cost need weight_out (finished by mot3d_edge_appearance[_views])");
     EdgeParams p;
     fill_params(p, dets, spec);
     p.row_ptr = row_ptr;
@@ -610,6 +696,39 @@ int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spe
                                                                spec->sigma_hist_sq, spec->sigma_bbox_sq, jt, row_ptr,
                                                                col, weight_inout, cost_out);
     M3_LAUNCH_CHECK("k_edge_appearance");
+    return MOT3D_OK;
+}
+
+int32_t mot3d_edge_appearance_views(const mot3d_dets *dets, const mot3d_views *views, const mot3d_cost_spec *spec,
+                                    int32_t direction, const int32_t *row_ptr, const int32_t *col,
+                                    double *weight_inout, int64_t *cost_out, int32_t *error_flag, void *stream) {
+    M3_CHECK_ARG(dets && views && spec, "dets/views/spec is NULL");
+    M3_CHECK_ARG(direction == MOT3D_DIR_IN || direction == MOT3D_DIR_OUT, "bad direction");
+    M3_CHECK_ARG(spec->max_jump >= 1 && spec->max_jump <= MOT3D_MAX_JUMP, "max_jump must be in [1, MOT3D_MAX_JUMP]");
+    M3_CHECK_ARG(spec->use_hist || spec->use_bbox, "mot3d_edge_appearance_views called without use_hist / use_bbox");
+    M3_CHECK_ARG(views->n == dets->n, "views->n != dets->n");
+    if (dets->n == 0) return MOT3D_OK;
+    M3_CHECK_ARG(dets->tkey && row_ptr && col && weight_inout && cost_out && error_flag, "NULL pointer");
+    M3_CHECK_ARG(views->view_ptr && (views->n_entries == 0 || views->view_id), "view_ptr/view_id is NULL");
+    M3_CHECK_ARG(!spec->use_bbox || views->n_entries == 0 || views->bbox, "use_bbox set but views->bbox is NULL");
+    M3_CHECK_ARG(!spec->use_hist || views->n_entries == 0 ||
+                     (views->hist && views->hist_channels > 0 && views->hist_bins > 0),
+                 "use_hist set but views->hist is NULL/empty");
+    JumpTable jt;
+    for (int i = 0; i < MOT3D_MAX_JUMP; i++) jt.v[i] = (i < spec->max_jump) ? spec->neg_exp_jump[i] : 0.0;
+    unsigned grid = (unsigned)((dets->n + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (direction == MOT3D_DIR_IN)
+        k_edge_appearance_views<MOT3D_DIR_IN><<<grid, 128, 0, st>>>(
+            dets->n, dets->tkey, views->view_ptr, views->view_id, views->bbox, views->n_entries, views->hist,
+            views->hist_channels, views->hist_bins, spec->use_hist, spec->use_bbox, spec->sigma_hist_sq,
+            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag);
+    else
+        k_edge_appearance_views<MOT3D_DIR_OUT><<<grid, 128, 0, st>>>(
+            dets->n, dets->tkey, views->view_ptr, views->view_id, views->bbox, views->n_entries, views->hist,
+            views->hist_channels, views->hist_bins, spec->use_hist, spec->use_bbox, spec->sigma_hist_sq,
+            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag);
+    M3_LAUNCH_CHECK("k_edge_appearance_views");
     return MOT3D_OK;
 }
 

@@ -598,7 +598,8 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     M3_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= dets->n, "bad row range");
     M3_CHECK_ARG(row_ptr_out && edge_capacity >= 0, "row_ptr_out is NULL / negative capacity");
     M3_CHECK_ARG(edge_capacity == 0 || (col_out && cost_out), "col_out/cost_out is NULL");
-    M3_CHECK_ARG(!spec->use_hist || weight_out, "use_hist needs weight_out (finished by mot3d_edge_appearance)");
+    M3_CHECK_ARG(!(spec->use_hist || spec->defer_cost) || weight_out,
+                 "use_hist / defer_cost need weight_out (finished by mot3d_edge_appearance[_views])");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rows = row_end - row_begin;
     if (rows == 0) {
@@ -628,7 +629,7 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     p.dim = dets->dim;
     p.max_jump = spec->max_jump;
     p.use_bbox = spec->use_bbox;
-    p.use_hist = spec->use_hist;
+    p.use_hist = (spec->use_hist || spec->defer_cost) ? 1 : 0;  // = "distance factor only, an appearance pass finishes"
     p.tkey = dets->tkey;
     p.pos = dets->pos;
     p.spos = dets->sorted_pos;

@@ -171,20 +171,45 @@ def _pack(sorted_dets, cspec):
     if any((not d.entry_points) or (not d.exit_point) for d in sorted_dets):
         flags = np.fromiter(((_lib.FLAG_ENTRY if d.entry_points else 0) | (_lib.FLAG_EXIT if d.exit_point else 0)
                              for d in sorted_dets), dtype=np.uint8, count=n)
-    bbox = hist = None
+    bbox = hist = views = None
     if cspec.kind == "detections_3d" and (cspec.use_bbox or cspec.use_hist):
-        raise NotImplementedError("weight_distance_detections_3d with use_color_histogram/use_bbox averages over the "
-                                  "shared 2D views (reference mot3d/weight_functions.py:55-71); only the position "
-                                  "term is built for 3D detections so far")
-    if cspec.use_bbox:
-        bbox = np.array([d.bbox for d in sorted_dets], dtype=np.float64).reshape(n, 4)
-    if cspec.use_hist:
-        hist = np.array([np.asarray(d.color_histogram, dtype=np.float64) for d in sorted_dets])
-        if hist.ndim != 3:
-            raise ValueError("color_histogram must be a list of C arrays of B bins for every detection")
+        views = _pack_views(sorted_dets, cspec)
+    else:
+        if cspec.use_bbox:
+            bbox = np.array([d.bbox for d in sorted_dets], dtype=np.float64).reshape(n, 4)
+        if cspec.use_hist:
+            hist = np.array([np.asarray(d.color_histogram, dtype=np.float64) for d in sorted_dets])
+            if hist.ndim != 3:
+                raise ValueError("color_histogram must be a list of C arrays of B bins for every detection")
     gp = np.array([0, n], dtype=np.int32)
     return DetectionBatch(gp, frame.astype(np.int32), np.ascontiguousarray(pos.T), conf, flags,
-                          None if bbox is None else np.ascontiguousarray(bbox.T), hist)
+                          None if bbox is None else np.ascontiguousarray(bbox.T), hist, views)
+
+
+def _pack_views(sorted_dets, cspec):
+    """Detection3D.detections_2d ({view: Detection2D}, reference mot3d/types.py:40-45) -> packed entries in each
+    detection's dict order, which is the order weight_distance_detections_3d averages in
+    (reference mot3d/weight_functions.py:55-71). View labels are mapped to integers."""
+    labels = {}
+    ptr, ids, bbs, hs = [0], [], [], []
+    for d in sorted_dets:
+        d2 = getattr(d, "detections_2d", None) or {}
+        for view, det in d2.items():
+            ids.append(labels.setdefault(view, len(labels)))
+            if cspec.use_bbox:
+                bbs.append(np.asarray(det.bbox, dtype=np.float64).reshape(4))
+            if cspec.use_hist:
+                hs.append(np.asarray(det.color_histogram, dtype=np.float64))
+        ptr.append(len(ids))
+    views = dict(view_ptr=np.array(ptr, dtype=np.int32), view_id=np.array(ids, dtype=np.int32))
+    if cspec.use_bbox:
+        views["bbox"] = np.ascontiguousarray(np.array(bbs, dtype=np.float64).reshape(len(ids), 4).T)
+    if cspec.use_hist:
+        h = np.array(hs, dtype=np.float64)
+        if len(ids) and h.ndim != 3:
+            raise ValueError("color_histogram must be a list of C arrays of B bins for every 2-D view")
+        views["hist"] = np.ascontiguousarray(h.reshape(len(ids), *h.shape[1:]) if len(ids) else np.zeros((0, 1, 1)))
+    return views
 
 
 class TrackingGraph(object):

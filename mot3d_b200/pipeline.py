@@ -60,16 +60,18 @@ class TrackPipeline(object):
         self.track_ptr = torch.empty(n + G + 1, **i32)
         self.track_det = torch.empty(n, **i32)
 
-    def run(self, batch, spec, spec_c=None, events=None):
+    def run(self, batch, spec, spec_c=None, events=None, before_extract=None):
         """batch: DetectionBatch on self.device. events: optional list of len(self.stages)+1 torch.cuda.Event recorded
-        around every stage on the current stream. Asynchronous: call check_overflow()/synchronize afterwards."""
+        around every stage on the current stream. before_extract: optional event the stream waits for before the
+        track outputs are overwritten (a consumer of the previous run's outputs on another stream).
+        Asynchronous: call check_overflow()/synchronize afterwards."""
         L = _lib.lib()
         dev = self.device
         n, G = batch.n, batch.n_graphs
         if n > self.n_max or G > self.g_max:
             raise ValueError("batch larger than the pipeline was sized for")
-        if spec.use_hist:
-            raise NotImplementedError("TrackPipeline: the appearance pass is wired through build_graphs only")
+        if spec.use_hist or (spec.kind == "detections_3d" and spec.use_bbox):
+            raise NotImplementedError("TrackPipeline: the appearance passes are wired through build_graphs only")
         cs = spec.to_c() if spec_c is None else spec_c
         st = _stream(dev)
         rec = (lambda k: events[k].record(torch.cuda.current_stream(dev))) if events is not None else (lambda k: None)
@@ -111,6 +113,8 @@ class TrackPipeline(object):
                                        _ptr(self.total_cost), None, _ptr(self.stats), _ptr(self.solve_ws),
                                        self.solve_ws_bytes, st))
         rec(k + 1)
+        if before_extract is not None:
+            torch.cuda.current_stream(dev).wait_event(before_extract)
         _lib.check(L.mot3d_extract_tracks(G, _ptr(batch.graph_ptr), _ptr(self.next), _ptr(self.prev),
                                           _ptr(self.track_count), _ptr(self.track_ptr), _ptr(self.track_det), st))
         rec(k + 2)

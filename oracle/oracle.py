@@ -157,7 +157,32 @@ def _hist_similarity(H1, H2):
     return scs / n_channels
 
 
-def build_transitions(frame, pos, spec, bbox=None, hist=None):
+def _views_terms(views, gi, gj, use_hist, use_bbox):
+    """weight_distance_detections_3d's per-view loop (mot3d/weight_functions.py:55-71) for the pairs (gi[k], gj[k]):
+    mean over the views of d1 (dict order) that d2 also has of (1 - NCC) and of (1 - bbox similarity).
+    views = dict(view_ptr, view_id, bbox [E,4] or None, hist [E,C,B] or None)."""
+    vp, vid = views["view_ptr"], views["view_id"]
+    mc = np.full(len(gi), np.nan)
+    mb = np.full(len(gi), np.nan)
+    for k, (i, j) in enumerate(zip(np.asarray(gi).tolist(), np.asarray(gj).tolist())):
+        sc, sb = [], []
+        for u in range(int(vp[i]), int(vp[i + 1])):
+            v = [t for t in range(int(vp[j]), int(vp[j + 1])) if vid[t] == vid[u]]
+            if not v:
+                continue
+            v = v[0]
+            if use_hist:
+                sc.append(1 - _hist_similarity(views["hist"][u][None], views["hist"][v][None])[0])
+            if use_bbox:
+                sb.append(1 - _bbox_similarity(views["bbox"][u][None], views["bbox"][v][None])[0])
+        if sc:
+            mc[k] = np.mean(sc)
+        if sb:
+            mb[k] = np.mean(sb)
+    return mc, mb
+
+
+def build_transitions(frame, pos, spec, bbox=None, hist=None, views=None):
     """Transition arcs post_i -> pre_j of build_graph's hot loop (mot3d/mot3d.py:106-141) for detections that are
     ALREADY in sorted order: every ordered pair with 0 < frame[j]-frame[i] <= max_jump whose cost is not None
     (weight_distance_detections_2d/_3d, mot3d/weight_functions.py:13-35, 43-75; the 3D variant with a single
@@ -191,12 +216,20 @@ def build_transitions(frame, pos, spec, bbox=None, hist=None):
         prod = np.exp(-dsel ** 2 / sd2)
         gi = ii + s
         gj = jj + a
-        if spec.use_color_histogram:
-            chs = 1 - _hist_similarity(hist[gi], hist[gj])
-            prod = prod * np.exp(-chs ** 2 / spec.sigma_color_histogram ** 2)
-        if spec.use_bbox:
-            bss = 1 - _bbox_similarity(bbox[gi], bbox[gj])
-            prod = prod * np.exp(-bss ** 2 / spec.sigma_box_size ** 2)
+        if views is not None and (spec.use_color_histogram or spec.use_bbox):
+            # 3-D detections: both terms averaged over the shared 2-D views (mot3d/weight_functions.py:55-71)
+            mc, mb = _views_terms(views, gi, gj, spec.use_color_histogram, spec.use_bbox)
+            if spec.use_color_histogram:
+                prod = prod * np.exp(-mc ** 2 / spec.sigma_color_histogram ** 2)
+            if spec.use_bbox:
+                prod = prod * np.exp(-mb ** 2 / spec.sigma_box_size ** 2)
+        else:
+            if spec.use_color_histogram:
+                chs = 1 - _hist_similarity(hist[gi], hist[gj])
+                prod = prod * np.exp(-chs ** 2 / spec.sigma_color_histogram ** 2)
+            if spec.use_bbox:
+                bss = 1 - _bbox_similarity(bbox[gi], bbox[gj])
+                prod = prod * np.exp(-bss ** 2 / spec.sigma_box_size ** 2)
         jump = frame[gj] - frame[gi]
         w = -np.exp(-(jump - 1) * spec.sigma_jump) * prod
         rows.append(gi)

@@ -171,9 +171,74 @@ def gen_synth(F, P, seed, extent=1000.0):
     return np.concatenate(frames), np.concatenate(positions)
 
 
+def case_multiview(mot3d, wf):
+    """(3b) synthetic 3-D detections seen in 2-4 of 4 camera views, both appearance terms of
+    weight_distance_detections_3d on (mot3d/weight_functions.py:43-75: averages over the shared views)."""
+    rng = np.random.RandomState(23)
+    P, F, V, C, B = 6, 18, 4, 3, 24
+    base = rng.rand(P, 3) * np.array([20.0, 20.0, 0.3]) + np.array([0, 0, 1.6])
+    vel = rng.randn(P, 3) * np.array([0.15, 0.15, 0.0])
+    proto = rng.rand(P, V, C, B)
+    dets = []
+    for f in range(F):
+        base = base + vel + rng.randn(P, 3) * np.array([0.03, 0.03, 0.005])
+        for p in range(P):
+            if rng.rand() < 0.08:
+                continue
+            seen = [v for v in rng.permutation(V).tolist() if rng.rand() < 0.75]  # dict order differs per detection
+            if len(seen) < 2:
+                seen = [int(x) for x in rng.permutation(V)[:2]]
+            d2 = {}
+            for v in seen:
+                h = proto[p, v] + 0.2 * rng.rand(C, B)
+                h = h - h.mean(axis=1, keepdims=True)
+                w, hh = 30 + rng.randn() * 3 + 4 * v, 80 + rng.randn() * 8 + 6 * v
+                x, y = rng.rand(2) * 500
+                d2["cam%d" % v] = mot3d.Detection2D(f, (x, y), view="cam%d" % v,
+                                                    color_histogram=[h[c] for c in range(C)],
+                                                    bbox=(x - w / 2, y - hh / 2, x + w / 2, y + hh / 2))
+            dets.append(mot3d.Detection3D(f, base[p].copy(), confidence=0.6 + 0.4 * rng.rand(), detections_2d=d2))
+    # views 0 and 1 are always shared here? no: make sure every linked pair shares a view (np.mean([]) is nan in the
+    # reference): give every detection camera 0
+    for d in dets:
+        if "cam0" not in d.detections_2d:
+            h = rng.rand(C, B)
+            h = h - h.mean(axis=1, keepdims=True)
+            d.detections_2d["cam0"] = mot3d.Detection2D(d.index, (0.0, 0.0), view="cam0",
+                                                        color_histogram=[h[c] for c in range(C)],
+                                                        bbox=(0.0, 0.0, 28.0 + rng.rand(), 75.0 + rng.rand()))
+    spec = dict(kind="3d", sigma_jump=1, sigma_distance=0.6, sigma_color_histogram=0.35, sigma_box_size=0.25,
+                max_distance=1.5, use_color_histogram=True, use_bbox=True, mul=1, bias=0.02,
+                weight_source_sink=0.7, max_jump=3)
+    wd = lambda d1, d2: wf.weight_distance_detections_3d(d1, d2, sigma_jump=1, sigma_distance=0.6,
+                                                         sigma_color_histogram=0.35, sigma_box_size=0.25,
+                                                         max_distance=1.5, use_color_histogram=True, use_bbox=True)
+    wc = lambda d: wf.weight_confidence_detections_3d(d, mul=1, bias=0.02)
+
+    def extra_views(sorted_dets):
+        names = sorted({v for d in sorted_dets for v in d.detections_2d})
+        vid = {v: i for i, v in enumerate(names)}
+        ptr, ids, bb, hh = [0], [], [], []
+        for d in sorted_dets:
+            for v, d2 in d.detections_2d.items():  # dict order = the order the reference iterates in
+                ids.append(vid[v])
+                bb.append(d2.bbox)
+                hh.append(np.asarray(d2.color_histogram, dtype=np.float64))
+            ptr.append(len(ids))
+        return dict(view_ptr=np.array(ptr, np.int32), view_id=np.array(ids, np.int32),
+                    view_bbox=np.array(bb, np.float64), view_hist=np.array(hh, np.float64))
+
+    freeze_detection_case(mot3d, "c3_synth_multiview", dets,
+                          dict(weight_source_sink=0.7, max_jump=3, weight_confidence=wc, weight_distance=wd),
+                          spec, extra_views)
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "c3_synth_multiview" in sys.argv[1:]:
+        return case_multiview(mot3d, wf)
+    case_multiview(mot3d, wf)
     from mot3d.utils import utils as ref_utils
     from mot3d.utils import trajectory as ref_traj
 

@@ -10,7 +10,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SCALE = 10 ** 7
 
 # Fixtures with detections (frame/pos/...) -> build + solve parity; the others are solver-only graphs.
-DETECTION_CASES = ["c1_simple_2d", "c3_soldiers_pass1", "c4_pets_view1_w0", "c4_pets_view1_w1",
+DETECTION_CASES = ["c1_simple_2d", "c3_soldiers_pass1", "c3_synth_multiview", "c4_pets_view1_w0", "c4_pets_view1_w1",
                    "c4_synth_appearance", "c5_small_f30_p12", "c5_window_f50_p100", "quirk_single_detection"]
 TRACKLET_CASES = ["c2_tracklets_pass2", "c3_soldiers_pass2", "c4_synth_tracklets"]
 GRAPH_CASES = DETECTION_CASES + TRACKLET_CASES + ["wrapper_test_graph", "mussp_seq07"]
@@ -30,6 +30,14 @@ def load(name):
     if "spec" in d:
         d["spec"] = json.loads(str(d["spec"]))
     return d
+
+
+def views_of(d):
+    """The 2-D views of a fixture of 3-D detections (entries in each detection's dict order), or None:
+    dict(view_ptr, view_id, bbox [E, 4], hist [E, C, B])."""
+    if "view_ptr" not in d:
+        return None
+    return dict(view_ptr=d["view_ptr"], view_id=d["view_id"], bbox=d["view_bbox"], hist=d["view_hist"])
 
 
 def all_cases():

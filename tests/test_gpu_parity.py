@@ -31,6 +31,10 @@ def _batch_from(d, mot3d, flags=None):
     b, order = mot3d.DetectionBatch.from_arrays(np.array([0, n]), d["frame"], d["pos"], d["conf"], flags=flags,
                                                 bbox=d.get("bbox"), hist=d.get("hist"))
     assert (order == np.arange(n)).all()  # fixtures are stored in node order
+    v = gu.views_of(d)
+    if v is not None:  # 3-D detections with their 2-D views (planar bbox on the device side)
+        b.views = dict(view_ptr=v["view_ptr"].astype(np.int32), view_id=v["view_id"].astype(np.int32),
+                       bbox=np.ascontiguousarray(v["bbox"].T), hist=np.ascontiguousarray(v["hist"]))
     return b
 
 
@@ -286,6 +290,62 @@ def test_public_api_drop_in():
     tail, head = d["tail"], d["head"]
     k = np.flatnonzero((tail == 3) & (head == 6))
     assert (w is None and len(k) == 0) or abs(w - d["w_float"][k[0]]) <= RTOL * abs(d["w_float"][k[0]])
+
+
+def test_public_api_multiview_3d_detections():
+    """Detection3D objects that carry their 2-D views ({view: Detection2D}, reference mot3d/types.py:40-45) through
+    build_graph / solve_graph with weight_distance_detections_3d(use_color_histogram=True, use_bbox=True): both
+    appearance terms averaged over the shared views in the tail detection's dict order (reference
+    mot3d/weight_functions.py:55-71). Text and trajectories are the reference's; a pair without a common view is an
+    error here (the reference computes nan)."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    d = gu.load("c3_synth_multiview")
+    n = len(d["frame"])
+    vp, vid, vb, vh = d["view_ptr"], d["view_id"], d["view_bbox"], d["view_hist"]
+
+    def views(i, drop=None):
+        out = {}
+        for u in range(int(vp[i]), int(vp[i + 1])):
+            if drop is not None and int(vid[u]) in drop:
+                continue
+            name = "cam%d" % int(vid[u])
+            out[name] = mot3d.Detection2D(int(d["frame"][i]), (0.0, 0.0), view=name,
+                                          color_histogram=[h for h in vh[u]], bbox=tuple(vb[u]))
+        return out
+
+    dets = [mot3d.Detection3D(int(d["frame"][i]), d["pos"][i], confidence=float(d["conf"][i]), detections_2d=views(i))
+            for i in range(n)]
+    s = d["spec"]
+    wd = lambda a, b: wf.weight_distance_detections_3d(a, b, sigma_jump=s["sigma_jump"],
+                                                       sigma_distance=s["sigma_distance"],
+                                                       sigma_color_histogram=s["sigma_color_histogram"],
+                                                       sigma_box_size=s["sigma_box_size"],
+                                                       max_distance=s["max_distance"], use_color_histogram=True,
+                                                       use_bbox=True)
+    wc = lambda x: wf.weight_confidence_detections_3d(x, mul=s["mul"], bias=s["bias"])
+    g = mot3d.build_graph(dets, weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"], verbose=False,
+                          weight_confidence=wc, weight_distance=wd)
+    tail, head, w = g.arcs()
+    assert (tail == d["tail"]).all() and (head == d["head"]).all()
+    np.testing.assert_allclose(w, d["w_float"], rtol=RTOL, atol=0)
+    trajectories = mot3d.solve_graph(g, verbose=False)
+    got = [[dets.index(x) for x in t] for t in trajectories]
+    gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
+    assert got == gold
+    # one pair through the same kernels
+    k = int(np.flatnonzero((d["tail"] % 2 == 1) & (d["tail"] != 1) & (d["head"] != 2 * n + 2))[0])
+    i, j = (int(d["tail"][k]) - 3) // 2, (int(d["head"][k]) - 2) // 2
+    w1 = wf.weight_distance_detections_3d(dets[i], dets[j], sigma_jump=s["sigma_jump"],
+                                          sigma_distance=s["sigma_distance"],
+                                          sigma_color_histogram=s["sigma_color_histogram"],
+                                          sigma_box_size=s["sigma_box_size"], max_distance=s["max_distance"])
+    assert abs(w1 - d["w_float"][k]) <= RTOL * abs(d["w_float"][k])
+    # no common view: nan in the reference, an error here
+    lonely = [mot3d.Detection3D(0, (0.0, 0.0, 0.0), detections_2d=views(i, drop={0, 1})),
+              mot3d.Detection3D(1, (0.1, 0.0, 0.0), detections_2d=views(j, drop={2, 3}))]
+    with pytest.raises(ValueError):
+        mot3d.build_graph(lonely, max_jump=2, verbose=False, weight_confidence=wc, weight_distance=wd)
 
 
 def test_batched_graphs_equal_single_graphs():

@@ -49,7 +49,8 @@ def test_build_restatement_matches_reference(name):
     d = gu.load(name)
     s = d["spec"]
     spec = oracle.CostSpec(**{k: v for k, v in s.items() if k != "kind"})
-    row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], spec, bbox=d.get("bbox"), hist=d.get("hist"))
+    row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], spec, bbox=d.get("bbox"), hist=d.get("hist"),
+                                               views=gu.views_of(d))
     n = len(d["frame"])
     tail, head, ww = oracle.graph_arcs(n, float(spec.weight_source_sink), oracle.node_weights(d["conf"], spec), 0.0,
                                        row_ptr, col, w)
