@@ -192,6 +192,7 @@ struct Counters {
 // ---- first shortest-path tree of every graph (before it is split into components): no flow yet, the network is a
 //      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
 //      State is written in the regrouped order; branch label = position of the detection whose S arc starts the path.
+template <int FT_LPN>
 __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     __shared__ int s_scan[33];
     const int g = blockIdx.x;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
     __syncthreads();
     // FT_LPN lanes per node, every lane keeps FT_U independent arc loads in flight: a layer of ~100 nodes with ~8
     // in-arcs each is one pass of the block and four dependent memory levels (row, source, position, label).
-    constexpr int FT_LPN = 2, FT_U = 4;
+    constexpr int FT_U = 4;
     const int sub = tid % FT_LPN, grp = tid / FT_LPN, ngrp = T / FT_LPN;
     int wide = 0;  // some cost needs more than 32 bits: the packed staging of k_ssp_solve is off
     for (int l = 0; l < L; l++) {
@@ -1270,7 +1271,20 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                                 comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
     if (rc) return rc;
     // 2. first shortest-path tree per graph; work queue order of the components
-    k_first_tree<<<n_graphs, 256, 0, st>>>(p);
+    {
+        // 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of the block. MOT3D_FT_THREADS /
+        // MOT3D_FT_LPN: bench experiments (1 lane per node and 128 threads put twice as many graphs on an SM).
+        int ft_threads = 256, ft_lpn = 2;
+        if (const char *e = getenv("MOT3D_FT_THREADS")) ft_threads = atoi(e);
+        if (const char *e = getenv("MOT3D_FT_LPN")) ft_lpn = atoi(e);
+        if (ft_threads != 64 && ft_threads != 128 && ft_threads != 192 && ft_threads != 256) ft_threads = 256;
+        if (ft_lpn == 1)
+            k_first_tree<1><<<n_graphs, ft_threads, 0, st>>>(p);
+        else if (ft_lpn == 4)
+            k_first_tree<4><<<n_graphs, ft_threads, 0, st>>>(p);
+        else
+            k_first_tree<2><<<n_graphs, ft_threads, 0, st>>>(p);
+    }
     M3_LAUNCH_CHECK("k_first_tree");
     // 3. successive shortest paths per component. Shared memory per block = the staging area of one component; blocks
     //    pull components from the work queue. Graphs of more than 1024 detections fall apart into components of a
