@@ -233,12 +233,95 @@ def case_multiview(mot3d, wf):
                           spec, extra_views)
 
 
+ONLINE_CONFIG = dict(
+    batch_size=50, completed_after=30,
+    detections=dict(weight_source_sink=1, max_jump=4, verbose=False,
+                    weight_distance=dict(sigma_distance=10, sigma_jump=4, sigma_color_histogram=0.1,
+                                         sigma_box_size=0.1, max_distance=30, use_color_histogram=False,
+                                         use_bbox=True),
+                    weight_confidence=dict(mul=0, bias=0)),
+    tracklets=dict(weight_source_sink=0.1, max_jump=40, length_endpoints=5, verbose=False,
+                   weight_distance=dict(sigma_color_histogram=0.3, sigma_motion=100, alpha=0.2, cutoff_motion=0.1,
+                                        cutoff_appearance=0.1, use_color_histogram=True),
+                   weight_confidence=dict(mul=0, bias=0.11)))
+
+
+def gen_online(F=200, P=8, seed=0):
+    """C4-synth: P people over a 768 x 576 image, per-frame miss probability 0.1, Poisson(1) false
+    positives, bbox (w ~ N(30,3), h ~ N(80,8)) around the position. Returns per-frame arrays."""
+    rng = np.random.RandomState(seed)
+    pos = rng.rand(P, 2) * np.array([768.0, 576.0])
+    vel = rng.randn(P, 2) * 1.0
+    frames = []
+    for f in range(F):
+        pos = pos + vel + rng.randn(P, 2) * 0.2
+        rows = []
+        for p in range(P):
+            if rng.rand() < 0.1:
+                continue
+            if (p == 0 and f > 70) or (p == 1 and f > 95) or (p == 2 and f < 60):
+                continue  # two people leave, one enters late: trajectories complete / start between batches
+            rows.append((pos[p, 0], pos[p, 1], 0.75 + 0.25 * rng.rand()))
+        for _ in range(rng.poisson(1.0)):
+            rows.append((rng.rand() * 768, rng.rand() * 576, 0.75 + 0.25 * rng.rand()))
+        out = []
+        for x, y, c in rows:
+            w, h = 30 + rng.randn() * 3, 80 + rng.randn() * 8
+            out.append((x, y, c, x - w / 2, y - h / 2, x + w / 2, y + h / 2))
+        frames.append(np.array(out, dtype=np.float64).reshape(-1, 7))
+    return frames
+
+
+def case_online(mot3d):
+    """(4d) the reference's own online loop (projects/PETS2009S2L1/singleview_tracking.py:76-134 Tracker2D.update,
+    tracking_routines.py, scene.py) on C4-synth, 4 batches of 50 frames; the scene after every batch is frozen."""
+    import collections
+    import collections.abc
+    collections.Iterable = collections.abc.Iterable  # tracking_routines.py:9 predates Python 3.10
+    sys.modules["multiview_matching"] = types.ModuleType("multiview_matching")  # not vendored, unused on this path
+    sys.modules["imageio"].imread = lambda *a, **k: None
+    sys.path.insert(0, os.path.join(REF, "projects/PETS2009S2L1"))
+    import singleview_tracking as sv
+    frames = gen_online()
+    cfg = ONLINE_CONFIG
+    scene = sv.Scene(cfg["completed_after"])
+    tracker = sv.Tracker2D(scene, None, cfg, image_size=(768, 576))
+    out = dict(det_ptr=np.cumsum([0] + [len(f) for f in frames]).astype(np.int64),
+               det=np.concatenate(frames), config=json.dumps(cfg))
+    B = cfg["batch_size"]
+    import io
+    import contextlib
+    for b in range(len(frames) // B):
+        dets = [[mot3d.Detection2D(f, r[:2].copy(), confidence=float(r[2]), bbox=tuple(r[3:7]))
+                 for r in frames[f]] for f in range(b * B, (b + 1) * B)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            tracker.update((b + 1) * B, dets)  # iterator.idx after the batch (feeders.py)
+        for name, store in (("active", scene.active), ("completed", scene.completed)):
+            ids = sorted(store)
+            out["b%d_%s_ids" % (b, name)] = np.array(ids, dtype=np.int64)
+            out["b%d_%s_ptr" % (b, name)] = np.cumsum([0] + [len(store[i]) for i in ids]).astype(np.int64)
+            out["b%d_%s_index" % (b, name)] = np.array([d.index for i in ids for d in store[i]], dtype=np.int64)
+            out["b%d_%s_pos" % (b, name)] = np.array([np.asarray(d.position, dtype=np.float64) for i in ids
+                                                      for d in store[i]]).reshape(-1, 2)
+            out["b%d_%s_bbox" % (b, name)] = np.array([np.asarray(d.bbox, dtype=np.float64) for i in ids
+                                                       for d in store[i]]).reshape(-1, 4)
+        print("online batch %d: active %d completed %d tracklets %d" % (b, len(scene.active), len(scene.completed),
+                                                                        len(scene.tracklets)))
+    out["n_tracklets"] = len(scene.tracklets)
+    path = os.path.join(HERE, "c4_online_loop.npz")
+    np.savez_compressed(path, **out)
+    print("%-22s (%d KB)" % ("c4_online_loop", os.path.getsize(path) // 1024))
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "c4_online_loop" in sys.argv[1:]:
+        return case_online(mot3d)
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
     case_multiview(mot3d, wf)
+    case_online(mot3d)
     from mot3d.utils import utils as ref_utils
     from mot3d.utils import trajectory as ref_traj
 

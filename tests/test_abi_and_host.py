@@ -201,3 +201,29 @@ def test_trajectory_glue(built):
     assert [[d.index for d in p] for p in mot3d.remove_short_trajectories(pieces, th_length=2)] == [[5, 6, 9], [10, 11, 14]]
     assert [d.index for d in mot3d.concat_tracklets(pieces)] == [d.index for d in traj]
     assert mot3d.split_trajectory_modulo([], length=5) == []
+
+
+def test_interpolate_trajectory_and_scene_bookkeeping():
+    """Host glue of the online loop (no GPU): hole filling like the reference's interpolate_trajectory
+    (mot3d/utils/trajectory.py:14-69) and Scene's id / completion rules (projects/PETS2009S2L1/scene.py:8-40)."""
+    import numpy as np
+    import mot3d_b200 as mot3d
+    from mot3d_b200.online import Scene
+    a = mot3d.Detection2D(3, np.array([0.0, 10.0]), bbox=(0.0, 0.0, 2.0, 4.0))
+    b = mot3d.Detection2D(7, np.array([8.0, 2.0]), bbox=(4.0, 4.0, 10.0, 12.0))
+    c = mot3d.Detection2D(8, np.array([9.0, 2.0]), bbox=(5.0, 4.0, 11.0, 12.0))
+    out = mot3d.interpolate_trajectory([a, b, c], attr_names=["position", "bbox"])
+    assert [d.index for d in out] == [3, 4, 5, 6, 7, 8]
+    assert out[0] is a and out[4] is b and out[5] is c
+    np.testing.assert_allclose(out[2].position, [4.0, 6.0])
+    np.testing.assert_allclose(out[1].bbox, [1.0, 1.0, 4.0, 6.0])
+    assert type(out[1]) is mot3d.Detection2D
+    scene = Scene(completed_after=5)
+    scene.update(None, [a])
+    scene.update(None, [b, c])
+    scene.update(0, [a, b])          # existing id: replaced
+    assert sorted(scene.active) == [0, 1] and scene.active[0] == [a, b]
+    scene.update_completed(13)       # 7 + 5 < 13: trajectory 0 is done; 8 + 5 < 13 is false
+    assert sorted(scene.completed) == [0] and sorted(scene.active) == [1]
+    scene.update(None, [c])
+    assert sorted(scene.active) == [1, 2]

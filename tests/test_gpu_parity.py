@@ -723,6 +723,39 @@ def test_two_pass_pipeline_drop_in():
         assert [d.index for d in j] == sorted(d.index for d in j)
 
 
+def test_online_window_loop_matches_reference():
+    """BASELINE config 4 (PETS-shaped online sliding-window tracking): mot3d_b200.online.Tracker2D / Scene, the mirror
+    of the reference's loop (projects/PETS2009S2L1/singleview_tracking.py:76-134, tracking_routines.py:16-52,
+    scene.py:8-52), over 4 batches of 50 frames of C4-synth. After every batch the scene - ids, frames, interpolated
+    positions and boxes of the active and the completed trajectories - must be what the reference's own loop left
+    (tests/golden/c4_online_loop.npz, made by running that loop unmodified)."""
+    import json
+    import mot3d_b200 as mot3d
+    from mot3d_b200.online import Scene, Tracker2D
+    d = gu.load("c4_online_loop")
+    cfg = json.loads(str(d["config"]))
+    scene = Scene(cfg["completed_after"])
+    tracker = Tracker2D(scene, None, cfg, image_size=(768, 576))
+    ptr, det = d["det_ptr"], d["det"]
+    B = cfg["batch_size"]
+    n_frames = len(ptr) - 1
+    for b in range(n_frames // B):
+        dets = [[mot3d.Detection2D(f, det[r, :2].copy(), confidence=float(det[r, 2]), bbox=tuple(det[r, 3:7]))
+                 for r in range(int(ptr[f]), int(ptr[f + 1]))] for f in range(b * B, (b + 1) * B)]
+        tracker.update((b + 1) * B, dets)
+        for name, store in (("active", scene.active), ("completed", scene.completed)):
+            ids = sorted(store)
+            assert ids == d["b%d_%s_ids" % (b, name)].tolist(), (b, name)
+            assert np.cumsum([0] + [len(store[i]) for i in ids]).tolist() == d["b%d_%s_ptr" % (b, name)].tolist()
+            assert [x.index for i in ids for x in store[i]] == d["b%d_%s_index" % (b, name)].tolist()
+            pos = np.array([np.asarray(x.position, dtype=np.float64) for i in ids for x in store[i]]).reshape(-1, 2)
+            box = np.array([np.asarray(x.bbox, dtype=np.float64) for i in ids for x in store[i]]).reshape(-1, 4)
+            np.testing.assert_allclose(pos, d["b%d_%s_pos" % (b, name)], rtol=1e-12, atol=1e-9)
+            np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)], rtol=1e-12, atol=1e-9)
+    assert len(scene.tracklets) == int(d["n_tracklets"])
+    assert len(scene.completed) == 2 and len(scene.active) == 6
+
+
 def test_components_against_scipy():
     """mot3d_components (csrc/components.cu): the regrouping of every graph by connected component of its transition
     arcs, checked against scipy on a ragged batch; repeated, because the union-find runs lock-free."""
