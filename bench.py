@@ -385,7 +385,8 @@ def run_ours(args):
                 "arc_pulls_per_graph_mean": float(stats[:, 3].mean()),
                 "phase_cycles_per_graph_mean": {k: float(stats[:, 4 + i].mean()) for i, k in enumerate(
                     ["sink_argmin", "list_branch", "stage_and_initial_labels", "walk", "fix_point", "certificate"])},
-                "components_finished_by_certificate_per_graph_mean": float(stats[:, 10].mean())}
+                "components_finished_by_certificate_per_graph_mean": float(stats[:, 10].mean()),
+                "components_finished_by_single_track_pass_per_graph_mean": float(stats[:, 24].mean())}
     roofline_build = {"bound": "hbm", "kernel": ("k_frame_sort + k_edge_build_fused" if pipe.fused else
                                  "k_frame_sort + k_edge_build_pruned<count> + scan + <fill> + k_edge_cost"),
                       "achieved": build_gbs, "peak": peak,

@@ -40,7 +40,7 @@ extern "C" {
 #define MOT3D_DIR_IN 0  /* CSR rows = arc heads (pre_j), columns = tails (post_i), ascending: what the solver pulls from */
 #define MOT3D_DIR_OUT 1 /* CSR rows = arc tails (post_i), columns = heads (pre_j), ascending: graph_to_text order */
 
-#define MOT3D_SOLVE_STATS 24 /* int64 per graph written to mot3d_solve_batch's stats_out */
+#define MOT3D_SOLVE_STATS 25 /* int64 per graph written to mot3d_solve_batch's stats_out */
 
 #define MOT3D_FLAG_ENTRY 1 /* Detection.entry_points (mot3d/types.py:24, mot3d/mot3d.py:90-91) */
 #define MOT3D_FLAG_EXIT 2  /* Detection.exit_point   (mot3d/types.py:25, mot3d/mot3d.py:98-99) */
@@ -251,7 +251,8 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
  *                   [11] = branches re-labelled, [12] = records listed for them, [13..14] = SM cycles of the sweep
  *                   warp in ascending / descending sweeps, [15..16] = ascending / descending steps, [17] (first graph of the
  *                   batch only) = cycles all solver blocks were busy, summed; [18..21] = [13..16] of the
- *                   components solved on the global staging area alone, [22] = how many, [23] = their cycles
+ *                   components solved on the global staging area alone, [22] = how many, [23] = their cycles; [24] =
+ *                   components finished by the single-track pass (k_single_track) without entering the solver
  * Acceptance rule of wrapper.cpp:199-267 on integers: path 1 always, then while cost < 0. */
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                           const int32_t *tkey, int64_t arc_capacity,

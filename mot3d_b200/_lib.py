@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libmot3d_b200.so")
 MAX_JUMP = 256
 INF_COST = 1 << 60
 DIR_IN, DIR_OUT = 0, 1
-SOLVE_STATS = 24  # include/mot3d_b200.h: MOT3D_SOLVE_STATS
+SOLVE_STATS = 25  # include/mot3d_b200.h: MOT3D_SOLVE_STATS
 FLAG_ENTRY, FLAG_EXIT = 1, 2
 
 E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4

@@ -127,6 +127,9 @@ struct SolveParams {
     int4 *job_tab;              // [n_cgraphs] the work queue, largest components first (k_job_order): x = first
                                 // position, y = detections (0 = nothing to do), z = graph, w = 1 if the costs are wide
     int32_t *n_cgraphs;         // device: [0] = number of component graphs, [1] = work-queue cursor
+    int32_t *job_meta;          // device: [0 .. 2*JOB_CLASSES) components per size class (k_single_track), then as many
+                                // scatter cursors (k_job_order), then [4*JOB_CLASSES] = length of the work queue
+    int32_t fast;               // 1 = k_single_track may finish single-track components
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
     // first shortest-path tree (k_first_tree), per regrouped position; values are regrouped positions too
@@ -193,7 +196,7 @@ struct Counters {
 //      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
 //      State is written in the regrouped order; branch label = position of the detection whose S arc starts the path.
 template <int FT_LPN>
-__global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
+__global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     __shared__ int s_scan[33];
     const int g = blockIdx.x;
     const int g0 = p.graph_ptr[g];
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
             best.idx = PAR_NONE;
             int q = 0;
             int64_t e_ = INF, c_ = 0, x_ = INF;
+            int64_t w_best = INF, w_min = INF;  // cost of the parent arc / of the cheapest in-arc (k_single_track)
             if (valid) {
                 const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
                 if (sub == 0) {  // the node's own costs: in flight together with the arc loads
@@ -279,11 +283,13 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
 #pragma unroll
                     for (int u = 0; u < FT_U; u++) {
                         wide |= (w[u] != (int64_t)(int)w[u]) ? 1 : 0;
+                        if (qi[u] >= 0 && w[u] < w_min) w_min = w[u];
                         if (di[u] < INF_CUT) {
                             const int64_t cand = di[u] + w[u];
                             if (cand < best.key || (cand == best.key && qi[u] < best.idx)) {
                                 best.key = cand;
                                 best.idx = qi[u];
+                                w_best = w[u];
                             }
                         }
                     }
@@ -292,7 +298,13 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
 #pragma unroll
             for (int d = 1; d < FT_LPN; d <<= 1) {  // lowest source position wins ties
                 const KeyIdx o = shfl_xor_ki(best, d);
-                if (o.key < best.key || (o.key == best.key && o.idx >= 0 && (best.idx < 0 || o.idx < best.idx))) best = o;
+                const int64_t ow = __shfl_xor_sync(0xffffffffu, w_best, d);
+                const int64_t om = __shfl_xor_sync(0xffffffffu, w_min, d);
+                if (o.key < best.key || (o.key == best.key && o.idx >= 0 && (best.idx < 0 || o.idx < best.idx))) {
+                    best = o;
+                    w_best = ow;
+                }
+                w_min = om < w_min ? om : w_min;
             }
             if (valid && sub == 0) {
                 int anc = best.idx >= 0 ? p.ws_anc_post[best.idx] : -1;
@@ -302,6 +314,11 @@ __global__ void __launch_bounds__(256) k_first_tree(const SolveParams p) {
                     best.idx = PAR_S;
                     anc = q;
                 }
+                // what solve_component's optimality certificate asks of this detection if its tree arc ends up
+                // matched: no negative entry / exit cost; the arc is the cheapest in-arc, costs mc <= 0, cn + mc <= 0
+                int cert = ((e_ < INF_CUT && e_ < 0) || (x_ < INF_CUT && x_ < 0)) ? 0 : 1;
+                if (best.idx >= 0 && !(w_best <= 0 && c_ + w_best <= 0 && w_min >= w_best)) cert = 0;
+                p.ws_pl[q] = cert;
                 if (best.key < INF_CUT) {
                     p.ws_dpre[q] = best.key;
                     p.ws_par[q] = best.idx;
@@ -979,42 +996,114 @@ __device__ __noinline__ void solve_component(const SolveParams &p, const int cg,
     __syncthreads();
 }
 
-// ---- work queue order: largest components first (longest-processing-time-first keeps the tail of the solver short:
-//      a component is solved by one block, path after path). One block: counting sort by size class, 4 classes per
-//      power of two; the order inside a class does not matter.
+// ---- single-track components. Three out of four components of a crowded window are one object seen once per frame:
+//      the first shortest path runs through all of its detections in order, the optimality certificate of
+//      solve_component (matched arcs are the cheapest in-arcs of their heads, no negative entry / exit cost) holds,
+//      and the component is finished with K = 1. That can be read off the first tree without staging anything: one
+//      warp per component checks parent chain, sink arg-min and the certificate bits k_first_tree left per detection
+//      (a few coalesced loads per lane, no arc is read again) and writes the track; k_job_order then leaves the component out of the solver's queue. The answer is exactly what
+//      solve_component would return (same sink by its tie-breaking, same acceptance rule); anything that does not
+//      qualify is left to it. first_sink[c] = FAST_DONE marks a finished component.
 constexpr int JOB_CLASSES = 64;
 __device__ __forceinline__ int job_class(int n) {
     if (n < 4) return n;
     const int lg = 31 - __clz(n);
     return 4 * (lg - 1) + ((n >> (lg - 2)) & 3);  // 4 -> 4, 8 -> 8, ..., 8192 -> 48
 }
-__global__ void __launch_bounds__(1024) k_job_order(const SolveParams p) {
+constexpr int FAST_DONE = -2;
+__device__ __forceinline__ void single_track(const SolveParams &p, const int c);
+__global__ void __launch_bounds__(256) k_single_track(const SolveParams p) {
+    // the number of components lives on the device: a fixed grid of warps strides over them
+    const int n_comp = p.n_cgraphs[0];
+    const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); c < n_comp; c += warps) single_track(p, c);
+}
+
+__device__ __forceinline__ bool single_track_try(const SolveParams &p, const int c, const int c0, const int n,
+                                                 const int g);
+// finished here, or counted into its size class for the solver's queue (k_job_order)
+__device__ __forceinline__ void single_track(const SolveParams &p, const int c) {
+    const int c0 = p.cgraph_ptr[c], n = p.cgraph_ptr[c + 1] - c0, g = p.cgraph_win[c];
+    if (n <= 0 || p.n_paths[g] < 0) return;  // empty, or the graph was skipped (arc buffer overflow)
+    if (p.fast && n <= 4096 && single_track_try(p, c, c0, n, g)) return;
+    if (lane_id() == 0) atomicAdd(&p.job_meta[job_class(n) + (n > p.rcap ? JOB_CLASSES : 0)], 1);
+}
+
+__device__ __forceinline__ bool single_track_try(const SolveParams &p, const int c, const int c0, const int n,
+                                                 const int g) {
+    const int lane = lane_id();
+    // the first tree is the chain c0 -> c0+1 -> ..., every detection passes the certificate (k_first_tree left one bit
+    // per detection, computed from the arcs it was reading anyway)
+    bool ok = true;
+    int64_t key_last = INF, key_rest = INF;
+    for (int i = lane; i < n && ok; i += 32) {
+        const int q = c0 + i;
+        const int par = p.ws_par[q];
+        ok = ((i == 0) ? (par == PAR_S) : (par == q - 1)) && p.ws_pl[q] != 0;
+        const int64_t ex = p.ex[p.comp_perm[q]];
+        const int64_t dpost = p.ws_dpost[q];
+        const int64_t key = (ex < INF_CUT && dpost < INF_CUT) ? dpost + ex : INF;
+        if (i == n - 1)
+            key_last = key;
+        else if (key < key_rest)
+            key_rest = key;
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        key_last = min(key_last, __shfl_xor_sync(0xffffffffu, key_last, d));
+        key_rest = min(key_rest, __shfl_xor_sync(0xffffffffu, key_rest, d));
+    }
+    // the sink arg-min of solve_component takes the lowest slot among equal keys: the last detection has to win
+    // strictly, and the path has to pay (wrapper.cpp:263-267)
+    if (!(key_last < key_rest) || key_last >= 0) return false;
+    // (3) the track
+    for (int i = lane; i < n; i += 32) {
+        const int d = p.comp_perm[c0 + i];
+        p.next_out[d] = (i + 1 < n) ? p.comp_perm[c0 + i + 1] : TERM;
+        p.prev_out[d] = (i > 0) ? p.comp_perm[c0 + i - 1] : TERM;
+    }
+    if (lane == 0) {
+        atomicAdd(&p.n_paths[g], 1);
+        atomicAdd((unsigned long long *)&p.total[g], (unsigned long long)key_last);
+        if (p.path_cost) p.path_cost[c0] = key_last;
+        p.first_sink[c] = FAST_DONE;
+        if (p.stats) atomicAdd((unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g + 24), 1ull);
+    }
+    return true;
+}
+
+// ---- work queue order: largest components first (longest-processing-time-first keeps the tail of the solver short:
+//      a component is solved by one block, path after path). One block: counting sort by size class, 4 classes per
+//      power of two; the order inside a class does not matter.
+__global__ void __launch_bounds__(256) k_job_order(const SolveParams p) {
     // two bands of size classes: components that do not fit the main kernel's staging area ("giants", solved by a
-    // launch of their own with a large staging area, see mot3d_solve_batch) come first
-    __shared__ int s_cnt[2 * JOB_CLASSES], s_start[2 * JOB_CLASSES];
-    const int n_jobs = p.n_cgraphs[0];
-    auto band_class = [&](int n) { return job_class(n) + (n > p.rcap ? JOB_CLASSES : 0); };
-    if (threadIdx.x < 2 * JOB_CLASSES) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x)
-        atomicAdd(&s_cnt[band_class(p.cgraph_ptr[c + 1] - p.cgraph_ptr[c])], 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    // launch of their own with a large staging area, see mot3d_solve_batch) come first. The class counts were taken by
+    // k_single_track; every block turns them into class starts and scatters its share of the components.
+    __shared__ int s_start[2 * JOB_CLASSES];
+    const int n_comp = p.n_cgraphs[0];
+    const int32_t *hist = p.job_meta;
+    int32_t *cursor = p.job_meta + 2 * JOB_CLASSES;
+    if (threadIdx.x < 2 * JOB_CLASSES) {
         int run = 0;
-        for (int b = 2 * JOB_CLASSES - 1; b >= 0; b--) {
-            s_start[b] = run;
-            run += s_cnt[b];
-            if (b == JOB_CLASSES) {
+        for (int b = 2 * JOB_CLASSES - 1; b > (int)threadIdx.x; b--) run += hist[b];
+        s_start[threadIdx.x] = run;
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == JOB_CLASSES - 1) {
                 p.n_cgraphs[2] = run;  // cursor of the main kernel's part of the queue
                 p.n_cgraphs[3] = run;  // number of giants = where that part starts
             }
+            if (threadIdx.x == 0) p.job_meta[4 * JOB_CLASSES] = run + hist[0];  // length of the queue
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < n_jobs; c += blockDim.x) {
+    auto band_class = [&](int n) { return job_class(n) + (n > p.rcap ? JOB_CLASSES : 0); };
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_comp; c += gridDim.x * blockDim.x) {
         const int c0 = p.cgraph_ptr[c], n = p.cgraph_ptr[c + 1] - c0, g = p.cgraph_win[c];
-        const bool skip = n <= 0 || p.n_paths[g] < 0;  // empty, or the graph was skipped (arc buffer overflow)
-        p.job_tab[atomicAdd(&s_start[band_class(n)], 1)] = make_int4(c0, skip ? 0 : n, g, p.win_wide[g] ? (c | (1 << 31)) : c);
+        // not queued: empty, the graph was skipped (arc buffer overflow), or k_single_track has finished the component
+        if (n <= 0 || p.n_paths[g] < 0 || p.first_sink[c] == FAST_DONE) continue;
+        const int b = band_class(n);
+        p.job_tab[s_start[b] + atomicAdd(&cursor[b], 1)] = make_int4(c0, n, g, p.win_wide[g] ? (c | (1 << 31)) : c);
     }
 }
 
@@ -1056,7 +1145,7 @@ __global__ void __launch_bounds__(256, 4) k_ssp_solve(const __grid_constant__ So
     // dependency, they drain disjoint parts of the queue and only meet in integer atomics); the main launch waits for
     // the giants' grid before it exits, so that whatever follows in the stream sees both finished.
     if (p.role == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int n_jobs = (p.role == 1) ? p.n_cgraphs[3] : p.n_cgraphs[0];
+    const int n_jobs = (p.role == 1) ? p.n_cgraphs[3] : p.job_meta[4 * JOB_CLASSES];
     int *const cursor = p.n_cgraphs + (p.role == 2 ? 2 : 1);
     const long long t_block0 = clock64();
 
@@ -1185,7 +1274,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     return a256(n * 8) * 3 + a256(n * 4) * 11 + a256(n * 16) + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
            a256(n * sizeof(RecT<false>)) + a256((e + n + 8) * sizeof(StArc)) +
-           a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512;
+           a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512 + a256((4 * JOB_CLASSES + 4) * sizeof(int32_t));
 }
 
 int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
@@ -1258,6 +1347,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     const size_t cws_bytes = mot3d_components_workspace_bytes(n_total, n_graphs);
     void *cws = take(cws_bytes);
     int32_t *n_cgraphs = (int32_t *)take(16);
+    p.job_meta = (int32_t *)take((4 * JOB_CLASSES + 4) * sizeof(int32_t));
     p.comp_perm = comp_perm;
     p.comp_inv = comp_inv;
     p.cgraph_ptr = cgraph_ptr;
@@ -1266,6 +1356,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.n_cgraphs = n_cgraphs;
 
     cudaStream_t st = (cudaStream_t)stream;
+    M3_CUDA(cudaMemsetAsync(p.job_meta, 0, (4 * JOB_CLASSES + 4) * sizeof(int32_t), st));
     // 1. connected components of every graph, detections regrouped by component
     int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
                                 comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
@@ -1317,14 +1408,31 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         const int t = atoi(e);
         if (t == 32 || t == 64 || t == 128 || t == 192 || t == 256) threads = t;
     }
-    k_job_order<<<1, 1024, 0, st>>>(p);  // after p.rcap is known: it splits the queue at that size
+    {
+        // after p.rcap is known: the queue is split at that size. One warp per component, 8 x 8 warps per SM striding
+        // over them: finished on the spot (single tracks) or counted into its size class; then the queue is laid out.
+        p.fast = getenv("MOT3D_SOLVE_NO_FAST") ? 0 : 1;
+        long long blocks = (long long)n_sm * 8;
+        if (blocks * 8 > n_total) blocks = (n_total + 7) / 8;
+        if (blocks < 1) blocks = 1;
+        k_single_track<<<(unsigned)blocks, 256, 0, st>>>(p);
+        M3_LAUNCH_CHECK("k_single_track");
+        long long jblocks = (n_total + 256 * 8 - 1) / (256 * 8);
+        if (jblocks > n_sm) jblocks = n_sm;
+        if (jblocks < 1) jblocks = 1;
+        k_job_order<<<(unsigned)jblocks, 256, 0, st>>>(p);
+    }
     M3_LAUNCH_CHECK("k_job_order");
     // Giants: components beyond the main staging area (C5: 0.2 % of them, several hundred detections, 6-9 tracks) are
     // sequential work for one block and would set the length of the whole solve if they ran on the global staging
     // area. They get a launch of their own - one 256-thread block per SM, room for 1024 records - which the main
     // launch overlaps (programmatic dependent launch, see k_ssp_solve).
     const bool split = p.rcap > 0 && (size_t)max_graph_nodes > rcap && !getenv("MOT3D_SOLVE_NO_GIANTS");
-    size_t g_rcap = 1024, g_smem = 0;
+    // room for 512 records: three giants' blocks per SM (crowded C5 windows: every giant has 257-384 detections and the
+    // longest of them sets the length of the launch; 1024 records = one block per SM was 0.23 ms slower per 1200
+    // windows). Larger components run on the global staging area. MOT3D_GIANT_RCAP: bench experiments.
+    size_t g_rcap = 512, g_smem = 0;
+    if (const char *e = getenv("MOT3D_GIANT_RCAP")) g_rcap = (size_t)atoi(e) & ~(size_t)7;
     if (split) {
         if (g_rcap > (size_t)((max_graph_nodes + 7) & ~7)) g_rcap = (size_t)((max_graph_nodes + 7) & ~7);
         g_smem = (16 + g_rcap * SM_BYTES_PER_REC + (g_rcap * 10 + 8) * SM_ARC_BYTES) & ~(size_t)15;
@@ -1346,7 +1454,10 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         pg.role = 1;
         pg.rcap = (int32_t)g_rcap;
         pg.racap = (int32_t)((g_smem - 16 - g_rcap * SM_BYTES_PER_REC) / SM_ARC_BYTES - 8);
-        long long g_grid = n_sm;
+        int g_per_sm = 1;
+        M3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_per_sm, k_ssp_solve, 256, g_smem));
+        if (g_per_sm < 1) g_per_sm = 1;
+        long long g_grid = (long long)n_sm * g_per_sm;
         if (g_grid > n_total / (long long)rcap + 1) g_grid = n_total / (long long)rcap + 1;  // giants are > rcap each
         k_ssp_solve<<<(unsigned)g_grid, 256, g_smem, st>>>(pg);
         M3_LAUNCH_CHECK("k_ssp_solve (giants)");

@@ -14,10 +14,10 @@ from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
 STAGES = ["make_keys", "node_costs", "frame_sort", "edge_build", "solve", "extract"]
 STAGES_UNFUSED = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
 # kernels launched by one run() (see the entry points in csrc/): keys 2, node costs 1, frame sort 1, single-pass
-# build 1 (unfused: edge count 1, scan 3, edge fill + cost 2), solve 8 (components 3, first tree, job order, solver
-# x2: giants + main, first-path rule), extract 1
-LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 8 + 1
-LAUNCHES_PER_RUN_UNFUSED = 2 + 1 + 1 + 1 + 3 + 2 + 8 + 1
+# build 1 (unfused: edge count 1, scan 3, edge fill + cost 2), solve 9 (components 3, first tree, single-track pass,
+# job order, solver x2: giants + main, first-path rule), extract 1
+LAUNCHES_PER_RUN = 2 + 1 + 1 + 1 + 9 + 1
+LAUNCHES_PER_RUN_UNFUSED = 2 + 1 + 1 + 1 + 3 + 2 + 9 + 1
 
 
 class TrackPipeline(object):
