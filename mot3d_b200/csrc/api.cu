@@ -55,6 +55,12 @@ const char *mot3d_last_error(void) { return g_err; }
 
 }  // extern "C"
 
+namespace m3 {
+int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
+                               int32_t *tkey, cudaStream_t st);
+int32_t launch_frame_sort_range(const mot3d_dets *d, int64_t row_begin, int64_t row_end, cudaStream_t st);
+}  // namespace m3
+
 // device bytes one pipeline pass over (n, n_graphs, edge_capacity) needs
 static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
     size_t b = 0;
@@ -89,13 +95,16 @@ static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
 // engines move chunk c+1 in and chunk c-1 out while the SMs work on chunk c, and the tail of one chunk's solver
 // (a few long components) overlaps the next chunk's build.
 constexpr int HOST_MAX_CHUNKS = 8;
+constexpr int HOST_MAX_PIECES = 8;               // H2D + build pieces per chunk
+constexpr int64_t HOST_PIECE_MIN_DETS = 150000;
 constexpr int64_t HOST_CHUNK_MIN_DETS = 400000;  // below this a chunk cannot fill the GPU
 
 struct HostCtx {
     int dev = -1;
     cudaStream_t s[HOST_MAX_CHUNKS];  // kernels + D2H of chunk c; earlier chunks have the higher priority
     cudaStream_t copy_in;             // all H2D copies, in chunk order
-    cudaEvent_t start, in[HOST_MAX_CHUNKS], done[HOST_MAX_CHUNKS];
+    cudaEvent_t start, in[HOST_MAX_CHUNKS * HOST_MAX_PIECES], done[HOST_MAX_CHUNKS];
+    int64_t *pinned_gbase = nullptr;  // key bases per graph (H2D source), grown with pinned_gptr
     int32_t *pinned = nullptr;  // [2 * HOST_MAX_CHUNKS]: overflow flag, arc count per chunk
     int32_t *pinned_gptr = nullptr;  // chunk-local graph_ptr arrays (H2D source), grown on demand
     size_t gptr_cap = 0;
@@ -116,8 +125,9 @@ static HostCtx *host_ctx() {
         if (prio > prio_lo) prio = prio_lo;
         if (cudaStreamCreateWithPriority(&c->s[i], cudaStreamNonBlocking, prio) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&c->in[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
+    for (int i = 0; i < HOST_MAX_CHUNKS * HOST_MAX_PIECES; i++)
+        if (cudaEventCreateWithFlags(&c->in[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithPriority(&c->copy_in, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&c->start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaHostAlloc((void **)&c->pinned, sizeof(int32_t) * 2 * HOST_MAX_CHUNKS, cudaHostAllocDefault) != cudaSuccess)
@@ -127,11 +137,15 @@ static HostCtx *host_ctx() {
 }
 
 // graphs [ga, gb) of the batch = detections [d0, d1): enqueue H2D, kernels and D2H on `st`. h_gptr = chunk-local
-// graph_ptr (host, must stay alive until the stream has consumed it); h_flags[0..1] receive overflow flag, arc count.
+// graph_ptr, h_gbase = key bases of its graphs (pinned host memory, must stay alive until the stream has consumed them);
+// h_flags[0..1] receive overflow flag, arc count. The inputs arrive in `pieces` slices of whole graphs (copy stream
+// `cin`, one event each): keys, node costs, frame sort and the single-pass arc build of a piece run while the next one
+// is on its way - the arc build continues the CSR of the piece before it through a device-side counter - and only the
+// solver waits for the whole chunk.
 static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *spec, mot3d_host_result *res, Arena &A,
-                             int32_t ga, int32_t gb, const int32_t *h_gptr, int32_t max_nodes, int64_t edge_capacity,
-                             int32_t *h_flags, cudaStream_t st, cudaStream_t cin, cudaEvent_t in_done,
-                             cudaEvent_t *trace) {
+                             int32_t ga, int32_t gb, const int32_t *h_gptr, const int64_t *h_gbase, int32_t max_nodes,
+                             int64_t edge_capacity, int32_t *h_flags, cudaStream_t st, cudaStream_t cin,
+                             cudaEvent_t *in_done, int pieces, cudaEvent_t *trace) {
     const int64_t d0 = hb->graph_ptr[ga], d1 = hb->graph_ptr[gb];
     const int64_t n = d1 - d0, N = hb->n;
     const int32_t G = gb - ga;
@@ -165,24 +179,12 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     int32_t *d_tdet = A.take<int32_t>(n);
     if (!A.ok) return MOT3D_E_CAPACITY;  // the caller retries with fewer chunks / reports
 
+    int64_t *d_arcs = A.take<int64_t>(1);
+    if (!A.ok) return MOT3D_E_CAPACITY;
     M3_CUDA(cudaMemcpyAsync(d_gptr, h_gptr, (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, cin));
-    M3_CUDA(cudaMemcpyAsync(d_frame, hb->frame + d0, (size_t)n * 4, cudaMemcpyHostToDevice, cin));
-    for (int k = 0; k < hb->dim; k++)
-        M3_CUDA(cudaMemcpyAsync(d_pos + (size_t)k * n, hb->pos + (size_t)k * N + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
-    M3_CUDA(cudaMemcpyAsync(d_conf, hb->conf + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
-    if (d_flags) M3_CUDA(cudaMemcpyAsync(d_flags, hb->flags + d0, (size_t)n, cudaMemcpyHostToDevice, cin));
-    if (d_bbox)
-        for (int k = 0; k < 4; k++)
-            M3_CUDA(cudaMemcpyAsync(d_bbox + (size_t)k * n, hb->bbox + (size_t)k * N + d0, (size_t)n * 8, cudaMemcpyHostToDevice, cin));
-    if (cin != st) {  // inputs travel on the copy stream (FIFO over the chunks); the chunk's own stream picks up from there
-        M3_CUDA(cudaEventRecord(in_done, cin));
-        M3_CUDA(cudaStreamWaitEvent(st, in_done, 0));
-    }
+    M3_CUDA(cudaMemcpyAsync(d_gbase, h_gbase, (size_t)G * 8, cudaMemcpyHostToDevice, cin));
     M3_CUDA(cudaMemsetAsync(d_over, 0, 4, st));
-    if (trace) M3_CUDA(cudaEventRecord(trace[0], st));
-
-    int32_t rc;
-    if ((rc = mot3d_make_keys(d_frame, d_gptr, G, spec->max_jump, d_tkey, d_gbase, st))) return rc;
+    M3_CUDA(cudaMemsetAsync(d_rowptr, 0, 4, st));
     mot3d_dets d;
     memset(&d, 0, sizeof(d));
     d.n = n;
@@ -194,11 +196,50 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     d.bbox = d_bbox;
     d.sorted_pos = d_spos;
     d.sorted_perm = d_sperm;
-    if ((rc = mot3d_node_costs(&d, spec, d_en, d_cn, d_ex, st))) return rc;
-    if ((rc = mot3d_frame_sort(&d, st))) return rc;
-    if ((rc = mot3d_edge_build(&d, spec, MOT3D_DIR_IN, 0, n, d_rowptr, edge_capacity, d_col, d_cost, nullptr, d_over,
-                               nullptr, nullptr, d_build, build_b, st)))
-        return rc;
+    int32_t rc;
+    if (pieces < 1) pieces = 1;
+    int32_t g_lo = 0;
+    bool first = true;
+    for (int pc = 0; pc < pieces; pc++) {
+        // graphs [g_lo, g_hi) of the chunk: cut where the detection count passes the next multiple of n / pieces
+        int32_t g_hi = g_lo;
+        const int64_t target = pc + 1 == pieces ? n : n * (pc + 1) / pieces;
+        while (g_hi < G && h_gptr[g_hi] < target) g_hi++;
+        if (pc + 1 == pieces) g_hi = G;
+        if (g_hi == g_lo) continue;
+        const int64_t r0 = h_gptr[g_lo], r1 = h_gptr[g_hi], m = r1 - r0;
+        if (m > 0) {
+            M3_CUDA(cudaMemcpyAsync(d_frame + r0, hb->frame + d0 + r0, (size_t)m * 4, cudaMemcpyHostToDevice, cin));
+            for (int k = 0; k < hb->dim; k++)
+                M3_CUDA(cudaMemcpyAsync(d_pos + (size_t)k * n + r0, hb->pos + (size_t)k * N + d0 + r0, (size_t)m * 8,
+                                        cudaMemcpyHostToDevice, cin));
+            M3_CUDA(cudaMemcpyAsync(d_conf + r0, hb->conf + d0 + r0, (size_t)m * 8, cudaMemcpyHostToDevice, cin));
+            if (d_flags) M3_CUDA(cudaMemcpyAsync(d_flags + r0, hb->flags + d0 + r0, (size_t)m, cudaMemcpyHostToDevice, cin));
+            if (d_bbox)
+                for (int k = 0; k < 4; k++)
+                    M3_CUDA(cudaMemcpyAsync(d_bbox + (size_t)k * n + r0, hb->bbox + (size_t)k * N + d0 + r0, (size_t)m * 8,
+                                            cudaMemcpyHostToDevice, cin));
+        }
+        if (cin != st) {  // inputs travel on the copy stream (FIFO over chunks and pieces); the chunk's stream picks up
+            M3_CUDA(cudaEventRecord(in_done[pc], cin));
+            M3_CUDA(cudaStreamWaitEvent(st, in_done[pc], 0));
+        }
+        if (m > 0) {
+            if ((rc = launch_make_keys_based(d_frame, d_gptr + g_lo, g_hi - g_lo, d_gbase + g_lo, d_tkey, st))) return rc;
+            mot3d_dets dp = d;  // per-detection outputs of this piece: plain offsets
+            dp.n = m;
+            dp.conf = d_conf + r0;
+            dp.flags = d_flags ? d_flags + r0 : nullptr;
+            if ((rc = mot3d_node_costs(&dp, spec, d_en + r0, d_cn + r0, d_ex + r0, st))) return rc;
+            if ((rc = launch_frame_sort_range(&d, r0, r1, st))) return rc;
+            if ((rc = mot3d_edge_build(&d, spec, MOT3D_DIR_IN, r0, r1, d_rowptr, edge_capacity, d_col, d_cost, nullptr,
+                                       d_over, first ? nullptr : d_arcs, d_arcs, d_build, build_b, st)))
+                return rc;
+            first = false;
+        }
+        if (trace && pc == 0) M3_CUDA(cudaEventRecord(trace[0], st));
+        g_lo = g_hi;
+    }
     if (trace) M3_CUDA(cudaEventRecord(trace[1], st));
     if ((rc = mot3d_solve_batch(G, n, d_gptr, max_nodes, d_tkey, edge_capacity, d_rowptr, d_col, d_cost, d_en, d_cn, d_ex, d_next, d_prev,
                                 d_np, d_total, nullptr, nullptr, d_solve, solve_b, st)))
@@ -254,6 +295,8 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     if (want > HOST_MAX_CHUNKS) want = HOST_MAX_CHUNKS;
     if (want > G) want = G;
     if (want < 1) want = 1;
+    double first_share = 0.5;
+    if (const char *e = getenv("MOT3D_HOST_SPLIT")) first_share = (atof(e) > 0 && atof(e) < 1) ? atof(e) : first_share;
     double edge_w = 1.0 / 3.0;  // size of the first and the last chunk relative to the inner ones
     if (const char *e = getenv("MOT3D_HOST_EDGE_WEIGHT")) edge_w = atof(e) > 0 ? atof(e) : edge_w;
     HostCtx *ctx = host_ctx();
@@ -266,9 +309,13 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
         ctx->gptr_cap = 0;
         const size_t cap = (size_t)(G + HOST_MAX_CHUNKS + 1) * 2;
         M3_CUDA(cudaHostAlloc((void **)&ctx->pinned_gptr, cap * sizeof(int32_t), cudaHostAllocDefault));
+        if (ctx->pinned_gbase) cudaFreeHost(ctx->pinned_gbase);
+        ctx->pinned_gbase = nullptr;
+        M3_CUDA(cudaHostAlloc((void **)&ctx->pinned_gbase, cap * sizeof(int64_t), cudaHostAllocDefault));
         ctx->gptr_cap = cap;
     }
     int32_t *h_gptr = ctx->pinned_gptr;
+    int64_t *h_gbase = ctx->pinned_gbase;
     const bool tracing = getenv("MOT3D_HOST_TRACE") != nullptr;
     if (tracing && !ctx->t0) {
         M3_CUDA(cudaEventCreate(&ctx->t0));
@@ -284,6 +331,11 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
         // a short first chunk gets the SMs going early, a short last one keeps the exposed D2H tail short
         double wsum = 0, wacc = 0, wgt[HOST_MAX_CHUNKS];
         for (int c = 0; c < chunks; c++) wsum += (wgt[c] = (chunks >= 3 && (c == 0 || c == chunks - 1)) ? edge_w : 1.0);
+        if (chunks == 2) {  // the second chunk's solver and D2H are the exposed tail: it gets the smaller share
+            wgt[0] = first_share;
+            wgt[1] = 1.0 - first_share;
+            wsum = 1.0;
+        }
         for (int c = 1, g = 0; c <= chunks; c++) {
             wacc += wgt[c - 1];
             const int64_t target = (int64_t)((double)n * (wacc / wsum));
@@ -293,7 +345,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
         }
         Arena A(device_ws, ws_bytes);
         M3_CUDA(cudaEventRecord(ctx->start, user));
-        if (nc > 1) M3_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->start, 0));
+        M3_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->start, 0));
         if (tracing) M3_CUDA(cudaEventRecord(ctx->t0, user));
         int64_t edges = 0;
         bool retry = false;
@@ -303,18 +355,28 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             const int32_t ga = cut[c], gb = cut[c + 1];
             const int64_t d0 = hb->graph_ptr[ga], nd = hb->graph_ptr[gb] - d0;
             int32_t max_nodes = 0;
+            int64_t key_base = 0;  // mot3d_make_keys: base = running sum of (frame span + max_jump + 1)
+            int64_t *hb_base = h_gbase + ga;
             for (int g = ga; g <= gb; g++) {
                 hg[g - ga] = (int32_t)(hb->graph_ptr[g] - d0);
-                if (g < gb && hb->graph_ptr[g + 1] - hb->graph_ptr[g] > max_nodes)
-                    max_nodes = hb->graph_ptr[g + 1] - hb->graph_ptr[g];
+                if (g < gb) {
+                    const int32_t a = hb->graph_ptr[g], b = hb->graph_ptr[g + 1];
+                    if (b - a > max_nodes) max_nodes = b - a;
+                    hb_base[g - ga] = key_base;
+                    key_base += (b > a ? (int64_t)hb->frame[b - 1] - (int64_t)hb->frame[a] : 0) + spec->max_jump + 1;
+                }
             }
             // the arc buffer is shared out by detection count; a chunk that needs more sends the batch through again
             // in one piece, so the capacity the caller has to provide does not depend on the chunking
             const int64_t cap = nc == 1 ? edge_capacity : (int64_t)((double)edge_capacity * ((double)nd / (double)n));
             cudaStream_t st = nc == 1 ? user : ctx->s[c];
             if (nc > 1) M3_CUDA(cudaStreamWaitEvent(st, ctx->start, 0));
-            rc = enqueue_chunk(hb, spec, res, A, ga, gb, hg, max_nodes, cap, ctx->pinned + 2 * c, st,
-                               nc == 1 ? user : ctx->copy_in, ctx->in[c], tracing ? ctx->trace[c] : nullptr);
+            int pieces = (int)(nd / HOST_PIECE_MIN_DETS);
+            if (const char *e = getenv("MOT3D_HOST_PIECES")) pieces = atoi(e);
+            if (pieces > HOST_MAX_PIECES) pieces = HOST_MAX_PIECES;
+            if (pieces < 1) pieces = 1;
+            rc = enqueue_chunk(hb, spec, res, A, ga, gb, hg, hb_base, max_nodes, cap, ctx->pinned + 2 * c, st,
+                               ctx->copy_in, ctx->in + c * HOST_MAX_PIECES, pieces, tracing ? ctx->trace[c] : nullptr);
             if (nc > 1 && rc == MOT3D_OK) {
                 M3_CUDA(cudaEventRecord(ctx->done[c], st));
                 M3_CUDA(cudaStreamWaitEvent(user, ctx->done[c], 0));

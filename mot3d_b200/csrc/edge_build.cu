@@ -569,6 +569,17 @@ int32_t mot3d_node_costs(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
 }  // extern "C"
 
 namespace m3 {
+// keys of graphs [0, n_graphs) of graph_ptr with their bases given (mot3d_track_batch_host computes them on the host and
+// sends the batch through in pieces)
+int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
+                               int32_t *tkey, cudaStream_t st) {
+    if (n_graphs <= 0) return MOT3D_OK;
+    int blocks = (n_graphs + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, base, tkey);
+    M3_LAUNCH_CHECK("k_make_keys");
+    return MOT3D_OK;
+}
 int32_t launch_frame_sort(const mot3d_dets *d, cudaStream_t st);
 int32_t launch_pruned(const mot3d_dets *d, const mot3d_cost_spec *s, int direction, bool fill, int32_t *row_count,
                       const int32_t *row_ptr, int64_t edge_capacity, int32_t *col, int64_t *cost, int32_t *overflow,

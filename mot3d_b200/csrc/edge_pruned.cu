@@ -78,21 +78,22 @@ constexpr int FS_CAP = 2048;  // staged x values; larger frame spans are read in
 
 __global__ void __launch_bounds__(FS_TPB) k_frame_sort(int64_t n, int dim, const int32_t *__restrict__ tkey,
                                                        const double *__restrict__ pos, double *__restrict__ spos,
-                                                       int32_t *__restrict__ sperm) {
+                                                       int32_t *__restrict__ sperm, int64_t row_begin, int64_t row_end) {
+    // rows [row_begin, row_end) of arrays of n detections (whole graphs: no frame straddles the range)
     __shared__ int s_key[FS_TPB];
     __shared__ int64_t s_edge[2];  // start of the block's first frame, end of its last frame
     __shared__ double s_x[FS_CAP];
-    const int64_t b0 = (int64_t)blockIdx.x * FS_TPB;
-    const int64_t b1 = (b0 + FS_TPB < n) ? b0 + FS_TPB : n;
+    const int64_t b0 = row_begin + (int64_t)blockIdx.x * FS_TPB;
+    const int64_t b1 = (b0 + FS_TPB < row_end) ? b0 + FS_TPB : row_end;
     const int64_t i = b0 + threadIdx.x;
-    const bool active = i < n;
+    const bool active = i < row_end;
     const int k = active ? tkey[i] : 0;
     s_key[threadIdx.x] = k;
     if (threadIdx.x < 32) {
-        const int64_t lo = warp_bound_i32<false>(tkey, 0, b0 + 1, tkey[b0]);
+        const int64_t lo = warp_bound_i32<false>(tkey, row_begin, b0 + 1, tkey[b0]);
         if (threadIdx.x == 0) s_edge[0] = lo;
     } else if (threadIdx.x < 64) {
-        const int64_t hi = warp_bound_i32<true>(tkey, b1 - 1, n, tkey[b1 - 1]);
+        const int64_t hi = warp_bound_i32<true>(tkey, b1 - 1, row_end, tkey[b1 - 1]);
         if (threadIdx.x == 32) s_edge[1] = hi;
     }
     __syncthreads();
@@ -397,12 +398,15 @@ using namespace m3;
 // internal entry points used by mot3d_edge_count / mot3d_edge_fill (edge_build.cu) when sorted copies are supplied
 namespace m3 {
 
-int32_t launch_frame_sort(const mot3d_dets *d, cudaStream_t st) {
-    k_frame_sort<<<(unsigned)((d->n + FS_TPB - 1) / FS_TPB), FS_TPB, 0, st>>>(d->n, d->dim, d->tkey, d->pos,
-                                                                               d->sorted_pos, d->sorted_perm);
+int32_t launch_frame_sort_range(const mot3d_dets *d, int64_t row_begin, int64_t row_end, cudaStream_t st) {
+    if (row_end <= row_begin) return MOT3D_OK;
+    k_frame_sort<<<(unsigned)((row_end - row_begin + FS_TPB - 1) / FS_TPB), FS_TPB, 0, st>>>(
+        d->n, d->dim, d->tkey, d->pos, d->sorted_pos, d->sorted_perm, row_begin, row_end);
     M3_LAUNCH_CHECK("k_frame_sort");
     return MOT3D_OK;
 }
+
+int32_t launch_frame_sort(const mot3d_dets *d, cudaStream_t st) { return launch_frame_sort_range(d, 0, d->n, st); }
 
 int32_t launch_pruned(const mot3d_dets *d, const mot3d_cost_spec *s, int direction, bool fill, int32_t *row_count,
                       const int32_t *row_ptr, int64_t edge_capacity, int32_t *col, int64_t *cost, int32_t *overflow,
