@@ -196,6 +196,13 @@ typedef struct mot3d_tracklets {
     const double *tail_hist;
     double *head_fit_ws;          /* scratch [n][dim][2]: line fits, written by mot3d_tracklet_edge_count */
     double *tail_fit_ws;
+    /* 3-D tracklets with use_hist (weight_distance_tracklets_3d, mot3d/weight_functions.py:146-158): the per-view 2-D
+     * tracklets of DetectionTracklet3D.tracklets_2d (mot3d/types.py:142-184), entries of tracklet i =
+     * [view_ptr[i], view_ptr[i+1]) in the dict's order. NULL = single-histogram mode (head_hist / tail_hist). */
+    const int32_t *view_ptr;      /* [n+1] */
+    const int32_t *view_id;       /* [view_ptr[n]] camera label */
+    const double *view_head_hist; /* [view_ptr[n]][C][B] median histogram at the head of the per-view tracklet */
+    const double *view_tail_hist; /* ... at its tail */
 } mot3d_tracklets;
 
 typedef struct mot3d_tracklet_spec {
@@ -211,7 +218,9 @@ typedef struct mot3d_tracklet_spec {
     double cutoff_appearance;
 } mot3d_tracklet_spec;
 
-/* rows = tail tracklet t1, columns = head tracklet t2 (ascending), i.e. the reference's arc order */
+/* rows = tail tracklet t1, columns = head tracklet t2 (ascending), i.e. the reference's arc order.
+ * overflow_flag: bit 0 = arcs beyond edge_capacity dropped; bit 1 = (view mode) two linked tracklets share no view: the
+ * reference's np.mean([]) is nan there, the arc gets weight nan and cost 0 */
 int32_t mot3d_tracklet_edge_count(const mot3d_tracklets *trk, const mot3d_tracklet_spec *spec, int32_t *row_count_out,
                                   void *stream);
 int32_t mot3d_tracklet_edge_fill(const mot3d_tracklets *trk, const mot3d_tracklet_spec *spec, const int32_t *row_ptr,

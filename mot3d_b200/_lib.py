@@ -51,7 +51,9 @@ class Tracklets(ctypes.Structure):
                 ("tail_idx", ctypes.c_void_p), ("head_pos", ctypes.c_void_p), ("tail_pos", ctypes.c_void_p),
                 ("tail_access_point", ctypes.c_void_p), ("head_has_hist", ctypes.c_void_p),
                 ("tail_has_hist", ctypes.c_void_p), ("head_hist", ctypes.c_void_p), ("tail_hist", ctypes.c_void_p),
-                ("head_fit_ws", ctypes.c_void_p), ("tail_fit_ws", ctypes.c_void_p)]
+                ("head_fit_ws", ctypes.c_void_p), ("tail_fit_ws", ctypes.c_void_p),
+                ("view_ptr", ctypes.c_void_p), ("view_id", ctypes.c_void_p), ("view_head_hist", ctypes.c_void_p),
+                ("view_tail_hist", ctypes.c_void_p)]
 
 
 class TrackletSpecC(ctypes.Structure):

@@ -29,6 +29,8 @@ struct TrkParams {
     const uint8_t *tail_access;          // [n] or NULL
     const uint8_t *head_has_hist, *tail_has_hist;  // [n] or NULL (= every end has one)
     const double *head_hist, *tail_hist;           // [n][C][B]
+    const int32_t *view_ptr, *view_id;             // per-view entries of 3-D tracklets (NULL = single histogram)
+    const double *view_head_hist, *view_tail_hist; // [entries][C][B]
     double sq_dist_max;  // < 0: no max_distance gate
     double sigma_motion_sq, sigma_hist_sq, alpha, cutoff_motion, cutoff_appearance;
     int32_t *row_count;
@@ -105,6 +107,22 @@ __device__ __forceinline__ double one_way_deviation(const TrkParams &p, const do
 }
 
 // weight of the arc t1 -> t2, or false when the reference returns None / the pair is outside the time window
+// 1 - color_histogram_similarity(h1, h2) (mot3d/distance_functions.py:21-34, unit channel weights)
+__device__ __forceinline__ double hist_dissimilarity(const TrkParams &p, const double *h1, const double *h2) {
+    double scs = 0.0;
+    for (int c = 0; c < p.C; c++) {
+        double ab = 0, aa = 0, bb = 0;
+        for (int b = 0; b < p.B; b++) {
+            const double u = h1[c * p.B + b], v = h2[c * p.B + b];
+            ab += u * v;
+            aa += u * u;
+            bb += v * v;
+        }
+        scs += ab / sqrt(aa * bb);
+    }
+    return 1.0 - scs / (double)p.C;
+}
+
 __device__ __forceinline__ bool tracklet_weight(const TrkParams &p, int i, int j, double *w_out) {
     const int hb = p.head_ptr[i + 1], ha = p.head_ptr[i];
     const int ta = p.tail_ptr[j], tb = p.tail_ptr[j + 1];
@@ -125,25 +143,37 @@ __device__ __forceinline__ bool tracklet_weight(const TrkParams &p, int i, int j
     const double dev = fwd + bwd;
     const double wm = exp(-(dev * dev) / p.sigma_motion_sq);
     if (wm < p.cutoff_motion) return false;
+    if (p.use_hist && p.view_ptr) {
+        // 3-D tracklets: mean over the views both have (t1's dict order) of 1 - NCC(head of t1's 2-D tracklet, tail of
+        // t2's) (mot3d/weight_functions.py:146-158); np.mean of < 8 values adds them left to right
+        double sum = 0.0;
+        int shared = 0;
+        for (int u = p.view_ptr[i]; u < p.view_ptr[i + 1]; u++) {
+            const int id = p.view_id[u];
+            for (int v = p.view_ptr[j]; v < p.view_ptr[j + 1]; v++)
+                if (p.view_id[v] == id) {
+                    sum = sum + hist_dissimilarity(p, p.view_head_hist + (size_t)u * p.C * p.B,
+                                                   p.view_tail_hist + (size_t)v * p.C * p.B);
+                    shared++;
+                    break;
+                }
+        }
+        if (shared == 0) {  // nan in the reference; reported through the overflow flag (bit 1) by the fill pass
+            *w_out = __longlong_as_double(0x7ff8000000000000ll);
+            return true;
+        }
+        const double mc = sum / (double)shared;
+        const double wa = exp(-(mc * mc) / p.sigma_hist_sq);
+        if (wa < p.cutoff_appearance) return false;
+        *w_out = -((1.0 - p.alpha) * wm + p.alpha * wa);
+        return true;
+    }
     const bool hist = p.use_hist && (!p.head_has_hist || p.head_has_hist[i]) && (!p.tail_has_hist || p.tail_has_hist[j]);
     if (!hist) {
         *w_out = -wm;
         return true;
     }
-    const double *h1 = p.head_hist + (size_t)i * p.C * p.B;
-    const double *h2 = p.tail_hist + (size_t)j * p.C * p.B;
-    double scs = 0.0;
-    for (int c = 0; c < p.C; c++) {
-        double ab = 0, aa = 0, bb = 0;
-        for (int b = 0; b < p.B; b++) {
-            const double u = h1[c * p.B + b], v = h2[c * p.B + b];
-            ab += u * v;
-            aa += u * u;
-            bb += v * v;
-        }
-        scs += ab / sqrt(aa * bb);
-    }
-    const double chs = 1.0 - scs / (double)p.C;
+    const double chs = hist_dissimilarity(p, p.head_hist + (size_t)i * p.C * p.B, p.tail_hist + (size_t)j * p.C * p.B);
     const double wa = exp(-(chs * chs) / p.sigma_hist_sq);
     if (wa < p.cutoff_appearance) return false;
     *w_out = -((1.0 - p.alpha) * wm + p.alpha * wa);
@@ -165,11 +195,13 @@ __global__ void __launch_bounds__(128) k_tracklet_edges(TrkParams p) {
         if (FILL && keep) {
             const int64_t e = base + cnt + __popc(m & ((1u << lane) - 1u));
             if (e < p.edge_capacity) {
+                const bool nan = w != w;
                 p.col[e] = j;
-                p.cost[e] = quantise_1e7(w);
+                p.cost[e] = nan ? 0 : quantise_1e7(w);
                 if (p.weight) p.weight[e] = w;
+                if (nan && p.overflow) atomicOr(p.overflow, 2);
             } else if (p.overflow) {
-                *p.overflow = 1;
+                atomicOr(p.overflow, 1);
             }
         }
         cnt += __popc(m);
@@ -184,8 +216,12 @@ static int32_t fill_trk(TrkParams &p, const mot3d_tracklets *t, const mot3d_trac
     M3_CHECK_ARG(t->n == 0 || (t->head_ptr && t->tail_ptr && t->head_idx && t->tail_idx && t->head_pos && t->tail_pos &&
                                t->head_fit_ws && t->tail_fit_ws),
                  "NULL tracklet array");
-    M3_CHECK_ARG(!s->use_hist || (t->head_hist && t->tail_hist && t->hist_channels > 0 && t->hist_bins > 0),
+    M3_CHECK_ARG(!s->use_hist || t->view_ptr ||
+                     (t->head_hist && t->tail_hist && t->hist_channels > 0 && t->hist_bins > 0),
                  "use_hist set but histograms are NULL/empty");
+    M3_CHECK_ARG(!(s->use_hist && t->view_ptr) ||
+                     (t->view_id && t->view_head_hist && t->view_tail_hist && t->hist_channels > 0 && t->hist_bins > 0),
+                 "view mode: view_id / view_head_hist / view_tail_hist is NULL or the histogram shape is empty");
     p.n = t->n;
     p.dim = t->dim;
     p.max_jump = s->max_jump;
@@ -209,6 +245,10 @@ static int32_t fill_trk(TrkParams &p, const mot3d_tracklets *t, const mot3d_trac
     p.tail_has_hist = t->tail_has_hist;
     p.head_hist = t->head_hist;
     p.tail_hist = t->tail_hist;
+    p.view_ptr = t->view_ptr;
+    p.view_id = t->view_id;
+    p.view_head_hist = t->view_head_hist;
+    p.view_tail_hist = t->view_tail_hist;
     p.sq_dist_max = s->sq_dist_max;
     p.sigma_motion_sq = s->sigma_motion_sq;
     p.sigma_hist_sq = s->sigma_hist_sq;

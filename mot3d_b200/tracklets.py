@@ -40,9 +40,25 @@ def pack_tracklets(tracklets, spec):
     out["flags"] = flags
     if spec.use_hist:
         if isinstance(tracklets[0], DetectionTracklet3D):
-            raise NotImplementedError("weight_distance_tracklets_3d with use_color_histogram averages over the shared "
-                                      "2D views (reference mot3d/weight_functions.py:146-158); only the motion term "
-                                      "is built for 3D tracklets")
+            # per-view 2-D tracklets, in each tracklet's dict order (reference mot3d/weight_functions.py:146-158)
+            labels = {}
+            ptr, ids, vh, vt = [0], [], [], []
+            for t in tracklets:
+                for view, t2 in t.tracklets_2d.items():
+                    h1, h2 = t2.head.color_histogram, t2.tail.color_histogram
+                    if h1 is None or h2 is None:
+                        raise ValueError("use_color_histogram=True but the 2D tracklet of view %r has no "
+                                         "color_histogram" % (view,))
+                    ids.append(labels.setdefault(view, len(labels)))
+                    vh.append(np.asarray(h1, dtype=np.float64))
+                    vt.append(np.asarray(h2, dtype=np.float64))
+                ptr.append(len(ids))
+            out["head_hist"] = out["tail_hist"] = None
+            out["view_ptr"] = np.array(ptr, dtype=np.int32)
+            out["view_id"] = np.array(ids, dtype=np.int32)
+            out["view_head_hist"] = np.array(vh, dtype=np.float64)
+            out["view_tail_hist"] = np.array(vt, dtype=np.float64)
+            return out
         hh = [getattr(t.head, "color_histogram", None) for t in tracklets]
         th = [getattr(t.tail, "color_histogram", None) for t in tracklets]
         shape = next((np.asarray(h).shape for h in hh + th if h is not None), None)
@@ -67,9 +83,11 @@ def build_tracklet_arcs(packed, spec, device=None):
     def up(a):
         return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     t_ = {k: up(packed.get(k)) for k in ("head_ptr", "tail_ptr", "head_idx", "tail_idx", "head_pos", "tail_pos",
-                                          "tail_access", "head_hist", "tail_hist", "head_has_hist", "tail_has_hist")}
+                                          "tail_access", "head_hist", "tail_hist", "head_has_hist", "tail_has_hist",
+                                          "view_ptr", "view_id", "view_head_hist", "view_tail_hist")}
     cs = spec.to_c()
-    use_hist = spec.use_hist and t_["head_hist"] is not None
+    view_mode = spec.use_hist and t_["view_ptr"] is not None and int(t_["view_id"].shape[0]) > 0
+    use_hist = spec.use_hist and (t_["head_hist"] is not None or view_mode)
     cs.use_hist = int(use_hist)
     fit_h = torch.empty(max(n, 1) * dim * 2, dtype=torch.float64, device=dev)
     fit_t = torch.empty(max(n, 1) * dim * 2, dtype=torch.float64, device=dev)
@@ -79,7 +97,11 @@ def build_tracklet_arcs(packed, spec, device=None):
     for name in ("head_ptr", "tail_ptr", "head_idx", "tail_idx", "head_pos", "tail_pos"):
         setattr(trk, name, t_[name].data_ptr())
     trk.tail_access_point = t_["tail_access"].data_ptr()
-    if use_hist:
+    if view_mode:
+        trk.hist_channels, trk.hist_bins = int(t_["view_head_hist"].shape[1]), int(t_["view_head_hist"].shape[2])
+        trk.view_ptr, trk.view_id = t_["view_ptr"].data_ptr(), t_["view_id"].data_ptr()
+        trk.view_head_hist, trk.view_tail_hist = t_["view_head_hist"].data_ptr(), t_["view_tail_hist"].data_ptr()
+    elif use_hist:
         trk.hist_channels, trk.hist_bins = int(t_["head_hist"].shape[1]), int(t_["head_hist"].shape[2])
         trk.head_hist, trk.tail_hist = t_["head_hist"].data_ptr(), t_["tail_hist"].data_ptr()
         trk.head_has_hist, trk.tail_has_hist = t_["head_has_hist"].data_ptr(), t_["tail_has_hist"].data_ptr()
@@ -98,6 +120,10 @@ def build_tracklet_arcs(packed, spec, device=None):
     overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(L.mot3d_tracklet_edge_fill(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_ptr), e, _ptr(col), _ptr(cost),
                                           _ptr(weight), _ptr(overflow), st))
+    flag = int(overflow.item())
+    if flag & 2:
+        raise ValueError("two linked 3-D tracklets share no 2-D view: weight_distance_tracklets_3d is nan for them "
+                         "(np.mean of an empty list, reference mot3d/weight_functions.py:146-158)")
     return (row_ptr.cpu().numpy().astype(np.int64), col[:e].cpu().numpy().astype(np.int64), weight[:e].cpu().numpy(),
             cost[:e].cpu().numpy())
 

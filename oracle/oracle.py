@@ -371,7 +371,20 @@ def build_tracklet_transitions(d, spec):
             wm = np.exp(-dev ** 2 / spec.sigma_motion ** 2)
             if wm < spec.cutoff_motion:
                 continue
-            if spec.use_color_histogram and has_hist is not None and has_hist[i] and has_hist[j]:
+            if spec.use_color_histogram and spec.kind == "tracklets_3d" and "t_view_ptr" in d:
+                # mean over the views both tracklets have (t1's dict order) of 1 - NCC(head of t1, tail of t2)
+                # (mot3d/weight_functions.py:146-158)
+                vp, vid = d["t_view_ptr"], d["t_view_id"]
+                sims = []
+                for u in range(int(vp[i]), int(vp[i + 1])):
+                    v = [t for t in range(int(vp[j]), int(vp[j + 1])) if vid[t] == vid[u]]
+                    if v:
+                        sims.append(1 - _hist_similarity(d["t_view_head_hist"][u], d["t_view_tail_hist"][v[0]]))
+                wa = np.exp(-np.mean(sims) ** 2 / spec.sigma_color_histogram ** 2)
+                if wa < spec.cutoff_appearance:
+                    continue
+                w = -((1 - spec.alpha) * wm + spec.alpha * wa)
+            elif spec.use_color_histogram and has_hist is not None and has_hist[i] and has_hist[j]:
                 chs = 1 - _hist_similarity(d["t_head_hist"][i], d["t_tail_hist"][j])
                 wa = np.exp(-chs ** 2 / spec.sigma_color_histogram ** 2)
                 if wa < spec.cutoff_appearance:

@@ -136,6 +136,22 @@ def tracklet_arrays(dts, dim):
         shape = next(h.shape for h in hh if h is not None)
         out["t_head_hist"] = np.array([np.zeros(shape) if h is None else h for h in hh])
         out["t_tail_hist"] = np.array([np.zeros(shape) if h is None else h for h in th])
+    if dts and hasattr(dts[0], "tracklets_2d"):
+        # 3-D tracklets: per view (dict order) the median histograms of the 2-D tracklet's two ends
+        names = sorted({v for t in dts for v in t.tracklets_2d})
+        vid = {v: i for i, v in enumerate(names)}
+        ptr, ids, vh, vt = [0], [], [], []
+        for t in dts:
+            for v, t2 in t.tracklets_2d.items():
+                if t2.head.color_histogram is None or t2.tail.color_histogram is None:
+                    continue
+                ids.append(vid[v])
+                vh.append(np.asarray(t2.head.color_histogram, dtype=np.float64))
+                vt.append(np.asarray(t2.tail.color_histogram, dtype=np.float64))
+            ptr.append(len(ids))
+        if ids:
+            out.update(t_view_ptr=np.array(ptr, np.int32), t_view_id=np.array(ids, np.int32),
+                       t_view_head_hist=np.array(vh), t_view_tail_hist=np.array(vt))
     return out
 
 
@@ -313,14 +329,58 @@ def case_online(mot3d):
     print("%-22s (%d KB)" % ("c4_online_loop", os.path.getsize(path) // 1024))
 
 
+def case_multiview_tracklets(mot3d, wf):
+    """(3c) tracklet linking of 3-D tracklets whose detections carry 2-D views with histograms:
+    weight_distance_tracklets_3d with use_color_histogram=True (mot3d/weight_functions.py:125-160: appearance averaged
+    over the shared views of the per-view 2-D tracklets, mot3d/types.py:142-184)."""
+    rng = np.random.RandomState(31)
+    P, F, V, C, B = 5, 60, 3, 3, 16
+    base = rng.rand(P, 3) * np.array([20.0, 20.0, 0.3]) + np.array([0, 0, 1.6])
+    vel = rng.randn(P, 3) * np.array([0.12, 0.12, 0.0])
+    proto = rng.rand(P, V, C, B)
+    tracks = [[] for _ in range(P)]
+    for f in range(F):
+        base = base + vel + rng.randn(P, 3) * np.array([0.02, 0.02, 0.004])
+        for p in range(P):
+            if (f // 6) % 3 == 2 and p % 2 == 0:
+                continue  # gaps that the linking has to bridge
+            d2 = {}
+            for v in [0] + [v for v in (1, 2) if rng.rand() < 0.7]:
+                h = proto[p, v] + 0.2 * rng.rand(C, B)
+                h = h - h.mean(axis=1, keepdims=True)
+                d2["cam%d" % v] = mot3d.Detection2D(f, tuple(rng.rand(2) * 500), view="cam%d" % v,
+                                                    color_histogram=[h[c] for c in range(C)], bbox=(0, 0, 30, 80))
+            tracks[p].append(mot3d.Detection3D(f, base[p].copy(), detections_2d=d2))
+    dts = []
+    from mot3d.utils import trajectory as ref_traj
+    for tr in tracks:
+        for piece in ref_traj.split_trajectory_modulo(tr, length=6):
+            if len(piece) > 2:
+                dts.append(mot3d.DetectionTracklet3D(piece, window=4))
+    order = rng.permutation(len(dts))
+    dts = [dts[i] for i in order]
+    spec = dict(kind="tracklets_3d", sigma_color_histogram=0.3, sigma_motion=1.5, alpha=0.6, cutoff_motion=0.1,
+                cutoff_appearance=0.1, max_distance=6.0, use_color_histogram=True, mul=0, bias=0.11,
+                weight_source_sink=0.1, max_jump=14)
+    wd = lambda t1, t2: wf.weight_distance_tracklets_3d(t1, t2, sigma_color_histogram=0.3, sigma_motion=1.5,
+                                                        alpha=0.6, cutoff_motion=0.1, cutoff_appearance=0.1,
+                                                        max_distance=6.0, use_color_histogram=True)
+    wc = lambda t: wf.weight_confidence_tracklets_3d(t, mul=0, bias=0.11)
+    freeze_tracklet_case(mot3d, "c3_synth_multiview_tracklets", dts,
+                         dict(weight_source_sink=0.1, max_jump=14, weight_confidence=wc, weight_distance=wd), spec, 3)
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "c3_synth_multiview_tracklets" in sys.argv[1:]:
+        return case_multiview_tracklets(mot3d, wf)
     if "c4_online_loop" in sys.argv[1:]:
         return case_online(mot3d)
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
     case_multiview(mot3d, wf)
+    case_multiview_tracklets(mot3d, wf)
     case_online(mot3d)
     from mot3d.utils import utils as ref_utils
     from mot3d.utils import trajectory as ref_traj

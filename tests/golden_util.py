@@ -12,7 +12,7 @@ SCALE = 10 ** 7
 # Fixtures with detections (frame/pos/...) -> build + solve parity; the others are solver-only graphs.
 DETECTION_CASES = ["c1_simple_2d", "c3_soldiers_pass1", "c3_synth_multiview", "c4_pets_view1_w0", "c4_pets_view1_w1",
                    "c4_synth_appearance", "c5_small_f30_p12", "c5_window_f50_p100", "quirk_single_detection"]
-TRACKLET_CASES = ["c2_tracklets_pass2", "c3_soldiers_pass2", "c4_synth_tracklets"]
+TRACKLET_CASES = ["c2_tracklets_pass2", "c3_soldiers_pass2", "c3_synth_multiview_tracklets", "c4_synth_tracklets"]
 GRAPH_CASES = DETECTION_CASES + TRACKLET_CASES + ["wrapper_test_graph", "mussp_seq07"]
 
 # muSSP works in doubles with tolerances (Graph.cpp:175 '> 1e-7', :367 '< 1e-6'); on this window it leaves an

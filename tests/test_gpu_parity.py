@@ -537,7 +537,11 @@ def _packed_from_fixture(d, dim):
                head_pos=np.ascontiguousarray(d["t_head_pos"].reshape(-1, dim).T),
                tail_pos=np.ascontiguousarray(d["t_tail_pos"].reshape(-1, dim).T), conf=d["t_conf"],
                tail_access=d["t_tail_access"].astype(np.uint8), flags=None)
-    if "t_head_hist" in d:
+    if "t_view_ptr" in d:  # 3-D tracklets with per-view histograms
+        out.update(head_hist=None, tail_hist=None, view_ptr=d["t_view_ptr"].astype(np.int32),
+                   view_id=d["t_view_id"].astype(np.int32), view_head_hist=d["t_view_head_hist"],
+                   view_tail_hist=d["t_view_tail_hist"])
+    elif "t_head_hist" in d:
         out.update(head_hist=d["t_head_hist"], tail_hist=d["t_tail_hist"],
                    head_has_hist=d["t_has_hist"].astype(np.uint8), tail_has_hist=d["t_has_hist"].astype(np.uint8))
     return out
@@ -618,6 +622,56 @@ def test_tracklet_public_api_drop_in(name):
     gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
     assert got == gold
     assert g.total_cost == gu.ref_total_units(d)
+
+
+def test_tracklet_public_api_multiview_3d():
+    """build_graph / solve_graph on DetectionTracklet3D objects whose per-view 2-D tracklets carry histograms:
+    weight_distance_tracklets_3d(use_color_histogram=True) averages the appearance term over the shared views
+    (reference mot3d/weight_functions.py:146-158). Arcs, weights, total and trajectories are the reference's."""
+    import types as pytypes
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    d = gu.load("c3_synth_multiview_tracklets")
+    s = d["spec"]
+    n = len(d["t_conf"])
+    hp, tp, vp = d["t_head_ptr"], d["t_tail_ptr"], d["t_view_ptr"]
+    tracklets = []
+    for i in range(n):
+        t = object.__new__(mot3d.DetectionTracklet3D)   # the ends as the reference's constructor leaves them
+        t._init_item(float(d["t_conf"][i]), None)
+        t.head = mot3d.Detection3D(int(d["t_head_idx"][hp[i + 1] - 1]), d["t_head_pos"][hp[i + 1] - 1])
+        t.head.indexes, t.head.positions = d["t_head_idx"][hp[i]:hp[i + 1]], d["t_head_pos"][hp[i]:hp[i + 1]]
+        t.tail = mot3d.Detection3D(int(d["t_tail_idx"][tp[i]]), d["t_tail_pos"][tp[i]])
+        t.tail.indexes, t.tail.positions = d["t_tail_idx"][tp[i]:tp[i + 1]], d["t_tail_pos"][tp[i]:tp[i + 1]]
+        t.head.access_point = t.tail.access_point = False
+        t.tracklets_2d = {}
+        for u in range(int(vp[i]), int(vp[i + 1])):
+            t.tracklets_2d["cam%d" % int(d["t_view_id"][u])] = pytypes.SimpleNamespace(
+                head=pytypes.SimpleNamespace(color_histogram=d["t_view_head_hist"][u]),
+                tail=pytypes.SimpleNamespace(color_histogram=d["t_view_tail_hist"][u]))
+        t.tracklet = [t.tail, t.head]
+        tracklets.append(t)
+    kw = {k: s[k] for k in ("sigma_color_histogram", "sigma_motion", "alpha", "cutoff_motion", "cutoff_appearance",
+                            "max_distance", "use_color_histogram")}
+    wd = lambda t1, t2: wf.weight_distance_tracklets_3d(t1, t2, **kw)
+    wc = lambda t: wf.weight_confidence_tracklets_3d(t, mul=s["mul"], bias=s["bias"])
+    g = mot3d.build_graph(tracklets, weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"], verbose=False,
+                          weight_confidence=wc, weight_distance=wd)
+    assert g is not None and len(g) == int(d["n_nodes"])
+    tail, head, w = g.arcs()
+    assert (tail == d["tail"]).all() and (head == d["head"]).all()
+    np.testing.assert_allclose(w, d["w_float"], rtol=RTOL, atol=0)
+    trajectories = mot3d.solve_graph(g, verbose=False)
+    got = [[tracklets.index(t) for t in tr] for tr in trajectories]
+    gold = [d["track_det"][d["track_ptr"][k]:d["track_ptr"][k + 1]].tolist() for k in range(len(d["track_ptr"]) - 1)]
+    assert got == gold
+    assert g.total_cost == gu.ref_total_units(d)
+    # no common view between two linkable tracklets: nan in the reference, an error here
+    for t in tracklets:
+        t.tracklets_2d = {("a" if tracklets.index(t) % 2 else "b"): next(iter(t.tracklets_2d.values()))}
+    with pytest.raises(ValueError):
+        mot3d.build_graph(tracklets, weight_source_sink=s["weight_source_sink"], max_jump=s["max_jump"],
+                          verbose=False, weight_confidence=wc, weight_distance=wd)
 
 
 # ------------------------------------------------------------------------------------------------------ fuzzing
@@ -754,6 +808,33 @@ def test_online_window_loop_matches_reference():
             np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)], rtol=1e-12, atol=1e-9)
     assert len(scene.tracklets) == int(d["n_tracklets"])
     assert len(scene.completed) == 2 and len(scene.active) == 6
+
+
+def test_single_track_pass_equals_full_solver(monkeypatch):
+    """k_single_track finishes most components of crowded windows straight from the first tree; what it writes must
+    be what the staged solver writes for the same components. 60 C5 windows (5 000 detections each, ~88 components
+    per window), solved with the pass on and off: same flow, same K, same totals, same path costs."""
+    import mot3d_b200 as mot3d
+    from bench import make_workload, DIST_KW, MAX_JUMP
+    gp, frame, pos, conf = make_workload(3, seed0=77)
+    spec = mot3d.CostSpec(kind="detections_2d", distance=DIST_KW, confidence=dict(mul=1, bias=0),
+                          weight_source_sink=1, max_jump=MAX_JUMP)
+    b, _ = mot3d.DetectionBatch.from_arrays(gp, frame, pos, conf)
+    db = b.to("cuda")
+    gb = mot3d.build_graphs(db, spec)
+    sol_fast = mot3d.solve_graphs(gb)
+    stats = sol_fast.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)
+    assert stats[:, 24].sum() > 0.5 * 60 * 80          # the pass did take most components
+    monkeypatch.setenv("MOT3D_SOLVE_NO_FAST", "1")
+    sol_full = mot3d.solve_graphs(gb)
+    assert sol_full.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)[:, 24].sum() == 0
+    n = db.n
+    assert (sol_fast.next[:n].cpu() == sol_full.next[:n].cpu()).all()
+    assert (sol_fast.prev[:n].cpu() == sol_full.prev[:n].cpu()).all()
+    assert (sol_fast.n_paths.cpu() == sol_full.n_paths.cpu()).all()
+    assert (sol_fast.total_cost.cpu() == sol_full.total_cost.cpu()).all()
+    assert (sol_fast.path_cost[:n].cpu() == sol_full.path_cost[:n].cpu()).all()
+    assert int(sol_fast.n_paths.sum().item()) == 60 * 100
 
 
 def test_components_against_scipy():
