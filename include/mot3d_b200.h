@@ -279,6 +279,18 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 int32_t mot3d_extract_tracks(int32_t n_graphs, const int32_t *graph_ptr, const int32_t *next, const int32_t *prev,
                              int32_t *track_count_out, int32_t *track_ptr_out, int32_t *track_det_out, void *stream);
 
+/* ---- input-side prep: merge_close_points (mot3d/utils/filt.py:6-24; examples/soldiers_3d/example.py:29-31) ---- */
+
+/* Per point set s = points [set_ptr[s], set_ptr[s+1]) (one frame): clusters = connected components of "distance <=
+ * eps" (DBSCAN with min_samples=1), numbered by their first member; every cluster replaced by the mean of its members.
+ *   points            [N][dim] row-major (as users hold them), dim <= 3;  max_set_points = largest set (<= 8192)
+ *   label_out[i]      cluster of point i inside its set
+ *   cluster_count_out [n_sets]
+ *   merged_out        [N][dim]: the means of set s are rows set_ptr[s] .. set_ptr[s] + cluster_count_out[s] - 1 */
+int32_t mot3d_merge_close_points(const int32_t *set_ptr, int32_t n_sets, int32_t max_set_points, int32_t dim,
+                                 const double *points, double eps, int32_t *label_out, int32_t *cluster_count_out,
+                                 double *merged_out, void *stream);
+
 /* ---- one call with HOST buffers: pack -> H2D -> build -> solve -> tracks -> D2H ------------------------------ */
 
 typedef struct mot3d_host_batch {

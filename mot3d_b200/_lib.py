@@ -101,6 +101,7 @@ SIGNATURES = {
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
     "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_merge_close_points": (_i32, [_vp, _i32, _i32, _i32, _vp, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_track_batch_host": (_i32, [ctypes.POINTER(HostBatch), _PS, ctypes.POINTER(HostResult), _vp, _sz, _i64, _vp]),
 }

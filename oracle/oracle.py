@@ -399,6 +399,35 @@ def build_tracklet_transitions(d, spec):
     np.add.at(row_ptr, np.asarray(rows, dtype=np.int64) + 1, 1)
     return np.cumsum(row_ptr), np.asarray(cols, dtype=np.int64), np.asarray(ws, dtype=np.float64)
 
+# ------------------------------------------------------------------------------------------------- input prep
+def merge_close_points(points, eps=0.3, return_indexes=False):
+    """mot3d/utils/filt.py:6-24 without sklearn: DBSCAN(min_samples=1) = connected components of "distance <= eps",
+    clusters in the order of their first member, each replaced by the mean of its members (index order)."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    if len(points) == 0:
+        return points
+    P = np.asarray(points, dtype=np.float64).reshape(len(points), -1)
+    d2 = np.zeros((len(P), len(P)))
+    for k in range(P.shape[1]):
+        d2 = d2 + (P[:, None, k] - P[None, :, k]) ** 2
+    _, lab = connected_components(csr_matrix(d2 <= eps * eps), directed=False)
+    first = {}
+    for i, l in enumerate(lab.tolist()):
+        first.setdefault(l, len(first))
+    lab = np.array([first[l] for l in lab.tolist()])
+    groups = [np.flatnonzero(lab == c) for c in range(len(first))]
+    if return_indexes:
+        return [g.tolist() for g in groups]
+    out = []
+    for g in groups:
+        acc = np.zeros(P.shape[1])
+        for q in g.tolist():
+            acc = acc + P[q]
+        out.append(acc / len(g))
+    return np.vstack(out)
+
+
 # ------------------------------------------------------------------------------------------------- solve
 def ssp_solve(n_nodes, tail1, head1, cost_units, path_cap=None):
     """C restatement on int64 units. tail1/head1 are 1-based as in the text. -> dict(flow, K, path_cost, total)."""

@@ -370,15 +370,46 @@ def case_multiview_tracklets(mot3d, wf):
                          dict(weight_source_sink=0.1, max_jump=14, weight_confidence=wc, weight_distance=wd), spec, 3)
 
 
+def case_merge_close_points(mot3d):
+    """(3a) the de-duplication in front of the 3-D example (examples/soldiers_3d/example.py:20-35): the reference's
+    merge_close_points (mot3d/utils/filt.py:6-24, sklearn DBSCAN) on every frame of detections_3d_head.json used
+    there, eps 0.25; plus return_indexes on a crowded synthetic set."""
+    from mot3d.utils import utils as ref_utils
+    from mot3d.utils import filt as ref_filt
+    det = ref_utils.json_read(os.path.join(REF, "examples/soldiers_3d/detections_3d_head.json"))
+    raw, merged = [], []
+    for index_frame in range(49650, 50000):
+        pts = det[str(index_frame)]
+        raw.append(np.asarray(pts, dtype=np.float64).reshape(-1, 3))
+        merged.append(np.asarray(ref_filt.merge_close_points(pts, eps=0.25), dtype=np.float64).reshape(-1, 3))
+    rng = np.random.RandomState(5)
+    crowd = rng.rand(400, 2) * 10.0
+    groups = ref_filt.merge_close_points(crowd, eps=0.3, return_indexes=True)
+    crowd_merged = ref_filt.merge_close_points(crowd, eps=0.3)
+    out = dict(raw_ptr=np.cumsum([0] + [len(r) for r in raw]).astype(np.int64), raw=np.concatenate(raw),
+               merged_ptr=np.cumsum([0] + [len(r) for r in merged]).astype(np.int64), merged=np.concatenate(merged),
+               crowd=crowd, crowd_merged=np.asarray(crowd_merged),
+               crowd_group_ptr=np.cumsum([0] + [len(g) for g in groups]).astype(np.int64),
+               crowd_group_idx=np.array([i for g in groups for i in g], dtype=np.int64))
+    path = os.path.join(HERE, "c3_merge_close_points.npz")
+    np.savez_compressed(path, **out)
+    print("%-22s frames=%d points %d -> %d; crowd 400 -> %d (%d KB)" % ("c3_merge_close_points", len(raw),
+                                                                         len(out["raw"]), len(out["merged"]),
+                                                                         len(groups), os.path.getsize(path) // 1024))
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "c3_merge_close_points" in sys.argv[1:]:
+        return case_merge_close_points(mot3d)
     if "c3_synth_multiview_tracklets" in sys.argv[1:]:
         return case_multiview_tracklets(mot3d, wf)
     if "c4_online_loop" in sys.argv[1:]:
         return case_online(mot3d)
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
+    case_merge_close_points(mot3d)
     case_multiview(mot3d, wf)
     case_multiview_tracklets(mot3d, wf)
     case_online(mot3d)

@@ -837,6 +837,29 @@ def test_single_track_pass_equals_full_solver(monkeypatch):
     assert int(sol_fast.n_paths.sum().item()) == 60 * 100
 
 
+def test_merge_close_points_matches_reference():
+    """mot3d_merge_close_points (csrc/filt.cu) vs the reference's merge_close_points (mot3d/utils/filt.py:6-24) on the
+    350 frames of examples/soldiers_3d (all frames in one launch) and on a crowded 400-point set with chains of
+    neighbours (cluster membership and order, means bit for bit)."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200.utils.filt import merge_close_points, merge_close_points_batch
+    d = gu.load("c3_merge_close_points")
+    rp, mp = d["raw_ptr"], d["merged_ptr"]
+    sets = [d["raw"][rp[f]:rp[f + 1]] for f in range(len(rp) - 1)]
+    got = merge_close_points_batch(sets, eps=0.25)
+    for f in range(len(sets)):
+        assert (np.asarray(got[f]).reshape(-1, 3) == d["merged"][mp[f]:mp[f + 1]]).all()
+    # the positions the 3-D golden vector was built from are exactly these
+    c3 = gu.load("c3_soldiers_pass1")
+    assert (np.concatenate([np.asarray(g).reshape(-1, 3) for g in got]) == c3["pos"]).all()
+    groups = merge_close_points(d["crowd"], eps=0.3, return_indexes=True)
+    gp = d["crowd_group_ptr"]
+    assert [len(g) for g in groups] == np.diff(gp).tolist()
+    assert [i for g in groups for i in g] == d["crowd_group_idx"].tolist()
+    assert (merge_close_points(d["crowd"], eps=0.3) == d["crowd_merged"]).all()
+    assert merge_close_points([], eps=0.3) == []
+
+
 def test_components_against_scipy():
     """mot3d_components (csrc/components.cu): the regrouping of every graph by connected component of its transition
     arcs, checked against scipy on a ragged batch; repeated, because the union-find runs lock-free."""

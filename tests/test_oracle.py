@@ -99,3 +99,18 @@ def test_tracklet_build_restatement_matches_reference(name):
     assert (tail == d["tail"]).all() and (head == d["head"]).all()
     np.testing.assert_allclose(ww, d["w_float"], rtol=1e-9, atol=0)
     gu.assert_costs_match(oracle.quantise(ww), d["cost"], d["w_float"])
+
+
+def test_merge_close_points_restatement_matches_reference():
+    """oracle.merge_close_points vs the reference's sklearn-DBSCAN version (mot3d/utils/filt.py:6-24) on the frames of
+    the 3-D example and on a crowded synthetic set (tests/golden/c3_merge_close_points.npz)."""
+    d = gu.load("c3_merge_close_points")
+    rp, mp = d["raw_ptr"], d["merged_ptr"]
+    for f in range(len(rp) - 1):
+        got = oracle.merge_close_points(d["raw"][rp[f]:rp[f + 1]], eps=0.25)
+        np.testing.assert_allclose(np.asarray(got).reshape(-1, 3), d["merged"][mp[f]:mp[f + 1]], rtol=1e-15, atol=0)
+    groups = oracle.merge_close_points(d["crowd"], eps=0.3, return_indexes=True)
+    gp = d["crowd_group_ptr"]
+    assert [len(g) for g in groups] == np.diff(gp).tolist()
+    assert [i for g in groups for i in g] == d["crowd_group_idx"].tolist()
+    np.testing.assert_allclose(oracle.merge_close_points(d["crowd"], eps=0.3), d["crowd_merged"], rtol=1e-15, atol=0)
