@@ -195,9 +195,12 @@ struct Counters {
 // ---- first shortest-path tree of every graph (before it is split into components): no flow yet, the network is a
 //      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
 //      State is written in the regrouped order; branch label = position of the detection whose S arc starts the path.
+constexpr int FT_W = 2048;  // ring of post / branch labels (power of two)
 template <int FT_LPN>
 __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     __shared__ int s_scan[33];
+    __shared__ int64_t s_dp[FT_W];
+    __shared__ int s_an[FT_W];
     const int g = blockIdx.x;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
@@ -244,12 +247,18 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     if (tid == 0) lvl[L] = n;
     __syncthreads();
     // FT_LPN lanes per node, every lane keeps FT_U independent arc loads in flight: a layer of ~100 nodes with ~8
-    // in-arcs each is one pass of the block and four dependent memory levels (row, source, position, label).
+    // in-arcs each is one pass of the block. Arcs only reach back max_jump frames, so the post labels and branch
+    // labels of the last FT_W detections live in a ring in shared memory: the chain a layer waits for is row offsets ->
+    // arcs -> shared memory (two global levels instead of four); a source that has left the ring (very dense frames)
+    // is read from global memory. Sources of one detection sit in the same component, where regrouped positions
+    // ascend with the detection index: ties go to the lowest detection index = lowest position, and the parent is kept
+    // as a detection index until the end of the sweep.
     constexpr int FT_U = 4;
     const int sub = tid % FT_LPN, grp = tid / FT_LPN, ngrp = T / FT_LPN;
     int wide = 0;  // some cost needs more than 32 bits: the packed staging of k_ssp_solve is off
     for (int l = 0; l < L; l++) {
         const int a = lvl[l], b = lvl[l + 1];
+        const int ring_lo = g0 + b - FT_W;  // global index of the oldest detection this layer may read from the ring
         for (int jb = a; jb < b; jb += ngrp) {
             const int j = jb + grp;  // detection (local)
             const bool valid = j < b;
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                     x_ = p.ex[g0 + j];
                 }
                 for (int kb = 0; kb < deg; kb += FT_LPN * FT_U) {
-                    int src[FT_U], qi[FT_U];
+                    int src[FT_U];
                     int64_t w[FT_U], di[FT_U];
 #pragma unroll
                     for (int u = 0; u < FT_U; u++) {
@@ -277,18 +286,23 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                         w[u] = k < deg ? p.in_cost[e0 + k] : 0;
                     }
 #pragma unroll
-                    for (int u = 0; u < FT_U; u++) qi[u] = src[u] >= 0 ? p.comp_inv[src[u]] : -1;  // position of the source
-#pragma unroll
-                    for (int u = 0; u < FT_U; u++) di[u] = qi[u] >= 0 ? p.ws_dpost[qi[u]] : INF;
+                    for (int u = 0; u < FT_U; u++) {
+                        if (src[u] < 0)
+                            di[u] = INF;
+                        else if (src[u] >= ring_lo)
+                            di[u] = s_dp[(src[u] - g0) & (FT_W - 1)];
+                        else
+                            di[u] = p.ws_dpost[p.comp_inv[src[u]]];
+                    }
 #pragma unroll
                     for (int u = 0; u < FT_U; u++) {
                         wide |= (w[u] != (int64_t)(int)w[u]) ? 1 : 0;
-                        if (qi[u] >= 0 && w[u] < w_min) w_min = w[u];
+                        if (src[u] >= 0 && w[u] < w_min) w_min = w[u];
                         if (di[u] < INF_CUT) {
                             const int64_t cand = di[u] + w[u];
-                            if (cand < best.key || (cand == best.key && qi[u] < best.idx)) {
+                            if (cand < best.key || (cand == best.key && src[u] < best.idx)) {
                                 best.key = cand;
-                                best.idx = qi[u];
+                                best.idx = src[u];
                                 w_best = w[u];
                             }
                         }
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                 }
             }
 #pragma unroll
-            for (int d = 1; d < FT_LPN; d <<= 1) {  // lowest source position wins ties
+            for (int d = 1; d < FT_LPN; d <<= 1) {  // lowest source wins ties
                 const KeyIdx o = shfl_xor_ki(best, d);
                 const int64_t ow = __shfl_xor_sync(0xffffffffu, w_best, d);
                 const int64_t om = __shfl_xor_sync(0xffffffffu, w_min, d);
@@ -307,7 +321,9 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                 w_min = om < w_min ? om : w_min;
             }
             if (valid && sub == 0) {
-                int anc = best.idx >= 0 ? p.ws_anc_post[best.idx] : -1;
+                int anc = -1;
+                if (best.idx >= 0)
+                    anc = best.idx >= ring_lo ? s_an[(best.idx - g0) & (FT_W - 1)] : p.ws_anc_post[p.comp_inv[best.idx]];
                 wide |= (fits_narrow(e_) && fits_narrow(x_) && c_ == (int64_t)(int)c_) ? 0 : 1;
                 if (e_ < best.key) {
                     best.key = e_;
@@ -319,16 +335,26 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                 int cert = ((e_ < INF_CUT && e_ < 0) || (x_ < INF_CUT && x_ < 0)) ? 0 : 1;
                 if (best.idx >= 0 && !(w_best <= 0 && c_ + w_best <= 0 && w_min >= w_best)) cert = 0;
                 p.ws_pl[q] = cert;
+                int64_t dpost = INF;
                 if (best.key < INF_CUT) {
+                    dpost = best.key + c_;
                     p.ws_dpre[q] = best.key;
-                    p.ws_par[q] = best.idx;
+                    p.ws_par[q] = best.idx;  // a detection index for now
                     p.ws_anc_pre[q] = anc;
-                    p.ws_dpost[q] = best.key + c_;
+                    p.ws_dpost[q] = dpost;
                     p.ws_anc_post[q] = anc;
+                } else {
+                    anc = -1;
                 }
+                s_dp[j & (FT_W - 1)] = dpost;
+                s_an[j & (FT_W - 1)] = anc;
             }
         }
         __syncthreads();
+    }
+    for (int i = tid; i < n; i += T) {  // parents: detection index -> regrouped position
+        const int par = p.ws_par[g0 + i];
+        if (par >= 0) p.ws_par[g0 + i] = p.comp_inv[par];
     }
     wide = __syncthreads_or(wide);
     if (tid == 0) p.win_wide[g] = wide;
