@@ -1488,6 +1488,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         k_ssp_solve<<<(unsigned)g_grid, 256, g_smem, st>>>(pg);
         M3_LAUNCH_CHECK("k_ssp_solve (giants)");
         p.role = 2;
+        if (getenv("MOT3D_SOLVE_ONLY_GIANTS")) return MOT3D_OK;  // profiling aid: statistics of the giants alone
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3((unsigned)grid);
