@@ -363,7 +363,10 @@ def run_ours(args):
         t = json.load(open(tf))
         if t.get("seqs") == S:
             traffic_solve, traffic_build = t.get("k_ssp_solve"), t.get("edge_build")
-    roofline = {"bound": "hbm", "kernel": "k_ssp_solve", "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_ssp_solve",
+                "kernels_in_launch_ms": "solve stage = k_components + k_first_tree + k_single_track + k_job_order + "
+                                        "k_ssp_solve (giants + main, overlapped) + k_first_path_rule",
+                "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
                 "frac": solve_gbs / peak, "traffic": traffic_solve, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": float(stage_ms[i_solve]),
                 "ascending_sweeps_per_graph_mean": float(stats[:, 0].mean()),
