@@ -454,6 +454,34 @@ def test_host_entry_point_chunked_pipeline(chunks, monkeypatch):
     assert e.value.code == -3
 
 
+@pytest.mark.parametrize("chunks,pieces", [(1, 1), (1, 4), (2, 3), (3, 8)])
+def test_host_entry_point_pieces_with_bbox(chunks, pieces, monkeypatch):
+    """The host entry point with the bbox term on (PETS window, use_bbox=True) and the inputs arriving in pieces: the
+    per-piece keys / node costs / frame sort / arc build (the build continuing the CSR through the device-side arc
+    counter) give what the device path gives, for every chunk x piece split."""
+    import mot3d_b200 as mot3d
+    d = gu.load("c4_pets_view1_w1")
+    spec = _spec_from(d["spec"], mot3d)
+    n = len(d["frame"])
+    reps = 7
+    gp = np.arange(reps + 1) * n
+    b, order = mot3d.DetectionBatch.from_arrays(gp, np.tile(d["frame"], reps), np.tile(d["pos"], (reps, 1)),
+                                                np.tile(d["conf"], reps), bbox=np.tile(d["bbox"], (reps, 1)))
+    assert (order == np.arange(reps * n)).all()
+    gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+    want = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                 sol.track_det.cpu().numpy())
+    gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist() for t in range(len(d["track_ptr"]) - 1)]
+    assert want == [gold] * reps
+    monkeypatch.setenv("MOT3D_HOST_CHUNKS", str(chunks))
+    monkeypatch.setenv("MOT3D_HOST_PIECES", str(pieces))
+    ht = mot3d.HostTracker(n_max=reps * n, g_max=reps, edge_capacity=gb.n_edges + 8 * reps, dim=2, with_bbox=True)
+    ht.load(b)
+    assert ht.run(spec.to_c()) == gb.n_edges
+    assert ht.tracks() == want
+    assert ht.h_total[:reps].tolist() == sol.total_cost.cpu().tolist()
+
+
 def test_entry_exit_flags_against_oracle():
     """entry_points / exit_point = False (mot3d/mot3d.py:90-99): muSSP cannot run such graphs (UB), the
     integer oracle can."""
