@@ -98,8 +98,12 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
             const int start = in_ptr[jl < n ? jl : n];  // rows beyond the graph: empty
             const int a0 = __shfl_sync(0xffffffffu, start, 0);
             const int a1 = in_ptr[j0 + 32 < n ? j0 + 32 : n];
+            // the sources of the next two steps are already on their way while this step works on shared memory
+            int src0 = a0 + lane < a1 ? p.in_src[a0 + lane] : 0;
+            int src1 = a0 + 32 + lane < a1 ? p.in_src[a0 + 32 + lane] : 0;
             for (int eb = a0; eb < a1; eb += 32) {
                 const int e = eb + lane;
+                const int src2 = e + 64 < a1 ? p.in_src[e + 64] : 0;
                 int lo = 0;  // the last row whose arcs start at or before e
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1) {
@@ -107,10 +111,12 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
                     if (s <= e) lo += step;
                 }
                 if (e < a1) {
-                    const int ri = cc_find(s_par, p.in_src[e] - g0);
+                    const int ri = cc_find(s_par, src0 - g0);
                     const int rj = cc_find(s_par, j0 + lo);
                     cc_unite(s_par, ri, rj);
                 }
+                src0 = src1;
+                src1 = src2;
             }
         }
     }
