@@ -224,12 +224,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
         return;
     }
     for (int i = tid; i < n; i += T) {  // regrouped positions of this graph are [g0, g0 + n) as well
-        const int q = g0 + i;
-        p.ws_dpre[q] = INF;
-        p.ws_dpost[q] = INF;
-        p.ws_par[q] = PAR_NONE;
-        p.ws_anc_pre[q] = -1;
-        p.ws_anc_post[q] = -1;
+        const int q = g0 + i;  // (distances, parent and branch labels are written by the sweep, reachable or not)
         p.first_cost[q] = INF;
         p.first_sink[q] = -1;
         if (p.path_cost) p.path_cost[q] = INF;
@@ -338,14 +333,16 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                 int64_t dpost = INF;
                 if (best.key < INF_CUT) {
                     dpost = best.key + c_;
-                    p.ws_dpre[q] = best.key;
-                    p.ws_par[q] = best.idx;  // a detection index for now
-                    p.ws_anc_pre[q] = anc;
-                    p.ws_dpost[q] = dpost;
-                    p.ws_anc_post[q] = anc;
-                } else {
+                } else {  // unreachable
+                    best.key = INF;
+                    best.idx = PAR_NONE;
                     anc = -1;
                 }
+                p.ws_dpre[q] = best.key;
+                p.ws_par[q] = best.idx;  // a detection index for now
+                p.ws_anc_pre[q] = anc;
+                p.ws_dpost[q] = dpost;
+                p.ws_anc_post[q] = anc;
                 s_dp[j & (FT_W - 1)] = dpost;
                 s_an[j & (FT_W - 1)] = anc;
             }
