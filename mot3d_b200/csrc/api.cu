@@ -96,7 +96,7 @@ static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
 // (a few long components) overlaps the next chunk's build.
 constexpr int HOST_MAX_CHUNKS = 8;
 constexpr int HOST_MAX_PIECES = 8;               // H2D + build pieces per chunk
-constexpr int64_t HOST_PIECE_MIN_DETS = 150000;
+constexpr int64_t HOST_PIECE_MIN_DETS = 400000;
 constexpr int64_t HOST_CHUNK_MIN_DETS = 400000;  // below this a chunk cannot fill the GPU
 
 struct HostCtx {
@@ -287,10 +287,12 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
         M3_CHECK_ARG(hb->graph_ptr[g + 1] >= hb->graph_ptr[g], "graph_ptr must be non-decreasing");
     M3_CHECK_ARG(hb->graph_ptr[0] == 0 && hb->graph_ptr[G] == n, "graph_ptr must span [0, n]");
 
-    // Number of chunks: MOT3D_HOST_CHUNKS, else two for batches large enough to keep the GPU busy with half of them.
-    // More chunks lose: the solver of a chunk cannot take less than ~2 ms (its largest components are sequential
-    // work, profiles/r01e_summary.md), so the chunks' solvers queue up instead of overlapping.
-    int want = n >= 2 * HOST_CHUNK_MIN_DETS ? 2 : 1;
+    // Number of chunks: MOT3D_HOST_CHUNKS, else one. Every solver launch has a floor of ~2.4 ms whatever its share of
+    // the batch (front end + its longest component, which is sequential work; profiles/r01g_summary.md), so two
+    // launches cost more than the copy overlap gains until a batch is several times the size of the bench's 6 M
+    // detections: with one chunk the pieces hide keys / sort / build behind the H2D copies (8.0 ms per 6 M detections;
+    // 2 chunks x 8 pieces 8.5 ms, 4 chunks 10.4 ms).
+    int want = n >= 40 * HOST_CHUNK_MIN_DETS ? 2 : 1;
     if (const char *e = getenv("MOT3D_HOST_CHUNKS")) want = atoi(e);
     if (want > HOST_MAX_CHUNKS) want = HOST_MAX_CHUNKS;
     if (want > G) want = G;
