@@ -311,6 +311,9 @@ typedef struct mot3d_host_result {
     int32_t *track_det;   /* host [n] */
     int64_t *total_cost;  /* host [n_graphs] */
     int64_t n_edges;      /* out: transition arcs built */
+    int64_t h2d_bytes;    /* out: bytes the call copied host -> device */
+    int64_t d2h_bytes;    /* out: bytes it copied device -> host (with one chunk only the K + 1 meaningful entries of
+                             every graph's track_ptr slice travel; the rest of track_ptr is left untouched) */
 } mot3d_host_result;
 
 size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity);

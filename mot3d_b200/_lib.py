@@ -71,7 +71,8 @@ class HostBatch(ctypes.Structure):
 
 class HostResult(ctypes.Structure):
     _fields_ = [("track_count", ctypes.c_void_p), ("track_ptr", ctypes.c_void_p), ("track_det", ctypes.c_void_p),
-                ("total_cost", ctypes.c_void_p), ("n_edges", ctypes.c_int64)]
+                ("total_cost", ctypes.c_void_p), ("n_edges", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
+                ("d2h_bytes", ctypes.c_int64)]
 
 
 _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t

@@ -368,13 +368,12 @@ class HostTracker(object):
             self.h_bbox[:4 * n] = torch.from_numpy(np.asarray(batch.bbox).reshape(-1))
 
     def h2d_bytes(self):
-        b = (self.G + 1) * 4 + self.n * 4 + self.n * 8 * self.dim + self.n * 8
-        if self.h_bbox is not None:
-            b += self.n * 32
-        return b
+        """Bytes the last run() copied host -> device (counted by the C call)."""
+        return self._h2d
 
     def d2h_bytes(self):
-        return self.G * 4 + (self.n + self.G) * 4 + self.n * 4 + self.G * 8 + 8
+        """Bytes the last run() copied device -> host."""
+        return self._d2h
 
     def run(self, spec_c):
         """One mot3d_track_batch_host call on the staged batch. Returns the number of transition arcs."""
@@ -396,6 +395,7 @@ class HostTracker(object):
             _lib.check(L.mot3d_track_batch_host(ctypes.byref(hb), ctypes.byref(spec_c), ctypes.byref(res),
                                                 _ptr(self.ws), self.ws_bytes, self.edge_capacity,
                                                 _stream(self.device)))
+        self._h2d, self._d2h = int(res.h2d_bytes), int(res.d2h_bytes)
         return int(res.n_edges)
 
     def tracks(self):

@@ -56,6 +56,33 @@ const char *mot3d_last_error(void) { return g_err; }
 }  // extern "C"
 
 namespace m3 {
+// Only K_g + 1 entries of graph g's slice of track_ptr are meaningful (include/mot3d_b200.h): they are packed for the
+// D2H copy (0.5 MB instead of 24 MB per 6 M detections) and spread out again on the host.
+__global__ void k_track_ptr_offsets(int n_graphs, const int32_t *__restrict__ track_count, int32_t *__restrict__ off) {
+    // single block: off[g] = sum_{h<g} (K_h + 1)
+    __shared__ int s_scan[33];
+    int run = 0;
+    for (int g0 = 0; g0 < n_graphs; g0 += blockDim.x) {
+        const int g = g0 + threadIdx.x;
+        const int v = g < n_graphs ? track_count[g] + 1 : 0;
+        int tot;
+        const int ex = block_excl_scan(v, s_scan, &tot);
+        if (g < n_graphs) off[g] = run + ex;
+        run += tot;
+    }
+}
+__global__ void k_track_ptr_pack(int n_graphs, const int32_t *__restrict__ graph_ptr,
+                                 const int32_t *__restrict__ track_count, const int32_t *__restrict__ off,
+                                 const int32_t *__restrict__ track_ptr, int32_t *__restrict__ packed) {
+    const int g = blockIdx.x;
+    if (g >= n_graphs) return;
+    const int32_t *src = track_ptr + graph_ptr[g] + g;
+    int32_t *dst = packed + off[g];
+    for (int k = threadIdx.x; k <= track_count[g]; k += blockDim.x) dst[k] = src[k];
+}
+}  // namespace m3
+
+namespace m3 {
 int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
                                int32_t *tkey, cudaStream_t st);
 int32_t launch_frame_sort_range(const mot3d_dets *d, int64_t row_begin, int64_t row_end, cudaStream_t st);
@@ -86,6 +113,7 @@ static size_t pass_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
     b += align256((size_t)g1 * 4);              // track_count
     b += align256((size_t)(n1 + g1) * 4);       // track_ptr
     b += align256((size_t)n1 * 4);              // track_det
+    b += align256((size_t)g1 * 4) + align256((size_t)(n1 + g1) * 4);  // packed track_ptr + offsets
     return b;
 }
 
@@ -145,7 +173,8 @@ static HostCtx *host_ctx() {
 static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *spec, mot3d_host_result *res, Arena &A,
                              int32_t ga, int32_t gb, const int32_t *h_gptr, const int64_t *h_gbase, int32_t max_nodes,
                              int64_t edge_capacity, int32_t *h_flags, cudaStream_t st, cudaStream_t cin,
-                             cudaEvent_t *in_done, int pieces, cudaEvent_t *trace) {
+                             cudaEvent_t *in_done, int pieces, cudaEvent_t *trace, cudaEvent_t counts_done,
+                             int32_t **d_packed_out) {
     const int64_t d0 = hb->graph_ptr[ga], d1 = hb->graph_ptr[gb];
     const int64_t n = d1 - d0, N = hb->n;
     const int32_t G = gb - ga;
@@ -180,6 +209,8 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     if (!A.ok) return MOT3D_E_CAPACITY;  // the caller retries with fewer chunks / reports
 
     int64_t *d_arcs = A.take<int64_t>(1);
+    int32_t *d_poff = d_packed_out ? A.take<int32_t>(G) : nullptr;
+    int32_t *d_packed = d_packed_out ? A.take<int32_t>(n + G) : nullptr;
     if (!A.ok) return MOT3D_E_CAPACITY;
     M3_CUDA(cudaMemcpyAsync(d_gptr, h_gptr, (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, cin));
     M3_CUDA(cudaMemcpyAsync(d_gbase, h_gbase, (size_t)G * 8, cudaMemcpyHostToDevice, cin));
@@ -250,7 +281,17 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     // the per-graph slices of the outputs sit at graph_ptr[g] + g / graph_ptr[g] (include/mot3d_b200.h), so a chunk's
     // outputs are one contiguous slice of the caller's arrays
     M3_CUDA(cudaMemcpyAsync(res->track_count + ga, d_tcount, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
-    M3_CUDA(cudaMemcpyAsync(res->track_ptr + d0 + ga, d_tptr, (size_t)(n + G) * 4, cudaMemcpyDeviceToHost, st));
+    if (d_packed_out) {
+        // the caller copies the packed track_ptr entries once it has the counts (they arrive first) and spreads them
+        M3_CUDA(cudaEventRecord(counts_done, st));
+        k_track_ptr_offsets<<<1, 1024, 0, st>>>(G, d_tcount, d_poff);
+        M3_LAUNCH_CHECK("k_track_ptr_offsets");
+        k_track_ptr_pack<<<G, 128, 0, st>>>(G, d_gptr, d_tcount, d_poff, d_tptr, d_packed);
+        M3_LAUNCH_CHECK("k_track_ptr_pack");
+        *d_packed_out = d_packed;
+    } else {
+        M3_CUDA(cudaMemcpyAsync(res->track_ptr + d0 + ga, d_tptr, (size_t)(n + G) * 4, cudaMemcpyDeviceToHost, st));
+    }
     M3_CUDA(cudaMemcpyAsync(res->track_det + d0, d_tdet, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     M3_CUDA(cudaMemcpyAsync(res->total_cost + ga, d_total, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
     M3_CUDA(cudaMemcpyAsync(h_flags, d_over, 4, cudaMemcpyDeviceToHost, st));
@@ -274,6 +315,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     M3_CHECK_ARG(hb->n_graphs >= 0 && hb->n >= 0, "negative sizes");
     M3_CHECK_ARG(!spec->use_hist, "mot3d_track_batch_host: colour histograms go through the device entry points");
     res->n_edges = 0;
+    res->h2d_bytes = res->d2h_bytes = 0;
     if (hb->n == 0 || hb->n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(hb->graph_ptr && hb->frame && hb->pos && hb->conf, "NULL host input");
     M3_CHECK_ARG(!spec->use_bbox || hb->bbox, "use_bbox set but bbox is NULL");
@@ -346,6 +388,9 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             if (g > cut[nc]) cut[++nc] = g;
         }
         Arena A(device_ws, ws_bytes);
+        const bool pack_ptr = nc == 1 && !getenv("MOT3D_HOST_NO_PACK");
+        int32_t *d_packed = nullptr;
+        int64_t packed_total = 0;
         M3_CUDA(cudaEventRecord(ctx->start, user));
         M3_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->start, 0));
         if (tracing) M3_CUDA(cudaEventRecord(ctx->t0, user));
@@ -378,7 +423,17 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             if (pieces > HOST_MAX_PIECES) pieces = HOST_MAX_PIECES;
             if (pieces < 1) pieces = 1;
             rc = enqueue_chunk(hb, spec, res, A, ga, gb, hg, hb_base, max_nodes, cap, ctx->pinned + 2 * c, st,
-                               ctx->copy_in, ctx->in + c * HOST_MAX_PIECES, pieces, tracing ? ctx->trace[c] : nullptr);
+                               ctx->copy_in, ctx->in + c * HOST_MAX_PIECES, pieces, tracing ? ctx->trace[c] : nullptr,
+                               ctx->done[0], pack_ptr ? &d_packed : nullptr);
+            if (pack_ptr && rc == MOT3D_OK) {
+                // one chunk: wait for the track counts only, then fetch sum(K + 1) packed entries into the tail of the
+                // caller's track_ptr (behind the track_det copy that is already queued)
+                M3_CUDA(cudaEventSynchronize(ctx->done[0]));
+                for (int g = 0; g < G; g++) packed_total += (int64_t)res->track_count[g] + 1;
+                if (packed_total > 0)
+                    M3_CUDA(cudaMemcpyAsync(res->track_ptr + (n + G - packed_total), d_packed, (size_t)packed_total * 4,
+                                            cudaMemcpyDeviceToHost, st));
+            }
             if (nc > 1 && rc == MOT3D_OK) {
                 M3_CUDA(cudaEventRecord(ctx->done[c], st));
                 M3_CUDA(cudaStreamWaitEvent(user, ctx->done[c], 0));
@@ -404,6 +459,16 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             rc = cuda_fail(se, "mot3d_track_batch_host");
             break;
         }
+        if (pack_ptr && packed_total > 0) {
+            // spread the packed entries out to graph_ptr[g] + g, ascending: the staging area at the tail never runs
+            // ahead of the slice being written (sum_{h>=g} (K_h + 1) <= (n - graph_ptr[g]) + (G - g))
+            const int32_t *src = res->track_ptr + (n + G - packed_total);
+            for (int g = 0; g < G; g++) {
+                const int32_t k1 = res->track_count[g] + 1;
+                memmove(res->track_ptr + hb->graph_ptr[g] + g, src, (size_t)k1 * 4);
+                src += k1;
+            }
+        }
         if (tracing)
             for (int c = 0; c < nc; c++) {
                 float t[4] = {0, 0, 0, 0};
@@ -418,6 +483,11 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             if (ctx->pinned[2 * c] || ctx->pinned[2 * c + 1] > cap) retry = true;
         }
         res->n_edges = edges;
+        // what travelled: graph_ptr + key bases, frame, positions, confidences [, flags, boxes] in; counts, totals,
+        // track_det, the (packed) track_ptr and two flags per chunk out
+        res->h2d_bytes += (int64_t)(G + nc) * 4 + (int64_t)G * 8 + n * (4 + 8 * hb->dim + 8) + (hb->flags ? n : 0) +
+                          (spec->use_bbox ? n * 32 : 0);
+        res->d2h_bytes += (int64_t)G * 12 + n * 4 + (pack_ptr ? packed_total * 4 : (n + G) * 4) + (int64_t)nc * 8;
         if (retry) {
             if (nc > 1 && edges <= edge_capacity) continue;  // the whole batch fits: run it in one piece
             set_error("edge capacity %lld too small: the batch has %lld transition arcs", (long long)edge_capacity,
