@@ -333,15 +333,15 @@ __global__ void k_graph_base(const int32_t *__restrict__ frame, const int32_t *_
     }
 }
 
-__global__ void k_make_keys(const int32_t *__restrict__ frame, const int32_t *__restrict__ graph_ptr, int n_graphs,
-                            const int64_t *__restrict__ base, int32_t *__restrict__ tkey) {
-    // one warp per graph, grid-stride over graphs
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_graphs; g += warps) {
+__global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ frame,
+                                                   const int32_t *__restrict__ graph_ptr, int n_graphs,
+                                                   const int64_t *__restrict__ base, int32_t *__restrict__ tkey) {
+    // one block per graph (grid-stride over graphs): a 5 000-detection window is 20 coalesced steps
+    for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
         const int a = graph_ptr[g], b = graph_ptr[g + 1];
         if (b <= a) continue;
         const int64_t shift = base[g] - (int64_t)frame[a];
-        for (int i = a + lane_id(); i < b; i += 32) tkey[i] = (int32_t)((int64_t)frame[i] + shift);
+        for (int i = a + threadIdx.x; i < b; i += blockDim.x) tkey[i] = (int32_t)((int64_t)frame[i] + shift);
     }
 }
 
@@ -545,8 +545,7 @@ int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t 
     cudaStream_t st = (cudaStream_t)stream;
     k_graph_base<<<1, 1024, 0, st>>>(frame, graph_ptr, n_graphs, max_jump, graph_base_ws);
     M3_LAUNCH_CHECK("k_graph_base");
-    int blocks = (n_graphs + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int blocks = n_graphs < 148 * 64 ? n_graphs : 148 * 64;
     k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, graph_base_ws, tkey_out);
     M3_LAUNCH_CHECK("k_make_keys");
     return MOT3D_OK;
@@ -574,8 +573,7 @@ namespace m3 {
 int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
                                int32_t *tkey, cudaStream_t st) {
     if (n_graphs <= 0) return MOT3D_OK;
-    int blocks = (n_graphs + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    int blocks = n_graphs < 148 * 64 ? n_graphs : 148 * 64;
     k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, base, tkey);
     M3_LAUNCH_CHECK("k_make_keys");
     return MOT3D_OK;
