@@ -193,7 +193,7 @@ def workload_config(seqs, n_gpus):
                         "20 windows x 50 frames (5000 detections) per sequence",
             "sequences_per_gpu": seqs, "graphs_per_gpu": int(seqs * 20), "detections_per_gpu": int(seqs * 100000),
             "max_jump": MAX_JUMP, "max_distance": 30, "parallelism": "graphs sharded over %d GPU(s), no data-path "
-            "collective" % n_gpus, "l2": "256 MiB L2 flush between timed iterations"}
+            "collective; track outputs all-gathered (NCCL) inside every step" % n_gpus, "l2": "256 MiB L2 flush between timed iterations"}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -235,24 +235,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    # ---- the only communication of the path: track outputs to every rank (rank 0 consumes them), three NCCL
+    # all-gathers. serial (default): on the launching stream right after the step's tracks. overlap
+    # (MOT3D_BENCH_GATHER=overlap): on a stream of its own, started with the next step and waited for by that step's
+    # solver. Measured at 8 GPUs (profiles/r01h_scaling.json): a gather that shares the SMs with the pipeline's
+    # kernels takes several times longer than alone (the solver keeps every SM busy with persistent blocks), so the
+    # overlap only pays while the step is long; packing the track_ptr slices with torch ops costs more than it saves.
+    gather_mode = os.environ.get("MOT3D_BENCH_GATHER", "serial")
+    comm_stream = torch.cuda.Stream(dev, priority=-1) if (world > 1 and gather_mode == "overlap") else None
     if world > 1:
         out_cnt = torch.empty(world * G, dtype=torch.int32, device=dev)
         out_det = torch.empty(world * n, dtype=torch.int32, device=dev)
         out_ptr = torch.empty(world * (n + G + 1), dtype=torch.int32, device=dev)
 
+    def all_gather_tracks():
+        dist.all_gather_into_tensor(out_cnt, pipe.track_count)
+        dist.all_gather_into_tensor(out_det, pipe.track_det)
+        dist.all_gather_into_tensor(out_ptr, pipe.track_ptr)
+
     def gather_results(after):
-        """The only communication of the path: track outputs to every rank (rank 0 consumes them), three NCCL
-        all-gathers on a stream of their own once `after` (an event on the launching stream) has passed. Returns the
-        event that marks them done: the next step's k_extract_tracks, which overwrites the buffers being sent, waits
-        for it, everything before it overlaps the transfer."""
+        """serial: on the launching stream, right where it is called. overlap: on a stream of its own once `after` (an
+        event on the launching stream) has passed; returns the event that marks it done, which the next step's solver
+        waits for (k_extract_tracks, which overwrites the buffers being sent, comes after the solver)."""
         if world == 1:
+            return None
+        if comm_stream is None:
+            all_gather_tracks()
             return None
         comm_stream.wait_event(after)
         with torch.cuda.stream(comm_stream):
-            dist.all_gather_into_tensor(out_cnt, pipe.track_count)
-            dist.all_gather_into_tensor(out_det, pipe.track_det)
-            dist.all_gather_into_tensor(out_ptr, pipe.track_ptr)
+            all_gather_tracks()
             done = torch.cuda.Event()
             done.record(comm_stream)
         return done
@@ -271,9 +283,10 @@ def run_ours(args):
     barrier()
     pipe.check_overflow()
 
-    # ---- timed: K steps, per-step CUDA events on the launching stream, L2 flushed between steps. The gather of step
-    #      k-1 starts with step k (after the flush, so none of it hides in untimed work) and has to be over before
-    #      step k extracts its tracks; the gather of the last step is waited for inside the last step's interval.
+    # ---- timed: K steps, per-step CUDA events on the launching stream, L2 flushed between steps. The gather of a step
+    #      runs inside the step's interval, right after its tracks (serial), or - MOT3D_BENCH_GATHER=overlap - starts
+    #      with the next step (after the flush, so none of it hides in untimed work) and is waited for by that step's
+    #      solver; the gather of the last step is then waited for inside the last step's interval.
     step_ms = []
     stage_ms = np.zeros(len(STAGES))
     barrier()
@@ -286,13 +299,17 @@ def run_ours(args):
         e_end = torch.cuda.Event(enable_timing=True)
         e_start = torch.cuda.Event(enable_timing=True)
         e_start.record(stream)
-        done = gather_results(e_start) if (pending is not None) else None
-        pipe.run(dbatch, spec, spec_c, events=ev, before_extract=done)
-        pending = ev[len(STAGES)]
-        if k == args.steps - 1:
-            done = gather_results(pending)
-            if done is not None:
-                stream.wait_event(done)
+        if comm_stream is None:
+            pipe.run(dbatch, spec, spec_c, events=ev)
+            gather_results(None)  # serial: inside the step, after its tracks
+        else:
+            done = gather_results(e_start) if (pending is not None) else None
+            pipe.run(dbatch, spec, spec_c, events=ev, before_solve=done)
+            pending = ev[len(STAGES)]
+            if k == args.steps - 1:
+                done = gather_results(pending)
+                if done is not None:
+                    stream.wait_event(done)
         e_end.record(stream)
         e_end.synchronize()
         step_ms.append(e_start.elapsed_time(e_end))
@@ -329,6 +346,9 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * n * args.steps / e2e_s
 
+    if world > 1:  # what arrived is what this rank sent (untimed check)
+        assert (out_det.view(world, n)[rank] == pipe.track_det).all()
+        assert (out_cnt.view(world, G)[rank] == pipe.track_count).all()
     # results of the two paths agree
     tracks_dev = pipe.tracks(graph_ptr)
     assert ht.tracks() == tracks_dev, "host-buffer path and device path disagree"

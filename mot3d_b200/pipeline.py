@@ -60,10 +60,11 @@ class TrackPipeline(object):
         self.track_ptr = torch.empty(n + G + 1, **i32)
         self.track_det = torch.empty(n, **i32)
 
-    def run(self, batch, spec, spec_c=None, events=None, before_extract=None):
+    def run(self, batch, spec, spec_c=None, events=None, before_extract=None, before_solve=None):
         """batch: DetectionBatch on self.device. events: optional list of len(self.stages)+1 torch.cuda.Event recorded
         around every stage on the current stream. before_extract: optional event the stream waits for before the
-        track outputs are overwritten (a consumer of the previous run's outputs on another stream).
+        track outputs are overwritten (a consumer of the previous run's outputs on another stream); before_solve: the
+        same wait placed in front of the solver instead (its persistent blocks starve a concurrent NCCL kernel).
         Asynchronous: call check_overflow()/synchronize afterwards."""
         L = _lib.lib()
         dev = self.device
@@ -106,6 +107,8 @@ class TrackPipeline(object):
                                          _ptr(self.overflow), st))
             k = 6
         rec(k)
+        if before_solve is not None:
+            torch.cuda.current_stream(dev).wait_event(before_solve)
         _lib.check(L.mot3d_solve_batch(G, n, _ptr(batch.graph_ptr), max_nodes, _ptr(self.tkey), self.edge_capacity,
                                        _ptr(self.row_ptr),
                                        _ptr(self.col), _ptr(self.cost), _ptr(self.entry_cost), _ptr(self.node_cost),
