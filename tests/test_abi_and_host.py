@@ -227,3 +227,57 @@ def test_interpolate_trajectory_and_scene_bookkeeping():
     assert sorted(scene.completed) == [0] and sorted(scene.active) == [1]
     scene.update(None, [c])
     assert sorted(scene.active) == [1, 2]
+
+
+def test_view_packing_follows_dict_order():
+    """Host packing of the 2-D views of 3-D detections / tracklets (no GPU): entries in every object's own dict order
+    (the order the reference's per-view loops iterate in, mot3d/weight_functions.py:55-71, 146-158), labels mapped to
+    integers consistently, planar bboxes."""
+    import types as pytypes
+    import numpy as np
+    import mot3d_b200 as mot3d
+    from mot3d_b200.mot3d import _pack_views
+    from mot3d_b200.tracklets import pack_tracklets
+
+    def d2(view, k):
+        return mot3d.Detection2D(0, (0.0, 0.0), view=view, color_histogram=[np.full(4, k + c, dtype=float) for c in range(3)],
+                                 bbox=(k, k + 1.0, k + 2.0, k + 3.0))
+
+    a = mot3d.Detection3D(0, (0.0, 0.0, 0.0), detections_2d={"camB": d2("camB", 1), "camA": d2("camA", 2)})
+    b = mot3d.Detection3D(1, (0.0, 0.0, 0.0), detections_2d={"camA": d2("camA", 3)})
+    c = mot3d.Detection3D(2, (0.0, 0.0, 0.0), detections_2d={})
+    spec = mot3d.CostSpec(kind="detections_3d", distance=dict(use_color_histogram=True, use_bbox=True))
+    v = _pack_views([a, b, c], spec)
+    assert v["view_ptr"].tolist() == [0, 2, 3, 3]
+    assert v["view_id"].tolist() == [0, 1, 1]                      # camB first seen -> 0, camA -> 1
+    assert v["bbox"].shape == (4, 3) and v["bbox"][:, 0].tolist() == [1.0, 2.0, 3.0, 4.0]
+    assert v["hist"].shape == (3, 3, 4) and v["hist"][1, 2, 0] == 4.0
+    only_bbox = _pack_views([a, b], mot3d.CostSpec(kind="detections_3d", distance=dict(use_color_histogram=False,
+                                                                                     use_bbox=True)))
+    assert "hist" not in only_bbox and only_bbox["bbox"].shape == (4, 3)
+
+    def end(idx, pos):
+        e = mot3d.Detection3D(idx[-1], pos[-1])
+        e.indexes, e.positions, e.access_point = idx, pos, False
+        return e
+
+    def trk(views):
+        t = object.__new__(mot3d.DetectionTracklet3D)
+        t._init_item(0.5, None)
+        t.head = end([3, 4], [np.zeros(3), np.ones(3)])
+        t.tail = end([0, 1], [np.zeros(3), np.ones(3)])
+        t.tracklets_2d = {name: pytypes.SimpleNamespace(head=pytypes.SimpleNamespace(color_histogram=np.full((3, 4), h)),
+                                                        tail=pytypes.SimpleNamespace(color_histogram=np.full((3, 4), -h)))
+                          for name, h in views}
+        return t
+
+    tspec = mot3d.TrackletCostSpec(kind="tracklets_3d", distance=dict(use_color_histogram=True))
+    packed = pack_tracklets([trk([("x", 1.0), ("y", 2.0)]), trk([("y", 3.0)])], tspec)
+    assert packed["view_ptr"].tolist() == [0, 2, 3] and packed["view_id"].tolist() == [0, 1, 1]
+    assert packed["view_head_hist"][2, 0, 0] == 3.0 and packed["view_tail_hist"][1, 0, 0] == -2.0
+    assert packed["head_hist"] is None
+    import pytest
+    with pytest.raises(ValueError):
+        t = trk([("x", 1.0)])
+        t.tracklets_2d["x"].head.color_histogram = None
+        pack_tracklets([t], tspec)
