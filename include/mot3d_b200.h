@@ -244,7 +244,8 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
 
 size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t arc_capacity);
 
-/* Successive shortest paths per graph on the residual network, one thread block per graph.
+/* Successive shortest paths on the residual network of every graph: each graph is split into its connected components,
+ * single-track components are finished from the first tree, the others are solved one per thread block from a work queue.
  *   in_ptr/in_src/in_cost : MOT3D_DIR_IN CSR of the transition arcs over the whole batch (in_src = global indices);
  *                   arc_capacity = entries present in in_src/in_cost: a graph whose rows reach beyond it (arc buffer
  *                   overflow during the build) is skipped and gets n_paths = -1

@@ -1,8 +1,8 @@
 """Batched tracking on the GPU: many independent graphs (windows / camera views / sequences) per call.
 
 DetectionBatch  packed detections (structure of arrays, torch tensors) for G graphs
-build_graphs    count -> scan -> fill of the windowed all-pairs edge kernel  (reference mot3d/mot3d.py:75-141)
-solve_graphs    successive-shortest-path kernel, one thread block per graph  (reference wrapper.cpp:171-317)
+build_graphs    frame sort + single-pass x-window arc build (or count -> scan -> fill)  (reference mot3d/mot3d.py:75-141)
+solve_graphs    components -> first tree -> single-track pass -> SSP per component    (reference wrapper.cpp:171-317)
 extract_tracks  flow-following kernel                                        (reference mot3d/mot3d.py:165-184)
 track_batch     the three in a row; track_batch_host: the same from pinned host buffers through one C-ABI call
 

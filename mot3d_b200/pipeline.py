@@ -1,7 +1,7 @@
 """TrackPipeline: the whole hot path on the device with preallocated buffers and no host synchronisation between
 stages -- keys -> node costs -> frame sort -> single-pass arc build -> solve -> tracks (fused=False: arc count -> row
 scan -> arc fill instead of the single-pass build). All graphs of a batch go
-through each kernel in one launch (one thread block per graph in the solver). This is what the batch scheduler runs
+through each kernel in one launch (the solver drains a work queue of connected components). This is what the batch scheduler runs
 per rank; bench.py times it stage by stage with CUDA events on the launching stream."""
 import ctypes
 
