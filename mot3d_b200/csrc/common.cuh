@@ -38,6 +38,7 @@ int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_p
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
                        int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream);
 
+constexpr int MOT3D_MAX_DEVICES = 64;  // per-device caches (launch parameters, host pipeline contexts)
 constexpr int64_t INF = MOT3D_INF_COST;
 constexpr int64_t INF_CUT = MOT3D_INF_COST / 2;  // anything >= this is "unreachable"
 
