@@ -193,7 +193,7 @@ def workload_config(seqs, n_gpus):
                         "20 windows x 50 frames (5000 detections) per sequence",
             "sequences_per_gpu": seqs, "graphs_per_gpu": int(seqs * 20), "detections_per_gpu": int(seqs * 100000),
             "max_jump": MAX_JUMP, "max_distance": 30, "parallelism": "graphs sharded over %d GPU(s), no data-path "
-            "collective; track outputs all-gathered (NCCL) inside every step" % n_gpus, "l2": "256 MiB L2 flush between timed iterations"}
+            "collective; track outputs gathered to rank 0 inside every step (one packed payload per rank, copy-engine put)" % n_gpus, "l2": "256 MiB L2 flush between timed iterations"}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -235,39 +235,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- the only communication of the path: track outputs to every rank (rank 0 consumes them), three NCCL
-    # all-gathers. serial (default): on the launching stream right after the step's tracks. overlap
-    # (MOT3D_BENCH_GATHER=overlap): on a stream of its own, started with the next step and waited for by that step's
-    # solver. Measured at 8 GPUs (profiles/r01h_scaling.json): a gather that shares the SMs with the pipeline's
-    # kernels takes several times longer than alone (the solver keeps every SM busy with persistent blocks), so the
-    # overlap only pays while the step is long; packing the track_ptr slices with torch ops costs more than it saves.
-    gather_mode = os.environ.get("MOT3D_BENCH_GATHER", "serial")
-    comm_stream = torch.cuda.Stream(dev, priority=-1) if (world > 1 and gather_mode == "overlap") else None
+    # ---- the only communication of the path: the track outputs of every rank go to rank 0, inside every step, right
+    # after the step's tracks on the launching stream (mot3d_b200.TrackGather: one fixed-size payload per rank, put
+    # into rank 0's receive slot by the copy engines through a CUDA IPC peer buffer; MOT3D_BENCH_GATHER=collective
+    # forces the torch.distributed gather of the same payload instead). Rank 0's step ends when every payload has
+    # landed (flag wait on its stream).
+    gather = None
     if world > 1:
-        out_cnt = torch.empty(world * G, dtype=torch.int32, device=dev)
-        out_det = torch.empty(world * n, dtype=torch.int32, device=dev)
-        out_ptr = torch.empty(world * (n + G + 1), dtype=torch.int32, device=dev)
+        gather = mot3d.TrackGather(n, G, device=dev, transport=os.environ.get("MOT3D_BENCH_GATHER", "auto"))
 
-    def all_gather_tracks():
-        dist.all_gather_into_tensor(out_cnt, pipe.track_count)
-        dist.all_gather_into_tensor(out_det, pipe.track_det)
-        dist.all_gather_into_tensor(out_ptr, pipe.track_ptr)
-
-    def gather_results(after):
-        """serial: on the launching stream, right where it is called. overlap: on a stream of its own once `after` (an
-        event on the launching stream) has passed; returns the event that marks it done, which the next step's solver
-        waits for (k_extract_tracks, which overwrites the buffers being sent, comes after the solver)."""
-        if world == 1:
-            return None
-        if comm_stream is None:
-            all_gather_tracks()
-            return None
-        comm_stream.wait_event(after)
-        with torch.cuda.stream(comm_stream):
-            all_gather_tracks()
-            done = torch.cuda.Event()
-            done.record(comm_stream)
-        return done
+    def gather_results():
+        if gather is not None:
+            gather.gather(dbatch.graph_ptr, pipe.track_count, pipe.track_ptr, pipe.track_det)
+            gather.release()  # (the bench has no consumer on rank 0; the payloads are checked after the timed region)
 
     # ---- warm-up
     stream = torch.cuda.current_stream(dev)
@@ -275,56 +255,60 @@ def run_ours(args):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         pipe.run(dbatch, spec, spec_c)
-        e = torch.cuda.Event()
-        e.record(stream)
-        done = gather_results(e)
-        if done is not None:
-            stream.wait_event(done)
+        gather_results()
     barrier()
     pipe.check_overflow()
 
     # ---- timed: K steps, per-step CUDA events on the launching stream, L2 flushed between steps. The gather of a step
-    #      runs inside the step's interval, right after its tracks (serial), or - MOT3D_BENCH_GATHER=overlap - starts
-    #      with the next step (after the flush, so none of it hides in untimed work) and is waited for by that step's
-    #      solver; the gather of the last step is then waited for inside the last step's interval.
+    #      runs inside the step's interval.
     step_ms = []
     stage_ms = np.zeros(len(STAGES))
+    gather_ms = 0.0
     barrier()
     sampler.mark()
     wall0 = time.time()
-    pending = None  # event after the extract of the previous step
     for k in range(args.steps):
         flush.fill_(k & 0xff)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(STAGES) + 1)]
         e_end = torch.cuda.Event(enable_timing=True)
         e_start = torch.cuda.Event(enable_timing=True)
         e_start.record(stream)
-        if comm_stream is None:
-            pipe.run(dbatch, spec, spec_c, events=ev)
-            gather_results(None)  # serial: inside the step, after its tracks
-        else:
-            done = gather_results(e_start) if (pending is not None) else None
-            pipe.run(dbatch, spec, spec_c, events=ev, before_solve=done)
-            pending = ev[len(STAGES)]
-            if k == args.steps - 1:
-                done = gather_results(pending)
-                if done is not None:
-                    stream.wait_event(done)
+        pipe.run(dbatch, spec, spec_c, events=ev)
+        gather_results()
         e_end.record(stream)
         e_end.synchronize()
         step_ms.append(e_start.elapsed_time(e_end))
         stage_ms += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(STAGES))])
+        gather_ms += ev[len(STAGES)].elapsed_time(e_end)
     barrier()
     wall = time.time() - wall0
     clocks = sampler.stop()
     total_ms = float(np.sum(step_ms))
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, gather_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms, gather_ms = float(t[0].item()), float(t[1].item())
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
     stage_ms /= args.steps
+    gather_ms /= args.steps
+    if gather is not None:
+        # what arrived at rank 0 is what every rank sent (untimed): rank 0 compares each slot with the payload the
+        # sender packs once more locally
+        assert not gather.timed_out(), "track gather timed out"
+        mine = torch.empty(2 * G + n, dtype=torch.int32, device=dev)
+        mot3d._lib.check(mot3d._lib.lib().mot3d_pack_tracks(
+            G, dbatch.graph_ptr.data_ptr(), pipe.track_count.data_ptr(), pipe.track_ptr.data_ptr(),
+            pipe.track_det.data_ptr(), mine.data_ptr(), stream.cuda_stream))
+        sent = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, sent, dst=0)
+        if rank == 0:
+            for r in range(world):
+                assert torch.equal(gather.payload(r), sent[r]), "rank %d: payload at rank 0 differs from what was sent" % r
+        gather_info = {"transport": gather.transport, "payload_bytes_per_rank": int(4 * (2 * G + n)),
+                       "ms_per_step_max_over_ranks": gather_ms}
+    else:
+        gather_info = None
 
     # ---- end to end through the C-ABI host-buffer call (pinned host in, pinned host out)
     ht = mot3d.HostTracker(n_max=n, g_max=G, edge_capacity=cap, dim=2, device=dev)
@@ -346,14 +330,13 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * n * args.steps / e2e_s
 
-    if world > 1:  # what arrived is what this rank sent (untimed check)
-        assert (out_det.view(world, n)[rank] == pipe.track_det).all()
-        assert (out_cnt.view(world, G)[rank] == pipe.track_count).all()
     # results of the two paths agree
     tracks_dev = pipe.tracks(graph_ptr)
     assert ht.tracks() == tracks_dev, "host-buffer path and device path disagree"
     assert (ht.h_total[:G].numpy() == pipe.total_cost.cpu().numpy()).all()
 
+    if gather is not None:
+        gather.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -445,7 +428,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "detections/s", "h2d_bytes_per_step": ht.h2d_bytes(),
                     "d2h_bytes_per_step": ht.d2h_bytes(), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "mot3d_track_batch_host (C ABI, pinned host buffers)"},
-            "gpu_launches": LAUNCHES_PER_RUN * args.steps, "roofline": roofline, "roofline_edge_build": roofline_build,
+            "track_gather": gather_info,
+            "gpu_launches": (LAUNCHES_PER_RUN + (2 if world > 1 else 0)) * args.steps, "roofline": roofline, "roofline_edge_build": roofline_build,
             "cpu_baseline": cpu_baseline, "clocks": clocks, "wall_s_timed_region": wall,
             "n_arcs_per_gpu": int(E), "paths_per_graph_mean": float(pipe.n_paths.cpu().numpy()[:G].mean())}
     print(json.dumps(line))

@@ -280,6 +280,42 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 int32_t mot3d_extract_tracks(int32_t n_graphs, const int32_t *graph_ptr, const int32_t *next, const int32_t *prev,
                              int32_t *track_count_out, int32_t *track_ptr_out, int32_t *track_det_out, void *stream);
 
+/* ---- track gather (multi-GPU): the only communication of the path ----------------------------------------------
+ * Whole graphs are sharded over the GPUs of a box; every rank sends its tracks to rank 0 as ONE
+ * fixed-size int32 payload, so that no size has to reach the host before the copy is issued:
+ *     payload = [ K_g (G words) | L_g (G words) | track_det (n words) ],   mot3d_track_payload_words(n, G) words
+ * K_g = tracks of graph g, L_g = detections on them; the first detection of every track carries
+ * MOT3D_TRACK_START_BIT, which makes the offsets of mot3d_extract_tracks redundant (mot3d_unpack_tracks rebuilds
+ * them). It stands in for the Python lists solve_graph returns (mot3d/mot3d.py:208-211) between processes. */
+#define MOT3D_TRACK_START_BIT 0x80000000u
+#define MOT3D_PEER_HANDLE_BYTES 64
+int64_t mot3d_track_payload_words(int64_t n_total, int32_t n_graphs);
+int32_t mot3d_pack_tracks(int32_t n_graphs, const int32_t *graph_ptr, const int32_t *track_count,
+                          const int32_t *track_ptr, const int32_t *track_det, int32_t *payload_out, void *stream);
+int32_t mot3d_unpack_tracks(int32_t n_graphs, const int32_t *graph_ptr, const int32_t *payload,
+                            int32_t *track_count_out, int32_t *track_ptr_out, int32_t *track_det_out, void *stream);
+/* Peer buffers: device memory allocated by the library (cudaMalloc, zeroed) that other processes of the box can
+ * open through CUDA IPC (the 64-byte handle travels by any host channel, e.g. torch.distributed's object broadcast).
+ * create/destroy in the owning process, open/close in the others. These four calls synchronise with the device. */
+int32_t mot3d_peer_buffer_create(size_t bytes, void **dev_ptr_out, unsigned char handle_out[MOT3D_PEER_HANDLE_BYTES]);
+int32_t mot3d_peer_buffer_open(const unsigned char handle[MOT3D_PEER_HANDLE_BYTES], void **dev_ptr_out);
+int32_t mot3d_peer_buffer_close(void *dev_ptr);
+int32_t mot3d_peer_buffer_destroy(void *dev_ptr);
+/* put: `bytes` from src (local) to peer_dst (opened peer buffer) by the copy engines, then `step` into *peer_flag
+ * (stream order: the flag lands after the payload). local_flag_scratch = one int32 of local device memory.
+ * wait (owner): a one-thread kernel on `stream` that returns once flags[r * stride_words] - step >= 0 for every
+ * r in [1, world); after ~2 s it gives up and writes the offending rank to *timeout_flag (device, 0 = fine). */
+int32_t mot3d_peer_put(void *peer_dst, const void *src, size_t bytes, int32_t *peer_flag, int32_t *local_flag_scratch,
+                       int32_t step, void *stream);
+int32_t mot3d_peer_wait(const int32_t *flags, int32_t stride_words, int32_t world, int32_t step, int32_t *timeout_flag,
+                        void *stream);
+/* flow control of a double-buffered slot: the owner publishes "consumed up to step s" with set_word on its own buffer,
+ * a sender waits with wait_word (one-thread kernel reading the peer word over NVLink until *word - need >= 0; gives
+ * up after ~2 s and sets *timeout_flag) before it overwrites the slot of step s + 2. */
+int32_t mot3d_peer_set_word(int32_t *word, int32_t value, void *stream);
+int32_t mot3d_peer_wait_word(const int32_t *word, int32_t need, int32_t *timeout_flag, void *stream);
+
+
 /* ---- input-side prep: merge_close_points (mot3d/utils/filt.py:6-24; examples/soldiers_3d/example.py:29-31) ---- */
 
 /* Per point set s = points [set_ptr[s], set_ptr[s+1]) (one frame): clusters = connected components of "distance <=

@@ -16,6 +16,6 @@ from . import weight_functions, distance_functions, types  # noqa: F401
 from .spec import CostSpec, TrackletCostSpec  # noqa: F401
 from .batch import (DetectionBatch, GraphBatch, HostTracker, build_graphs, solve_graphs, extract_tracks,  # noqa: F401
                     track_batch, tracks_to_lists)
-from .scheduler import shard_graphs, gather_tracks  # noqa: F401
+from .scheduler import shard_graphs, gather_tracks, TrackGather, pack_tracks_host, unpack_tracks_host  # noqa: F401
 from . import online  # noqa: F401
 from ._lib import Mot3dError, version  # noqa: F401

@@ -11,6 +11,8 @@ INF_COST = 1 << 60
 DIR_IN, DIR_OUT = 0, 1
 SOLVE_STATS = 25  # include/mot3d_b200.h: MOT3D_SOLVE_STATS
 FLAG_ENTRY, FLAG_EXIT = 1, 2
+TRACK_START_BIT = 0x80000000
+PEER_HANDLE_BYTES = 64
 
 E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4
 
@@ -102,6 +104,17 @@ SIGNATURES = {
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
     "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_track_payload_words": (_i64, [_i64, _i32]),
+    "mot3d_pack_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_unpack_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_peer_buffer_create": (_i32, [_sz, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p]),
+    "mot3d_peer_buffer_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "mot3d_peer_buffer_close": (_i32, [_vp]),
+    "mot3d_peer_buffer_destroy": (_i32, [_vp]),
+    "mot3d_peer_put": (_i32, [_vp, _vp, _sz, _vp, _vp, _i32, _vp]),
+    "mot3d_peer_wait": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "mot3d_peer_set_word": (_i32, [_vp, _i32, _vp]),
+    "mot3d_peer_wait_word": (_i32, [_vp, _i32, _vp, _vp]),
     "mot3d_merge_close_points": (_i32, [_vp, _i32, _i32, _i32, _vp, ctypes.c_double, _vp, _vp, _vp, _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_track_batch_host": (_i32, [ctypes.POINTER(HostBatch), _PS, ctypes.POINTER(HostResult), _vp, _sz, _i64, _vp]),

@@ -193,6 +193,17 @@ def test_gather_tracks_gloo_world2(built, tmp_path):
     assert "GATHER_OK" in outs[0]
 
 
+def test_track_payload_host_mirror_and_gloo_gather(built):
+    """TrackGather over a gloo group of two processes with ragged shards (host mirror of the device payload)."""
+    port = 31500 + os.getpid() % 2000
+    worker = os.path.join(ROOT, "tests", "gather_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(port), "cpu"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]
+
+
 def test_trajectory_glue(built):
     import mot3d_b200 as mot3d
     traj = [mot3d.Detection2D(i, (i, 0)) for i in [3, 4, 5, 6, 9, 10, 11, 14, 15, 21]]

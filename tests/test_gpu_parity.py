@@ -953,3 +953,59 @@ def test_components_against_scipy():
             assert (cptr[c:c + k] == starts).all() and (cgraph[c:c + k] == g).all()
             c += k
         assert c == n_cg
+
+
+@pytest.mark.gpu
+def test_track_payload_pack_unpack_on_device():
+    """mot3d_pack_tracks == its numpy mirror bit for bit; mot3d_unpack_tracks restores count / ptr / det."""
+    torch = _torch()
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    d = gu.load("c5_window_f50_p100")
+    spec = _spec_from(d["spec"], mot3d)
+    b1 = _batch_from(d, mot3d)
+    # two graphs in one batch (the second one shifted, so that its tracks differ)
+    gp = np.array([0, b1.n, 2 * b1.n], dtype=np.int32)
+    hb, _ = mot3d.DetectionBatch.from_arrays(gp, np.concatenate([b1.frame, b1.frame]),
+                                             np.concatenate([b1.pos.T, b1.pos.T + 0.25]), np.concatenate([b1.conf, b1.conf]))
+    db = hb.to("cuda")
+    gb, sol = mot3d.track_batch(db, spec)
+    n, G = db.n, db.n_graphs
+    L = _lib.lib()
+    payload = torch.full((int(L.mot3d_track_payload_words(n, G)),), -1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.mot3d_pack_tracks(G, db.graph_ptr.data_ptr(), sol.track_count.data_ptr(), sol.track_ptr.data_ptr(),
+                                   sol.track_det.data_ptr(), payload.data_ptr(), st))
+    want = mot3d.pack_tracks_host(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                  sol.track_det.cpu().numpy())
+    assert np.array_equal(payload.cpu().numpy(), want)
+    cnt = torch.zeros(G, dtype=torch.int32, device="cuda")
+    ptr = torch.zeros(n + G + 1, dtype=torch.int32, device="cuda")
+    det = torch.zeros(n, dtype=torch.int32, device="cuda")
+    _lib.check(L.mot3d_unpack_tracks(G, db.graph_ptr.data_ptr(), payload.data_ptr(), cnt.data_ptr(), ptr.data_ptr(),
+                                     det.data_ptr(), st))
+    from mot3d_b200.batch import tracks_to_lists
+    got = tracks_to_lists(gp, cnt.cpu().numpy(), ptr.cpu().numpy(), det.cpu().numpy())
+    assert got == tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(), sol.track_det.cpu().numpy())
+    assert got == mot3d.unpack_tracks_host(gp, want)
+    assert sum(len(t) for t in got[0]) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["p2p", "collective"])
+def test_two_gpu_sharded_solve_and_gather(transport):
+    """Two ranks, one GPU each: shard_graphs over a ragged mix, TrackPipeline per rank, TrackGather to rank 0, compared
+    with one GPU solving everything (tests/gather_worker.py). Skipped on a single-GPU box."""
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    import subprocess
+    import sys
+    port = 33500 + os.getpid() % 2000 + (7 if transport == "p2p" else 0)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gather_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(port), "gpu", transport], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK transport=%s" % transport in outs[0], outs
