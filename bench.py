@@ -16,6 +16,7 @@ dominant kernel (+ roofline_edge_build), cpu_baseline timed on this box's host c
 muSSP solver compiled from the reference's sources (oracle/_ref) when present, else the C port; all host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -310,6 +311,25 @@ def run_ours(args):
     else:
         gather_info = None
 
+    # ---- kernel boundaries inside the solve stage (untimed extra steps; mot3d_solve_trace_events records CUDA events
+    #      between the kernels of the calling thread's next solves): feeds the per-kernel roofline entries
+    SOLVE_PARTS = ["k_components (+offsets, fill)", "k_first_tree", "k_single_track + k_job_order",
+                   "k_ssp_solve (one launch per band, overlapped)", "k_first_path_rule"]
+    solve_part_ms = np.zeros(len(SOLVE_PARTS))
+    tev = [torch.cuda.Event(enable_timing=True) for _ in range(len(SOLVE_PARTS) + 1)]
+    for e in tev:
+        e.record(stream)  # creates the underlying cudaEvent_t
+    tev_arr = (ctypes.c_void_p * len(tev))(*[e.cuda_event for e in tev])
+    TRACE_STEPS = 3
+    for k in range(TRACE_STEPS):
+        flush.fill_(k & 0xff)
+        mot3d._lib.check(mot3d._lib.lib().mot3d_solve_trace_events(tev_arr, len(tev)))
+        pipe.run(dbatch, spec, spec_c)
+        mot3d._lib.check(mot3d._lib.lib().mot3d_solve_trace_events(None, 0))
+        torch.cuda.synchronize(dev)
+        solve_part_ms += np.array([tev[i].elapsed_time(tev[i + 1]) for i in range(len(SOLVE_PARTS))])
+    solve_part_ms /= TRACE_STEPS
+
     # ---- end to end through the C-ABI host-buffer call (pinned host in, pinned host out)
     ht = mot3d.HostTracker(n_max=n, g_max=G, edge_capacity=cap, dim=2, device=dev)
     ht.load(host_batch)
@@ -366,7 +386,7 @@ def run_ours(args):
         t = json.load(open(tf))
         if t.get("seqs") == S:
             traffic_solve, traffic_build = t.get("k_ssp_solve"), t.get("edge_build")
-    roofline = {"bound": "hbm", "kernel": "k_ssp_solve",
+    roofline_stage = {"bound": "hbm", "kernel": "solve stage",
                 "kernels_in_launch_ms": "solve stage = k_components + k_first_tree + k_single_track + k_job_order + "
                                         "k_ssp_solve (giants + main, overlapped) + k_first_path_rule",
                 "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
@@ -393,11 +413,51 @@ def run_ours(args):
                     ["sink_argmin", "list_branch", "stage_and_initial_labels", "walk", "fix_point", "certificate"])},
                 "components_finished_by_certificate_per_graph_mean": float(stats[:, 10].mean()),
                 "components_finished_by_single_track_pass_per_graph_mean": float(stats[:, 24].mean())}
+    # the dominant kernel alone: k_ssp_solve (all band launches; they overlap), bytes = what its relabelling rounds and
+    # its staging pulled (the first tree's share of the counters taken out), time = CUDA events around its launches
+    ssp_bytes = max(solve_bytes - (12.0 * E + 40.0 * n), 0.0)
+    ssp_ms = float(solve_part_ms[3])
+    ssp_gbs = ssp_bytes / (ssp_ms * 1e-3) / 1e9 if ssp_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_ssp_solve", "achieved": ssp_gbs, "peak": peak, "unit": "GB/s",
+                "frac": ssp_gbs / peak, "traffic": traffic_solve, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ssp_bytes, "launch_ms": ssp_ms,
+                "note": "latency bound by construction (dependent relabelling rounds in shared memory); "
+                        "roofline_solve_stage has the whole stage, roofline_kernels every kernel"}
     roofline_build = {"bound": "hbm", "kernel": ("k_frame_sort + k_edge_build_fused" if pipe.fused else
                                  "k_frame_sort + k_edge_build_pruned<count> + scan + <fill> + k_edge_cost"),
                       "achieved": build_gbs, "peak": peak,
                       "unit": "GB/s", "frac": build_gbs / peak, "traffic": traffic_build,
                       "algorithmic_bytes_per_launch": build_bytes, "launch_ms": float(build_ms)}
+
+    # ---- one entry per kernel (or back-to-back kernel group): live CUDA-event time, algorithmic bytes, DRAM traffic of
+    #      the committed ncu capture of this configuration when there is one
+    tk = {}
+    if os.path.exists(tf):
+        t = json.load(open(tf))
+        if t.get("seqs") == S:
+            tk = t.get("per_kernel", {})
+    ft_bytes = 12.0 * E + 40.0 * n  # first tree: every arc (4 B source + 8 B cost) and every node (2 x 20 B) once
+    per_kernel = []
+
+    def kernel_entry(name, ms, nbytes, what):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        per_kernel.append({"kernel": name, "ms": float(ms), "algorithmic_bytes": float(nbytes), "bytes_are": what,
+                           "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "traffic": tk.get(name.split(" ")[0])})
+
+    if pipe.fused:
+        kernel_entry("k_frame_sort", stage_ms[STAGES.index("frame_sort")], n * (4 + 16 + 16 + 4.0),
+                     "keys + positions in, x-sorted positions + permutation out")
+        kernel_entry("k_edge_build_fused", stage_ms[STAGES.index("edge_build")], n * 28.0 + 4.0 * (n + 1) + E * 12.0,
+                     "sorted detections in, row_ptr + 12 B per arc out")
+    kernel_entry(SOLVE_PARTS[0], solve_part_ms[0], 4.0 * E + 4.0 * (n + 1) + 16.0 * n,
+                 "in-CSR structure in, permutation / inverse / component table out")
+    kernel_entry(SOLVE_PARTS[1], solve_part_ms[1], ft_bytes + 24.0 * n,
+                 "12 B per arc + node costs in, distances / parent / branch labels out")
+    kernel_entry(SOLVE_PARTS[2], solve_part_ms[2], 36.0 * n, "first-tree labels in, tracks of single-track components out")
+    kernel_entry(SOLVE_PARTS[3], solve_part_ms[3], max(solve_bytes - ft_bytes, 0.0),
+                 "12 B per arc pull + 20 B per node pull (staging + relabelling rounds, counted by the kernel)")
+    kernel_entry(SOLVE_PARTS[4], solve_part_ms[4], 8.0 * G, "path counts")
+    kernel_entry("k_extract_tracks", stage_ms[STAGES.index("extract")], 20.0 * n, "next / prev in, tracks out")
 
     # ---- CPU baseline on this box (rank 0, N=1 only), bounded sample
     cpu_baseline = None
@@ -429,7 +489,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": ht.d2h_bytes(), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "mot3d_track_batch_host (C ABI, pinned host buffers)"},
             "track_gather": gather_info,
-            "gpu_launches": (LAUNCHES_PER_RUN + (2 if world > 1 else 0)) * args.steps, "roofline": roofline, "roofline_edge_build": roofline_build,
+            "gpu_launches": (LAUNCHES_PER_RUN + (2 if world > 1 else 0)) * args.steps, "roofline": roofline, "roofline_solve_stage": roofline_stage, "roofline_edge_build": roofline_build,
+            "roofline_kernels": per_kernel,
             "cpu_baseline": cpu_baseline, "clocks": clocks, "wall_s_timed_region": wall,
             "n_arcs_per_gpu": int(E), "paths_per_graph_mean": float(pipe.n_paths.cpu().numpy()[:G].mean())}
     print(json.dumps(line))

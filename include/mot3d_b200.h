@@ -93,9 +93,16 @@ const char *mot3d_last_error(void);
 /* ---- graph build: replaces build_graph's loops (mot3d/mot3d.py:75-141) + graph_to_text (:218-226) ------------ */
 
 /* tkey[i] = frame[i] - frame[first of graph] + base(graph), base = running sum of (frame span + max_jump + 1).
- * graph_base_ws: scratch of n_graphs int64. */
+ * graph_base_ws: scratch of n_graphs int64. Preconditions every later stage relies on are checked on the way and
+ * reported by OR-ing bits into *error_flags (device int32, optional; the same word mot3d_edge_build's overflow_flag
+ * uses, so one read-back covers the build): MOT3D_ERR_UNSORTED = the frames of a graph are not non-decreasing,
+ * MOT3D_ERR_KEY_RANGE = the keys of the batch do not fit 31 bits (sum of frame spans too large: split the batch). */
+#define MOT3D_ERR_ARC_CAPACITY 1 /* mot3d_edge_build / mot3d_edge_fill: more arcs than edge_capacity */
+#define MOT3D_ERR_WINDOW 2       /* mot3d_edge_build: more than 2^24 detections inside one time window */
+#define MOT3D_ERR_UNSORTED 4
+#define MOT3D_ERR_KEY_RANGE 8
 int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, int32_t max_jump,
-                        int32_t *tkey_out, int64_t *graph_base_ws, void *stream);
+                        int32_t *tkey_out, int64_t *graph_base_ws, int32_t *error_flags, void *stream);
 
 /* per-detection arc costs: entry (S->pre), node (pre->post, weight_confidence_detections, weight_functions.py:37-38),
  * exit (post->T).  MOT3D_INF_COST where flags forbid the arc. */
@@ -271,6 +278,13 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
                           int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
 
+/* Measurement hook: the calling thread's next mot3d_solve_batch calls record events[k] (cudaEvent_t, may be NULL) on
+ * their stream at the kernel boundaries of the solve: 0 = start, 1 = after the connected components, 2 = after the first
+ * tree, 3 = after the single-track pass and the queue order, 4 = after the successive-shortest-path launches, 5 = end.
+ * events = NULL switches it off. The array must stay alive while the hook is set. */
+#define MOT3D_SOLVE_TRACE_EVENTS 6
+int32_t mot3d_solve_trace_events(void **events, int32_t n_events);
+
 /* ---- trajectories: replaces _run_ssp's tail (mot3d/mot3d.py:165-184) ---------------------------------------- */
 
 /* Tracks of graph g, ordered by their first detection (= the reference's DFS order over SOURCE's successors):
@@ -327,6 +341,22 @@ int32_t mot3d_peer_wait_word(const int32_t *word, int32_t need, int32_t *timeout
 int32_t mot3d_merge_close_points(const int32_t *set_ptr, int32_t n_sets, int32_t max_set_points, int32_t dim,
                                  const double *points, double eps, int32_t *label_out, int32_t *cluster_count_out,
                                  double *merged_out, void *stream);
+
+/* ---- input-side prep: color_histogram (mot3d/distance_functions.py:10-19) ------------------------------------- */
+
+/* Histograms of image patches, all boxes of an image in one launch, written straight into the `hist` array of
+ * mot3d_dets. For box b the patch is image[ymin:ymax, xmin:xmax] (numpy slice semantics: bounds clipped to the image):
+ * 8-bit RGB -> CIE Lab exactly as cv2.cvtColor(patch, cv2.COLOR_RGB2LAB) on uint8 (integer tables, bit-exact), then per
+ * requested channel np.histogram(values, bins=n_bins, range=(0, 255)) minus its mean.
+ *   image_rgb    device uint8 [height][row_stride_bytes], pixels interleaved R, G, B
+ *   boxes        device int32 [n_boxes][4] = xmin, ymin, xmax, ymax
+ *   channels     HOST int32 [n_channels], Lab channel per output row (reference default (0, 1, 2))
+ *   bin_of_value device uint16 [256]: histogram bin of every 8-bit value; may be NULL for n_bins == 255 (the reference's
+ *                default: bin v for v < 255, value 255 joins bin 254)
+ *   hist_out     device float64 [n_boxes][n_channels][n_bins] */
+int32_t mot3d_color_histograms(const uint8_t *image_rgb, int32_t height, int32_t width, int64_t row_stride_bytes,
+                               const int32_t *boxes, int32_t n_boxes, const int32_t *channels, int32_t n_channels,
+                               int32_t n_bins, const uint16_t *bin_of_value, double *hist_out, void *stream);
 
 /* ---- one call with HOST buffers: pack -> H2D -> build -> solve -> tracks -> D2H ------------------------------ */
 

@@ -15,6 +15,7 @@ TRACK_START_BIT = 0x80000000
 PEER_HANDLE_BYTES = 64
 
 E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = -1, -2, -3, -4
+ERR_ARC_CAPACITY, ERR_WINDOW, ERR_UNSORTED, ERR_KEY_RANGE = 1, 2, 4, 8  # MOT3D_ERR_*: bits of the build's flag word
 
 
 class Mot3dError(RuntimeError):
@@ -84,7 +85,7 @@ _PD, _PS = ctypes.POINTER(Dets), ctypes.POINTER(CostSpecC)
 SIGNATURES = {
     "mot3d_version": (ctypes.c_char_p, []),
     "mot3d_last_error": (ctypes.c_char_p, []),
-    "mot3d_make_keys": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "mot3d_make_keys": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mot3d_node_costs": (_i32, [_PD, _PS, _vp, _vp, _vp, _vp]),
     "mot3d_frame_sort": (_i32, [_PD, _vp]),
     "mot3d_edge_count": (_i32, [_PD, _PS, _i32, _vp, _vp]),
@@ -103,6 +104,7 @@ SIGNATURES = {
     "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
+    "mot3d_solve_trace_events": (_i32, [_vp, _i32]),
     "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_track_payload_words": (_i64, [_i64, _i32]),
     "mot3d_pack_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -116,6 +118,8 @@ SIGNATURES = {
     "mot3d_peer_set_word": (_i32, [_vp, _i32, _vp]),
     "mot3d_peer_wait_word": (_i32, [_vp, _i32, _vp, _vp]),
     "mot3d_merge_close_points": (_i32, [_vp, _i32, _i32, _i32, _vp, ctypes.c_double, _vp, _vp, _vp, _vp]),
+    "mot3d_color_histograms": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, ctypes.POINTER(ctypes.c_int32), _i32, _i32, _vp, _vp,
+                                      _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_track_batch_host": (_i32, [ctypes.POINTER(HostBatch), _PS, ctypes.POINTER(HostResult), _vp, _sz, _i64, _vp]),
 }

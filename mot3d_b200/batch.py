@@ -142,6 +142,16 @@ def _dets_struct(b, tkey, spec, sorted_pos=None, sorted_perm=None):
     return d
 
 
+def _raise_key_errors(flag):
+    """MOT3D_ERR_UNSORTED / MOT3D_ERR_KEY_RANGE left by mot3d_make_keys (include/mot3d_b200.h)."""
+    if flag & _lib.ERR_UNSORTED:
+        raise ValueError("the detections of a graph are not sorted by frame (DetectionBatch.from_arrays(sort=True) "
+                         "sorts them; mot3d.build_graph always does)")
+    if flag & _lib.ERR_KEY_RANGE:
+        raise _lib.Mot3dError(_lib.E_UNSUPPORTED, "the frame spans of the batch add up to more than 2^31 time keys: "
+                              "split the batch")
+
+
 def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=None, pruned=True, fused=True):
     """Graph build on the device. `batch` must already live on a CUDA device (DetectionBatch.to).
     pruned=True: per-frame x-sorted copies + window search; fused=True (needs pruned): the single-pass kernel
@@ -164,11 +174,12 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
     gb.dets, gb.spec, gb.cspec, gb.direction = batch, spec, cs_real, direction
     i32 = dict(dtype=torch.int32, device=dev)
     i64 = dict(dtype=torch.int64, device=dev)
+    overflow = torch.zeros(1, **i32)  # MOT3D_ERR_* bits of the keys and the arc build, read back once
     if keys is None:
         tkey = torch.empty(max(n, 1), **i32)
         base = torch.empty(max(G, 1), **i64)
         _lib.check(L.mot3d_make_keys(_ptr(batch.frame), _ptr(batch.graph_ptr), G, spec.max_jump, _ptr(tkey),
-                                     _ptr(base), st))
+                                     _ptr(base), _ptr(overflow), st))
     else:
         tkey = keys
     gb.tkey = tkey
@@ -190,23 +201,23 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
         row_ptr = torch.empty(n + 1, **i32)
         ws_bytes = L.mot3d_edge_build_workspace_bytes(n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        overflow = torch.zeros(1, **i32)
         cap = max(16 * n, 1024)
         while True:
             gb.col = torch.empty(cap, **i32)
             gb.cost = torch.empty(cap, **i64)
             gb.weight = torch.empty(cap, dtype=torch.float64, device=dev) if need_w else None
-            overflow.zero_()
             _lib.check(L.mot3d_edge_build(ctypes.byref(d), ctypes.byref(cs), direction, 0, n, _ptr(row_ptr), cap,
                                           _ptr(gb.col), _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), None, None,
                                           _ptr(ws), ws_bytes, st))
             n_edges = int(row_ptr[n].item())  # the one host read-back of the build
             flag = int(overflow.item())
-            if flag & 2:
+            _raise_key_errors(flag)
+            if flag & _lib.ERR_WINDOW:
                 raise _lib.Mot3dError(_lib.E_UNSUPPORTED, "more than 2^24 detections inside one time window")
             if n_edges <= cap:
                 break
             cap = n_edges
+            overflow.zero_()
         gb.n_edges = n_edges
         gb.row_ptr = row_ptr
         gb.col = gb.col[:max(n_edges, 1)]
@@ -226,7 +237,7 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
         gb.col = torch.empty(max(n_edges, 1), **i32)
         gb.cost = torch.empty(max(n_edges, 1), **i64)
         gb.weight = torch.empty(max(n_edges, 1), dtype=torch.float64, device=dev) if need_w else None
-        overflow = torch.zeros(1, **i32)
+        _raise_key_errors(int(overflow.item()))
         _lib.check(L.mot3d_edge_fill(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), n_edges,
                                      _ptr(gb.col), _ptr(gb.cost), _ptr(gb.weight), _ptr(overflow), st))
     if views_mode:

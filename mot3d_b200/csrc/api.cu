@@ -84,7 +84,7 @@ __global__ void k_track_ptr_pack(int n_graphs, const int32_t *__restrict__ graph
 
 namespace m3 {
 int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
-                               int32_t *tkey, cudaStream_t st);
+                               int32_t *tkey, int32_t *err, cudaStream_t st);
 int32_t launch_frame_sort_range(const mot3d_dets *d, int64_t row_begin, int64_t row_end, cudaStream_t st);
 }  // namespace m3
 
@@ -256,7 +256,7 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
             M3_CUDA(cudaStreamWaitEvent(st, in_done[pc], 0));
         }
         if (m > 0) {
-            if ((rc = launch_make_keys_based(d_frame, d_gptr + g_lo, g_hi - g_lo, d_gbase + g_lo, d_tkey, st))) return rc;
+            if ((rc = launch_make_keys_based(d_frame, d_gptr + g_lo, g_hi - g_lo, d_gbase + g_lo, d_tkey, d_over, st))) return rc;
             mot3d_dets dp = d;  // per-detection outputs of this piece: plain offsets
             dp.n = m;
             dp.conf = d_conf + r0;
@@ -410,8 +410,16 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
                     const int32_t a = hb->graph_ptr[g], b = hb->graph_ptr[g + 1];
                     if (b - a > max_nodes) max_nodes = b - a;
                     hb_base[g - ga] = key_base;
-                    key_base += (b > a ? (int64_t)hb->frame[b - 1] - (int64_t)hb->frame[a] : 0) + spec->max_jump + 1;
+                    const int64_t span = b > a ? (int64_t)hb->frame[b - 1] - (int64_t)hb->frame[a] : 0;
+                    key_base += (span > 0 ? span : 0) + spec->max_jump + 1;
                 }
+            }
+            if (key_base < 0 || key_base > (int64_t)0x7fffffff - MOT3D_MAX_JUMP - 1) {
+                // (unsorted frames can make a span negative: the device check of the keys reports those)
+                set_error("the frame spans of graphs [%d, %d) add up to %lld time keys, beyond 31 bits: split the batch",
+                          ga, gb, (long long)key_base);
+                rc = MOT3D_E_UNSUPPORTED;
+                break;
             }
             // the arc buffer is shared out by detection count; a chunk that needs more sends the batch through again
             // in one piece, so the capacity the caller has to provide does not depend on the chunking
@@ -480,8 +488,17 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             const int64_t nd = (int64_t)hb->graph_ptr[cut[c + 1]] - hb->graph_ptr[cut[c]];
             const int64_t cap = nc == 1 ? edge_capacity : (int64_t)((double)edge_capacity * ((double)nd / (double)n));
             edges += ctx->pinned[2 * c + 1];
-            if (ctx->pinned[2 * c] || ctx->pinned[2 * c + 1] > cap) retry = true;
+            const int32_t flag = ctx->pinned[2 * c];
+            if (flag & MOT3D_ERR_UNSORTED) {
+                set_error("the frames of a graph are not non-decreasing (graphs [%d, %d))", cut[c], cut[c + 1]);
+                rc = MOT3D_E_INVALID;
+            } else if (flag & (MOT3D_ERR_KEY_RANGE | MOT3D_ERR_WINDOW)) {
+                set_error("time keys beyond 31 bits or more than 2^24 detections inside one time window");
+                rc = MOT3D_E_UNSUPPORTED;
+            }
+            if ((flag & MOT3D_ERR_ARC_CAPACITY) || ctx->pinned[2 * c + 1] > cap) retry = true;
         }
+        if (rc != MOT3D_OK) break;
         res->n_edges = edges;
         // what travelled: graph_ptr + key bases, frame, positions, confidences [, flags, boxes] in; counts, totals,
         // track_det, the (packed) track_ptr and two flags per chunk out

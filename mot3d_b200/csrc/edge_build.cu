@@ -303,7 +303,7 @@ __global__ void k_graph_base(const int32_t *__restrict__ frame, const int32_t *_
         if (g < n_graphs) {
             int a = graph_ptr[g], b = graph_ptr[g + 1];
             int64_t span = (b > a) ? ((int64_t)frame[b - 1] - (int64_t)frame[a]) : 0;
-            v = span + max_jump + 1;
+            v = (span > 0 ? span : 0) + max_jump + 1;  // (negative: unsorted frames, reported by k_make_keys)
         }
         int64_t incl = v;
 #pragma unroll
@@ -335,14 +335,33 @@ __global__ void k_graph_base(const int32_t *__restrict__ frame, const int32_t *_
 
 __global__ void __launch_bounds__(256) k_make_keys(const int32_t *__restrict__ frame,
                                                    const int32_t *__restrict__ graph_ptr, int n_graphs,
-                                                   const int64_t *__restrict__ base, int32_t *__restrict__ tkey) {
-    // one block per graph (grid-stride over graphs): a 5 000-detection window is 20 coalesced steps
+                                                   const int64_t *__restrict__ base, int32_t *__restrict__ tkey,
+                                                   int32_t *__restrict__ err) {
+    // one block per graph (grid-stride over graphs): a 5 000-detection window is 20 coalesced steps. Every build path
+    // and the solver's layering rely on keys that are non-decreasing and fit 32 bits with room for a jump: both are
+    // checked on the way (err: MOT3D_ERR_UNSORTED / MOT3D_ERR_KEY_RANGE, reported by the caller of the build).
+    // A graph that fails gets harmless keys (all equal / clamped: monotone, no arcs worth anything), so that the kernels
+    // behind this one stay inside their arrays whatever the caller does with the flag.
+    int bad = 0;
+    const int64_t key_max = (int64_t)0x7fffffff - MOT3D_MAX_JUMP - 1;
     for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
         const int a = graph_ptr[g], b = graph_ptr[g + 1];
         if (b <= a) continue;
+        int unsorted = 0;
+        for (int i = a + 1 + threadIdx.x; i < b; i += blockDim.x) unsorted |= frame[i - 1] > frame[i] ? 1 : 0;
+        unsorted = __syncthreads_or(unsorted);
+        if (unsorted) bad |= MOT3D_ERR_UNSORTED;
         const int64_t shift = base[g] - (int64_t)frame[a];
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) tkey[i] = (int32_t)((int64_t)frame[i] + shift);
+        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+            int64_t key = unsorted ? base[g] : (int64_t)frame[i] + shift;
+            if (key < 0 || key > key_max) {
+                bad |= MOT3D_ERR_KEY_RANGE;
+                key = key < 0 ? 0 : key_max;
+            }
+            tkey[i] = (int32_t)key;
+        }
     }
+    if (bad && err) atomicOr(err, bad);
 }
 
 // ---------------------------------------------------------------------------------------- exclusive scan (3 phases)
@@ -538,7 +557,7 @@ using namespace m3;
 extern "C" {
 
 int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, int32_t max_jump,
-                        int32_t *tkey_out, int64_t *graph_base_ws, void *stream) {
+                        int32_t *tkey_out, int64_t *graph_base_ws, int32_t *error_flags, void *stream) {
     M3_CHECK_ARG(n_graphs >= 0, "n_graphs < 0");
     if (n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(frame && graph_ptr && tkey_out && graph_base_ws, "NULL pointer");
@@ -546,7 +565,7 @@ int32_t mot3d_make_keys(const int32_t *frame, const int32_t *graph_ptr, int32_t 
     k_graph_base<<<1, 1024, 0, st>>>(frame, graph_ptr, n_graphs, max_jump, graph_base_ws);
     M3_LAUNCH_CHECK("k_graph_base");
     int blocks = n_graphs < 148 * 64 ? n_graphs : 148 * 64;
-    k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, graph_base_ws, tkey_out);
+    k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, graph_base_ws, tkey_out, error_flags);
     M3_LAUNCH_CHECK("k_make_keys");
     return MOT3D_OK;
 }
@@ -571,10 +590,10 @@ namespace m3 {
 // keys of graphs [0, n_graphs) of graph_ptr with their bases given (mot3d_track_batch_host computes them on the host and
 // sends the batch through in pieces)
 int32_t launch_make_keys_based(const int32_t *frame, const int32_t *graph_ptr, int32_t n_graphs, const int64_t *base,
-                               int32_t *tkey, cudaStream_t st) {
+                               int32_t *tkey, int32_t *err, cudaStream_t st) {
     if (n_graphs <= 0) return MOT3D_OK;
     int blocks = n_graphs < 148 * 64 ? n_graphs : 148 * 64;
-    k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, base, tkey);
+    k_make_keys<<<blocks, 256, 0, st>>>(frame, graph_ptr, n_graphs, base, tkey, err);
     M3_LAUNCH_CHECK("k_make_keys");
     return MOT3D_OK;
 }

@@ -164,6 +164,10 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     const int32_t *tkey = p.tkey + g0;
     const int32_t *in_ptr = p.in_ptr + g0;
     const int32_t *inv = p.comp_inv + g0;
+    // first_cost / first_sink are indexed by component, and the components of a graph may be numbered anywhere in
+    // [0, n_total): the whole batch's arrays are cleared by mot3d_solve_batch before this launch
+    for (int i = tid; i < n; i += T)
+        if (p.path_cost) p.path_cost[g0 + i] = INF;
     if ((int64_t)in_ptr[n] > p.arc_capacity) {  // arc buffer overflow (reported by the fill kernel): skipped
         if (tid == 0) p.n_paths[g] = -1;
         for (int i = tid; i < n; i += T) {
@@ -171,12 +175,6 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
             p.prev_out[g0 + i] = NONE;
         }
         return;
-    }
-    for (int i = tid; i < n; i += T) {  // regrouped positions of this graph are [g0, g0 + n) as well
-        const int q = g0 + i;  // (distances, parent and branch labels are written by the sweep, reachable or not)
-        p.first_cost[q] = INF;
-        p.first_sink[q] = -1;
-        if (p.path_cost) p.path_cost[q] = INF;
     }
     int32_t *lvl = p.ws_lvl + g0 + g;
     int L = 0;
@@ -589,6 +587,13 @@ __global__ void k_extract_tracks(int n_graphs, const int32_t *__restrict__ graph
 
 static size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// measurement hook (mot3d_solve_trace_events): events recorded at the kernel boundaries of the next solve of this thread
+static thread_local cudaEvent_t *g_trace_events = nullptr;
+static thread_local int g_trace_count = 0;
+static inline void trace_mark(int k, cudaStream_t st) {
+    if (g_trace_events && k < g_trace_count && g_trace_events[k]) cudaEventRecord(g_trace_events[k], st);
+}
+
 // ---- per-device facts and launch parameters are looked up once, not on every call
 // Launch shapes of the bands: threads per block, blocks per SM. Band SM_BANDS = the global staging area.
 static const int kBandThreads[SM_BANDS + 1] = {128, 256, 512, 256};
@@ -741,14 +746,18 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 
     cudaStream_t st = (cudaStream_t)stream;
     M3_CUDA(cudaMemsetAsync(p.job_meta, 0, JOB_META_INTS * sizeof(int32_t), st));
+    M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
+    trace_mark(0, st);
     // 1. connected components of every graph, detections regrouped by component
     int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
                                 comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
     if (rc) return rc;
+    trace_mark(1, st);
     // 2. first shortest-path tree per graph: 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of
     //    the block
     k_first_tree<2><<<n_graphs, 256, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_tree");
+    trace_mark(2, st);
     // 3. successive shortest paths per component, one launch per band of the work queue (see k_job_order)
     const DevInfo *di = dev_info();
     if (!di) return cuda_fail(cudaGetLastError(), "device attributes / shared memory limits of the solver kernels");
@@ -774,6 +783,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         k_job_order<<<(unsigned)jblocks, 256, 0, st>>>(p);
     }
     M3_LAUNCH_CHECK("k_job_order");
+    trace_mark(3, st);
     // Which shared-memory bands can hold a component of this batch at all: a component of n detections needs at most
     // staging_bytes(n, n (n - 1) / 2). The launch for the global staging area is always there (costs beyond 32 bits
     // are only known on the device); so is band 0.
@@ -813,9 +823,17 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         }
     }
     M3_LAUNCH_CHECK("k_ssp_solve");
+    trace_mark(4, st);
     // 4. the reference's "first path is always kept" rule, per graph
     k_first_path_rule<<<(n_graphs + 127) / 128, 128, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_path_rule");
+    trace_mark(5, st);
+    return MOT3D_OK;
+}
+
+int32_t mot3d_solve_trace_events(void **events, int32_t n_events) {
+    g_trace_events = (cudaEvent_t *)events;
+    g_trace_count = events ? n_events : 0;
     return MOT3D_OK;
 }
 

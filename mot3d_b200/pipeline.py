@@ -81,7 +81,7 @@ class TrackPipeline(object):
             max_nodes = batch.max_graph_nodes()
         rec(0)
         _lib.check(L.mot3d_make_keys(_ptr(batch.frame), _ptr(batch.graph_ptr), G, spec.max_jump, _ptr(self.tkey),
-                                     _ptr(self.gbase), st))
+                                     _ptr(self.gbase), _ptr(self.overflow), st))
         rec(1)
         d = _dets_struct(batch, self.tkey, spec, self.sorted_pos, self.sorted_perm)
         _lib.check(L.mot3d_node_costs(ctypes.byref(d), ctypes.byref(cs), _ptr(self.entry_cost), _ptr(self.node_cost),
@@ -124,7 +124,11 @@ class TrackPipeline(object):
         self._n, self._G = n, G
 
     def check_overflow(self):
-        if int(self.overflow.item()) != 0:
+        flag = int(self.overflow.item())
+        if flag & (_lib.ERR_UNSORTED | _lib.ERR_KEY_RANGE):
+            from .batch import _raise_key_errors
+            _raise_key_errors(flag)
+        if flag != 0:
             raise _lib.Mot3dError(_lib.E_CAPACITY, "edge capacity %d too small (batch has %d arcs)" %
                                   (self.edge_capacity, int(self.row_ptr[self._n].item())))
 

@@ -398,9 +398,42 @@ def case_merge_close_points(mot3d):
                                                                          len(groups), os.path.getsize(path) // 1024))
 
 
+def case_color_histogram(mot3d):
+    """(N3) the reference's color_histogram (mot3d/distance_functions.py:10-19, cv2 + numpy) on patches of a seeded
+    synthetic RGB frame, cropped the way the feeder does (projects/PETS2009S2L1/feeders.py:104:
+    img[ymin:ymax, xmin:xmax]): default arguments, a channel subset, other bin counts, boxes reaching beyond the
+    image (numpy clips the slice)."""
+    rng = np.random.RandomState(11)
+    H, W = 240, 320
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 255 // (W - 1)), (yy * 255 // (H - 1)), ((xx + yy) * 255 // (H + W - 2))], axis=-1)
+    img = np.clip(img + rng.randint(-40, 41, size=img.shape), 0, 255).astype(np.uint8)
+    img[100:140, 200:260] = rng.randint(0, 256, size=(40, 60, 3))  # a patch of arbitrary colours
+    img[0:30, 0:30] = 255
+    img[30:60, 0:30] = 0
+    boxes = [(10, 20, 60, 140), (200, 100, 260, 140), (0, 0, 30, 60), (150, 30, 151, 31), (300, 200, 340, 260),
+             (5, 5, 320, 240), (100, 50, 180, 230), (250, 10, 319, 90)]
+    for _ in range(8):
+        x0, y0 = rng.randint(0, W - 8), rng.randint(0, H - 8)
+        boxes.append((x0, y0, x0 + rng.randint(4, 90), y0 + rng.randint(4, 120)))
+    boxes = np.array(boxes, dtype=np.int32)
+    out = dict(image=img, boxes=boxes)
+    for tag, kw in (("default", {}), ("ch12_n64", dict(channels=(1, 2), N=64)), ("ch0_n100", dict(channels=(0,), N=100)),
+                    ("ch210_n300", dict(channels=(2, 1, 0), N=300))):
+        hs = []
+        for xmin, ymin, xmax, ymax in boxes:
+            hs.append(np.array(mot3d.color_histogram(img[ymin:ymax, xmin:xmax], **kw), dtype=np.float64))
+        out["hist_" + tag] = np.stack(hs)
+    path = os.path.join(HERE, "color_histogram.npz")
+    np.savez_compressed(path, **out)
+    print("%-22s boxes=%d (%d KB)" % ("color_histogram", len(boxes), os.path.getsize(path) // 1024))
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "color_histogram" in sys.argv[1:]:
+        return case_color_histogram(mot3d)
     if "c3_merge_close_points" in sys.argv[1:]:
         return case_merge_close_points(mot3d)
     if "c3_synth_multiview_tracklets" in sys.argv[1:]:
@@ -409,6 +442,7 @@ def main():
         return case_online(mot3d)
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
+    case_color_histogram(mot3d)
     case_merge_close_points(mot3d)
     case_multiview(mot3d, wf)
     case_multiview_tracklets(mot3d, wf)

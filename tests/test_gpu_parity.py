@@ -1009,3 +1009,41 @@ def test_two_gpu_sharded_solve_and_gather(transport):
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK transport=%s" % transport in outs[0], outs
+
+
+def test_key_preconditions_are_reported():
+    """Time keys must be non-decreasing inside a graph and fit 31 bits over the batch (csrc/edge_build.cu: k_make_keys);
+    both are reported by the device path and by the host-buffer call instead of producing wrong arcs."""
+    import mot3d_b200 as mot3d
+    d = gu.load("c5_small_f30_p12")
+    spec = _spec_from(d["spec"], mot3d)
+    n = len(d["frame"])
+    dev = _torch().device("cuda")
+    # (1) frames of a graph out of order, sorting switched off
+    fr = d["frame"].copy()
+    fr[[3, n - 4]] = fr[[n - 4, 3]]
+    b, _ = mot3d.DetectionBatch.from_arrays(np.array([0, n]), fr, d["pos"], d["conf"], sort=False)
+    with pytest.raises(ValueError):
+        mot3d.build_graphs(b.to(dev), spec)
+    ht = mot3d.HostTracker(n_max=n, g_max=1, edge_capacity=20000, dim=2)
+    ht.load(b)
+    with pytest.raises(mot3d.Mot3dError) as e:
+        ht.run(spec.to_c())
+    assert e.value.code == -1
+    # (2) sparse frame indices: three graphs spanning 2^30 frames each do not fit the batch's 31-bit key space
+    fr = d["frame"].astype(np.int64).copy()
+    fr[fr == fr.max()] = 1 << 30
+    b3, _ = mot3d.DetectionBatch.from_arrays(np.array([0, n, 2 * n, 3 * n]), np.r_[fr, fr, fr],
+                                             np.r_[d["pos"], d["pos"], d["pos"]], np.r_[d["conf"], d["conf"], d["conf"]])
+    with pytest.raises(mot3d.Mot3dError) as e:
+        mot3d.build_graphs(b3.to(dev), spec)
+    assert e.value.code == -4
+    ht3 = mot3d.HostTracker(n_max=3 * n, g_max=3, edge_capacity=60000, dim=2)
+    ht3.load(b3)
+    with pytest.raises(mot3d.Mot3dError) as e:
+        ht3.run(spec.to_c())
+    assert e.value.code == -4
+    # one such graph alone is fine, and equals the graph with the gap closed up to max_jump + 1
+    b1, _ = mot3d.DetectionBatch.from_arrays(np.array([0, n]), fr, d["pos"], d["conf"])
+    g1 = mot3d.build_graphs(b1.to(dev), spec)
+    assert g1.n_edges > 0
