@@ -745,6 +745,8 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.n_cgraphs = n_cgraphs;
 
     cudaStream_t st = (cudaStream_t)stream;
+    const DevInfo *di = dev_info();
+    if (!di) return cuda_fail(cudaGetLastError(), "device attributes / shared memory limits of the solver kernels");
     M3_CUDA(cudaMemsetAsync(p.job_meta, 0, JOB_META_INTS * sizeof(int32_t), st));
     M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
     trace_mark(0, st);
@@ -759,8 +761,6 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     M3_LAUNCH_CHECK("k_first_tree");
     trace_mark(2, st);
     // 3. successive shortest paths per component, one launch per band of the work queue (see k_job_order)
-    const DevInfo *di = dev_info();
-    if (!di) return cuda_fail(cudaGetLastError(), "device attributes / shared memory limits of the solver kernels");
     const int n_sm = di->n_sm;
     for (int b = 0; b < SM_BANDS; b++) {
         p.band_bytes[b] = di->band_bytes[b];
