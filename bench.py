@@ -133,7 +133,10 @@ def _cpu_window(args):
     n = len(frame)
     row_ptr, col, w = oracle.build_transitions(frame, pos, spec)
     tail, head, ww = oracle.graph_arcs(n, 1.0, oracle.node_weights(np.full(n, 0.9), spec), 0.0, row_ptr, col, w)
-    if use_ref:
+    if use_ref == "text":  # what mot3d itself does: graph_to_text lines -> wrapper.cpp's parse -> muSSP
+        lines = oracle.arcs_to_text(2 * n + 2, tail, head, ww)
+        res = oracle.mussp_solve_text(lines, len(tail))
+    elif use_ref:
         res = oracle.mussp_solve(2 * n + 2, tail, head, np.round(ww, 7))
     else:
         res = oracle.ssp_solve(2 * n + 2, tail, head, oracle.quantise(ww))
@@ -478,6 +481,23 @@ def run_ours(args):
                                   (len(wins), "vendored muSSP from the reference zip (oracle/_ref)" if use_ref else
                                    "C port (oracle/ssp_oracle.c)", os.cpu_count() or 1),
                         "ms_per_window": 1e3 * dt / len(wins)}
+        if use_ref:  # the same windows through the reference's text interface (mot3d/mot3d.py:218-226,
+            # wrapper.cpp:39-88), fewer of them
+            t0 = time.time()
+            done_t = sum(_cpu_window((f, p, "text")) for f, p in wins[:8])
+            dt_t = time.time() - t0
+            cpu_baseline["text_interface"] = {"value": done_t / dt_t, "unit": "detections/s", "cores": 1,
+                                              "sample": "%d of those windows: graph_to_text lines + wrapper.cpp's parse "
+                                                        "+ muSSP" % min(8, len(wins)),
+                                              "ms_per_window": 1e3 * dt_t / min(8, len(wins))}
+
+    # ---- one graph at a time (SURVEY.md 8d metric ii): p50 / p99 per window on the reference's configurations, beside
+    #      the reference's CPU path (tools/window_latency.py); N=1 only, bounded
+    latency = None
+    if world == 1 and not args.no_latency:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import window_latency
+        latency = window_latency.measure(reps=args.latency_reps, budget_s=3.0, cpu=not args.no_cpu)
 
     line = {"metric": METRIC, "value": value, "unit": "detections/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -491,7 +511,7 @@ def run_ours(args):
             "track_gather": gather_info,
             "gpu_launches": (LAUNCHES_PER_RUN + (2 if world > 1 else 0)) * args.steps, "roofline": roofline, "roofline_solve_stage": roofline_stage, "roofline_edge_build": roofline_build,
             "roofline_kernels": per_kernel,
-            "cpu_baseline": cpu_baseline, "clocks": clocks, "wall_s_timed_region": wall,
+            "cpu_baseline": cpu_baseline, "latency": latency, "clocks": clocks, "wall_s_timed_region": wall,
             "n_arcs_per_gpu": int(E), "paths_per_graph_mean": float(pipe.n_paths.cpu().numpy()[:G].mean())}
     print(json.dumps(line))
     if world > 1:
@@ -508,6 +528,8 @@ def main():
     ap.add_argument("--seqs", type=int, default=60, help="sequences (of 20 windows) per GPU and step")
     ap.add_argument("--cpu-windows", type=int, default=40, help="windows in the single-thread CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the per-window latency section")
+    ap.add_argument("--latency-reps", type=int, default=40)
     ap.add_argument("--unfused", action="store_true", help="count -> scan -> fill graph build instead of the "
                     "single-pass kernel (device-resident arm only)")
     args = ap.parse_args()

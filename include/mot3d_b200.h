@@ -278,6 +278,13 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
                           int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
 
+/* path_cost_out of mot3d_solve_batch -> per graph the accepted path costs ascending (the order muSSP finds them,
+ * wrapper.cpp:199-267) at the front of the graph's slice, MOT3D_INF_COST behind them. In place; scratch: int64 [n_total].
+ * Quadratic in the paths of one graph: a graph with more than max_paths of them is left as it is and *too_many_flag
+ * (device int32, caller clears it) is set. */
+int32_t mot3d_order_path_costs(int32_t n_graphs, const int32_t *graph_ptr, int64_t *path_cost, int64_t *scratch,
+                               int32_t max_paths, int32_t *too_many_flag, void *stream);
+
 /* Measurement hook: the calling thread's next mot3d_solve_batch calls record events[k] (cudaEvent_t, may be NULL) on
  * their stream at the kernel boundaries of the solve: 0 = start, 1 = after the connected components, 2 = after the first
  * tree, 3 = after the single-track pass and the queue order, 4 = after the successive-shortest-path launches, 5 = end.

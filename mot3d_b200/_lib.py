@@ -104,6 +104,7 @@ SIGNATURES = {
     "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
+    "mot3d_order_path_costs": (_i32, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mot3d_solve_trace_events": (_i32, [_vp, _i32]),
     "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_track_payload_words": (_i64, [_i64, _i32]),

@@ -272,7 +272,7 @@ class Solution(object):
         self.track_count = self.track_ptr = self.track_det = None
 
 
-def solve_graphs(gb, want_path_costs=True):
+def solve_graphs(gb, want_path_costs=False):
     L = _lib.lib()
     if gb.direction != _lib.DIR_IN:
         raise ValueError("the solver pulls over in-arcs: build with direction=DIR_IN")
@@ -302,11 +302,16 @@ def solve_graphs(gb, want_path_costs=True):
     if want_path_costs and n:
         # the kernel leaves the accepted path costs grouped by connected component inside every graph's slice
         # (MOT3D_INF_COST elsewhere); present them per graph in the order the reference finds them (ascending)
-        gp = b.graph_ptr.to(torch.int64)
-        gid = torch.repeat_interleave(torch.arange(G, device=dev), gp[1:] - gp[:-1])
-        v, o = torch.sort(sol.path_cost[:n], stable=True)
-        _, o2 = torch.sort(gid[o], stable=True)
-        sol.path_cost = torch.cat([v[o2], sol.path_cost[n:]])
+        scratch = torch.empty(n, **i64)
+        many = torch.zeros(1, **i32)
+        _lib.check(L.mot3d_order_path_costs(G, _ptr(b.graph_ptr), _ptr(sol.path_cost), _ptr(scratch), 8192, _ptr(many),
+                                            st))
+        if int(many.item()):  # a graph with more than 8192 tracks: not worth a kernel of its own
+            gp = b.graph_ptr.to(torch.int64)
+            gid = torch.repeat_interleave(torch.arange(G, device=dev), gp[1:] - gp[:-1])
+            v, o = torch.sort(sol.path_cost[:n], stable=True)
+            _, o2 = torch.sort(gid[o], stable=True)
+            sol.path_cost = torch.cat([v[o2], sol.path_cost[n:]])
     return sol
 
 
@@ -337,10 +342,10 @@ def tracks_to_lists(graph_ptr, track_count, track_ptr, track_det):
     return out
 
 
-def track_batch(batch, spec):
+def track_batch(batch, spec, want_path_costs=False):
     """build + solve + extract on the device; returns (GraphBatch, Solution)."""
     gb = build_graphs(batch, spec)
-    sol = solve_graphs(gb)
+    sol = solve_graphs(gb, want_path_costs=want_path_costs)
     extract_tracks(gb, sol)
     return gb, sol
 

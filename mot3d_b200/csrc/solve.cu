@@ -539,6 +539,58 @@ __global__ void k_first_path_rule(const SolveParams p) {
     if (p.path_cost) p.path_cost[p.cgraph_ptr[c_begin]] = best;
 }
 
+// ---- accepted path costs per graph in the order the reference finds them (ascending: successive shortest paths never
+//      get cheaper). The solver leaves them grouped by component inside the graph's slice, MOT3D_INF_COST elsewhere.
+//      One block per graph: stable compaction of the entries into `scratch`, then every entry is written at its rank
+//      (ties by position: equal values are indistinguishable), the rest of the slice is MOT3D_INF_COST.
+//      Quadratic in the number of paths of ONE graph (tiles of the compacted list go through shared memory).
+constexpr int PC_TILE = 2048;
+__global__ void __launch_bounds__(256) k_order_path_costs(int n_graphs, const int32_t *__restrict__ graph_ptr,
+                                                          int64_t *__restrict__ path_cost, int64_t *__restrict__ scratch,
+                                                          int32_t *__restrict__ too_many, int max_paths) {
+    __shared__ int s_scan[33];
+    __shared__ int64_t s_tile[PC_TILE];
+    const int g = blockIdx.x;
+    const int g0 = graph_ptr[g];
+    const int n = graph_ptr[g + 1] - g0;
+    const int T = blockDim.x, tid = threadIdx.x;
+    int64_t *v = path_cost + g0, *c = scratch + g0;
+    int K = 0;
+    for (int base = 0; base < n; base += T) {
+        const int i = base + tid;
+        const int64_t x = i < n ? v[i] : INF;
+        const int f = x < INF_CUT ? 1 : 0;
+        int tot;
+        const int ex_ = block_excl_scan(f, s_scan, &tot);
+        if (f) c[K + ex_] = x;
+        K += tot;
+    }
+    __syncthreads();
+    if (K > max_paths) {  // left grouped by component; the caller orders this graph some other way
+        if (tid == 0) atomicOr(too_many, 1);
+        return;
+    }
+    for (int i = tid; i < n; i += T) v[i] = INF;
+    __syncthreads();
+    for (int ib = 0; ib < K; ib += T) {
+        const int i = ib + tid;
+        const int64_t x = i < K ? c[i] : INF;
+        int rank = 0;
+        for (int jb = 0; jb < K; jb += PC_TILE) {
+            const int m = min(PC_TILE, K - jb);
+            __syncthreads();
+            for (int j = tid; j < m; j += T) s_tile[j] = c[jb + j];
+            __syncthreads();
+            if (i < K)
+                for (int j = 0; j < m; j++) {
+                    const int64_t y = s_tile[j];
+                    rank += (y < x || (y == x && jb + j < i)) ? 1 : 0;
+                }
+        }
+        if (i < K) v[rank] = x;
+    }
+}
+
 // Tracks of each graph, ordered by first detection (the reference enumerates S's successors in node order,
 // mot3d/mot3d.py:175-176, and keeps the post-nodes of each path).
 __global__ void k_extract_tracks(int n_graphs, const int32_t *__restrict__ graph_ptr, const int32_t *__restrict__ next,
@@ -828,6 +880,17 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     k_first_path_rule<<<(n_graphs + 127) / 128, 128, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_path_rule");
     trace_mark(5, st);
+    return MOT3D_OK;
+}
+
+int32_t mot3d_order_path_costs(int32_t n_graphs, const int32_t *graph_ptr, int64_t *path_cost, int64_t *scratch,
+                               int32_t max_paths, int32_t *too_many_flag, void *stream) {
+    M3_CHECK_ARG(n_graphs >= 0 && max_paths >= 0, "negative sizes");
+    if (n_graphs == 0) return MOT3D_OK;
+    M3_CHECK_ARG(graph_ptr && path_cost && scratch && too_many_flag, "NULL pointer");
+    k_order_path_costs<<<n_graphs, 256, 0, (cudaStream_t)stream>>>(n_graphs, graph_ptr, path_cost, scratch, too_many_flag,
+                                                                  max_paths);
+    M3_LAUNCH_CHECK("k_order_path_costs");
     return MOT3D_OK;
 }
 

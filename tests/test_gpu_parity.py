@@ -185,7 +185,7 @@ def test_build_solve_extract_matches_mussp(name):
     d = gu.load(name)
     spec = _spec_from(d["spec"], mot3d)
     b = _batch_from(d, mot3d).to("cuda")
-    gb, sol = mot3d.track_batch(b, spec)
+    gb, sol = mot3d.track_batch(b, spec, want_path_costs=True)
     n = len(d["frame"])
     ref = _solve_checks(name, d, sol, n)
     tracks = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
@@ -211,7 +211,7 @@ def test_solver_on_reference_graphs(name):
     from mot3d_b200 import dimacs
     d = gu.load(name)
     gb, perm = dimacs.graph_from_arcs(int(d["n_nodes"]), d["tail"], d["head"], d["cost"])
-    sol = mot3d.solve_graphs(gb)
+    sol = mot3d.solve_graphs(gb, want_path_costs=True)
     ref = _solve_checks(name, d, sol, len(perm))
     # same flow as muSSP (these optima are unique): successor of every detection
     n = len(perm)
@@ -494,7 +494,7 @@ def test_entry_exit_flags_against_oracle():
     flags = (rng.rand(n) < 0.6).astype(np.uint8) * _lib.FLAG_ENTRY | (rng.rand(n) < 0.6).astype(np.uint8) * _lib.FLAG_EXIT
     spec = _spec_from(d["spec"], mot3d)
     b = _batch_from(d, mot3d, flags=flags).to("cuda")
-    gb, sol = mot3d.track_batch(b, spec)
+    gb, sol = mot3d.track_batch(b, spec, want_path_costs=True)
     s = d["spec"]
     ospec = oracle.CostSpec(**{k: v for k, v in s.items() if k != "kind"})
     row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], ospec)
@@ -709,6 +709,7 @@ def test_random_graphs_against_oracle():
     and a feasible flow of exactly that cost for every graph. Exercises the component split, the first-path rule and
     the work queue on shapes the golden vectors do not cover."""
     import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
     from oracle import oracle
     rng = np.random.RandomState(123)
     G = 300
@@ -729,9 +730,10 @@ def test_random_graphs_against_oracle():
                               weight_source_sink=wss, max_jump=3)
         b, order = mot3d.DetectionBatch.from_arrays(gp, np.concatenate(frames), np.concatenate(poss),
                                                     np.concatenate(confs))
-        gb, sol = mot3d.track_batch(b.to("cuda"), spec)
+        gb, sol = mot3d.track_batch(b.to("cuda"), spec, want_path_costs=True)
         K = sol.n_paths.cpu().numpy()
         total = sol.total_cost.cpu().numpy()
+        path_cost = sol.path_cost.cpu().numpy()
         tracks = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
                                        sol.track_det.cpu().numpy())
         ospec = oracle.CostSpec(weight_source_sink=wss, max_jump=3, mul=mul, bias=bias, **kw)
@@ -747,6 +749,9 @@ def test_random_graphs_against_oracle():
             ref = oracle.ssp_solve(2 * n + 2, tail, head, cost)
             assert K[g] == ref["K"], (g, n, K[g], ref["K"])
             assert total[g] == ref["total"], (g, n, total[g], ref["total"])
+            # path costs in the order the reference finds them, the rest of the graph's slice is "no path"
+            assert (path_cost[gp[g]:gp[g] + K[g]] == ref["path_cost"]).all(), g
+            assert (path_cost[gp[g] + K[g]:gp[g + 1]] == _lib.INF_COST).all(), g
             # our tracks form a feasible flow of exactly that cost
             arc = {(int(t), int(h)): int(c) for t, h, c in zip(tail, head, cost)}
             got = 0
@@ -850,11 +855,11 @@ def test_single_track_pass_equals_full_solver(monkeypatch):
     b, _ = mot3d.DetectionBatch.from_arrays(gp, frame, pos, conf)
     db = b.to("cuda")
     gb = mot3d.build_graphs(db, spec)
-    sol_fast = mot3d.solve_graphs(gb)
+    sol_fast = mot3d.solve_graphs(gb, want_path_costs=True)
     stats = sol_fast.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)
     assert stats[:, 24].sum() > 0.5 * 60 * 80          # the pass did take most components
     monkeypatch.setenv("MOT3D_SOLVE_NO_FAST", "1")
-    sol_full = mot3d.solve_graphs(gb)
+    sol_full = mot3d.solve_graphs(gb, want_path_costs=True)
     assert sol_full.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)[:, 24].sum() == 0
     n = db.n
     assert (sol_fast.next[:n].cpu() == sol_full.next[:n].cpu()).all()
