@@ -160,12 +160,21 @@ def _pack(sorted_dets, cspec):
     from .batch import DetectionBatch
     n = len(sorted_dets)
     dim = cspec.dim
-    frame = np.fromiter((d.index for d in sorted_dets), dtype=np.int64, count=n)
+    idx = [d.index for d in sorted_dets]
+    frame = np.fromiter(idx, dtype=np.int64, count=n)
+    if any(f != i for f, i in zip(frame.tolist(), idx)):
+        raise ValueError("detection.index must be an integer frame number (the time keys of the arc kernels are "
+                         "integers); got a fractional index")
     if n and (frame.min() < -2 ** 31 or frame.max() >= 2 ** 31):
         raise ValueError("frame indices must fit in int32")
     pos = np.empty((n, dim), dtype=np.float64)
     for i, d in enumerate(sorted_dets):
-        pos[i] = np.asarray(d.position, dtype=np.float64).reshape(-1)[:dim]
+        q = np.asarray(d.position, dtype=np.float64).reshape(-1)
+        if q.shape[0] != dim:
+            # the reference's euclidean() takes whatever coordinates there are; the kernels take exactly `dim`
+            raise ValueError("detection %d has a %d-D position but the cost function is for %d-D detections" %
+                             (i, q.shape[0], dim))
+        pos[i] = q
     conf = np.fromiter((d.confidence for d in sorted_dets), dtype=np.float64, count=n)
     flags = None
     if any((not d.entry_points) or (not d.exit_point) for d in sorted_dets):
@@ -304,6 +313,9 @@ for _name in ("to_networkx", "__getattr__", "__iter__", "__contains__", "__getit
 
 def _build_tracklet_graph(tracklets, weight_source_sink, max_jump, verbose, weight_confidence, weight_distance):
     from .tracklets import pack_tracklets, build_tracklet_arcs
+    if any(type(t) is not type(tracklets[0]) for t in tracklets):
+        raise NotImplementedError("build_graph on a list that mixes 2-D and 3-D tracklets: the reference's mixed costs "
+                                  "cannot run either (mot3d/weight_functions.py:174)")
     tspec = _recover_tracklet_spec(tracklets, weight_source_sink, max_jump, weight_confidence, weight_distance)
     n = len(tracklets)
     if verbose:
@@ -453,3 +465,18 @@ def _evaluate_pair(kind, d1, d2, kwargs):
     if gb.n_edges == 0:
         return None
     return float(gb.weight[0].item())
+
+
+def _evaluate_tracklet_pair(kind, t1, t2, kwargs):
+    """weight_distance_tracklets_*(t1, t2, **kwargs) for one real pair, on the GPU: the two-tracklet arc build
+    (csrc/tracklet.cu). Like the reference it needs t2.tail to start after t1.head ends
+    (mot3d/distance_functions.py:49)."""
+    from .tracklets import pack_tracklets, build_tracklet_arcs
+    i1, i2 = t1.head.indexes, t2.tail.indexes
+    assert i2[0] > i1[-1], "idxs2[0]={} idxs1[-1]={} tracklet2 cannot be more recent than tracklet1!".format(i2[0], i1[-1])
+    ts = _spec.TrackletCostSpec(kind=kind, distance=kwargs, max_jump=2 ** 30)
+    row_ptr, col, weight, _ = build_tracklet_arcs(pack_tracklets([t1, t2], ts), ts)
+    for e in range(int(row_ptr[0]), int(row_ptr[1])):
+        if int(col[e]) == 1:
+            return float(weight[e])
+    return None

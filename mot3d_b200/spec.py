@@ -11,6 +11,8 @@ SCALE = 10 ** 7  # costs are integers in units of 1e-7, the precision of graph_t
 
 def quantise_scalar(w):
     """What the reference's text carries for weight w: "{:0.7f}".format(w), as an integer number of 1e-7 units."""
+    if not np.isfinite(float(w)):
+        raise ValueError("cost %r is not finite: the reference would hand muSSP the text %r" % (w, "{:0.7f}".format(float(w))))
     s = "{:0.7f}".format(float(w))
     neg = s.startswith("-")
     whole, frac = s.lstrip("-").split(".")

@@ -16,7 +16,8 @@ __all__ = ["weight_distance_detections_2d", "weight_confidence_detections", "wei
            "weight_distance_detections_3d", "weight_confidence_detections_3d", "weight_distance_tracklets_2d",
            "weight_confidence_tracklets_2d", "weight_distance_tracklets_3d", "weight_confidence_tracklets_3d",
            "weight_distance_detections_auto", "weight_confidence_detections_auto",
-           "weight_distance_tracklets_auto", "weight_confidence_tracklets_auto"]
+           "weight_distance_tracklets_auto", "weight_confidence_tracklets_auto", "project_points",
+           "weight_distance_tracklet3d_tracklet2d", "weight_distance_tracklet2d_tracklet3d"]
 
 
 def _pair_on_gpu(kind, d1, d2, kwargs):
@@ -47,8 +48,9 @@ def weight_distance_detections_3d(d1, d2, sigma_jump=1, sigma_distance=2, sigma_
 def weight_confidence_detections(detection, mul=1, bias=0):
     if _spec.is_probe(detection):
         return _spec.record("confidence", dict(mul=mul, bias=bias))
-    raise TypeError("weight_confidence_detections is a cost descriptor for build_graph; the value for a detection "
-                    "is -(confidence*mul + bias) and is computed by the CUDA build kernel")
+    # a single real item: the reference's one-line value (mot3d/weight_functions.py:37-38); build_graph itself never
+    # comes here (k_node_costs computes the same expression for all detections at once)
+    return -(detection.confidence * mul + bias)
 
 
 def weight_confidence_detections_2d(detection, **kwargs):
@@ -59,10 +61,9 @@ def weight_confidence_detections_3d(detection, **kwargs):
     return weight_confidence_detections(detection, **kwargs)
 
 
-def _tracklets_pending(name):
-    raise TypeError(
-        "%s is a cost descriptor for build_graph: the arithmetic runs in the CUDA kernel "
-        "(mot3d_b200/csrc/tracklet.cu) for all pairs at once; there is no CPU evaluation of a single pair" % name)
+def _tracklet_pair_on_gpu(kind, t1, t2, kwargs):
+    from .mot3d import _evaluate_tracklet_pair
+    return _evaluate_tracklet_pair(kind, t1, t2, kwargs)
 
 
 def weight_distance_tracklets_2d(t1, t2, sigma_color_histogram=0.3, sigma_motion=50, alpha=0.7, cutoff_motion=0.1,
@@ -72,7 +73,7 @@ def weight_distance_tracklets_2d(t1, t2, sigma_color_histogram=0.3, sigma_motion
               use_color_histogram=use_color_histogram)
     if _spec.is_probe(t1):
         return _spec.record("tracklets_2d", kw)
-    _tracklets_pending("weight_distance_tracklets_2d")
+    return _tracklet_pair_on_gpu("tracklets_2d", t1, t2, kw)
 
 
 def weight_distance_tracklets_3d(t1, t2, sigma_color_histogram=0.3, sigma_motion=5, alpha=0.7, cutoff_motion=0.1,
@@ -82,7 +83,7 @@ def weight_distance_tracklets_3d(t1, t2, sigma_color_histogram=0.3, sigma_motion
               use_color_histogram=use_color_histogram)
     if _spec.is_probe(t1):
         return _spec.record("tracklets_3d", kw)
-    _tracklets_pending("weight_distance_tracklets_3d")
+    return _tracklet_pair_on_gpu("tracklets_3d", t1, t2, kw)
 
 
 def weight_confidence_tracklets_2d(tracklet, **kwargs):
@@ -115,13 +116,35 @@ def weight_confidence_detections_auto(d, config2d={}, config3d={}):
     raise RuntimeError("Unable to pick the pick the correct weight confidence for detections [{}].".format(type(d)))
 
 
+_MIXED = ("mixed 2-D / 3-D tracklet costs are not provided: the reference's own implementation cannot run "
+          "(mot3d/weight_functions.py:174 passes np.float32 as the `order` argument of np.reshape, a TypeError on "
+          "every input), so there is no behaviour to reproduce")
+
+
+def project_points(points, calib):
+    raise NotImplementedError(_MIXED)
+
+
+def weight_distance_tracklet3d_tracklet2d(t1, t2, calib={}, **kwargs):
+    raise NotImplementedError(_MIXED)
+
+
+def weight_distance_tracklet2d_tracklet3d(t1, t2, calib={}, **kwargs):
+    raise NotImplementedError(_MIXED)
+
+
 def weight_distance_tracklets_auto(t1, t2, config2d={}, config3d={}, calib={}):
-    if _is(t1, "DetectionTracklet2D") and _is(t2, "DetectionTracklet2D"):
+    """Type dispatch of the reference (mot3d/weight_functions.py:201-221)."""
+    is_t1_2d, is_t2_2d = _is(t1, "DetectionTracklet2D"), _is(t2, "DetectionTracklet2D")
+    is_t1_3d, is_t2_3d = _is(t1, "DetectionTracklet3D"), _is(t2, "DetectionTracklet3D")
+    if is_t1_2d and is_t2_2d:
         return weight_distance_tracklets_2d(t1, t2, **config2d)
-    if _is(t1, "DetectionTracklet3D") and _is(t2, "DetectionTracklet3D"):
+    if is_t1_3d and is_t2_3d:
         return weight_distance_tracklets_3d(t1, t2, **config3d)
-    raise NotImplementedError("mixed 2D/3D tracklet costs (reference mot3d/weight_functions.py:177-201) need camera "
-                              "projection; out of scope of the hot path")
+    if (is_t1_3d and is_t2_2d) or (is_t1_2d and is_t2_3d):
+        raise NotImplementedError(_MIXED)
+    raise RuntimeError("Unable to pick the pick the correct weight distance for tracklets [{},{}].".format(type(t1),
+                                                                                                           type(t2)))
 
 
 def weight_confidence_tracklets_auto(t, config2d={}, config3d={}):

@@ -429,9 +429,40 @@ def case_color_histogram(mot3d):
     print("%-22s boxes=%d (%d KB)" % ("color_histogram", len(boxes), os.path.getsize(path) // 1024))
 
 
+def case_clipped_arcs(mot3d, wf):
+    """(a9) a graph on which muSSP's Graph::invalid_edge_rm (Graph.cpp:86-111) really clips arcs: entering costs
+    -0.3 (weight_source_sink < 0), so every transition weaker than that (w > exit + entry = -0.3) is removed by the
+    reference before it solves. Noisy detections with drop-outs make about a third of the arcs that weak."""
+    rng = np.random.RandomState(9)
+    F, P = 30, 10
+    pos = rng.rand(P, 2) * 100.0
+    vel = rng.randn(P, 2) * 1.5
+    dets = []
+    for f in range(F):
+        pos = pos + vel + rng.randn(P, 2) * 1.0
+        for q in range(P):
+            if rng.rand() < 0.85:
+                dets.append(mot3d.Detection2D(f, pos[q] + rng.randn(2) * 1.5, confidence=float(0.3 + 0.6 * rng.rand())))
+    kw = dict(sigma_jump=1, sigma_distance=6, max_distance=25, use_color_histogram=False, use_bbox=False)
+    spec = dict(kind="2d", sigma_color_histogram=0.3, sigma_box_size=0.3, mul=1, bias=0, weight_source_sink=-0.3,
+                max_jump=4, **kw)
+    wd = lambda d1, d2: wf.weight_distance_detections_2d(d1, d2, **kw)
+    wc = lambda d: wf.weight_confidence_detections_2d(d, mul=1, bias=0)
+
+    def extra(sorted_dets):
+        return {}
+    g, _ = freeze_detection_case(mot3d, "a9_clipped_arcs", dets,
+                                 dict(weight_source_sink=-0.3, max_jump=4, weight_confidence=wc, weight_distance=wd),
+                                 spec, extra)
+    w = np.array([d["weight"] for u, v, d in g.edges(data=True) if u % 2 == 1 and u != 1 and v != len(g)])
+    print("    transitions %d, clipped by invalid_edge_rm (w > -0.3): %d" % (len(w), int((w > -0.3).sum())))
+
+
 def main():
     mot3d = import_reference()
     import mot3d.weight_functions as wf
+    if "a9_clipped_arcs" in sys.argv[1:]:
+        return case_clipped_arcs(mot3d, wf)
     if "color_histogram" in sys.argv[1:]:
         return case_color_histogram(mot3d)
     if "c3_merge_close_points" in sys.argv[1:]:
@@ -443,6 +474,7 @@ def main():
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
     case_color_histogram(mot3d)
+    case_clipped_arcs(mot3d, wf)
     case_merge_close_points(mot3d)
     case_multiview(mot3d, wf)
     case_multiview_tracklets(mot3d, wf)

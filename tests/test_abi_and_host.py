@@ -292,3 +292,79 @@ def test_view_packing_follows_dict_order():
         t = trk([("x", 1.0)])
         t.tracklets_2d["x"].head.color_histogram = None
         pack_tracklets([t], tspec)
+
+
+def test_dimacs_text_round_trip_on_files(built, tmp_path):
+    """N4 at file level: save_graph (reference mot3d/mot3d.py:255-265) writes the lines graph_to_text made; reading the
+    file back and parsing it (dimacs.parse_text, the text side of wrapper.cpp:39-88) gives the golden arcs with their
+    exact 1e-7 costs, for a detection graph, a tracklet graph and muSSP's own sample."""
+    import golden_util as gu
+    from oracle import oracle
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import dimacs
+    for name in ("c1_simple_2d", "c2_tracklets_pass2", "a9_clipped_arcs", "wrapper_test_graph"):
+        d = gu.load(name)
+        w = d["w_float"] if "w_float" in d else d["cost"].astype(np.float64) * 1e-7
+        lines = oracle.arcs_to_text(int(d["n_nodes"]), d["tail"], d["head"], w)
+        path = str(tmp_path / (name + ".txt"))
+        mot3d.save_graph(lines, path)
+        back = open(path).read().splitlines()
+        assert back == lines
+        if "sha" in d and "w_float" in d:
+            assert oracle.text_sha(back) == str(d["sha"])
+        n_nodes, tail, head, cost = dimacs.parse_text(back)
+        assert n_nodes == int(d["n_nodes"])
+        assert (tail == d["tail"]).all() and (head == d["head"]).all() and (cost == d["cost"]).all()
+    # signs, missing fraction digits, comments
+    n, t, h, c = dimacs.parse_text(["p min 4 3", "c comment", "a 1 2 -0.5", "a 2 3 1", "a 3 4 +0.0000001"])
+    assert n == 4 and c.tolist() == [-5000000, 10000000, 1]
+
+
+def test_scene_save_load_round_trip(tmp_path):
+    """Scene.save / Scene.load (reference projects/PETS2009S2L1/scene.py:41-52): the pickle carries active, completed
+    and the tracklets under the reference's keys; the counters are rebuilt from the lengths."""
+    import pickle
+    import mot3d_b200 as mot3d
+    from mot3d_b200.online import Scene
+    sc = Scene(completed_after=5)
+    for k in range(4):
+        sc.update(None, [mot3d.Detection2D(f, (float(k), float(f)), confidence=0.5 + 0.1 * k) for f in range(k, k + 3)])
+    sc.store_tracklet([mot3d.Detection2D(0, (1.0, 2.0))])
+    sc.update_completed(time_index=8)      # tracks ending before frame 3 are completed
+    assert sorted(sc.completed) == [0] and sorted(sc.active) == [1, 2, 3]
+    path = str(tmp_path / "scene.pickle")
+    sc.save(path)
+    raw = pickle.load(open(path, "rb"))
+    assert sorted(raw) == ["active", "completed", "trackelts"]
+    other = Scene()
+    other.load(path)
+    assert sorted(other.active) == [1, 2, 3] and sorted(other.completed) == [0]
+    assert other.id_last == 4 and other.id_last_tracklet == 1
+    assert [d.index for d in other.active[2]] == [2, 3, 4] and other.active[3][0].confidence == 0.8
+    assert other.tracklets[0][0].position == (1.0, 2.0)
+
+
+def test_costs_on_real_items_and_input_checks(built):
+    """weight_confidence_* on a real detection / tracklet is the reference's value (mot3d/weight_functions.py:37-38);
+    packing refuses what the kernels cannot represent instead of truncating it."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    from mot3d_b200 import mot3d as m3
+    from mot3d_b200.spec import CostSpec, quantise_scalar
+    det = mot3d.Detection2D(3, (1.0, 2.0), confidence=0.83)
+    assert wf.weight_confidence_detections(det, mul=2.0, bias=0.1) == -(0.83 * 2.0 + 0.1)
+    assert wf.weight_confidence_detections_2d(det) == -0.83
+    trk = mot3d.DetectionTracklet2D([det], confidence=0.4)
+    assert wf.weight_confidence_tracklets_2d(trk, mul=1.5, bias=-0.2) == -(0.4 * 1.5 - 0.2)
+    assert wf.weight_confidence_detections_auto(det, config2d=dict(mul=3)) == -(0.83 * 3)
+    cs = CostSpec(kind="detections_2d")
+    with pytest.raises(ValueError):
+        m3._pack([mot3d.Detection3D(0, (1.0, 2.0, 3.0))], cs)          # z would be dropped
+    with pytest.raises(ValueError):
+        m3._pack([mot3d.Detection2D(0.5, (1.0, 2.0))], cs)             # fractional frame index
+    with pytest.raises(ValueError):
+        quantise_scalar(float("inf"))
+    with pytest.raises(ValueError):
+        quantise_scalar(float("nan"))
+    with pytest.raises(NotImplementedError):
+        wf.weight_distance_tracklets_auto(trk, mot3d.DetectionTracklet3D([mot3d.Detection3D(5, (0.0, 0.0, 0.0))]))

@@ -1052,3 +1052,67 @@ def test_key_preconditions_are_reported():
     b1, _ = mot3d.DetectionBatch.from_arrays(np.array([0, n]), fr, d["pos"], d["conf"])
     g1 = mot3d.build_graphs(b1.to(dev), spec)
     assert g1.n_edges > 0
+
+
+def test_graph_file_to_solution(tmp_path):
+    """N4 end to end at file level: graph_to_text -> save_graph -> file -> dimacs.parse_text -> graph_from_arcs -> CUDA
+    solve: K and total of the reference for a detection graph built here, its golden, and the adversarial a9 graph."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import dimacs
+    for name in ("c1_simple_2d", "a9_clipped_arcs", "c5_small_f30_p12"):
+        d = gu.load(name)
+        spec = _spec_from(d["spec"], mot3d)
+        b = _batch_from(d, mot3d).to("cuda")
+        out = mot3d.build_graphs(b, spec, direction=mot3d._lib.DIR_OUT, with_weights=True)
+        n = len(d["frame"])
+        from oracle import oracle
+        row_ptr = out.row_ptr.cpu().numpy().astype(np.int64)
+        tail, head, ww = oracle.graph_arcs(n, float(d["spec"]["weight_source_sink"]),
+                                           -(d["conf"] * d["spec"]["mul"] + d["spec"]["bias"]), 0.0, row_ptr,
+                                           out.col[:out.n_edges].cpu().numpy().astype(np.int64),
+                                           out.weight[:out.n_edges].cpu().numpy())
+        path = str(tmp_path / (name + ".txt"))
+        mot3d.save_graph(oracle.arcs_to_text(2 * n + 2, tail, head, ww), path)
+        n_nodes, t2, h2, c2 = dimacs.parse_text(open(path).read().splitlines())
+        assert n_nodes == int(d["n_nodes"]) and (t2 == d["tail"]).all() and (h2 == d["head"]).all()
+        gu.assert_costs_match(c2, d["cost"], d["w_float"])
+        gb, perm = dimacs.graph_from_arcs(n_nodes, t2, h2, d["cost"])
+        sol = mot3d.solve_graphs(gb)
+        assert int(sol.n_paths[0].item()) == int(d["K"])
+        assert int(sol.total_cost[0].item()) == gu.ref_total_units(d)
+
+
+def test_tracklet_costs_on_real_pairs():
+    """weight_distance_tracklets_2d(t1, t2, ...) called on two real tracklets evaluates that pair on the GPU (the
+    two-tracklet arc build): the reference's arc weights of the tracklet fixture, None where the reference has no arc."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    d = gu.load("c4_synth_tracklets")
+    s = d["spec"]
+    n = len(d["t_conf"])
+    hp = d["t_head_ptr"]
+    tracklets = []
+    for i in range(n):
+        idx, pts = d["t_head_idx"][hp[i]:hp[i + 1]], d["t_head_pos"][hp[i]:hp[i + 1]]
+        hist = [h for h in d["t_head_hist"][i]] if "t_head_hist" in d else None
+        tracklets.append(mot3d.DetectionTracklet2D([mot3d.Detection2D(int(f), p, color_histogram=hist, bbox=[0, 0, 1, 1])
+                                                    for f, p in zip(idx, pts)]))
+    kw = {k: s[k] for k in ("sigma_color_histogram", "sigma_motion", "alpha", "cutoff_motion", "cutoff_appearance",
+                            "max_distance", "use_color_histogram")}
+    tail, head = d["tail"].astype(np.int64), d["head"].astype(np.int64)
+    m = np.flatnonzero((tail % 2 == 1) & (tail != 1) & (head != int(d["n_nodes"])))
+    arcs = {((int(tail[e]) - 3) // 2, (int(head[e]) - 2) // 2): float(d["w_float"][e]) for e in m}
+    assert len(arcs) > 4
+    for (i, j), w in list(arcs.items())[:8]:
+        got = wf.weight_distance_tracklets_2d(tracklets[i], tracklets[j], **kw)
+        assert got is not None and abs(got - w) <= RTOL * abs(w), (i, j, got, w)
+    # ordered pairs in time without an arc in the reference's graph: None (cut-offs / max_distance), within max_jump
+    miss = 0
+    for i in range(n):
+        for j in range(n):
+            jump = tracklets[j].tail.index - tracklets[i].head.index
+            if 0 < jump <= s["max_jump"] and (i, j) not in arcs and miss < 4:
+                assert wf.weight_distance_tracklets_2d(tracklets[i], tracklets[j], **kw) is None
+                miss += 1
+    with pytest.raises(AssertionError):  # the reference's linear_motion asserts the order in time
+        wf.weight_distance_tracklets_2d(tracklets[1], tracklets[1], **kw)
