@@ -109,6 +109,13 @@ struct SolveParams {
     int32_t *ws_hop;
     int32_t *ws_pl;
     StArc *ws_arc;         // [arc_capacity + n_total + 8]: the list of detection d starts at in_ptr[d] + d
+    // staging area of solve_big.cuh (components beyond the shared-memory bands, 32-bit costs)
+    longlong2 *big_res_e;  // [n_total]
+    int4 *big_res_f;       // [n_total]
+    unsigned *big_listed;  // [n_total / 32 + n_total + 8]
+    int32_t *big_arc;      // 3 x [big_arc_stride]: cost, source, out-arc head; blocks handed out through big_arc_next
+    int64_t big_arc_stride;
+    unsigned long long *big_arc_next;
 };
 
 __device__ __forceinline__ KeyIdx group_min(KeyIdx best, unsigned mask) {
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
 
 #include "solve_global.cuh"
 #include "solve_sm.cuh"
+#include "solve_big.cuh"
 
 // ---- single-track components. Three out of four components of a crowded window are one object seen once per frame:
 //      the first shortest path runs through all of its detections in order, the optimality certificate of
@@ -499,7 +507,12 @@ __global__ void __launch_bounds__(BT, MINB) k_ssp_solve(const __grid_constant__ 
         bool done = false;
         if (SHARED && n <= p.rcap && staging_bytes(n, 0) <= p.sbytes)
             done = solve_component_sm(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work);
-        if (!done) solve_component_global(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, 0);
+        if (!done) {
+            if (p.win_wide[g])
+                solve_component_global(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, 0);
+            else
+                solve_component_big(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work);
+        }
     }
     if (p.chain & 2) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -712,7 +725,8 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     return a256(n * 8) * 3 + a256(n * 4) * 12 + a256(n * 16) + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
-           a256(n * sizeof(GRec)) + a256((e + n + 8) * sizeof(StArc)) +
+           a256(n * sizeof(GRec)) + a256((e + n + 8) * sizeof(StArc)) + a256(n * 16) * 2 + a256((n / 32 + n + 8) * 4) +
+           a256((e + 8) * 12) + 256 +
            a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512 + a256(JOB_META_INTS * sizeof(int32_t));
 }
 
@@ -789,6 +803,12 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     int32_t *n_cgraphs = (int32_t *)take(16);
     p.job_meta = (int32_t *)take(JOB_META_INTS * sizeof(int32_t));
     p.comp_class = (int32_t *)take(n_cap * 4);
+    p.big_res_e = (longlong2 *)take(n_cap * 16);
+    p.big_res_f = (int4 *)take(n_cap * 16);
+    p.big_listed = (unsigned *)take((n_cap / 32 + n_cap + 8) * 4);
+    p.big_arc_stride = (int64_t)e_cap + 8;
+    p.big_arc = (int32_t *)take((e_cap + 8) * 12);
+    p.big_arc_next = (unsigned long long *)take(256);
     p.comp_perm = comp_perm;
     p.comp_inv = comp_inv;
     p.cgraph_ptr = cgraph_ptr;
@@ -800,6 +820,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     const DevInfo *di = dev_info();
     if (!di) return cuda_fail(cudaGetLastError(), "device attributes / shared memory limits of the solver kernels");
     M3_CUDA(cudaMemsetAsync(p.job_meta, 0, JOB_META_INTS * sizeof(int32_t), st));
+    M3_CUDA(cudaMemsetAsync(p.big_arc_next, 0, sizeof(unsigned long long), st));
     M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
     trace_mark(0, st);
     // 1. connected components of every graph, detections regrouped by component

@@ -1,0 +1,458 @@
+// Block-per-component solver for components that fit no shared-memory band (solve_sm.cuh) but whose costs fit 32
+// bits: the staging area lives in GLOBAL memory (it stays in L2: 110 bytes per record, 12 per arc), slots are 32 bits,
+// any size. Included by solve.cu. Costs beyond 32 bits go to solve_global.cuh.
+//
+// Same successive shortest paths as solve_sm.cuh (arg-min over the sinks, path walk, certificate, exact re-labelling of
+// the branch that hung from the path's first arc by synchronous pull rounds), with one difference that matters at this
+// size: a round only touches the records whose inputs moved in the round before. Publishing a post label puts the
+// heads of the node's out-arcs on the next round's work list (the out-arc lists are staged next to the in-arc lists);
+// publishing a pre label on a track lists the track's previous record (reversed matched arc); a bit per record keeps a
+// record from being listed twice. A round costs what its frontier costs, not what the component costs: a 100 000-
+// detection graph whose tracks run over 1 000 frames needs thousands of rounds per path, each a handful of records.
+#pragma once
+
+struct BigCursor {  // bump allocator of the arc area: every component takes exactly its number of in-arcs, once
+    unsigned long long next;
+};
+
+__device__ __noinline__ void solve_component_big(const SolveParams &p, const int cg, const int c0, const int n, const int g,
+                                                 int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
+    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
+    SRec *const rec = (SRec *)(p.ws_rec + c0);  // (an 80-byte slot per record of the area solve_global.cuh uses)
+    longlong2 *const res_e = p.big_res_e + c0;  // staged results of a round: new labels ...
+    int4 *const res_f = p.big_res_f + c0;       // ... parent, branches, what moved (1 = pre, 2 = post)
+    int *const hop = p.ws_hop + c0;             // detections whose matched in-arc changed (path walk); second work list
+    int *const pl = p.ws_pl + c0;               // work list of a relabelling round
+    unsigned char *const flg = (unsigned char *)(p.ws_tk + c0);  // DL_* of the branch being re-labelled
+    int *const out_off = p.ws_bl + c0;          // out-arcs of record i: out_dst[out_off[i] .. out_off[i + 1])
+    unsigned *const listed = p.big_listed + (c0 >> 5) + cg;  // bit per record: on the next round's work list (every
+                                                             // component has its own words: + component index)
+    const int32_t *const perm = p.comp_perm + c0;
+
+    // ---- stage the component. Arc offsets by a block scan over contiguous chunks of records.
+    const int chunk = (n + T - 1) / T;
+    const int i0 = min(tid * chunk, n), i1 = min(i0 + chunk, n);
+    int my_arcs = 0;
+    for (int i = i0; i < i1; i++) {
+        const int d = perm[i];
+        my_arcs += p.in_ptr[d + 1] - p.in_ptr[d];
+    }
+    int tot;
+    int a0 = block_excl_scan1(my_arcs, s_scan, 0, &tot);
+    // the component's arcs: three arrays (cost, source slot of every in-arc; head slot of every out-arc) in a block of
+    // the arc area taken from a bump allocator (every component asks for exactly its number of in-arcs, once: the area
+    // of arc_capacity entries per array cannot run out)
+    if (tid == 0) s_ok[6] = (int)atomicAdd(p.big_arc_next, (unsigned long long)tot);
+    for (int w = tid; w < (n >> 5) + 1; w += T) listed[w] = 0;
+    __syncthreads();
+    int32_t *const arc_cost = p.big_arc + s_ok[6];
+    int *const arc_src = arc_cost + p.big_arc_stride;
+    int *const out_dst = arc_src + p.big_arc_stride;
+    int *const out_cnt = (int *)res_e;  // while staging: out-degree, then fill cursor of every record
+    PhaseClock cnt;
+    cnt.w = s_work;
+    cnt.t_mark = clock64();
+    // records: every load of a record is issued before any is used (one memory level after the permutation)
+    for (int i = i0; i < i1; i++) {
+        const int q = c0 + i, d = perm[i];
+        const int e0 = p.in_ptr[d], e1 = p.in_ptr[d + 1];
+        const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
+        const int64_t dpre = p.ws_dpre[q], dpost = p.ws_dpost[q];
+        const int64_t en = p.en[d], cn = p.cn[d], ex = p.ex[d];
+        SRec r;
+        r.A = make_int4(e1 - e0, a0, NONE, NONE);
+        r.F = make_int4(par >= 0 ? par - c0 : par, ap_ >= 0 ? ap_ - c0 : -1, ao_ >= 0 ? ao_ - c0 : -1, e0);
+        r.E = make_longlong2(dpre, dpost);
+        r.W = make_int4(en >= INF_CUT ? NO_ARC32 : (int)en, (int)cn, ex >= INF_CUT ? NO_ARC32 : (int)ex, 0);
+        rec[i] = r;
+        a0 += e1 - e0;
+        out_cnt[4 * i] = 0;  // (res_e is 16 bytes per record: one counter in each)
+    }
+    cnt.add(0, tot);
+    __syncthreads();
+    for (int ib = 0; ib < n; ib += ngrp) {  // arc lists: one lane group per record, two independent arcs per lane
+        const int i = ib + grp;
+        if (i < n) {
+            const int e0 = rec[i].F.w, deg = rec[i].A.x, off = rec[i].A.y;
+            for (int kb = sub; kb < deg; kb += 2 * LPN) {
+                const int k1 = kb + LPN;
+                const bool two = k1 < deg;
+                const int src0 = p.in_src[e0 + kb], src1 = p.in_src[e0 + (two ? k1 : kb)];
+                const int64_t w0 = p.in_cost[e0 + kb], w1 = p.in_cost[e0 + (two ? k1 : kb)];
+                const int q0 = p.comp_inv[src0] - c0, q1 = p.comp_inv[src1] - c0;
+                arc_cost[off + kb] = (int)w0;
+                arc_src[off + kb] = q0;
+                atomicAdd(&out_cnt[4 * q0], 1);
+                if (two) {
+                    arc_cost[off + k1] = (int)w1;
+                    arc_src[off + k1] = q1;
+                    atomicAdd(&out_cnt[4 * q1], 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {   // out-arc lists: offsets by a block scan of the out-degrees, then every in-arc is entered at its source
+        int my_out = 0;
+        for (int i = i0; i < i1; i++) my_out += out_cnt[4 * i];
+        int tot_out;
+        int o0 = block_excl_scan1(my_out, s_scan, 1, &tot_out);
+        for (int i = i0; i < i1; i++) {
+            const int c = out_cnt[4 * i];
+            out_off[i] = o0;
+            out_cnt[4 * i] = o0;  // fill cursor
+            o0 += c;
+        }
+        __syncthreads();
+        for (int ib = 0; ib < n; ib += ngrp) {
+            const int i = ib + grp;
+            if (i < n) {
+                const int deg = rec[i].A.x, off = rec[i].A.y;
+                for (int k = sub; k < deg; k += LPN) out_dst[atomicAdd(&out_cnt[4 * arc_src[off + k]], 1)] = i;
+            }
+        }
+    }
+    __syncthreads();
+    cnt.tick(2);
+
+    const unsigned lt = (1u << lane_id()) - 1u;
+    int K = 0, n_used = 0;
+    int64_t total = 0;
+    for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+        // ---- cheapest way into T
+        KeyIdx best;
+        best.key = INF;
+        best.idx = -1;
+        for (int i = tid; i < n; i += T) {
+            const int64_t d = rec[i].E.y;
+            const int x = rec[i].W.z;
+            if (rec[i].A.w != TERM && d < INF_CUT && x != NO_ARC32) {
+                KeyIdx v;
+                v.key = d + x;
+                v.idx = i;
+                best = min_ki(best, v);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const KeyIdx o = shfl_xor_ki(best, d);
+            const bool take = o.key < best.key || (o.key == best.key && (unsigned)o.idx < (unsigned)best.idx);
+            best.key = take ? o.key : best.key;
+            best.idx = take ? o.idx : best.idx;
+        }
+        if (lane_id() == 0) s_red[warp_id()] = best;
+        __syncthreads();
+        KeyIdx sink;
+        sink.key = INF;
+        sink.idx = -1;
+        for (int k = 0; k < (T + 31) >> 5; k++) {
+            const KeyIdx o = s_red[k];
+            if (o.key < sink.key || (o.key == sink.key && (unsigned)o.idx < (unsigned)sink.idx)) sink = o;
+        }
+        __syncthreads();  // s_red is rewritten next iteration
+        cnt.tick(0);
+        if (sink.idx < 0) break;  // T unreachable
+        if (sink.key >= 0) {      // the first-path rule belongs to the whole graph (k_first_path_rule)
+            if (K == 0 && tid == 0) {
+                p.first_cost[cg] = sink.key;
+                p.first_sink[cg] = c0 + sink.idx;
+            }
+            break;
+        }
+        const int root = rec[sink.idx].F.z;
+        if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        // ---- augment: walk the path back from T and rewrite next / prev
+        if (tid == 0) {
+            int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
+            for (int step = 0; step <= n; step++) {
+                const int4 A = rec[cur].A;         // z = prev, w = next
+                const int par_cur = rec[cur].F.x;  // in flight together: the parent of pre_cur (used when cur joins)
+                rec[cur].A.w = nxt_new;
+                int m, q;
+                if (A.z == NONE) {  // post_cur came from pre_cur: detection cur joins a track
+                    m = cur;
+                    q = par_cur;
+                    joined++;
+                } else {  // post_cur came from pre_m, m = its old successor: the arc cur -> m is cancelled
+                    m = A.w;
+                    q = PAR_NONE;
+                    while (m >= 0) {
+                        q = rec[m].F.x;
+                        if (q != PAR_POST) break;
+                        const int m2 = rec[m].A.w;  // pre_m came from post_m: m leaves its track
+                        rec[m].A.w = NONE;
+                        rec[m].A.z = NONE;
+                        m = m2;
+                        joined--;
+                    }
+                }
+                if (m < 0) break;  // cannot happen on a consistent residual state
+                if (q < 0) {       // PAR_S: the path starts here
+                    rec[m].A.z = TERM;
+                    ok = 1;
+                    break;
+                }
+                rec[m].A.z = q;
+                hop[nhop++] = m;  // the cost of the newly matched arc q -> m is looked up below
+                nxt_new = m;
+                cur = q;
+            }
+            s_ok[0] = ok;
+            s_ok[1] = nhop;
+            s_ok[7] = joined;
+        }
+        __syncthreads();
+        cnt.tick(3);
+        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        n_used += s_ok[7];
+        for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
+            const int m = hop[h], q = rec[m].A.z;
+            const int off = rec[m].A.y, deg = rec[m].A.x;
+            for (int k = 0; k < deg; k++)
+                if ((int)arc_src[off + k] == q) {
+                    rec[m].W.w = arc_cost[off + k];
+                    break;
+                }
+        }
+        if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
+        K++;
+        total += sink.key;
+        __syncthreads();
+        // ---- finished? (every detection on a track + the certificate of the header)
+        if (n_used == n) {
+            bool good = true;
+            for (int ib = 0; ib < n; ib += ngrp) {
+                const int i = ib + grp;
+                if (i < n) {
+                    const int4 A = rec[i].A;
+                    const int4 W = rec[i].W;
+                    if ((W.x != NO_ARC32 && W.x < 0) || (W.z != NO_ARC32 && W.z < 0)) good = false;
+                    if (A.z >= 0) {
+                        const int mc = W.w;
+                        if (mc > 0 || (int64_t)W.y + mc > 0) good = false;
+                        for (int k = sub; k < A.x; k += LPN)
+                            if ((int)arc_src[A.y + k] != A.z && arc_cost[A.y + k] < mc) good = false;
+                    }
+                }
+            }
+            const bool done = __syncthreads_and(good);
+            cnt.tick(6);
+            if (done) {
+                cnt.add(3, 1);
+                break;
+            }
+        }
+        // ---- the branch hanging from S -> pre_root loses its labels; its records are the first round's work list
+        int n_mine = 0;
+        if (tid == 0) s_ok[3] = 0;
+        __syncthreads();
+        for (int base = 0; base < n; base += T) {
+            const int s = base + tid;
+            int f = 0;
+            if (s < n) {
+                int4 F = rec[s].F;
+                f = (F.y == root ? 1 : 0) | (F.z == root ? 2 : 0);  // 1 = pre node, 2 = post node in the branch
+                flg[s] = (unsigned char)f;
+                if (f) {
+                    longlong2 E = rec[s].E;
+                    if (f & 1) {
+                        E.x = INF;
+                        F.x = PAR_NONE;
+                        F.y = -1;
+                    }
+                    if (f & 2) {
+                        E.y = INF;
+                        F.z = -1;
+                    }
+                    rec[s].E = E;
+                    rec[s].F = F;
+                    n_mine++;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+            if (m) {
+                int at = 0;
+                if (lane_id() == 0) at = atomicAdd(&s_ok[3], __popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (f) pl[at + __popc(m & lt)] = s;
+            }
+        }
+        cnt.add(1, 1);
+        __syncthreads();
+        cnt.tick(1);
+        int n_arc_pull = 0, n_relax = 0, rounds = 0;
+        // two work lists (pl, hop) and their lengths (s_ok[3], s_ok[4]) alternate between the rounds
+#pragma unroll 1
+        for (; rounds < 4 * n + 8; rounds++) {
+            const int *const cur = (rounds & 1) ? hop : pl;
+            int *const nxt = (rounds & 1) ? pl : hop;
+            int *const n_next = &s_ok[3 + ((rounds + 1) & 1)];
+            const int n_work = s_ok[3 + (rounds & 1)];
+            if (n_work == 0) break;  // nothing moved in the round before: fix-point
+            if (tid == 0) *n_next = 0;
+            // (A) relax the listed records from the labels of the round before, four lanes per record; the results are
+            //     staged
+#pragma unroll 1
+            for (int wi = grp; wi < n_work; wi += ngrp) {
+                const int s = cur[wi];
+                // (its bit comes off the list here: set bits are exactly the records waiting on the next list, and the
+                // words are all zero again when the rounds end)
+                if (sub == 0) atomicAnd(&listed[s >> 5], ~(1u << (s & 31)));
+                const int f = flg[s];
+                const int4 A = rec[s].A;  // x = in-degree, y = first arc, z = prev, w = next
+                const int4 W = rec[s].W;
+                const longlong2 E = rec[s].E;
+                const int4 F = rec[s].F;
+                int64_t dpre = E.x, dpost = E.y;
+                int par = F.x, apre = F.y, apost = F.z;
+                if ((f & 2) && A.w >= 0) {  // on a track: reversed matched arc pre_next -> post_s
+                    const int64_t dm = rec[A.w].E.x;
+                    if (dm < INF_CUT && dm - (int64_t)rec[A.w].W.w < dpost) {
+                        dpost = dm - (int64_t)rec[A.w].W.w;
+                        apost = rec[A.w].F.y;
+                    }
+                }
+                if (f & 1) {
+                    const int32_t *const ac = arc_cost + A.y;
+                    const int *const as = arc_src + A.y;
+                    int64_t key = INF;
+                    int kpar = 0x7fffffff;
+#pragma unroll 1
+                    for (int k = sub; k < A.x; k += 2 * LPN) {  // two independent arc / label loads in flight
+                        const int k1 = k + LPN < A.x ? k + LPN : k;
+                        const int s0 = as[k], s1 = as[k1];
+                        const int64_t c0_ = rec[s0].E.y + (int64_t)ac[k], c1_ = rec[s1].E.y + (int64_t)ac[k1];
+                        // (an unlabelled source gives INF + cost: it loses against every labelled one, see below)
+                        if (s0 != A.z && (c0_ < key || (c0_ == key && s0 < kpar))) {  // lowest slot wins ties
+                            key = c0_;
+                            kpar = s0;
+                        }
+                        if (s1 != A.z && (c1_ < key || (c1_ == key && s1 < kpar))) {
+                            key = c1_;
+                            kpar = s1;
+                        }
+                    }
+#pragma unroll
+                    for (int d = 1; d < LPN; d <<= 1) {
+                        const int64_t ok_ = __shfl_xor_sync(gmask, key, d);
+                        const int op = __shfl_xor_sync(gmask, kpar, d);
+                        if (ok_ < key || (ok_ == key && op < kpar)) {
+                            key = ok_;
+                            kpar = op;
+                        }
+                    }
+                    if (sub == 0) n_arc_pull += A.x;
+                    int kanc = -1;
+                    if (key < INF_CUT) {
+                        kanc = rec[kpar].F.z;
+                    } else {
+                        key = INF;
+                        kpar = PAR_NONE;
+                    }
+                    if (A.z != TERM && W.x != NO_ARC32 && (int64_t)W.x < key) {
+                        key = W.x;
+                        kpar = PAR_S;
+                        kanc = s;
+                    }
+                    if (A.z != NONE && dpost < INF_CUT && dpost - (int64_t)W.y < key) {  // reversed node arc
+                        key = dpost - (int64_t)W.y;
+                        kpar = PAR_POST;
+                        kanc = apost;
+                    }
+                    if (key < dpre) {
+                        dpre = key;
+                        par = kpar;
+                        apre = kanc;
+                    }
+                }
+                if ((f & 2) && A.z == NONE && dpre < INF_CUT && dpre + (int64_t)W.y < dpost) {
+                    dpost = dpre + (int64_t)W.y;  // unused record: post hangs from the own pre node
+                    apost = apre;
+                }
+                if (sub == 0) {
+                    const int upd = (dpre != E.x ? 1 : 0) | (dpost != E.y ? 2 : 0);
+                    if (upd) res_e[wi] = make_longlong2(dpre, dpost);
+                    res_f[wi] = make_int4(par, apre, apost, upd);
+                    n_relax++;
+                }
+            }
+            __syncthreads();  // every label of the round before has been read
+#pragma unroll 1
+            for (int wi = tid; wi < n_work; wi += T) {  // (B) publish, and list what reads a label that moved
+                const int4 rf = res_f[wi];
+                if (rf.w) {
+                    const int s = cur[wi];
+                    rec[s].E = res_e[wi];
+                    int4 F = rec[s].F;
+                    F.x = rf.x;
+                    F.y = rf.y;
+                    F.z = rf.z;
+                    rec[s].F = F;
+                    if (rf.w & 2) {  // post label: the heads of the out-arcs whose pre node is being re-labelled
+                        const int o0 = out_off[s], o1 = s + 1 < n ? (int)out_off[s + 1] : tot;
+                        for (int k = o0; k < o1; k++) {
+                            const int d = out_dst[k];
+                            const unsigned bit = 1u << (d & 31);
+                            if ((flg[d] & 1) && !(atomicOr(&listed[d >> 5], bit) & bit))
+                                nxt[atomicAdd(n_next, 1)] = d;
+                        }
+                    }
+                    if (rf.w & 1) {  // pre label on a track: the post node of the record before it (reversed matched arc)
+                        const int d = rec[s].A.z;
+                        if (d >= 0 && (flg[d] & 2)) {
+                            const unsigned bit = 1u << (d & 31);
+                            if (!(atomicOr(&listed[d >> 5], bit) & bit)) nxt[atomicAdd(n_next, 1)] = d;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (p.stats) {  // work counters of this branch
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                n_arc_pull += __shfl_xor_sync(0xffffffffu, n_arc_pull, d);
+                n_relax += __shfl_xor_sync(0xffffffffu, n_relax, d);
+                n_mine += __shfl_xor_sync(0xffffffffu, n_mine, d);
+            }
+            if (lane_id() == 0) {
+                atomicAdd((unsigned long long *)&s_work[2], (unsigned long long)(2 * n_relax));
+                atomicAdd((unsigned long long *)&s_work[3], (unsigned long long)n_arc_pull);
+                atomicAdd((unsigned long long *)&s_work[8], (unsigned long long)n_mine);
+            }
+            if (tid == 0) s_work[0] += rounds + 1;
+        }
+        __syncthreads();
+        cnt.tick(4);
+    }
+    // ---- results of this component: flow in detection indices, totals added to its graph
+    __syncthreads();
+    if (tid == 0) {
+        if (K) {
+            atomicAdd(&p.n_paths[g], K);
+            atomicAdd((unsigned long long *)&p.total[g], (unsigned long long)total);
+        }
+        if (p.stats) {
+            unsigned long long *o = (unsigned long long *)(p.stats + (size_t)MOT3D_SOLVE_STATS * g);
+            atomicAdd(&o[0], (unsigned long long)s_work[0]);
+            atomicAdd(&o[2], (unsigned long long)s_work[2]);
+            atomicAdd(&o[3], (unsigned long long)(s_work[17] + s_work[3]));
+            for (int k = 0; k < 6; k++) atomicAdd(&o[4 + k], (unsigned long long)s_work[10 + k]);
+            atomicAdd(&o[9], (unsigned long long)s_work[16]);
+            atomicAdd(&o[10], (unsigned long long)s_work[20]);
+            atomicAdd(&o[11], (unsigned long long)s_work[18]);
+            atomicAdd(&o[12], (unsigned long long)s_work[8]);
+            atomicAdd(&o[13], (unsigned long long)s_work[14]);
+            atomicAdd(&o[15], (unsigned long long)s_work[0]);
+        }
+    }
+    for (int i = tid; i < n; i += T) {
+        const int a = rec[i].A.w, b = rec[i].A.z;
+        const int d = perm[i];
+        p.next_out[d] = a >= 0 ? perm[a] : a;
+        p.prev_out[d] = b >= 0 ? perm[b] : b;
+    }
+    __syncthreads();
+}
