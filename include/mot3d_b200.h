@@ -90,6 +90,13 @@ typedef struct mot3d_cost_spec {
 const char *mot3d_version(void);
 const char *mot3d_last_error(void);
 
+/* Process-wide test hooks / tuning knobs (no environment variables are read). value = NaN puts the built-in default
+ * back. Names: "host_chunks", "host_pieces", "host_split", "host_edge_weight", "host_trace", "host_no_pack"
+ * (mot3d_track_batch_host: how the batch is cut; timings to stderr; unpacked track_ptr), "edge_cap", "edge_acap"
+ * (mot3d_edge_build: staging capacities, 0 forces the global-memory paths), "solve_no_fast" (no single-track pass),
+ * "big_delta" (bucket width of solve_big.cuh in cost units). MOT3D_E_INVALID for an unknown name. */
+int32_t mot3d_set_option(const char *name, double value);
+
 /* ---- graph build: replaces build_graph's loops (mot3d/mot3d.py:75-141) + graph_to_text (:218-226) ------------ */
 
 /* tkey[i] = frame[i] - frame[first of graph] + base(graph), base = running sum of (frame span + max_jump + 1).
@@ -147,10 +154,11 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
                          int64_t *arc_total_out, void *ws, size_t ws_bytes, void *stream);
 
 /* colour-histogram factor (color_histogram_similarity, mot3d/distance_functions.py:21-34) multiplied in, then the
- * bbox and jump factors, then quantisation. One warp per row. */
+ * bbox and jump factors, then quantisation. One warp per row. arc_capacity = entries of col / weight / cost: rows that
+ * reach beyond it (a build that ran out of capacity and said so) are clipped. */
 int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction,
-                              const int32_t *row_ptr, const int32_t *col, double *weight_inout, int64_t *cost_out,
-                              void *stream);
+                              const int32_t *row_ptr, const int32_t *col, int64_t arc_capacity, double *weight_inout,
+                              int64_t *cost_out, void *stream);
 
 /* The 2-D views of 3-D detections (Detection3D.detections_2d, mot3d/types.py:40-45): detection i owns the entries
  * [view_ptr[i], view_ptr[i+1]) in the iteration order of its dict. */
@@ -174,7 +182,8 @@ typedef struct mot3d_views {
  *               there and the text it feeds muSSP undefined; the arc gets weight nan and cost 0 */
 int32_t mot3d_edge_appearance_views(const mot3d_dets *dets, const mot3d_views *views, const mot3d_cost_spec *spec,
                                     int32_t direction, const int32_t *row_ptr, const int32_t *col,
-                                    double *weight_inout, int64_t *cost_out, int32_t *error_flag, void *stream);
+                                    int64_t arc_capacity, double *weight_inout, int64_t *cost_out,
+                                    int32_t *error_flag, void *stream);
 
 /* ---- tracklet linking (second pass): replaces build_graph on DetectionTracklet lists (mot3d/mot3d.py:106-141)
  *      with weight_distance_tracklets_2d/_3d (mot3d/weight_functions.py:80-160) and linear_motion

@@ -85,6 +85,7 @@ _PD, _PS = ctypes.POINTER(Dets), ctypes.POINTER(CostSpecC)
 SIGNATURES = {
     "mot3d_version": (ctypes.c_char_p, []),
     "mot3d_last_error": (ctypes.c_char_p, []),
+    "mot3d_set_option": (_i32, [ctypes.c_char_p, ctypes.c_double]),
     "mot3d_make_keys": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mot3d_node_costs": (_i32, [_PD, _PS, _vp, _vp, _vp, _vp]),
     "mot3d_frame_sort": (_i32, [_PD, _vp]),
@@ -94,8 +95,8 @@ SIGNATURES = {
     "mot3d_edge_fill": (_i32, [_PD, _PS, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_edge_build_workspace_bytes": (_sz, [_i64]),
     "mot3d_edge_build": (_i32, [_PD, _PS, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "mot3d_edge_appearance_views": (_i32, [_PD, ctypes.POINTER(Views), _PS, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_edge_appearance": (_i32, [_PD, _PS, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "mot3d_edge_appearance_views": (_i32, [_PD, ctypes.POINTER(Views), _PS, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "mot3d_tracklet_edge_count": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _vp]),
     "mot3d_tracklet_edge_fill": (_i32, [ctypes.POINTER(Tracklets), ctypes.POINTER(TrackletSpecC), _vp, _i64, _vp, _vp,
                                         _vp, _vp, _vp]),
@@ -147,6 +148,11 @@ def lib():
 def check(code):
     if code != 0:
         raise Mot3dError(code, lib().mot3d_last_error().decode())
+
+
+def set_option(name, value=None):
+    """mot3d_set_option: test hooks / tuning knobs of the library; value=None restores the built-in default."""
+    check(lib().mot3d_set_option(name.encode(), float("nan") if value is None else float(value)))
 
 
 def version():

@@ -253,14 +253,14 @@ def build_graphs(batch, spec, direction=_lib.DIR_IN, with_weights=False, keys=No
                 vs.hist_channels, vs.hist_bins = int(v["hist"].shape[1]), int(v["hist"].shape[2])
             err = torch.zeros(1, **i32)
             _lib.check(L.mot3d_edge_appearance_views(ctypes.byref(d), ctypes.byref(vs), ctypes.byref(cs_real), direction,
-                                                     _ptr(gb.row_ptr), _ptr(gb.col), _ptr(gb.weight), _ptr(gb.cost),
-                                                     _ptr(err), st))
+                                                     _ptr(gb.row_ptr), _ptr(gb.col), n_edges, _ptr(gb.weight),
+                                                     _ptr(gb.cost), _ptr(err), st))
             if int(err.item()):
                 raise ValueError("two linked 3-D detections share no 2-D view: weight_distance_detections_3d is nan "
                                  "for them (np.mean of an empty list, reference mot3d/weight_functions.py:55-71)")
     elif spec.use_hist:
         _lib.check(L.mot3d_edge_appearance(ctypes.byref(d), ctypes.byref(cs), direction, _ptr(row_ptr), _ptr(gb.col),
-                                           _ptr(gb.weight), _ptr(gb.cost), st))
+                                           n_edges, _ptr(gb.weight), _ptr(gb.cost), st))
     return gb
 
 

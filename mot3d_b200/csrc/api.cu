@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace m3 {
@@ -300,7 +302,39 @@ static int32_t enqueue_chunk(const mot3d_host_batch *hb, const mot3d_cost_spec *
     return MOT3D_OK;
 }
 
+namespace m3 {
+static const char *const kOptionNames[OPT_COUNT] = {"host_chunks", "host_split", "host_edge_weight", "host_trace",
+                                                    "host_no_pack", "host_pieces", "edge_cap", "edge_acap",
+                                                    "solve_no_fast", "big_delta"};
+static std::atomic<uint64_t> g_option_bits[OPT_COUNT];  // the double's bits; 0 = unset (0.0 is stored as -0.0's twin)
+static std::atomic<uint32_t> g_option_set{0};
+bool option(Option which, double *value) {
+    if (!((g_option_set.load(std::memory_order_acquire) >> which) & 1u)) return false;
+    const uint64_t bits = g_option_bits[which].load(std::memory_order_relaxed);
+    memcpy(value, &bits, sizeof(double));
+    return true;
+}
+}  // namespace m3
+
 extern "C" {
+
+int32_t mot3d_set_option(const char *name, double value) {
+    M3_CHECK_ARG(name, "option name is NULL");
+    for (int k = 0; k < OPT_COUNT; k++)
+        if (strcmp(name, kOptionNames[k]) == 0) {
+            if (value != value) {  // NaN: back to the built-in default
+                g_option_set.fetch_and(~(1u << k), std::memory_order_release);
+            } else {
+                uint64_t bits;
+                memcpy(&bits, &value, sizeof(double));
+                g_option_bits[k].store(bits, std::memory_order_relaxed);
+                g_option_set.fetch_or(1u << k, std::memory_order_release);
+            }
+            return MOT3D_OK;
+        }
+    set_error("unknown option '%s'", name);
+    return MOT3D_E_INVALID;
+}
 
 size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t edge_capacity) {
     if (n < 0 || n_graphs < 0 || edge_capacity < 0) return 0;
@@ -335,14 +369,15 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     // detections: with one chunk the pieces hide keys / sort / build behind the H2D copies (8.0 ms per 6 M detections;
     // 2 chunks x 8 pieces 8.5 ms, 4 chunks 10.4 ms).
     int want = n >= 40 * HOST_CHUNK_MIN_DETS ? 2 : 1;
-    if (const char *e = getenv("MOT3D_HOST_CHUNKS")) want = atoi(e);
+    double ov;
+    if (option(OPT_HOST_CHUNKS, &ov)) want = (int)ov;
     if (want > HOST_MAX_CHUNKS) want = HOST_MAX_CHUNKS;
     if (want > G) want = G;
     if (want < 1) want = 1;
     double first_share = 0.5;
-    if (const char *e = getenv("MOT3D_HOST_SPLIT")) first_share = (atof(e) > 0 && atof(e) < 1) ? atof(e) : first_share;
+    if (option(OPT_HOST_SPLIT, &ov) && ov > 0 && ov < 1) first_share = ov;
     double edge_w = 1.0 / 3.0;  // size of the first and the last chunk relative to the inner ones
-    if (const char *e = getenv("MOT3D_HOST_EDGE_WEIGHT")) edge_w = atof(e) > 0 ? atof(e) : edge_w;
+    if (option(OPT_HOST_EDGE_WEIGHT, &ov) && ov > 0) edge_w = ov;
     HostCtx *ctx = host_ctx();
     if (!ctx) return cuda_fail(cudaGetLastError(), "mot3d_track_batch_host: stream/event/pinned scratch creation");
 
@@ -360,7 +395,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
     }
     int32_t *h_gptr = ctx->pinned_gptr;
     int64_t *h_gbase = ctx->pinned_gbase;
-    const bool tracing = getenv("MOT3D_HOST_TRACE") != nullptr;
+    const bool tracing = option(OPT_HOST_TRACE, &ov) && ov != 0;
     if (tracing && !ctx->t0) {
         M3_CUDA(cudaEventCreate(&ctx->t0));
         for (int c = 0; c < HOST_MAX_CHUNKS; c++)
@@ -388,7 +423,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             if (g > cut[nc]) cut[++nc] = g;
         }
         Arena A(device_ws, ws_bytes);
-        const bool pack_ptr = nc == 1 && !getenv("MOT3D_HOST_NO_PACK");
+        const bool pack_ptr = nc == 1 && !(option(OPT_HOST_NO_PACK, &ov) && ov != 0);
         int32_t *d_packed = nullptr;
         int64_t packed_total = 0;
         M3_CUDA(cudaEventRecord(ctx->start, user));
@@ -427,7 +462,7 @@ int32_t mot3d_track_batch_host(const mot3d_host_batch *hb, const mot3d_cost_spec
             cudaStream_t st = nc == 1 ? user : ctx->s[c];
             if (nc > 1) M3_CUDA(cudaStreamWaitEvent(st, ctx->start, 0));
             int pieces = (int)(nd / HOST_PIECE_MIN_DETS);
-            if (const char *e = getenv("MOT3D_HOST_PIECES")) pieces = atoi(e);
+            if (option(OPT_HOST_PIECES, &ov)) pieces = (int)ov;
             if (pieces > HOST_MAX_PIECES) pieces = HOST_MAX_PIECES;
             if (pieces < 1) pieces = 1;
             rc = enqueue_chunk(hb, spec, res, A, ga, gb, hg, hb_base, max_nodes, cap, ctx->pinned + 2 * c, st,

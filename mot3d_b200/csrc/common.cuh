@@ -38,6 +38,14 @@ int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_p
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
                        int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream);
 
+// Process-wide options (mot3d_set_option): test hooks and tuning knobs that used to be environment variables. An option
+// that was never set (or was reset with NaN) reports false and leaves the built-in default alone.
+enum Option {
+    OPT_HOST_CHUNKS, OPT_HOST_SPLIT, OPT_HOST_EDGE_WEIGHT, OPT_HOST_TRACE, OPT_HOST_NO_PACK, OPT_HOST_PIECES,
+    OPT_EDGE_CAP, OPT_EDGE_ACAP, OPT_SOLVE_NO_FAST, OPT_BIG_DELTA, OPT_COUNT
+};
+bool option(Option which, double *value);
+
 constexpr int MOT3D_MAX_DEVICES = 64;  // per-device caches (launch parameters, host pipeline contexts)
 constexpr int64_t INF = MOT3D_INF_COST;
 constexpr int64_t INF_CUT = MOT3D_INF_COST / 2;  // anything >= this is "unreachable"

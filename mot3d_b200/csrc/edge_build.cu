@@ -234,11 +234,12 @@ __global__ void __launch_bounds__(128) k_edge_appearance(int64_t n, const int32_
                                                          const __grid_constant__ JumpTable jt,
                                                          const int32_t *__restrict__ row_ptr,
                                                          const int32_t *__restrict__ col, double *__restrict__ weight,
-                                                         int64_t *__restrict__ cost) {
+                                                         int64_t *__restrict__ cost, int64_t arc_cap) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (r >= n) return;
     const int l = lane_id();
-    const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    // (rows reaching beyond the arc arrays: the build ran out of capacity and has reported it)
+    const int e0 = (int)min((int64_t)row_ptr[r], arc_cap), e1 = (int)min((int64_t)row_ptr[r + 1], arc_cap);
     const double *hr = hist + r * (int64_t)C * B;
     for (int e = e0; e < e1; e++) {
         const int64_t o = col[e];
@@ -466,11 +467,11 @@ __global__ void __launch_bounds__(128) k_edge_appearance_views(
     const double *__restrict__ vhist, int C, int B, int use_hist, int use_bbox, double sigma_hist_sq,
     double sigma_bbox_sq, const __grid_constant__ JumpTable jt, const int32_t *__restrict__ row_ptr,
     const int32_t *__restrict__ col, double *__restrict__ weight, int64_t *__restrict__ cost,
-    int32_t *__restrict__ error_flag) {
+    int32_t *__restrict__ error_flag, int64_t arc_cap) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (r >= n) return;
     const int l = lane_id();
-    const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    const int e0 = (int)min((int64_t)row_ptr[r], arc_cap), e1 = (int)min((int64_t)row_ptr[r + 1], arc_cap);
     for (int e = e0; e < e1; e++) {
         const int64_t o = col[e];
         const int64_t a = (DIR == MOT3D_DIR_OUT) ? r : o;  // d1: the earlier detection
@@ -701,8 +702,8 @@ int32_t mot3d_edge_fill(const mot3d_dets *dets, const mot3d_cost_spec *spec, int
 }
 
 int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spec, int32_t direction,
-                              const int32_t *row_ptr, const int32_t *col, double *weight_inout, int64_t *cost_out,
-                              void *stream) {
+                              const int32_t *row_ptr, const int32_t *col, int64_t arc_capacity, double *weight_inout,
+                              int64_t *cost_out, void *stream) {
     int32_t rc = check_dets(dets, spec);
     if (rc) return rc;
     M3_CHECK_ARG(spec->use_hist, "mot3d_edge_appearance called without use_hist");
@@ -717,19 +718,20 @@ int32_t mot3d_edge_appearance(const mot3d_dets *dets, const mot3d_cost_spec *spe
         k_edge_appearance<MOT3D_DIR_IN><<<grid, 128, 0, st>>>(dets->n, dets->tkey, dets->hist, dets->hist_channels,
                                                               dets->hist_bins, dets->bbox, spec->use_bbox,
                                                               spec->sigma_hist_sq, spec->sigma_bbox_sq, jt, row_ptr,
-                                                              col, weight_inout, cost_out);
+                                                              col, weight_inout, cost_out, arc_capacity);
     else
         k_edge_appearance<MOT3D_DIR_OUT><<<grid, 128, 0, st>>>(dets->n, dets->tkey, dets->hist, dets->hist_channels,
                                                                dets->hist_bins, dets->bbox, spec->use_bbox,
                                                                spec->sigma_hist_sq, spec->sigma_bbox_sq, jt, row_ptr,
-                                                               col, weight_inout, cost_out);
+                                                               col, weight_inout, cost_out, arc_capacity);
     M3_LAUNCH_CHECK("k_edge_appearance");
     return MOT3D_OK;
 }
 
 int32_t mot3d_edge_appearance_views(const mot3d_dets *dets, const mot3d_views *views, const mot3d_cost_spec *spec,
                                     int32_t direction, const int32_t *row_ptr, const int32_t *col,
-                                    double *weight_inout, int64_t *cost_out, int32_t *error_flag, void *stream) {
+                                    int64_t arc_capacity, double *weight_inout, int64_t *cost_out,
+                                    int32_t *error_flag, void *stream) {
     M3_CHECK_ARG(dets && views && spec, "dets/views/spec is NULL");
     M3_CHECK_ARG(direction == MOT3D_DIR_IN || direction == MOT3D_DIR_OUT, "bad direction");
     M3_CHECK_ARG(spec->max_jump >= 1 && spec->max_jump <= MOT3D_MAX_JUMP, "max_jump must be in [1, MOT3D_MAX_JUMP]");
@@ -750,12 +752,12 @@ int32_t mot3d_edge_appearance_views(const mot3d_dets *dets, const mot3d_views *v
         k_edge_appearance_views<MOT3D_DIR_IN><<<grid, 128, 0, st>>>(
             dets->n, dets->tkey, views->view_ptr, views->view_id, views->bbox, views->n_entries, views->hist,
             views->hist_channels, views->hist_bins, spec->use_hist, spec->use_bbox, spec->sigma_hist_sq,
-            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag);
+            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag, arc_capacity);
     else
         k_edge_appearance_views<MOT3D_DIR_OUT><<<grid, 128, 0, st>>>(
             dets->n, dets->tkey, views->view_ptr, views->view_id, views->bbox, views->n_entries, views->hist,
             views->hist_channels, views->hist_bins, spec->use_hist, spec->use_bbox, spec->sigma_hist_sq,
-            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag);
+            spec->sigma_bbox_sq, jt, row_ptr, col, weight_inout, cost_out, error_flag, arc_capacity);
     M3_LAUNCH_CHECK("k_edge_appearance_views");
     return MOT3D_OK;
 }

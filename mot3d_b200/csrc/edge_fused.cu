@@ -653,7 +653,7 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     p.arc_base_in = arc_base_in;
     p.arc_total_out = arc_total_out;
     // Shared memory per CTA, four CTAs per SM: candidates 20 (28 in 3-D) bytes each, the tile's rows 16 (24), arcs 4,
-    // the pass-1 cache 4 bytes per row and frame. MOT3D_EDGE_CAP / MOT3D_EDGE_ACAP override the split (tests, bench).
+    // the pass-1 cache 4 bytes per row and frame. mot3d_set_option("edge_cap" / "edge_acap") overrides the split (tests).
     p.cache_j = spec->max_jump <= EF_CACHE_J ? spec->max_jump : 0;
     const int per_cand = 8 + 8 + (dets->dim == 3 ? 8 : 0) + 4;
     const int rows_b = EF_TPB * 8 * dets->dim;
@@ -663,8 +663,9 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     if ((cap + 4) * per_cand > budget - 8192) cap = ((budget - 8192) / per_cand - 4) & ~3;  // room for 2048 arcs
     if (cap < 0) cap = 0;
     int acap = ((budget - (cap + 4) * per_cand - 16) / 4) & ~3;
-    if (const char *e = getenv("MOT3D_EDGE_CAP")) cap = atoi(e) & ~3;
-    if (const char *e = getenv("MOT3D_EDGE_ACAP")) acap = atoi(e) & ~3;
+    double ov;  // test hooks: force the staging modes (tests/test_gpu_parity.py)
+    if (option(OPT_EDGE_CAP, &ov)) cap = (int)ov & ~3;
+    if (option(OPT_EDGE_ACAP, &ov)) acap = (int)ov & ~3;
     if (cap > 65000) cap = 65000;  // slots of staged candidates are packed into 16 bits
     if (cap < 0) cap = 0;
     if (acap < 0) acap = 0;

@@ -112,7 +112,11 @@ struct SolveParams {
     // staging area of solve_big.cuh (components beyond the shared-memory bands, 32-bit costs)
     longlong2 *big_res_e;  // [n_total]
     int4 *big_res_f;       // [n_total]
-    unsigned *big_listed;  // [n_total / 32 + n_total + 8]
+    unsigned *big_listed;  // [n_total / 16 + n_total + 8]
+    longlong2 *big_old_e;  // [n_total]
+    long long *big_prio;   // [n_total]
+    int *big_far;          // [2 * n_total]
+    long long big_delta;   // width of a bucket of label increases
     int32_t *big_arc;      // 3 x [big_arc_stride]: cost, source, out-arc head; blocks handed out through big_arc_next
     int64_t big_arc_stride;
     unsigned long long *big_arc_next;
@@ -145,6 +149,20 @@ __device__ __forceinline__ int block_excl_scan1(int v, int *scratch, int phase, 
     *total = tot;
     return base + incl - v;
 }
+
+// Block-wide sum; scratch must hold 33 ints. Two barriers.
+__device__ __forceinline__ int block_sum(int v, int *scratch) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if (lane_id() == 0) scratch[warp_id()] = v;
+    __syncthreads();
+    int tot = 0;
+    for (int k = 0; k < (int)((blockDim.x + 31) >> 5); k++) tot += scratch[k];
+    __syncthreads();
+    return tot;
+}
+constexpr int BIG_MIN_WIDTH = 48;  // detections per frame layer from which solve_big.cuh takes a component
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -508,7 +526,21 @@ __global__ void __launch_bounds__(BT, MINB) k_ssp_solve(const __grid_constant__ 
         if (SHARED && n <= p.rcap && staging_bytes(n, 0) <= p.sbytes)
             done = solve_component_sm(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work);
         if (!done) {
-            if (p.win_wide[g])
+            // Beyond the shared-memory bands. Two solvers on staging areas in global memory: layer sweeps
+            // (solve_global.cuh: a step per frame layer, cheap when few sweeps settle a branch - long thin components)
+            // and bucketed rounds over pushed work lists (solve_big.cuh: a step per record of the longest new path,
+            // indifferent to how often that path changes direction - crowded components, where the sweeps alternate
+            // dozens of times). Crowded = at least BIG_MIN_WIDTH detections per frame layer; costs beyond 32 bits always
+            // take the sweeps.
+            bool sweeps = p.win_wide[g] != 0;
+            if (!sweeps) {
+                int starts = 0;
+                for (int i = tid; i < n; i += BT)
+                    starts += (i == 0 || p.tkey[p.comp_perm[c0 + i]] != p.tkey[p.comp_perm[c0 + i - 1]]) ? 1 : 0;
+                const int layers = block_sum(starts, s_scan);
+                sweeps = (long long)n < (long long)BIG_MIN_WIDTH * layers;
+            }
+            if (sweeps)
                 solve_component_global(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work, 0);
             else
                 solve_component_big(p, cg, c0, n, g, s_scan, s_red, s_ok, s_work);
@@ -725,7 +757,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     return a256(n * 8) * 3 + a256(n * 4) * 12 + a256(n * 16) + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
-           a256(n * sizeof(GRec)) + a256((e + n + 8) * sizeof(StArc)) + a256(n * 16) * 2 + a256((n / 32 + n + 8) * 4) +
+           a256(n * sizeof(GRec)) + a256((e + n + 8) * sizeof(StArc)) + a256(n * 16) * 3 + a256(n * 8) * 2 + a256((n / 16 + n + 8) * 4) +
            a256((e + 8) * 12) + 256 +
            a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512 + a256(JOB_META_INTS * sizeof(int32_t));
 }
@@ -805,7 +837,13 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     p.comp_class = (int32_t *)take(n_cap * 4);
     p.big_res_e = (longlong2 *)take(n_cap * 16);
     p.big_res_f = (int4 *)take(n_cap * 16);
-    p.big_listed = (unsigned *)take((n_cap / 32 + n_cap + 8) * 4);
+    p.big_listed = (unsigned *)take((n_cap / 16 + n_cap + 8) * 4);
+    p.big_old_e = (longlong2 *)take(n_cap * 16);
+    p.big_prio = (long long *)take(n_cap * 8);
+    p.big_far = (int *)take(n_cap * 8);
+    p.big_delta = BIG_DELTA;
+    double ov;
+    if (option(OPT_BIG_DELTA, &ov) && ov >= 0) p.big_delta = (long long)ov;
     p.big_arc_stride = (int64_t)e_cap + 8;
     p.big_arc = (int32_t *)take((e_cap + 8) * 12);
     p.big_arc_next = (unsigned long long *)take(256);
@@ -841,7 +879,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     }
     // test hook (tests/test_gpu_parity.py::test_single_track_pass_equals_full_solver): every component through the
     // full solver
-    p.fast = getenv("MOT3D_SOLVE_NO_FAST") ? 0 : 1;
+    p.fast = (option(OPT_SOLVE_NO_FAST, &ov) && ov != 0) ? 0 : 1;
     {
         // one warp per component, 8 x 8 warps per SM striding over them: finished on the spot (single tracks) or
         // counted into its band and size class; then the queue is laid out

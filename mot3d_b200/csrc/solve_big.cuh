@@ -11,6 +11,8 @@
 // detection graph whose tracks run over 1 000 frames needs thousands of rounds per path, each a handful of records.
 #pragma once
 
+constexpr long long BIG_DELTA = 1ll << 26;  // width of a bucket of label increases, in cost units (1e-7)
+
 struct BigCursor {  // bump allocator of the arc area: every component takes exactly its number of in-arcs, once
     unsigned long long next;
 };
@@ -27,8 +29,12 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
     int *const pl = p.ws_pl + c0;               // work list of a relabelling round
     unsigned char *const flg = (unsigned char *)(p.ws_tk + c0);  // DL_* of the branch being re-labelled
     int *const out_off = p.ws_bl + c0;          // out-arcs of record i: out_dst[out_off[i] .. out_off[i + 1])
-    unsigned *const listed = p.big_listed + (c0 >> 5) + cg;  // bit per record: on the next round's work list (every
-                                                             // component has its own words: + component index)
+    unsigned *const listed = p.big_listed + (c0 >> 4) + cg;  // two bits per record: on the next round's work list /
+                                                             // on the waiting list (every component has its own
+                                                             // words: + component index)
+    longlong2 *const old_e = p.big_old_e + c0;  // labels of the branch before the path was flipped: the potentials
+    long long *const prio = p.big_prio + c0;    // smallest label increase among the inputs a listed record waits for
+    int *const far0 = p.big_far + 2 * (size_t)c0, *const far1 = far0 + n;  // the waiting list, two buffers
     const int32_t *const perm = p.comp_perm + c0;
 
     // ---- stage the component. Arc offsets by a block scan over contiguous chunks of records.
@@ -45,7 +51,8 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
     // the arc area taken from a bump allocator (every component asks for exactly its number of in-arcs, once: the area
     // of arc_capacity entries per array cannot run out)
     if (tid == 0) s_ok[6] = (int)atomicAdd(p.big_arc_next, (unsigned long long)tot);
-    for (int w = tid; w < (n >> 5) + 1; w += T) listed[w] = 0;
+    for (int w = tid; w < (n >> 4) + 1; w += T) listed[w] = 0;
+    for (int i = tid; i < n; i += T) prio[i] = INF;
     __syncthreads();
     int32_t *const arc_cost = p.big_arc + s_ok[6];
     int *const arc_src = arc_cost + p.big_arc_stride;
@@ -257,6 +264,7 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
                 flg[s] = (unsigned char)f;
                 if (f) {
                     longlong2 E = rec[s].E;
+                    old_e[s] = E;
                     if (f & 1) {
                         E.x = INF;
                         F.x = PAR_NONE;
@@ -282,15 +290,75 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
         cnt.add(1, 1);
         __syncthreads();
         cnt.tick(1);
-        int n_arc_pull = 0, n_relax = 0, rounds = 0;
-        // two work lists (pl, hop) and their lengths (s_ok[3], s_ok[4]) alternate between the rounds
+        int n_arc_pull = 0, n_relax = 0, rounds = 0, n_far = 0, far_buf = 0;
+        // Order of work. Labels only rise when a path is taken out (the old labels are potentials: every residual arc
+        // has a non-negative reduced cost), and a label that has risen by less is final earlier - Dijkstra's order on
+        // the increases. The rounds follow it bucket by bucket: a record is listed with the smallest increase among the
+        // labels it waits for (prio); increases up to the threshold thr go on the next round's list, larger ones on a
+        // waiting list. When the rounds of a bucket have reached their fix-point the threshold moves to the smallest
+        // increase waiting (+ BIG_DELTA) and the waiting list is split again. Tentative labels that a better one would
+        // overwrite anyway (a track started afresh at every node of the branch, detours over neighbouring tracks) are
+        // then never passed on. Any order gives the same fix-point; this one keeps the rounds' frontiers thin.
+        // two work lists (pl, hop) and their lengths (s_ok[3], s_ok[4]) alternate between the rounds; s_ok[5] = length
+        // of the waiting list being written
+        long long thr = -1;  // first round: everything the branch's records pass on waits
+        if (tid == 0) s_ok[5] = 0;
 #pragma unroll 1
-        for (; rounds < 4 * n + 8; rounds++) {
+        for (; rounds < 64 * n + 64; rounds++) {
             const int *const cur = (rounds & 1) ? hop : pl;
             int *const nxt = (rounds & 1) ? pl : hop;
             int *const n_next = &s_ok[3 + ((rounds + 1) & 1)];
-            const int n_work = s_ok[3 + (rounds & 1)];
-            if (n_work == 0) break;  // nothing moved in the round before: fix-point
+            int n_work = s_ok[3 + (rounds & 1)];
+            if (n_work == 0) {
+                // ---- the bucket is done: next threshold, and the waiting records below it become the work list
+                n_far = s_ok[5];
+                if (n_far == 0) break;  // fix-point
+                int *const fa = far_buf ? far1 : far0, *const fb = far_buf ? far0 : far1;
+                long long lo = INF;
+                for (int k = tid; k < n_far; k += T) lo = min(lo, prio[fa[k]]);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                __syncthreads();  // (everybody has read the list lengths)
+                if (lane_id() == 0) s_red[warp_id()].key = lo;
+                if (tid == 0) {
+                    s_ok[5] = 0;
+                    s_ok[3 + (rounds & 1)] = 0;
+                }
+                __syncthreads();
+                lo = INF;
+                for (int k = 0; k < (T + 31) >> 5; k++) lo = min(lo, (long long)s_red[k].key);
+                thr = lo >= INF_CUT ? INF : lo + p.big_delta;
+                int *const cur_w = (rounds & 1) ? hop : pl;
+                for (int kb = 0; kb < n_far; kb += T) {
+                    const int k = kb + tid;
+                    int d = -1, where = 0;  // 1 = work list, 2 = keeps waiting, 0 = relaxed meanwhile: dropped
+                    if (k < n_far) {
+                        d = fa[k];
+                        const long long pr = prio[d];
+                        where = pr >= INF_CUT ? 0 : (pr <= thr ? 1 : 2);
+                    }
+                    if (where != 2 && d >= 0) {
+                        const unsigned sh = (d & 15) * 2;
+                        const unsigned old = atomicAnd(&listed[d >> 4], ~(2u << sh));  // off the waiting list
+                        if (where == 1 && ((old | atomicOr(&listed[d >> 4], 1u << sh)) >> sh & 1u)) where = 0;  // listed already
+                    }
+                    const unsigned m1 = __ballot_sync(0xffffffffu, where == 1), m2 = __ballot_sync(0xffffffffu, where == 2);
+                    int a1 = 0, a2 = 0;
+                    if (lane_id() == 0) {
+                        if (m1) a1 = atomicAdd(&s_ok[3 + (rounds & 1)], __popc(m1));
+                        if (m2) a2 = atomicAdd(&s_ok[5], __popc(m2));
+                    }
+                    a1 = __shfl_sync(0xffffffffu, a1, 0);
+                    a2 = __shfl_sync(0xffffffffu, a2, 0);
+                    if (where == 1) cur_w[a1 + __popc(m1 & lt)] = d;
+                    if (where == 2) fb[a2 + __popc(m2 & lt)] = d;
+                }
+                far_buf ^= 1;
+                __syncthreads();
+                n_work = s_ok[3 + (rounds & 1)];
+                if (n_work == 0) continue;  // (everything waiting had been relaxed meanwhile: look again)
+            }
+            __syncthreads();  // (the list lengths have been read)
             if (tid == 0) *n_next = 0;
             // (A) relax the listed records from the labels of the round before, four lanes per record; the results are
             //     staged
@@ -299,7 +367,10 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
                 const int s = cur[wi];
                 // (its bit comes off the list here: set bits are exactly the records waiting on the next list, and the
                 // words are all zero again when the rounds end)
-                if (sub == 0) atomicAnd(&listed[s >> 5], ~(1u << (s & 31)));
+                if (sub == 0) {
+                    atomicAnd(&listed[s >> 4], ~(1u << ((s & 15) * 2)));
+                    prio[s] = INF;
+                }
                 const int f = flg[s];
                 const int4 A = rec[s].A;  // x = in-degree, y = first arc, z = prev, w = next
                 const int4 W = rec[s].W;
@@ -380,32 +451,41 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
             }
             __syncthreads();  // every label of the round before has been read
 #pragma unroll 1
-            for (int wi = tid; wi < n_work; wi += T) {  // (B) publish, and list what reads a label that moved
-                const int4 rf = res_f[wi];
+            for (int wi = grp; wi < n_work; wi += ngrp) {  // (B) publish, and list what reads a label that moved: four
+                const int4 rf = res_f[wi];                  //     lanes per record, one out-arc each
                 if (rf.w) {
                     const int s = cur[wi];
-                    rec[s].E = res_e[wi];
-                    int4 F = rec[s].F;
-                    F.x = rf.x;
-                    F.y = rf.y;
-                    F.z = rf.z;
-                    rec[s].F = F;
+                    // by how much the labels that moved have risen since the path was flipped
+                    const longlong2 En = res_e[wi], Eo = old_e[s];
+                    const int o0 = out_off[s], o1 = s + 1 < n ? (int)out_off[s + 1] : tot;
+                    const int prv = rec[s].A.z;
+                    if (sub == 0) {
+                        rec[s].E = En;
+                        int4 F = rec[s].F;
+                        F.x = rf.x;
+                        F.y = rf.y;
+                        F.z = rf.z;
+                        rec[s].F = F;
+                    }
+                    int *const far_w = far_buf ? far1 : far0;
+                    auto list = [&](int d, long long inc) {
+                        atomicMin(&prio[d], inc);
+                        const unsigned sh = (d & 15) * 2;
+                        if (inc <= thr) {
+                            if (!(atomicOr(&listed[d >> 4], 1u << sh) >> sh & 1u)) nxt[atomicAdd(n_next, 1)] = d;
+                        } else {
+                            if (!(atomicOr(&listed[d >> 4], 2u << sh) >> sh & 2u)) far_w[atomicAdd(&s_ok[5], 1)] = d;
+                        }
+                    };
                     if (rf.w & 2) {  // post label: the heads of the out-arcs whose pre node is being re-labelled
-                        const int o0 = out_off[s], o1 = s + 1 < n ? (int)out_off[s + 1] : tot;
-                        for (int k = o0; k < o1; k++) {
+                        const long long inc = En.y - Eo.y;
+                        for (int k = o0 + sub; k < o1; k += LPN) {
                             const int d = out_dst[k];
-                            const unsigned bit = 1u << (d & 31);
-                            if ((flg[d] & 1) && !(atomicOr(&listed[d >> 5], bit) & bit))
-                                nxt[atomicAdd(n_next, 1)] = d;
+                            if (flg[d] & 1) list(d, inc);
                         }
                     }
-                    if (rf.w & 1) {  // pre label on a track: the post node of the record before it (reversed matched arc)
-                        const int d = rec[s].A.z;
-                        if (d >= 0 && (flg[d] & 2)) {
-                            const unsigned bit = 1u << (d & 31);
-                            if (!(atomicOr(&listed[d >> 5], bit) & bit)) nxt[atomicAdd(n_next, 1)] = d;
-                        }
-                    }
+                    // pre label on a track: the post node of the record before it (reversed matched arc)
+                    if ((rf.w & 1) && sub == LPN - 1 && prv >= 0 && (flg[prv] & 2)) list(prv, En.x - Eo.x);
                 }
             }
             __syncthreads();

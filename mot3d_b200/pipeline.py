@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .batch import _ptr, _stream, _dets_struct, tracks_to_lists
+from .batch import _ptr, _stream, _dets_struct, _views_mode, tracks_to_lists
 
 STAGES = ["make_keys", "node_costs", "frame_sort", "edge_build", "solve", "extract"]
 STAGES_UNFUSED = ["make_keys", "node_costs", "frame_sort", "edge_count", "row_scan", "edge_fill", "solve", "extract"]
@@ -59,6 +59,8 @@ class TrackPipeline(object):
         self.track_count = torch.empty(G, **i32)
         self.track_ptr = torch.empty(n + G + 1, **i32)
         self.track_det = torch.empty(n, **i32)
+        self.weight = None   # float64 [E] arc weights, allocated when a cost with an appearance term comes through
+        self.app_err = None
 
     def run(self, batch, spec, spec_c=None, events=None, before_extract=None, before_solve=None):
         """batch: DetectionBatch on self.device. events: optional list of len(self.stages)+1 torch.cuda.Event recorded
@@ -71,9 +73,20 @@ class TrackPipeline(object):
         n, G = batch.n, batch.n_graphs
         if n > self.n_max or G > self.g_max:
             raise ValueError("batch larger than the pipeline was sized for")
-        if spec.use_hist or (spec.kind == "detections_3d" and spec.use_bbox):
-            raise NotImplementedError("TrackPipeline: the appearance passes are wired through build_graphs only")
         cs = spec.to_c() if spec_c is None else spec_c
+        views_mode = _views_mode(spec)
+        cs_real = cs
+        if views_mode:
+            # 3-D detections with per-view appearance: the build leaves the distance factor in weight[] and
+            # mot3d_edge_appearance_views finishes the arcs (as build_graphs does)
+            cs = spec.to_c()
+            cs.use_hist, cs.use_bbox, cs.defer_cost = 0, 0, 1
+        need_w = bool(spec.use_hist or views_mode)
+        if need_w and not self.fused:
+            raise NotImplementedError("TrackPipeline(fused=False): the appearance passes need the single-pass build")
+        if need_w and self.weight is None:
+            self.weight = torch.empty(self.edge_capacity, dtype=torch.float64, device=dev)
+            self.app_err = torch.zeros(1, dtype=torch.int32, device=dev)
         st = _stream(dev)
         rec = (lambda k: events[k].record(torch.cuda.current_stream(dev))) if events is not None else (lambda k: None)
         max_nodes = getattr(batch, "_max_nodes", None)
@@ -92,9 +105,28 @@ class TrackPipeline(object):
         rec(3)
         if self.fused:
             _lib.check(L.mot3d_edge_build(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, 0, n, _ptr(self.row_ptr),
-                                          self.edge_capacity, _ptr(self.col), _ptr(self.cost), None,
+                                          self.edge_capacity, _ptr(self.col), _ptr(self.cost),
+                                          _ptr(self.weight) if need_w else None,
                                           _ptr(self.overflow), None, None, _ptr(self.build_ws), self.build_ws_bytes,
                                           st))
+            if views_mode:
+                v = batch.views
+                vs = _lib.Views()
+                vs.n, vs.n_entries = n, int(v["view_id"].shape[0])
+                vs.view_ptr, vs.view_id = v["view_ptr"].data_ptr(), v["view_id"].data_ptr()
+                if spec.use_bbox:
+                    vs.bbox = v["bbox"].data_ptr()
+                if spec.use_hist:
+                    vs.hist = v["hist"].data_ptr()
+                    vs.hist_channels, vs.hist_bins = int(v["hist"].shape[1]), int(v["hist"].shape[2])
+                _lib.check(L.mot3d_edge_appearance_views(ctypes.byref(d), ctypes.byref(vs), ctypes.byref(cs_real),
+                                                         _lib.DIR_IN, _ptr(self.row_ptr), _ptr(self.col),
+                                                         self.edge_capacity, _ptr(self.weight), _ptr(self.cost),
+                                                         _ptr(self.app_err), st))
+            elif spec.use_hist:
+                _lib.check(L.mot3d_edge_appearance(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_ptr),
+                                                   _ptr(self.col), self.edge_capacity, _ptr(self.weight),
+                                                   _ptr(self.cost), st))
             k = 4
         else:
             _lib.check(L.mot3d_edge_count(ctypes.byref(d), ctypes.byref(cs), _lib.DIR_IN, _ptr(self.row_count), st))
@@ -124,6 +156,9 @@ class TrackPipeline(object):
         self._n, self._G = n, G
 
     def check_overflow(self):
+        if self.app_err is not None and int(self.app_err.item()):
+            raise ValueError("two linked 3-D detections share no 2-D view: weight_distance_detections_3d is nan for "
+                             "them (reference mot3d/weight_functions.py:55-71)")
         flag = int(self.overflow.item())
         if flag & (_lib.ERR_UNSORTED | _lib.ERR_KEY_RANGE):
             from .batch import _raise_key_errors

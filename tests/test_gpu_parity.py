@@ -13,6 +13,25 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-6  # float edge weights, BASELINE.json north_star
 
 
+def _opt(monkeypatch, name, value):
+    """Set a library option (mot3d_set_option) for the duration of one test; _reset_options restores the default."""
+    from mot3d_b200 import _lib
+    _lib.set_option(name, value)
+    _PENDING.append(name)
+
+
+_PENDING = []
+
+
+@pytest.fixture(autouse=True)
+def _reset_options():
+    yield
+    if _PENDING:
+        from mot3d_b200 import _lib
+        while _PENDING:
+            _lib.set_option(_PENDING.pop(), None)
+
+
 def _torch():
     import torch
     return torch
@@ -109,9 +128,9 @@ def test_fused_build_equals_two_pass_build(name, cap, acap, monkeypatch):
     spec = _spec_from(d["spec"], mot3d)
     b = _batch_from(d, mot3d).to("cuda")
     if cap is not None:
-        monkeypatch.setenv("MOT3D_EDGE_CAP", str(cap))
+        _opt(monkeypatch, "edge_cap", cap)
     if acap is not None:
-        monkeypatch.setenv("MOT3D_EDGE_ACAP", str(acap))
+        _opt(monkeypatch, "edge_acap", acap)
     for direction in (_lib.DIR_IN, _lib.DIR_OUT):
         two = mot3d.build_graphs(b, spec, direction=direction, with_weights=True, fused=False)
         one = mot3d.build_graphs(b, spec, direction=direction, with_weights=True, fused=True)
@@ -438,7 +457,7 @@ def test_host_entry_point_chunked_pipeline(chunks, monkeypatch):
     gb, sol = mot3d.track_batch(b.to("cuda"), spec)
     want_tracks = mot3d.tracks_to_lists(gp, sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
                                         sol.track_det.cpu().numpy())
-    monkeypatch.setenv("MOT3D_HOST_CHUNKS", str(chunks))
+    _opt(monkeypatch, "host_chunks", chunks)
     for cap in (gb.n_edges + 64, gb.n_edges):  # roomy, then exact: the crowded chunk overflows its share
         ht = mot3d.HostTracker(n_max=n + 5, g_max=len(gp) + 2, edge_capacity=cap, dim=2)
         ht.load(b)
@@ -473,8 +492,8 @@ def test_host_entry_point_pieces_with_bbox(chunks, pieces, monkeypatch):
                                  sol.track_det.cpu().numpy())
     gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist() for t in range(len(d["track_ptr"]) - 1)]
     assert want == [gold] * reps
-    monkeypatch.setenv("MOT3D_HOST_CHUNKS", str(chunks))
-    monkeypatch.setenv("MOT3D_HOST_PIECES", str(pieces))
+    _opt(monkeypatch, "host_chunks", chunks)
+    _opt(monkeypatch, "host_pieces", pieces)
     ht = mot3d.HostTracker(n_max=reps * n, g_max=reps, edge_capacity=gb.n_edges + 8 * reps, dim=2, with_bbox=True)
     ht.load(b)
     assert ht.run(spec.to_c()) == gb.n_edges
@@ -858,7 +877,7 @@ def test_single_track_pass_equals_full_solver(monkeypatch):
     sol_fast = mot3d.solve_graphs(gb, want_path_costs=True)
     stats = sol_fast.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)
     assert stats[:, 24].sum() > 0.5 * 60 * 80          # the pass did take most components
-    monkeypatch.setenv("MOT3D_SOLVE_NO_FAST", "1")
+    _opt(monkeypatch, "solve_no_fast", 1)
     sol_full = mot3d.solve_graphs(gb, want_path_costs=True)
     assert sol_full.stats.cpu().numpy().reshape(-1, mot3d._lib.SOLVE_STATS)[:, 24].sum() == 0
     n = db.n
@@ -1122,3 +1141,32 @@ def test_tracklet_costs_on_real_pairs(name):
                 miss += 1
     with pytest.raises(AssertionError):  # the reference's linear_motion asserts the order in time
         fn(tracklets[1], tracklets[1], **kw)
+
+
+@pytest.mark.parametrize("name", ["c4_synth_appearance", "c3_synth_multiview", "c5_small_f30_p12"])
+def test_track_pipeline_with_appearance_costs(name):
+    """TrackPipeline (the scheduler's per-rank path: preallocated buffers, no host synchronisation) with the appearance
+    terms: colour histograms + boxes of 2-D detections, per-view terms of 3-D detections. Same arcs, costs, totals and
+    tracks as build_graphs / solve_graphs, i.e. the reference's."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200.pipeline import TrackPipeline
+    d = gu.load(name)
+    spec = _spec_from(d["spec"], mot3d)
+    n = len(d["frame"])
+    b = _batch_from(d, mot3d).to("cuda")
+    gb, sol = mot3d.track_batch(b, spec)
+    pipe = TrackPipeline(n, 1, gb.n_edges + 16, dim=b.dim)
+    for _ in range(2):  # (buffers are reused from run to run)
+        pipe.run(b, spec)
+    pipe.check_overflow()
+    E = gb.n_edges
+    assert pipe.n_edges() == E
+    assert (pipe.col[:E] == gb.col[:E]).all() and (pipe.cost[:E] == gb.cost[:E]).all()
+    assert int(pipe.total_cost[0].item()) == int(sol.total_cost[0].item()) == gu.ref_total_units(d)
+    gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist() for t in range(len(d["track_ptr"]) - 1)]
+    assert pipe.tracks(np.array([0, n]))[0] == gold
+    # too small an arc buffer: reported, and the appearance pass stays inside it
+    small = TrackPipeline(n, 1, max(E // 2, 1), dim=b.dim)
+    small.run(b, spec)
+    with pytest.raises(mot3d.Mot3dError):
+        small.check_overflow()
