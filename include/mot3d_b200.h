@@ -358,6 +358,40 @@ int32_t mot3d_merge_close_points(const int32_t *set_ptr, int32_t n_sets, int32_t
                                  const double *points, double eps, int32_t *label_out, int32_t *cluster_count_out,
                                  double *merged_out, void *stream);
 
+/* ---- device-resident glue between the detection pass and the tracklet pass (one graph) ------------------------ */
+
+/* Tracks of pass 1 (mot3d_extract_tracks on ONE graph of n detections) -> the tracklets of pass 2, without leaving the
+ * device: split_trajectory_modulo(length) + remove_short_trajectories(th_length) (mot3d/utils/trajectory.py:216-248) and
+ * the head / tail windows of DetectionTracklet2D/3D(tracklet, window) (mot3d/types.py:94-184; window 0 = None).
+ * Tracklets come out ordered by the frame they start in (key_out, the solver's time key of pass 2: an arc only leads to
+ * a tracklet that starts after its tail ends, so the order is topological); the reference keeps them in track order -
+ * the linked trajectories are the same, their numbering is not.
+ *   trk_first_out[k], trk_len_out[k] : tracklet k = entries [first, first + len) of track_det
+ *   head_ptr_out / tail_ptr_out [n+1], head_idx_out / tail_idx_out [n], head_pos_out / tail_pos_out [dim][n] planar with
+ *   stride n: the arrays of mot3d_tracklets (set n_head_points = n_tail_points = n there)
+ *   n_tracklets_out : device int32 */
+size_t mot3d_tracklets_from_tracks_workspace_bytes(int64_t n);
+int32_t mot3d_tracklets_from_tracks(int32_t n, int32_t dim, const int32_t *frame, const double *pos,
+                                    const int32_t *track_count, const int32_t *track_ptr, const int32_t *track_det,
+                                    int32_t split_length, int32_t th_length, int32_t window, int32_t *n_tracklets_out,
+                                    int32_t *trk_first_out, int32_t *trk_len_out, int32_t *key_out, int32_t *head_ptr_out,
+                                    int32_t *tail_ptr_out, int32_t *head_idx_out, int32_t *tail_idx_out,
+                                    double *head_pos_out, double *tail_pos_out, void *ws, size_t ws_bytes, void *stream);
+
+/* Out-CSR of mot3d_tracklet_edge_fill (rows = arc tails) -> the solver's inputs for one graph of *n_nodes_dev nodes
+ * (<= n_nodes_max): in-CSR, constant entry / node / exit costs, graph_ptr = {0, n}. ws: int32 [n_nodes_max + 1]. */
+int32_t mot3d_tracklet_graph_in_csr(const int32_t *n_nodes_dev, int32_t n_nodes_max, const int32_t *row_ptr,
+                                    const int32_t *col, const int64_t *cost, int64_t entry_cost, int64_t node_cost,
+                                    int64_t exit_cost, int32_t *in_ptr_out, int32_t *in_src_out, int64_t *in_cost_out,
+                                    int64_t *entry_out, int64_t *node_out, int64_t *exit_out, int32_t *graph_ptr_out,
+                                    int32_t *ws, void *stream);
+
+/* Chains of tracklets (mot3d_extract_tracks of pass 2) -> chains of detections (concat_tracklets,
+ * mot3d/utils/trajectory.py:11-12): out_ptr [K + 1], out_det = indices of pass-1 detections. */
+int32_t mot3d_concat_tracklets(const int32_t *track_count, const int32_t *track_ptr, const int32_t *track_trk,
+                               const int32_t *trk_first, const int32_t *trk_len, const int32_t *track_det_pass1,
+                               int32_t *out_count, int32_t *out_ptr, int32_t *out_det, void *stream);
+
 /* ---- input-side prep: color_histogram (mot3d/distance_functions.py:10-19) ------------------------------------- */
 
 /* Histograms of image patches, all boxes of an image in one launch, written straight into the `hist` array of

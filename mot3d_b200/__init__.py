@@ -18,4 +18,5 @@ from .batch import (DetectionBatch, GraphBatch, HostTracker, build_graphs, solve
                     track_batch, tracks_to_lists)
 from .scheduler import shard_graphs, gather_tracks, TrackGather, pack_tracks_host, unpack_tracks_host  # noqa: F401
 from . import online  # noqa: F401
+from .twopass import link_tracks  # noqa: F401
 from ._lib import Mot3dError, version  # noqa: F401

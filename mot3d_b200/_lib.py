@@ -120,6 +120,12 @@ SIGNATURES = {
     "mot3d_peer_set_word": (_i32, [_vp, _i32, _vp]),
     "mot3d_peer_wait_word": (_i32, [_vp, _i32, _vp, _vp]),
     "mot3d_merge_close_points": (_i32, [_vp, _i32, _i32, _i32, _vp, ctypes.c_double, _vp, _vp, _vp, _vp]),
+    "mot3d_tracklets_from_tracks_workspace_bytes": (_sz, [_i64]),
+    "mot3d_tracklets_from_tracks": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mot3d_tracklet_graph_in_csr": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp]),
+    "mot3d_concat_tracklets": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mot3d_color_histograms": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, ctypes.POINTER(ctypes.c_int32), _i32, _i32, _vp, _vp,
                                       _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),

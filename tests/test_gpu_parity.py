@@ -1170,3 +1170,62 @@ def test_track_pipeline_with_appearance_costs(name):
     small.run(b, spec)
     with pytest.raises(mot3d.Mot3dError):
         small.check_overflow()
+
+
+@pytest.mark.parametrize("case", ["c3_soldiers_3d", "c5_small_2d_window"])
+def test_device_resident_two_pass_equals_host_glue(case):
+    """link_tracks (pass 1 -> tracklets -> pass 2 -> trajectories on the device, csrc/twopass.cu) against the drop-in
+    path on Python objects (split_trajectory_modulo / remove_short_trajectories / DetectionTracklet / build_graph /
+    solve_graph / concat_tracklets), which is pinned to the reference (test_two_pass_pipeline_drop_in and the pass-2
+    fixtures). C3 is examples/soldiers_3d/example.py: 3-D detections, length 10, th_length 2, whole tracklets at both ends;
+    the 2-D case uses windows of 3 frames."""
+    import mot3d_b200 as mot3d
+    import mot3d_b200.weight_functions as wf
+    if case == "c3_soldiers_3d":
+        d = gu.load("c3_soldiers_pass1")
+        length, th, window = 10, 2, None
+        tkw = dict(sigma_color_histogram=0.3, sigma_motion=3, alpha=0.7, cutoff_motion=0.1, cutoff_appearance=0.1,
+                   max_distance=None, use_color_histogram=False)
+        kind, wss2, mj2 = "tracklets_3d", 0.1, 30
+    else:
+        d = gu.load("c5_small_f30_p12")
+        length, th, window = 5, 1, 3
+        tkw = dict(sigma_color_histogram=0.3, sigma_motion=20, alpha=0.7, cutoff_motion=0.1, cutoff_appearance=0.1,
+                   max_distance=60, use_color_histogram=False)
+        kind, wss2, mj2 = "tracklets_2d", 0.2, 12
+    spec = _spec_from(d["spec"], mot3d)
+    n = len(d["frame"])
+    b = _batch_from(d, mot3d).to("cuda")
+    gb, sol = mot3d.track_batch(b, spec)
+    tracks1 = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                    sol.track_det.cpu().numpy())[0]
+    tspec = mot3d.TrackletCostSpec(kind=kind, distance=tkw, confidence=dict(mul=1, bias=0), weight_source_sink=wss2,
+                                   max_jump=mj2)
+    got, info = mot3d.link_tracks(b, sol, tspec, split_length=length, th_length=th, window=window)
+    # ---- the same through the objects
+    three_d = kind == "tracklets_3d"
+    Det = mot3d.Detection3D if three_d else mot3d.Detection2D
+    dets = [Det(int(d["frame"][i]), d["pos"][i], confidence=float(d["conf"][i])) for i in range(n)]
+    index_of = {id(x): i for i, x in enumerate(dets)}
+    pieces = []
+    for t in tracks1:
+        pieces += mot3d.split_trajectory_modulo([dets[i] for i in t], length=length)
+    pieces = mot3d.remove_short_trajectories(pieces, th_length=th)
+    Trk = mot3d.DetectionTracklet3D if three_d else mot3d.DetectionTracklet2D
+    dts = [Trk(pc, window=window) for pc in pieces]
+    assert info["n_tracklets"] == len(dts)
+    fn = wf.weight_distance_tracklets_3d if three_d else wf.weight_distance_tracklets_2d
+    g2 = mot3d.build_graph(dts, weight_source_sink=wss2, max_jump=mj2, verbose=False,
+                           weight_confidence=lambda t: wf.weight_confidence_tracklets_2d(t, mul=1, bias=0),
+                           weight_distance=lambda a, c: fn(a, c, **tkw))
+    assert g2 is not None and g2.n_transitions == info["n_arcs"]
+    final = mot3d.solve_graph(g2, verbose=False)
+    want = [[index_of[id(x)] for x in mot3d.concat_tracklets([t.tracklet for t in tr])] for tr in final]
+    assert g2.total_cost == info["total_cost"]
+    assert sorted(got) == sorted(want)
+    # the tracklets themselves: same pieces, ordered by the frame they start in
+    first, ln, key = (x.cpu().numpy() for x in info["tracklets"])
+    td = sol.track_det.cpu().numpy()
+    mine = sorted(tuple(td[f:f + l].tolist()) for f, l in zip(first, ln))
+    assert mine == sorted(tuple(index_of[id(x)] for x in pc) for pc in pieces)
+    assert (np.diff(key) >= 0).all()
