@@ -368,7 +368,7 @@ int32_t mot3d_merge_close_points(const int32_t *set_ptr, int32_t n_sets, int32_t
  * the linked trajectories are the same, their numbering is not.
  *   trk_first_out[k], trk_len_out[k] : tracklet k = entries [first, first + len) of track_det
  *   head_ptr_out / tail_ptr_out [n+1], head_idx_out / tail_idx_out [n], head_pos_out / tail_pos_out [dim][n] planar with
- *   stride n: the arrays of mot3d_tracklets (set n_head_points = n_tail_points = n there)
+ *   stride n: the arrays of struct mot3d_tracklets, with n_head_points = n_tail_points = n there
  *   n_tracklets_out : device int32 */
 size_t mot3d_tracklets_from_tracks_workspace_bytes(int64_t n);
 int32_t mot3d_tracklets_from_tracks(int32_t n, int32_t dim, const int32_t *frame, const double *pos,
