@@ -693,12 +693,20 @@ static inline void trace_mark(int k, cudaStream_t st) {
 
 // ---- per-device facts and launch parameters are looked up once, not on every call
 // Launch shapes of the bands: threads per block, blocks per SM. Band SM_BANDS = the global staging area.
-static const int kBandThreads[SM_BANDS + 1] = {128, 256, 512, 256};
-static const int kBandBlocks[SM_BANDS + 1] = {8, 3, 1, 3};
+#ifndef M3_B0T
+#define M3_B0T 128
+#define M3_B0B 10
+#endif
+#ifndef M3_B1T
+#define M3_B1T 256
+#define M3_B1B 3
+#endif
+static const int kBandThreads[SM_BANDS + 1] = {M3_B0T, M3_B1T, 512, 256};
+static const int kBandBlocks[SM_BANDS + 1] = {M3_B0B, M3_B1B, 1, 3};
 static const void *band_kernel(int b) {
     switch (b) {
-        case 0: return (const void *)k_ssp_solve<128, 8, true>;
-        case 1: return (const void *)k_ssp_solve<256, 3, true>;
+        case 0: return (const void *)k_ssp_solve<M3_B0T, M3_B0B, true>;
+        case 1: return (const void *)k_ssp_solve<M3_B1T, M3_B1B, true>;
         case 2: return (const void *)k_ssp_solve<512, 1, true>;
         default: return (const void *)k_ssp_solve<256, 3, false>;
     }
@@ -868,7 +876,10 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     trace_mark(1, st);
     // 2. first shortest-path tree per graph: 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of
     //    the block
-    k_first_tree<2><<<n_graphs, 256, 0, st>>>(p);
+#ifndef M3_FT_T
+#define M3_FT_T 256
+#endif
+    k_first_tree<2><<<n_graphs, M3_FT_T, 0, st>>>(p);
     M3_LAUNCH_CHECK("k_first_tree");
     trace_mark(2, st);
     // 3. successive shortest paths per component, one launch per band of the work queue (see k_job_order)
@@ -927,8 +938,8 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
         cfg.blockDim = dim3((unsigned)kBandThreads[b]);
         cfg.dynamicSmemBytes = (size_t)pb.sbytes;
         switch (b) {
-            case 0: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<128, 8, true>, pb)); break;
-            case 1: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<256, 3, true>, pb)); break;
+            case 0: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<M3_B0T, M3_B0B, true>, pb)); break;
+            case 1: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<M3_B1T, M3_B1B, true>, pb)); break;
             case 2: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<512, 1, true>, pb)); break;
             default: M3_CUDA(cudaLaunchKernelEx(&cfg, k_ssp_solve<256, 3, false>, pb)); break;
         }
