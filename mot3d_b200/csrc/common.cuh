@@ -36,7 +36,21 @@ int32_t cuda_fail(cudaError_t e, const char *what);
 int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                        const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
-                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream);
+                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream,
+                       int32_t g_first, int32_t g_count, bool finish);
+
+// csrc/solve.cu: mot3d_solve_batch in phases, for a caller whose graphs become ready in pieces (mot3d_track_batch_host):
+// SOLVE_BEGIN once, SOLVE_FRONT for every range of graphs [g_first, g_first + g_count) whose in-CSR is complete
+// (connected components + first shortest-path tree: per-graph kernels), SOLVE_BACK once when all of them are through
+// (component numbering, single-track pass, work queue, successive shortest paths, first-path rule). Same arguments
+// in every call.
+enum { SOLVE_BEGIN = 1, SOLVE_FRONT = 2, SOLVE_BACK = 4, SOLVE_ALL = 7 };
+int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t n_graphs, int64_t n_total,
+                           const int32_t *graph_ptr, int32_t max_graph_nodes, const int32_t *tkey, int64_t arc_capacity,
+                           const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
+                           const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
+                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
+                           int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
 
 // Process-wide options (mot3d_set_option): test hooks and tuning knobs that used to be environment variables. An option
 // that was never set (or was reset with NaN) reports false and leaves the built-in default alone.

@@ -22,6 +22,7 @@ constexpr int CC_MAX_SORT = 8192;
 
 struct CompParams {
     int32_t n_graphs;
+    int32_t g_first;       // first graph of this launch (block b works on graph g_first + b)
     int32_t cap;           // shared-memory capacity in detections (<= CC_MAX_SORT); larger graphs are kept whole
     const int32_t *graph_ptr;
     const int32_t *in_ptr;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
     __shared__ int s_scan[33];
     int *s_par = s_dyn;          // [cap] parent -> root -> component rank -> regrouped position
     int *s_cnt = s_dyn + p.cap;  // [cap] rank of a root -> detections per component -> placement cursor
-    const int g = blockIdx.x;
+    const int g = blockIdx.x + p.g_first;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
     const int T = blockDim.x, tid = threadIdx.x;
@@ -229,10 +230,14 @@ __global__ void k_comp_fill(int n_graphs, const int32_t *__restrict__ graph_ptr,
 
 // max_graph_nodes sizes the shared memory of k_components (8 bytes per detection of the largest graph); the exported
 // entry point does not know it and asks for the CC_MAX_SORT worst case.
+// Graphs [g_first, g_first + g_count) are split in this call; `finish` numbers the components of ALL n_graphs graphs
+// (every graph must have been through a call by then): a caller whose graphs arrive in pieces splits each piece as it
+// lands and finishes once (mot3d_track_batch_host).
 int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                        const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
-                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream) {
+                       int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream,
+                       int32_t g_first, int32_t g_count, bool finish) {
     M3_CHECK_ARG(n_graphs >= 0 && n_total >= 0, "negative sizes");
     M3_CHECK_ARG(n_cgraphs_out, "n_cgraphs_out is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -270,13 +275,18 @@ int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_p
     const size_t smem = (size_t)cap * 2 * sizeof(int);
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_components<<<n_graphs, CC_TPB, smem, st>>>(p);
-    M3_LAUNCH_CHECK("k_components");
-    k_comp_offsets<<<1, 1024, 0, st>>>(n_graphs, graph_ptr, p.win_ncomp, win_cbase, n_cgraphs_out);
-    M3_LAUNCH_CHECK("k_comp_offsets");
-    k_comp_fill<<<n_graphs, 128, 0, st>>>(n_graphs, graph_ptr, p.win_ncomp, win_cbase, p.win_cstart, cgraph_ptr_out,
-                                         cgraph_graph_out);
-    M3_LAUNCH_CHECK("k_comp_fill");
+    p.g_first = g_first;
+    if (g_count > 0) {
+        k_components<<<g_count, CC_TPB, smem, st>>>(p);
+        M3_LAUNCH_CHECK("k_components");
+    }
+    if (finish) {
+        k_comp_offsets<<<1, 1024, 0, st>>>(n_graphs, graph_ptr, p.win_ncomp, win_cbase, n_cgraphs_out);
+        M3_LAUNCH_CHECK("k_comp_offsets");
+        k_comp_fill<<<n_graphs, 128, 0, st>>>(n_graphs, graph_ptr, p.win_ncomp, win_cbase, p.win_cstart, cgraph_ptr_out,
+                                             cgraph_graph_out);
+        M3_LAUNCH_CHECK("k_comp_fill");
+    }
     return MOT3D_OK;
 }
 
@@ -298,7 +308,7 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
                          size_t ws_bytes, void *stream) {
     return components_run(n_graphs, n_total, graph_ptr, CC_MAX_SORT, in_ptr, in_src, arc_capacity, comp_perm_out,
                           comp_inv_out, cgraph_ptr_out, cgraph_graph_out, graph_cbase_out, n_cgraphs_out, ws, ws_bytes,
-                          stream);
+                          stream, 0, n_graphs, true);
 }
 
 }  // extern "C"

@@ -54,6 +54,7 @@ constexpr int SM_BANDS = 3;  // bands of the work queue solved in shared memory 
 
 struct SolveParams {
     int32_t n_graphs;
+    int32_t g_first;  // k_first_tree: block b works on graph g_first + b
     int32_t rcap;    // shared-memory staging area of this launch: most records a component may have ...
     int32_t sbytes;  // ... and its size in bytes
     int32_t role;   // queue band this launch drains (SM_BANDS = the global staging area's)
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     __shared__ int s_scan[33];
     __shared__ int64_t s_dp[FT_W];
     __shared__ int s_an[FT_W];
-    const int g = blockIdx.x;
+    const int g = blockIdx.x + p.g_first;
     const int g0 = p.graph_ptr[g];
     const int n = p.graph_ptr[g + 1] - g0;
     const int T = blockDim.x, tid = threadIdx.x;
@@ -776,6 +777,20 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           const int64_t *exit_cost, int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out,
                           int64_t *total_cost_out, int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes,
                           void *stream) {
+    return m3::solve_batch_phased(SOLVE_ALL, 0, n_graphs, n_graphs, n_total, graph_ptr, max_graph_nodes, tkey,
+                                  arc_capacity, in_ptr, in_src, in_cost, entry_cost, node_cost, exit_cost, next_out,
+                                  prev_out, n_paths_out, total_cost_out, path_cost_out, stats_out, ws, ws_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace m3 {
+int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t n_graphs, int64_t n_total,
+                           const int32_t *graph_ptr, int32_t max_graph_nodes, const int32_t *tkey, int64_t arc_capacity,
+                           const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
+                           const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
+                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
+                           int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream) {
     M3_CHECK_ARG(n_graphs >= 0 && max_graph_nodes >= 0 && arc_capacity >= 0, "negative sizes");
     if (n_graphs == 0) return MOT3D_OK;
     M3_CHECK_ARG(graph_ptr && tkey && in_ptr && entry_cost && node_cost && exit_cost, "NULL input");
@@ -797,6 +812,7 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     };
     SolveParams p;
     p.n_graphs = n_graphs;
+    p.g_first = 0;
     p.rcap = 0;
     p.sbytes = 0;
     p.chain = 0;
@@ -865,13 +881,17 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     cudaStream_t st = (cudaStream_t)stream;
     const DevInfo *di = dev_info();
     if (!di) return cuda_fail(cudaGetLastError(), "device attributes / shared memory limits of the solver kernels");
-    M3_CUDA(cudaMemsetAsync(p.job_meta, 0, JOB_META_INTS * sizeof(int32_t), st));
-    M3_CUDA(cudaMemsetAsync(p.big_arc_next, 0, sizeof(unsigned long long), st));
-    M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
+    M3_CHECK_ARG(g_first >= 0 && g_count >= 0 && g_first + g_count <= n_graphs, "graph range outside the batch");
+    if (phases & SOLVE_BEGIN) {
+        M3_CUDA(cudaMemsetAsync(p.job_meta, 0, JOB_META_INTS * sizeof(int32_t), st));
+        M3_CUDA(cudaMemsetAsync(p.big_arc_next, 0, sizeof(unsigned long long), st));
+        M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
+    }
     trace_mark(0, st);
     // 1. connected components of every graph, detections regrouped by component
     int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
-                                comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream);
+                                comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream, g_first,
+                                (phases & SOLVE_FRONT) ? g_count : 0, (phases & SOLVE_BACK) != 0);
     if (rc) return rc;
     trace_mark(1, st);
     // 2. first shortest-path tree per graph: 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of
@@ -879,9 +899,13 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
 #ifndef M3_FT_T
 #define M3_FT_T 256
 #endif
-    k_first_tree<2><<<n_graphs, M3_FT_T, 0, st>>>(p);
-    M3_LAUNCH_CHECK("k_first_tree");
+    if ((phases & SOLVE_FRONT) && g_count > 0) {
+        p.g_first = g_first;
+        k_first_tree<2><<<g_count, M3_FT_T, 0, st>>>(p);
+        M3_LAUNCH_CHECK("k_first_tree");
+    }
     trace_mark(2, st);
+    if (!(phases & SOLVE_BACK)) return MOT3D_OK;
     // 3. successive shortest paths per component, one launch per band of the work queue (see k_job_order)
     const int n_sm = di->n_sm;
     for (int b = 0; b < SM_BANDS; b++) {
@@ -952,6 +976,9 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
     trace_mark(5, st);
     return MOT3D_OK;
 }
+}  // namespace m3
+
+extern "C" {
 
 int32_t mot3d_order_path_costs(int32_t n_graphs, const int32_t *graph_ptr, int64_t *path_cost, int64_t *scratch,
                                int32_t max_paths, int32_t *too_many_flag, void *stream) {
