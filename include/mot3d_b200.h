@@ -438,6 +438,11 @@ size_t mot3d_track_batch_workspace_bytes(int64_t n, int32_t n_graphs, int64_t ed
 int32_t mot3d_track_batch_host(const mot3d_host_batch *batch, const mot3d_cost_spec *spec, mot3d_host_result *result,
                                void *device_ws, size_t ws_bytes, int64_t edge_capacity, void *stream);
 
+/* mot3d_track_batch_host keeps a few streams, events and small pinned buffers per calling host thread and device,
+ * created on first use. A thread that is done with the call may release them (every device it used); the next call
+ * creates them again. Nothing of the caller's may be in flight. */
+int32_t mot3d_host_release(void);
+
 #ifdef __cplusplus
 }
 #endif

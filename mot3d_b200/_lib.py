@@ -129,6 +129,7 @@ SIGNATURES = {
     "mot3d_color_histograms": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, ctypes.POINTER(ctypes.c_int32), _i32, _i32, _vp, _vp,
                                       _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "mot3d_host_release": (_i32, []),
     "mot3d_track_batch_host": (_i32, [ctypes.POINTER(HostBatch), _PS, ctypes.POINTER(HostResult), _vp, _sz, _i64, _vp]),
 }
 

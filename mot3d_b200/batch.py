@@ -414,6 +414,12 @@ class HostTracker(object):
         self._h2d, self._d2h = int(res.h2d_bytes), int(res.d2h_bytes)
         return int(res.n_edges)
 
+    def close(self):
+        """Release the streams / events / pinned scratch mot3d_track_batch_host keeps for this host thread
+        (mot3d_host_release); the next run() creates them again."""
+        torch.cuda.synchronize(self.device)
+        _lib.check(_lib.lib().mot3d_host_release())
+
     def tracks(self):
         return tracks_to_lists(self.h_graph_ptr[:self.G + 1].numpy(), self.h_track_count.numpy(),
                                self.h_track_ptr.numpy(), self.h_track_det.numpy())

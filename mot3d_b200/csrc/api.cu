@@ -138,15 +138,49 @@ struct HostCtx {
     int32_t *pinned = nullptr;  // [2 * HOST_MAX_CHUNKS]: overflow flag, arc count per chunk
     int32_t *pinned_gptr = nullptr;  // chunk-local graph_ptr arrays (H2D source), grown on demand
     size_t gptr_cap = 0;
-    cudaEvent_t t0 = nullptr, trace[HOST_MAX_CHUNKS][4];  // MOT3D_HOST_TRACE=1: H2D done, build done, solve done, D2H done
+    cudaEvent_t t0 = nullptr, trace[HOST_MAX_CHUNKS][4];  // "host_trace": H2D done, build done, solve done, D2H done
+    // released by mot3d_host_release (not from a destructor: at process exit the CUDA runtime may be gone already)
+    void release() {
+        if (dev < 0) return;
+        int cur = -1;
+        const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess;
+        for (int i = 0; i < HOST_MAX_CHUNKS; i++) {
+            cudaStreamDestroy(s[i]);
+            cudaEventDestroy(done[i]);
+        }
+        for (int i = 0; i < HOST_MAX_CHUNKS * HOST_MAX_PIECES; i++) cudaEventDestroy(in[i]);
+        cudaStreamDestroy(copy_in);
+        cudaEventDestroy(start);
+        if (t0) {
+            cudaEventDestroy(t0);
+            for (int c = 0; c < HOST_MAX_CHUNKS; c++)
+                for (int k = 0; k < 4; k++) cudaEventDestroy(trace[c][k]);
+            t0 = nullptr;
+        }
+        if (pinned) cudaFreeHost(pinned);
+        if (pinned_gptr) cudaFreeHost(pinned_gptr);
+        if (pinned_gbase) cudaFreeHost(pinned_gbase);
+        pinned = pinned_gptr = nullptr;
+        pinned_gbase = nullptr;
+        gptr_cap = 0;
+        dev = -1;
+        if (switched) cudaSetDevice(cur);
+        cudaGetLastError();
+    }
 };
+struct HostCtxSet {
+    HostCtx ctx[MOT3D_MAX_DEVICES];
+};
+static HostCtxSet *host_ctx_set() {
+    static thread_local HostCtxSet set;
+    return &set;
+}
 
 // per host thread and device: streams, events and a pinned scratch for the two scalars read back per chunk
 static HostCtx *host_ctx() {
-    static thread_local HostCtx ctx[16];
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    HostCtx *c = &ctx[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MOT3D_MAX_DEVICES) return nullptr;
+    HostCtx *c = &host_ctx_set()->ctx[dev];
     if (c->dev == dev) return c;
     int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
     if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return nullptr;
@@ -331,6 +365,12 @@ bool option(Option which, double *value) {
 }  // namespace m3
 
 extern "C" {
+
+int32_t mot3d_host_release(void) {
+    HostCtxSet *set = host_ctx_set();
+    for (int d = 0; d < MOT3D_MAX_DEVICES; d++) set->ctx[d].release();
+    return MOT3D_OK;
+}
 
 int32_t mot3d_set_option(const char *name, double value) {
     M3_CHECK_ARG(name, "option name is NULL");

@@ -416,6 +416,9 @@ def test_host_buffer_entry_point():
     gold = [d["track_det"][d["track_ptr"][t]:d["track_ptr"][t + 1]].tolist() for t in range(len(d["track_ptr"]) - 1)]
     assert ht.tracks() == [gold, gold]
     assert ht.h_total[:2].tolist() == [gu.ref_total_units(d)] * 2
+    # the per-thread streams / events / pinned scratch can be released and come back on the next call
+    ht.close()
+    assert ht.run(spec.to_c()) == n_edges and ht.tracks() == [gold, gold]
     # too small an arc buffer is reported, not silently truncated
     small = mot3d.HostTracker(n_max=2 * n, g_max=2, edge_capacity=100, dim=2)
     small.load(b)
