@@ -167,14 +167,19 @@ def _pack(sorted_dets, cspec):
                          "integers); got a fractional index")
     if n and (frame.min() < -2 ** 31 or frame.max() >= 2 ** 31):
         raise ValueError("frame indices must fit in int32")
-    pos = np.empty((n, dim), dtype=np.float64)
-    for i, d in enumerate(sorted_dets):
-        q = np.asarray(d.position, dtype=np.float64).reshape(-1)
-        if q.shape[0] != dim:
-            # the reference's euclidean() takes whatever coordinates there are; the kernels take exactly `dim`
-            raise ValueError("detection %d has a %d-D position but the cost function is for %d-D detections" %
-                             (i, q.shape[0], dim))
-        pos[i] = q
+    try:  # one conversion for the usual case: every position is a flat sequence of `dim` numbers
+        pos = np.array([d.position for d in sorted_dets], dtype=np.float64)
+    except ValueError:
+        pos = None
+    if pos is None or pos.ndim != 2 or pos.shape[1] != dim:
+        pos = np.empty((n, dim), dtype=np.float64)
+        for i, d in enumerate(sorted_dets):
+            q = np.asarray(d.position, dtype=np.float64).reshape(-1)
+            if q.shape[0] != dim:
+                # the reference's euclidean() takes whatever coordinates there are; the kernels take exactly `dim`
+                raise ValueError("detection %d has a %d-D position but the cost function is for %d-D detections" %
+                                 (i, q.shape[0], dim))
+            pos[i] = q
     conf = np.fromiter((d.confidence for d in sorted_dets), dtype=np.float64, count=n)
     flags = None
     if any((not d.entry_points) or (not d.exit_point) for d in sorted_dets):
