@@ -23,6 +23,8 @@
 // Tiles that do not fit the staging areas (very dense frames) run the same code on the global arrays.
 // The arc offset of the first tile can continue a device-side counter, so consecutive launches over row ranges
 // append to one CSR (software pipeline of mot3d_track_batch_host).
+#include <atomic>
+
 #include "common.cuh"
 
 namespace m3 {
@@ -673,11 +675,19 @@ int32_t mot3d_edge_build(const mot3d_dets *dets, const mot3d_cost_spec *spec, in
     p.acap = acap;
     const size_t smem = (size_t)(cap + 4) * per_cand + (size_t)rows_b + (size_t)acap * 4 + (size_t)p.cache_j * EF_TPB * 4 + 16;
     M3_CUDA(cudaMemsetAsync(ws, 0, need, st));
+    // (the shared-memory limit of a kernel is a per-device attribute: set when it has to grow, not on every call)
+    static std::atomic<int> smem_set[MOT3D_MAX_DEVICES][2];
+    int dev = 0;
+    M3_CUDA(cudaGetDevice(&dev));
+    const int di = direction == MOT3D_DIR_IN ? 0 : 1;
+    const bool grow = dev < 0 || dev >= MOT3D_MAX_DEVICES || smem_set[dev][di].load(std::memory_order_relaxed) < (int)smem;
     if (direction == MOT3D_DIR_IN) {
-        M3_CUDA(cudaFuncSetAttribute(k_edge_build_fused<MOT3D_DIR_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (grow) M3_CUDA(cudaFuncSetAttribute(k_edge_build_fused<MOT3D_DIR_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (grow && dev >= 0 && dev < MOT3D_MAX_DEVICES) smem_set[dev][di].store((int)smem, std::memory_order_relaxed);
         k_edge_build_fused<MOT3D_DIR_IN><<<(unsigned)tiles, EF_TPB, smem, st>>>(p);
     } else {
-        M3_CUDA(cudaFuncSetAttribute(k_edge_build_fused<MOT3D_DIR_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (grow) M3_CUDA(cudaFuncSetAttribute(k_edge_build_fused<MOT3D_DIR_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (grow && dev >= 0 && dev < MOT3D_MAX_DEVICES) smem_set[dev][di].store((int)smem, std::memory_order_relaxed);
         k_edge_build_fused<MOT3D_DIR_OUT><<<(unsigned)tiles, EF_TPB, smem, st>>>(p);
     }
     M3_LAUNCH_CHECK("k_edge_build_fused");

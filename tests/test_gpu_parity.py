@@ -1232,3 +1232,33 @@ def test_device_resident_two_pass_equals_host_glue(case):
     mine = sorted(tuple(td[f:f + l].tolist()) for f, l in zip(first, ln))
     assert mine == sorted(tuple(index_of[id(x)] for x in pc) for pc in pieces)
     assert (np.diff(key) >= 0).all()
+
+
+def test_c3_with_baseline_max_jump_4():
+    """BASELINE.json quotes soldiers_3d with max_jump=4 (the example itself uses 8, which the golden vector pins): the
+    same detections with max_jump=4 against the oracle - arcs, K, total, tracks - and against the live muSSP where it
+    was compiled (total; its tolerances may leave it a few units above the exact optimum)."""
+    import mot3d_b200 as mot3d
+    from oracle import oracle
+    d = gu.load("c3_soldiers_pass1")
+    s = dict(d["spec"], max_jump=4)
+    spec = _spec_from(s, mot3d)
+    n = len(d["frame"])
+    b = _batch_from(d, mot3d).to("cuda")
+    gb, sol = mot3d.track_batch(b, spec, want_path_costs=True)
+    ospec = oracle.CostSpec(**{k: v for k, v in s.items() if k != "kind"})
+    row_ptr, col, w = oracle.build_transitions(d["frame"], d["pos"], ospec)
+    assert gb.n_edges == len(col)
+    tail, head, ww = oracle.graph_arcs(n, float(ospec.weight_source_sink), oracle.node_weights(d["conf"], ospec), 0.0,
+                                       row_ptr, col, w)
+    cost = oracle.quantise(ww)
+    ref = oracle.ssp_solve(2 * n + 2, tail, head, cost)
+    K = int(sol.n_paths[0].item())
+    assert K == ref["K"] and int(sol.total_cost[0].item()) == ref["total"]
+    assert (sol.path_cost[:K].cpu().numpy() == ref["path_cost"]).all()
+    tracks = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                   sol.track_det.cpu().numpy())[0]
+    assert tracks == oracle.tracks_from_flow(n, tail, head, ref["flow"])
+    if oracle.have_ref():
+        live = oracle.mussp_solve(2 * n + 2, tail, head, np.round(ww, 7))
+        assert 0 <= oracle.flow_cost(cost, live["flow"]) - ref["total"] <= 2
