@@ -1262,3 +1262,60 @@ def test_c3_with_baseline_max_jump_4():
     if oracle.have_ref():
         live = oracle.mussp_solve(2 * n + 2, tail, head, np.round(ww, 7))
         assert 0 <= oracle.flow_cost(cost, live["flow"]) - ref["total"] <= 2
+
+
+@pytest.mark.parametrize("shape", ["crowd_big", "crowd_thin", "crowd_wide_costs", "band1", "band2"])
+def test_large_components_against_oracle(shape):
+    """Components beyond band 0 of the solver, one connected crowd each, against the integer oracle (K, total, every
+    path cost, a feasible flow of that cost): solve_big.cuh (crowded: bucketed rounds over pushed work lists),
+    solve_global.cuh (thin components, and costs beyond 32 bits), and the larger shared-memory bands of solve_sm.cuh."""
+    import mot3d_b200 as mot3d
+    from oracle import oracle
+    P, F, extent, wss, seed = {"crowd_big": (64, 48, 140.0, 1.0, 11), "crowd_thin": (18, 170, 70.0, 1.0, 12),
+                               "crowd_wide_costs": (40, 40, 110.0, 1.0, 13), "band1": (7, 45, 60.0, 1.0, 14),
+                               "band2": (14, 55, 75.0, 0.5, 15)}[shape]
+    rng = np.random.RandomState(seed)
+    pos = rng.rand(P, 2) * extent
+    vel = rng.randn(P, 2) * 1.2
+    frames, poss, confs = [], [], []
+    for f in range(F):
+        pos = pos + vel + rng.randn(P, 2) * 0.5
+        vel = np.where((pos < 0) | (pos > extent), -vel, vel)  # people stay in the room: one connected crowd
+        keep = rng.rand(P) < 0.93
+        frames.append(np.full(int(keep.sum()), f))
+        poss.append(pos[keep] + rng.randn(int(keep.sum()), 2) * 0.8)
+        confs.append(0.4 + 0.6 * rng.rand(int(keep.sum())))
+    frame, xy, conf = np.concatenate(frames), np.concatenate(poss), np.concatenate(confs)
+    n = len(frame)
+    kw = dict(sigma_jump=1, sigma_distance=9, max_distance=28, use_color_histogram=False, use_bbox=False)
+    mul = 400 if shape == "crowd_wide_costs" else 1  # node costs of -(160 .. 400): beyond 32 bits in 1e-7 units
+    spec = mot3d.CostSpec(kind="detections_2d", distance=kw, confidence=dict(mul=mul, bias=0), weight_source_sink=wss,
+                          max_jump=5)
+    b, _ = mot3d.DetectionBatch.from_arrays(np.array([0, n]), frame, xy, conf)
+    gb, sol = mot3d.track_batch(b.to("cuda"), spec, want_path_costs=True)
+    ospec = oracle.CostSpec(weight_source_sink=wss, max_jump=5, mul=mul, bias=0, **kw)
+    row_ptr, col, w = oracle.build_transitions(frame, xy, ospec)
+    assert gb.n_edges == len(col)
+    tail, head, ww = oracle.graph_arcs(n, float(wss), oracle.node_weights(conf, ospec), 0.0, row_ptr, col, w)
+    cost = oracle.quantise(ww)
+    ref = oracle.ssp_solve(2 * n + 2, tail, head, cost)
+    K = int(sol.n_paths[0].item())
+    assert K == ref["K"] and K >= 1
+    assert int(sol.total_cost[0].item()) == ref["total"]
+    assert (sol.path_cost[:K].cpu().numpy() == ref["path_cost"]).all()
+    # the components really are large: the biggest one holds most of the detections
+    stats = sol.stats.cpu().numpy()
+    tracks = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
+                                   sol.track_det.cpu().numpy())[0]
+    arc = {(int(t), int(h)): int(c) for t, h, c in zip(tail, head, cost)}
+    got, used = 0, set()
+    for t in tracks:
+        got += arc[(1, 2 + 2 * t[0])] + arc[(3 + 2 * t[-1], 2 * n + 2)]
+        for a_, b_ in zip(t[:-1], t[1:]):
+            got += arc[(3 + 2 * a_, 2 + 2 * b_)]
+        for d_ in t:
+            assert d_ not in used
+            used.add(d_)
+            got += arc[(2 + 2 * d_, 3 + 2 * d_)]
+    assert got == ref["total"] and len(tracks) == K
+    assert int(stats[11]) >= 1  # at least one branch was re-labelled: the solver proper ran
