@@ -1,21 +1,26 @@
 // Block-per-component solver for components that fit no shared-memory band (solve_sm.cuh) but whose costs fit 32
-// bits: the staging area lives in GLOBAL memory (it stays in L2: 110 bytes per record, 12 per arc), slots are 32 bits,
-// any size. Included by solve.cu. Costs beyond 32 bits go to solve_global.cuh.
+// bits: the staging area lives in GLOBAL memory (it stays in L2: 150 bytes per record, 12 per arc), slots are 32 bits,
+// any size. Included by solve.cu. Costs beyond 32 bits, and thin components, go to solve_global.cuh (k_ssp_solve picks).
 //
 // Same successive shortest paths as solve_sm.cuh (arg-min over the sinks, path walk, certificate, exact re-labelling of
-// the branch that hung from the path's first arc by synchronous pull rounds), with one difference that matters at this
-// size: a round only touches the records whose inputs moved in the round before. Publishing a post label puts the
-// heads of the node's out-arcs on the next round's work list (the out-arc lists are staged next to the in-arc lists);
-// publishing a pre label on a track lists the track's previous record (reversed matched arc); a bit per record keeps a
-// record from being listed twice. A round costs what its frontier costs, not what the component costs: a 100 000-
-// detection graph whose tracks run over 1 000 frames needs thousands of rounds per path, each a handful of records.
+// the branch that hung from the path's first arc by synchronous pull rounds), with two differences that matter at this
+// size:
+//   pushed work lists   a round only touches the records whose inputs moved in the round before. Publishing a post label
+//                       puts the heads of the node's out-arcs on the next round's work list (the out-arc lists are
+//                       staged next to the in-arc lists); publishing a pre label on a track lists the track's previous
+//                       record (reversed matched arc); bits per record keep a record from being listed twice. A round
+//                       costs what its frontier costs, not what the component costs.
+//   Dijkstra's order    the labels before the flip are potentials (every residual arc has a non-negative reduced cost,
+//                       Johnson; what muSSP's heap works on, Graph.cpp:394-503), so a label that rises by less is
+//                       final earlier. Records are listed with the smallest increase among the inputs they wait for;
+//                       increases beyond the current threshold wait on a second list that is split again when the
+//                       rounds of the bucket have reached their fix-point (threshold = smallest waiting increase +
+//                       BIG_DELTA). Tentative labels that a better one overwrites anyway are never passed on: 10x fewer
+//                       relaxations on a 98 000-detection component; any order reaches the same exact fix-point.
 #pragma once
 
-constexpr long long BIG_DELTA = 1ll << 26;  // width of a bucket of label increases, in cost units (1e-7)
-
-struct BigCursor {  // bump allocator of the arc area: every component takes exactly its number of in-arcs, once
-    unsigned long long next;
-};
+constexpr long long BIG_DELTA = 1ll << 26;  // width of a bucket of label increases, in cost units (1e-7): measured
+                                            // on C5-whole, 2^18 4.3 s, 2^22 2.3 s, 2^24 1.9 s, 2^26 1.27 s, 1e9 1.40 s
 
 __device__ __noinline__ void solve_component_big(const SolveParams &p, const int cg, const int c0, const int n, const int g,
                                                  int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work) {

@@ -1,5 +1,12 @@
-import sys, time, json
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+"""Solver statistics on C5-whole-shaped graphs (one graph of F frames x 100 detections): solve time, rounds, pulls.
+    python tools/c5whole_stats.py [frames]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np, torch
 import mot3d_b200 as mot3d
 from window_latency import _gen
