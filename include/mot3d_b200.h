@@ -287,6 +287,22 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                           int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
                           int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
 
+/* mot3d_solve_batch in phases, for a caller whose graphs become ready in pieces (mot3d_track_batch_host does this with
+ * the pieces of its H2D pipeline): MOT3D_SOLVE_BEGIN once, MOT3D_SOLVE_FRONT
+ * for every range of graphs [g_first, g_first + g_count) whose in-CSR rows are complete (connected components + first
+ * shortest-path tree: per-graph kernels, a third of the stage), MOT3D_SOLVE_BACK once when every graph has been through
+ * FRONT (component numbering, single-track pass, work queue, successive shortest paths, first-path rule). Phases may be
+ * OR-ed; all calls take the same arrays; calls on different streams must be ordered by the caller (events). */
+#define MOT3D_SOLVE_BEGIN 1
+#define MOT3D_SOLVE_FRONT 2
+#define MOT3D_SOLVE_BACK 4
+int32_t mot3d_solve_batch_phase(int32_t phases, int32_t g_first, int32_t g_count, int32_t n_graphs, int64_t n_total,
+                                const int32_t *graph_ptr, int32_t max_graph_nodes, const int32_t *tkey,
+                                int64_t arc_capacity, const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
+                                const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
+                                int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
+                                int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream);
+
 /* path_cost_out of mot3d_solve_batch -> per graph the accepted path costs ascending (the order muSSP finds them,
  * wrapper.cpp:199-267) at the front of the graph's slice, MOT3D_INF_COST behind them. In place; scratch: int64 [n_total].
  * Quadratic in the paths of one graph: a graph with more than max_paths of them is left as it is and *too_many_flag

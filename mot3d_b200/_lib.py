@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "libmot3d_b200.so")
 MAX_JUMP = 256
 INF_COST = 1 << 60
 DIR_IN, DIR_OUT = 0, 1
+SOLVE_BEGIN, SOLVE_FRONT, SOLVE_BACK = 1, 2, 4  # MOT3D_SOLVE_*: phases of mot3d_solve_batch_phase
 SOLVE_STATS = 25  # include/mot3d_b200.h: MOT3D_SOLVE_STATS
 FLAG_ENTRY, FLAG_EXIT = 1, 2
 TRACK_START_BIT = 0x80000000
@@ -105,6 +106,8 @@ SIGNATURES = {
     "mot3d_solve_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mot3d_solve_batch": (_i32, [_i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _sz, _vp]),
+    "mot3d_solve_batch_phase": (_i32, [_i32, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mot3d_order_path_costs": (_i32, [_i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "mot3d_solve_trace_events": (_i32, [_vp, _i32]),
     "mot3d_extract_tracks": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -782,6 +782,19 @@ int32_t mot3d_solve_batch(int32_t n_graphs, int64_t n_total, const int32_t *grap
                                   prev_out, n_paths_out, total_cost_out, path_cost_out, stats_out, ws, ws_bytes, stream);
 }
 
+/* mot3d_solve_batch in phases (include/mot3d_b200.h) */
+int32_t mot3d_solve_batch_phase(int32_t phases, int32_t g_first, int32_t g_count, int32_t n_graphs, int64_t n_total,
+                                const int32_t *graph_ptr, int32_t max_graph_nodes, const int32_t *tkey,
+                                int64_t arc_capacity, const int32_t *in_ptr, const int32_t *in_src, const int64_t *in_cost,
+                                const int64_t *entry_cost, const int64_t *node_cost, const int64_t *exit_cost,
+                                int32_t *next_out, int32_t *prev_out, int32_t *n_paths_out, int64_t *total_cost_out,
+                                int64_t *path_cost_out, int64_t *stats_out, void *ws, size_t ws_bytes, void *stream) {
+    M3_CHECK_ARG(phases > 0 && (phases & ~SOLVE_ALL) == 0, "phases: bits MOT3D_SOLVE_BEGIN / _FRONT / _BACK");
+    return m3::solve_batch_phased(phases, g_first, g_count, n_graphs, n_total, graph_ptr, max_graph_nodes, tkey,
+                                  arc_capacity, in_ptr, in_src, in_cost, entry_cost, node_cost, exit_cost, next_out,
+                                  prev_out, n_paths_out, total_cost_out, path_cost_out, stats_out, ws, ws_bytes, stream);
+}
+
 }  // extern "C"
 
 namespace m3 {

@@ -1319,3 +1319,44 @@ def test_large_components_against_oracle(shape):
             got += arc[(2 + 2 * d_, 3 + 2 * d_)]
     assert got == ref["total"] and len(tracks) == K
     assert int(stats[11]) >= 1  # at least one branch was re-labelled: the solver proper ran
+
+
+def test_solve_in_phases_equals_one_call():
+    """mot3d_solve_batch_phase: BEGIN, FRONT over three ranges of graphs (as their rows become ready), BACK - the same
+    flow, K and totals as mot3d_solve_batch in one call."""
+    import ctypes
+    import mot3d_b200 as mot3d
+    from mot3d_b200 import _lib
+    from mot3d_b200.batch import _ptr, _stream
+    torch = _torch()
+    d = gu.load("c5_small_f30_p12")
+    spec = _spec_from(d["spec"], mot3d)
+    n, G = len(d["frame"]), 7
+    gp = np.arange(G + 1) * n
+    b, _ = mot3d.DetectionBatch.from_arrays(gp, np.tile(d["frame"], G), np.tile(d["pos"], (G, 1)), np.tile(d["conf"], G))
+    gb = mot3d.build_graphs(b.to("cuda"), spec)
+    sol = mot3d.solve_graphs(gb)
+    dev = gb.tkey.device
+    L = _lib.lib()
+    N = n * G
+    nxt = torch.empty(N, dtype=torch.int32, device=dev)
+    prv = torch.empty(N, dtype=torch.int32, device=dev)
+    K = torch.zeros(G, dtype=torch.int32, device=dev)
+    tot = torch.zeros(G, dtype=torch.int64, device=dev)
+    wsb = L.mot3d_solve_workspace_bytes(N, G, gb.n_edges)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+
+    def phase(ph, g0, gc):
+        _lib.check(L.mot3d_solve_batch_phase(ph, g0, gc, G, N, _ptr(gb.dets.graph_ptr), n, _ptr(gb.tkey), gb.n_edges,
+                                             _ptr(gb.row_ptr), _ptr(gb.col), _ptr(gb.cost), _ptr(gb.entry_cost),
+                                             _ptr(gb.node_cost), _ptr(gb.exit_cost), _ptr(nxt), _ptr(prv), _ptr(K),
+                                             _ptr(tot), None, None, _ptr(ws), wsb, _stream(dev)))
+    phase(_lib.SOLVE_BEGIN, 0, 0)
+    phase(_lib.SOLVE_FRONT, 0, 2)
+    phase(_lib.SOLVE_FRONT, 2, 4)
+    phase(_lib.SOLVE_FRONT | _lib.SOLVE_BACK, 6, 1)
+    assert torch.equal(nxt, sol.next[:N]) and torch.equal(prv, sol.prev[:N])
+    assert torch.equal(K, sol.n_paths[:G]) and torch.equal(tot, sol.total_cost[:G])
+    assert tot.cpu().tolist() == [gu.ref_total_units(d)] * G
+    with pytest.raises(mot3d.Mot3dError):
+        phase(8, 0, 0)
