@@ -316,7 +316,7 @@ def run_ours(args):
 
     # ---- kernel boundaries inside the solve stage (untimed extra steps; mot3d_solve_trace_events records CUDA events
     #      between the kernels of the calling thread's next solves): feeds the per-kernel roofline entries
-    SOLVE_PARTS = ["k_components (+offsets, fill)", "k_first_tree", "k_single_track + k_job_order",
+    SOLVE_PARTS = ["k_first_tree", "k_components_tree (+offsets, fill)", "k_single_track + k_job_order",
                    "k_ssp_solve (one launch per band, overlapped)", "k_first_path_rule"]
     solve_part_ms = np.zeros(len(SOLVE_PARTS))
     tev = [torch.cuda.Event(enable_timing=True) for _ in range(len(SOLVE_PARTS) + 1)]
@@ -390,7 +390,7 @@ def run_ours(args):
         if t.get("seqs") == S:
             traffic_solve, traffic_build = t.get("k_ssp_solve"), t.get("edge_build")
     roofline_stage = {"bound": "hbm", "kernel": "solve stage",
-                "kernels_in_launch_ms": "solve stage = k_components + k_first_tree + k_single_track + k_job_order + "
+                "kernels_in_launch_ms": "solve stage = k_first_tree + k_components_tree + k_single_track + k_job_order + "
                                         "k_ssp_solve (giants + main, overlapped) + k_first_path_rule",
                 "achieved": solve_gbs, "peak": peak, "unit": "GB/s",
                 "frac": solve_gbs / peak, "traffic": traffic_solve, "peak_source": peak_src,
@@ -452,10 +452,10 @@ def run_ours(args):
                      "keys + positions in, x-sorted positions + permutation out")
         kernel_entry("k_edge_build_fused", stage_ms[STAGES.index("edge_build")], n * 28.0 + 4.0 * (n + 1) + E * 12.0,
                      "sorted detections in, row_ptr + 12 B per arc out")
-    kernel_entry(SOLVE_PARTS[0], solve_part_ms[0], 4.0 * E + 4.0 * (n + 1) + 16.0 * n,
-                 "in-CSR structure in, permutation / inverse / component table out")
-    kernel_entry(SOLVE_PARTS[1], solve_part_ms[1], ft_bytes + 24.0 * n,
+    kernel_entry(SOLVE_PARTS[0], solve_part_ms[0], ft_bytes + 24.0 * n,
                  "12 B per arc + node costs in, distances / parent / branch labels out")
+    kernel_entry(SOLVE_PARTS[1], solve_part_ms[1], 4.0 * E + 4.0 * (n + 1) + 16.0 * n + 64.0 * n,
+                 "in-CSR structure + first tree in, permutation / inverse / component table + regrouped tree out")
     kernel_entry(SOLVE_PARTS[2], solve_part_ms[2], 36.0 * n, "first-tree labels in, tracks of single-track components out")
     kernel_entry(SOLVE_PARTS[3], solve_part_ms[3], max(solve_bytes - ft_bytes, 0.0),
                  "12 B per arc pull + 20 B per node pull (staging + relabelling rounds, counted by the kernel)")

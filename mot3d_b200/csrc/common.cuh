@@ -32,12 +32,24 @@ int32_t cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return m3::cuda_fail(e__, name);  \
     } while (0)
 
+// What k_first_tree leaves per detection (in detection order; k_components_tree moves it to the regrouped order):
+// exact distances of the pre / post node, parent of the pre node (detection index / PAR_*), branch label (detection
+// whose S arc starts the node's tree path, -1 = unreachable) and the bit k_single_track's certificate asks for.
+struct __align__(16) FtTmp {
+    int64_t dpre, dpost;
+    int32_t par, anc, cert, pad;
+};
+struct FtOut {  // first tree: detection order in, regrouped order out (parents and branch labels as positions)
+    const FtTmp *tmp;
+    FtTmp *out;
+};
+
 // csrc/components.cu: mot3d_components with the shared-memory footprint sized by the largest graph of the batch
 int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_ptr, int32_t max_graph_nodes,
                        const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
                        int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream,
-                       int32_t g_first, int32_t g_count, bool finish);
+                       int32_t g_first, int32_t g_count, bool finish, const FtOut *tree);
 
 // csrc/solve.cu: mot3d_solve_batch in phases, for a caller whose graphs become ready in pieces (mot3d_track_batch_host):
 // SOLVE_BEGIN once, SOLVE_FRONT for every range of graphs [g_first, g_first + g_count) whose in-CSR is complete

@@ -32,6 +32,7 @@ struct CompParams {
     int32_t *comp_inv;     // [n_total] out: regrouped position (global) of every detection
     int32_t *win_ncomp;    // [n_graphs] out: components per graph
     int32_t *win_cstart;   // [n_total] out: graph g's component c starts at regrouped position win_cstart[g0 + c]
+    FtOut tree;            // k_components_tree: the first tree, detection order in, regrouped order out
 };
 
 // Union-find on shared memory, safe under concurrent hooks: parents only ever decrease, so any value read is an
@@ -190,6 +191,157 @@ __global__ void __launch_bounds__(CC_TPB) k_components(const CompParams p) {
     if (tid == 0) p.win_ncomp[g] = ncomp;
 }
 
+// ---- the same split for the solver, which has the first shortest-path tree of every graph by then (k_first_tree runs
+//      before this kernel). All nodes of a tree branch - the nodes whose tree path starts with the same S arc - are
+//      connected by tree arcs, which are arcs of the graph: the union-find starts with every detection hooked under its
+//      branch root, and an arc only matters when the parents of its two ends differ - a few per cent of the arcs of a
+//      tracking window, where the old kernel ran two finds and a compare-and-swap attempt for every arc (117 thread
+//      instructions per arc, most of k_components' time). One thread per row: the common case is a load of the source
+//      and one shared-memory read. Unreachable detections (no branch) are their own roots and are united through
+//      their arcs like any other node, so the partition is exactly the connected components of the arc graph.
+//      The kernel also moves the first tree from detection order (FtTmp) to the regrouped order the solver stages
+//      from, turning parents and branch labels into positions on the way.
+__global__ void __launch_bounds__(CC_TPB) k_components_tree(const CompParams p) {
+    extern __shared__ int s_dyn[];
+    __shared__ int s_scan[33];
+    int *s_par = s_dyn;          // [cap] parent -> root -> component rank -> regrouped position
+    int *s_cnt = s_dyn + p.cap;  // [cap] rank of a root -> detections per component -> placement cursor
+    const int g = blockIdx.x + p.g_first;
+    const int g0 = p.graph_ptr[g];
+    const int n = p.graph_ptr[g + 1] - g0;
+    const int T = blockDim.x, tid = threadIdx.x;
+    if (n <= 0) {
+        if (tid == 0) p.win_ncomp[g] = 0;
+        return;
+    }
+    const int32_t *in_ptr = p.in_ptr + g0;
+    const FtTmp *tmp = p.tree.tmp + g0;
+    const bool overflow = (int64_t)in_ptr[n] > p.arc_capacity;  // arc buffer overflow: reported by the fill kernel
+    const bool split = n <= p.cap && !overflow;
+    if (!split) {  // kept whole: one component, identity order (an overflowed graph has no tree and is skipped later)
+        for (int i = tid; i < n; i += T) {
+            p.comp_perm[g0 + i] = g0 + i;
+            p.comp_inv[g0 + i] = g0 + i;
+            if (!overflow) p.tree.out[g0 + i] = tmp[i];
+        }
+        if (tid == 0) {
+            p.win_ncomp[g] = 1;
+            p.win_cstart[g0] = g0;
+        }
+        return;
+    }
+    for (int i = tid; i < n; i += T) {
+        const int a = tmp[i].anc;
+        s_par[i] = a >= 0 ? a - g0 : i;  // (a branch root's label is the root itself)
+    }
+    __syncthreads();
+    // ---- arcs between different branches. A warp takes 32 consecutive rows: their arcs are one contiguous range, read
+    //      with coalesced, independent loads; the row of an arc is found by a binary search over the 32 row starts held
+    //      by the lanes. The two ends of nearly every arc have the same parent (same branch, or united already): a
+    //      find / unite only where they differ.
+    {
+        const int lane = lane_id(), nwarp = T >> 5;
+        volatile int *vpar = s_par;
+        for (int j0 = warp_id() * 32; j0 < n; j0 += nwarp * 32) {
+            const int jl = j0 + lane;
+            const int start = in_ptr[jl < n ? jl : n];  // rows beyond the graph: empty
+            const int a0 = __shfl_sync(0xffffffffu, start, 0);
+            const int a1 = in_ptr[j0 + 32 < n ? j0 + 32 : n];
+            int src0 = a0 + lane < a1 ? p.in_src[a0 + lane] : 0;
+            int src1 = a0 + 32 + lane < a1 ? p.in_src[a0 + 32 + lane] : 0;
+            for (int eb = a0; eb < a1; eb += 32) {
+                const int e = eb + lane;
+                const int src2 = e + 64 < a1 ? p.in_src[e + 64] : 0;
+                int lo = 0;  // the last row whose arcs start at or before e
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int s = __shfl_sync(0xffffffffu, start, (lo + step) & 31);
+                    if (s <= e) lo += step;
+                }
+                if (e < a1 && vpar[src0 - g0] != vpar[j0 + lo]) {
+                    const int ri = cc_find(s_par, src0 - g0);
+                    const int rj = cc_find(s_par, j0 + lo);
+                    if (ri != rj) cc_unite(s_par, ri, rj);
+                }
+                src0 = src1;
+                src1 = src2;
+            }
+        }
+    }
+    __syncthreads();
+    // flatten: every detection points at its root (read-only chase; only the owner writes an entry)
+    for (int i = tid; i < n; i += T) {
+        volatile int *par = s_par;
+        int r = par[i], q = par[r];
+        while (q != r) {
+            r = q;
+            q = par[r];
+        }
+        par[i] = r;
+    }
+    __syncthreads();
+    // ---- rank the roots (a branch root is the earliest detection of its branch and roots hook under smaller roots:
+    //      the root of a component is its smallest detection, ascending root = ascending first detection)
+    int ncomp = 0;
+    for (int base = 0; base < n; base += T) {
+        const int i = base + tid;
+        const int f = (i < n && s_par[i] == i) ? 1 : 0;
+        int tot;
+        const int ex = block_excl_scan(f, s_scan, &tot);
+        if (f) s_cnt[i] = ncomp + ex;
+        ncomp += tot;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) s_par[i] = s_cnt[s_par[i]];  // own entry only: nobody else reads s_par[i] here
+    __syncthreads();
+    for (int c = tid; c < ncomp; c += T) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) atomicAdd(&s_cnt[s_par[i]], 1);
+    __syncthreads();
+    int run = 0;
+    for (int base = 0; base < ncomp; base += T) {  // exclusive scan of the component sizes -> component starts
+        const int c = base + tid;
+        const int v = c < ncomp ? s_cnt[c] : 0;
+        int tot;
+        const int ex = block_excl_scan(v, s_scan, &tot);
+        if (c < ncomp) {
+            s_cnt[c] = run + ex;
+            p.win_cstart[g0 + c] = g0 + run + ex;
+        }
+        run += tot;
+    }
+    __syncthreads();
+    // ---- stable placement: one warp walks the detections in order, lanes of the same component share a cursor bump
+    if (tid < 32) {
+        const unsigned lt = (1u << tid) - 1u;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + tid;
+            const int r = i < n ? s_par[i] : -1;
+            const unsigned m = __match_any_sync(0xffffffffu, r);
+            const int leader = __ffs(m) - 1;
+            int start = 0;
+            if (tid == leader && r >= 0) {
+                start = s_cnt[r];
+                s_cnt[r] = start + __popc(m);
+            }
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (i < n) s_par[i] = start + __popc(m & lt);
+        }
+    }
+    __syncthreads();
+    // ---- permutation, and the first tree in the regrouped order (parents and branch labels become positions)
+    for (int i = tid; i < n; i += T) {
+        const int q = s_par[i];
+        p.comp_inv[g0 + i] = g0 + q;
+        p.comp_perm[g0 + q] = g0 + i;
+        FtTmp t = tmp[i];
+        t.par = t.par >= 0 ? g0 + s_par[t.par - g0] : t.par;
+        t.anc = t.anc >= 0 ? g0 + s_par[t.anc - g0] : -1;
+        p.tree.out[g0 + q] = t;  // one 32-byte record per position: one sector per detection
+    }
+    if (tid == 0) p.win_ncomp[g] = ncomp;
+}
+
 // component graphs of the whole batch: cgraph_ptr (positions in the regrouped order) and the graph each belongs to
 __global__ void k_comp_offsets(int n_graphs, const int32_t *__restrict__ graph_ptr, const int32_t *__restrict__ win_ncomp,
                                int32_t *__restrict__ win_cbase, int32_t *__restrict__ n_cgraphs) {
@@ -237,7 +389,7 @@ int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_p
                        const int32_t *in_ptr, const int32_t *in_src, int64_t arc_capacity, int32_t *comp_perm_out,
                        int32_t *comp_inv_out, int32_t *cgraph_ptr_out, int32_t *cgraph_graph_out,
                        int32_t *graph_cbase_out, int32_t *n_cgraphs_out, void *ws, size_t ws_bytes, void *stream,
-                       int32_t g_first, int32_t g_count, bool finish) {
+                       int32_t g_first, int32_t g_count, bool finish, const FtOut *tree) {
     M3_CHECK_ARG(n_graphs >= 0 && n_total >= 0, "negative sizes");
     M3_CHECK_ARG(n_cgraphs_out, "n_cgraphs_out is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -276,7 +428,13 @@ int32_t components_run(int32_t n_graphs, int64_t n_total, const int32_t *graph_p
     if (smem > 48 * 1024)
         M3_CUDA(cudaFuncSetAttribute(k_components, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.g_first = g_first;
-    if (g_count > 0) {
+    if (g_count > 0 && tree) {  // the solver's path: the first tree is there, see k_components_tree
+        p.tree = *tree;
+        if (smem > 48 * 1024)
+            M3_CUDA(cudaFuncSetAttribute(k_components_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_components_tree<<<g_count, CC_TPB, smem, st>>>(p);
+        M3_LAUNCH_CHECK("k_components_tree");
+    } else if (g_count > 0) {
         k_components<<<g_count, CC_TPB, smem, st>>>(p);
         M3_LAUNCH_CHECK("k_components");
     }
@@ -308,7 +466,7 @@ int32_t mot3d_components(int32_t n_graphs, int64_t n_total, const int32_t *graph
                          size_t ws_bytes, void *stream) {
     return components_run(n_graphs, n_total, graph_ptr, CC_MAX_SORT, in_ptr, in_src, arc_capacity, comp_perm_out,
                           comp_inv_out, cgraph_ptr_out, cgraph_graph_out, graph_cbase_out, n_cgraphs_out, ws, ws_bytes,
-                          stream, 0, n_graphs, true);
+                          stream, 0, n_graphs, true, nullptr);
 }
 
 }  // extern "C"

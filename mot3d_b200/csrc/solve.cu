@@ -96,13 +96,10 @@ struct SolveParams {
     int32_t fast;               // 1 = k_single_track may finish single-track components
     int64_t *first_cost;        // [n_total] per component: cost of its first path when that was not kept (>= 0)
     int32_t *first_sink;        // [n_total] ... and the position where it ends
-    // first shortest-path tree (k_first_tree), per regrouped position; values are regrouped positions too
-    int64_t *ws_dpre;
-    int64_t *ws_dpost;
-    int32_t *ws_par;       // parent of the pre node: PAR_S / PAR_NONE / position of the source detection
-    int32_t *ws_anc_pre;   // branch = position of the detection whose S->pre arc starts the node's tree path
-    int32_t *ws_anc_post;
+    // (the first shortest-path tree lives in ft / ft_tmp, see FtTmp)
     int32_t *ws_lvl;       // [n_total + n_graphs] frame layers
+    FtTmp *ft_tmp;         // [n_total] what k_first_tree leaves, in detection order (k_components_tree regroups it)
+    FtTmp *ft;             // [n_total] ... and in the regrouped order, parents / branch labels as positions
     // global staging area (components that do not fit shared memory; spilled arc lists of those that do)
     GRec *ws_rec;          // [n_total]
     int32_t *ws_tk;        // [n_total] layer keys
@@ -169,7 +166,8 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 
 // ---- first shortest-path tree of every graph (before it is split into components): no flow yet, the network is a
 //      DAG, one pull sweep over the frame layers with the whole block (Graph::shortest_path_dag, Graph.cpp:139-187).
-//      State is written in the regrouped order; branch label = position of the detection whose S arc starts the path.
+//      State is written in detection order (FtTmp; k_components_tree moves it to the regrouped order); parent and
+//      branch label (the detection whose S arc starts the node's tree path) are global detection indices.
 constexpr int FT_W = 2048;  // ring of post / branch labels (power of two)
 template <int FT_LPN>
 __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
@@ -189,7 +187,6 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
     if (n <= 0) return;
     const int32_t *tkey = p.tkey + g0;
     const int32_t *in_ptr = p.in_ptr + g0;
-    const int32_t *inv = p.comp_inv + g0;
     // first_cost / first_sink are indexed by component, and the components of a graph may be numbered anywhere in
     // [0, n_total): the whole batch's arrays are cleared by mot3d_solve_batch before this launch
     for (int i = tid; i < n; i += T)
@@ -233,13 +230,11 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
             KeyIdx best;
             best.key = INF;
             best.idx = PAR_NONE;
-            int q = 0;
             int64_t e_ = INF, c_ = 0, x_ = INF;
             int64_t w_best = INF, w_min = INF;  // cost of the parent arc / of the cheapest in-arc (k_single_track)
             if (valid) {
                 const int e0 = in_ptr[j], deg = in_ptr[j + 1] - e0;
                 if (sub == 0) {  // the node's own costs: in flight together with the arc loads
-                    q = inv[j];
                     e_ = p.en[g0 + j];
                     c_ = p.cn[g0 + j];
                     x_ = p.ex[g0 + j];
@@ -260,7 +255,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                         else if (src[u] >= ring_lo)
                             di[u] = s_dp[(src[u] - g0) & (FT_W - 1)];
                         else
-                            di[u] = p.ws_dpost[p.comp_inv[src[u]]];
+                            di[u] = p.ft_tmp[src[u]].dpost;
                     }
 #pragma unroll
                     for (int u = 0; u < FT_U; u++) {
@@ -291,18 +286,17 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
             if (valid && sub == 0) {
                 int anc = -1;
                 if (best.idx >= 0)
-                    anc = best.idx >= ring_lo ? s_an[(best.idx - g0) & (FT_W - 1)] : p.ws_anc_post[p.comp_inv[best.idx]];
+                    anc = best.idx >= ring_lo ? s_an[(best.idx - g0) & (FT_W - 1)] : p.ft_tmp[best.idx].anc;
                 wide |= (fits_narrow(e_) && fits_narrow(x_) && c_ == (int64_t)(int)c_) ? 0 : 1;
                 if (e_ < best.key) {
                     best.key = e_;
                     best.idx = PAR_S;
-                    anc = q;
+                    anc = g0 + j;
                 }
                 // what solve_component's optimality certificate asks of this detection if its tree arc ends up
                 // matched: no negative entry / exit cost; the arc is the cheapest in-arc, costs mc <= 0, cn + mc <= 0
                 int cert = ((e_ < INF_CUT && e_ < 0) || (x_ < INF_CUT && x_ < 0)) ? 0 : 1;
                 if (best.idx >= 0 && !(w_best <= 0 && c_ + w_best <= 0 && w_min >= w_best)) cert = 0;
-                p.ws_pl[q] = cert;
                 int64_t dpost = INF;
                 if (best.key < INF_CUT) {
                     dpost = best.key + c_;
@@ -311,20 +305,19 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                     best.idx = PAR_NONE;
                     anc = -1;
                 }
-                p.ws_dpre[q] = best.key;
-                p.ws_par[q] = best.idx;  // a detection index for now
-                p.ws_anc_pre[q] = anc;
-                p.ws_dpost[q] = dpost;
-                p.ws_anc_post[q] = anc;
+                FtTmp t;
+                t.dpre = best.key;
+                t.dpost = dpost;
+                t.par = best.idx;
+                t.anc = anc;
+                t.cert = cert;
+                t.pad = 0;
+                p.ft_tmp[g0 + j] = t;
                 s_dp[j & (FT_W - 1)] = dpost;
                 s_an[j & (FT_W - 1)] = anc;
             }
         }
         __syncthreads();
-    }
-    for (int i = tid; i < n; i += T) {  // parents: detection index -> regrouped position
-        const int par = p.ws_par[g0 + i];
-        if (par >= 0) p.ws_par[g0 + i] = p.comp_inv[par];
     }
     wide = __syncthreads_or(wide);
     if (tid == 0) p.win_wide[g] = wide;
@@ -412,10 +405,11 @@ __device__ __forceinline__ bool single_track_try(const SolveParams &p, const int
     int64_t key_last = INF, key_rest = INF;
     for (int i = lane; i < n && ok; i += 32) {
         const int q = c0 + i;
-        const int par = p.ws_par[q];
-        ok = ((i == 0) ? (par == PAR_S) : (par == q - 1)) && p.ws_pl[q] != 0;
+        const FtTmp t = p.ft[q];
+        const int par = t.par;
+        ok = ((i == 0) ? (par == PAR_S) : (par == q - 1)) && t.cert != 0;
         const int64_t ex = p.ex[p.comp_perm[q]];
-        const int64_t dpost = p.ws_dpost[q];
+        const int64_t dpost = t.dpost;
         const int64_t key = (ex < INF_CUT && dpost < INF_CUT) ? dpost + ex : INF;
         if (i == n - 1)
             key_last = key;
@@ -571,7 +565,7 @@ __global__ void k_first_path_rule(const SolveParams p) {
     for (int step = 0; step < p.n_total; step++) {
         const int d = p.comp_perm[q];
         p.next_out[d] = nx;
-        const int pq = p.ws_par[q];
+        const int pq = p.ft[q].par;
         if (pq < 0) {
             p.prev_out[d] = TERM;
             break;
@@ -766,6 +760,7 @@ size_t mot3d_solve_workspace_bytes(int64_t n_total, int32_t n_graphs, int64_t ar
     size_t n = (size_t)(n_total > 0 ? n_total : 1), g = (size_t)(n_graphs > 0 ? n_graphs : 1);
     size_t e = (size_t)(arc_capacity > 0 ? arc_capacity : 1);
     return a256(n * 8) * 3 + a256(n * 4) * 12 + a256(n * 16) + a256((n + g) * 4) * 2 + a256(g * 4) * 2 +
+           a256(n * sizeof(FtTmp)) * 2 +
            a256(n * sizeof(GRec)) + a256((e + n + 8) * sizeof(StArc)) + a256(n * 16) * 3 + a256(n * 8) * 2 + a256((n / 16 + n + 8) * 4) +
            a256((e + 8) * 12) + 256 +
            a256(mot3d_components_workspace_bytes(n_total, n_graphs)) + 512 + a256(JOB_META_INTS * sizeof(int32_t));
@@ -846,12 +841,8 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
     p.path_cost = path_cost_out;
     p.stats = stats_out;
     p.arc_capacity = arc_capacity;
-    p.ws_dpre = (int64_t *)take(n_cap * 8);
-    p.ws_dpost = (int64_t *)take(n_cap * 8);
+    p.ft = (FtTmp *)take(n_cap * sizeof(FtTmp));
     p.first_cost = (int64_t *)take(n_cap * 8);
-    p.ws_par = (int32_t *)take(n_cap * 4);
-    p.ws_anc_pre = (int32_t *)take(n_cap * 4);
-    p.ws_anc_post = (int32_t *)take(n_cap * 4);
     p.ws_tk = (int32_t *)take(n_cap * 4);
     p.ws_bl = (int32_t *)take(n_cap * 4);
     p.ws_hop = (int32_t *)take(n_cap * 4);
@@ -872,6 +863,7 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
     int32_t *n_cgraphs = (int32_t *)take(16);
     p.job_meta = (int32_t *)take(JOB_META_INTS * sizeof(int32_t));
     p.comp_class = (int32_t *)take(n_cap * 4);
+    p.ft_tmp = (FtTmp *)take(n_cap * sizeof(FtTmp));
     p.big_res_e = (longlong2 *)take(n_cap * 16);
     p.big_res_f = (int4 *)take(n_cap * 16);
     p.big_listed = (unsigned *)take((n_cap / 16 + n_cap + 8) * 4);
@@ -901,13 +893,7 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
         M3_CUDA(cudaMemsetAsync(p.first_sink, 0xff, n_cap * sizeof(int32_t), st));  // -1 = component has no first path
     }
     trace_mark(0, st);
-    // 1. connected components of every graph, detections regrouped by component
-    int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
-                                comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream, g_first,
-                                (phases & SOLVE_FRONT) ? g_count : 0, (phases & SOLVE_BACK) != 0);
-    if (rc) return rc;
-    trace_mark(1, st);
-    // 2. first shortest-path tree per graph: 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of
+    // 1. first shortest-path tree per graph: 2 lanes per node, 256 threads: a layer of ~100 detections is one pass of
     //    the block
 #ifndef M3_FT_T
 #define M3_FT_T 256
@@ -917,6 +903,16 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
         k_first_tree<2><<<g_count, M3_FT_T, 0, st>>>(p);
         M3_LAUNCH_CHECK("k_first_tree");
     }
+    trace_mark(1, st);
+    // 2. connected components of every graph (from the branches of the tree and the arcs between them), detections
+    //    and tree regrouped by component
+    FtOut tree;
+    tree.tmp = p.ft_tmp;
+    tree.out = p.ft;
+    int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
+                                comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream, g_first,
+                                (phases & SOLVE_FRONT) ? g_count : 0, (phases & SOLVE_BACK) != 0, &tree);
+    if (rc) return rc;
     trace_mark(2, st);
     if (!(phases & SOLVE_BACK)) return MOT3D_OK;
     // 3. successive shortest paths per component, one launch per band of the work queue (see k_job_order)

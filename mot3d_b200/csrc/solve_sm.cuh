@@ -119,8 +119,9 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
     for (int i = i0; i < i1; i++) {
         const int q = c0 + i, d = perm[i];
         const int e0 = p.in_ptr[d], e1 = p.in_ptr[d + 1];
-        const int par = p.ws_par[q], ap_ = p.ws_anc_pre[q], ao_ = p.ws_anc_post[q];
-        const int64_t dpre = p.ws_dpre[q], dpost = p.ws_dpost[q];
+        const FtTmp ft = p.ft[q];
+        const int par = ft.par, ap_ = ft.anc, ao_ = ft.anc;
+        const int64_t dpre = ft.dpre, dpost = ft.dpost;
         const int64_t en = p.en[d], cn = p.cn[d], ex = p.ex[d];
         const int key = p.tkey[d];
         SRec r;
