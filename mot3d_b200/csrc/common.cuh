@@ -41,6 +41,7 @@ struct __align__(16) FtTmp {
 };
 struct FtOut {  // first tree: detection order in, regrouped order out (parents and branch labels as positions)
     const FtTmp *tmp;
+    const int32_t *anc;  // the branch labels once more, 4 bytes per detection: what the union-find starts from
     FtTmp *out;
 };
 

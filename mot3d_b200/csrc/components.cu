@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CC_TPB) k_components_tree(const CompParams p) 
         return;
     }
     for (int i = tid; i < n; i += T) {
-        const int a = tmp[i].anc;
+        const int a = p.tree.anc[g0 + i];
         s_par[i] = a >= 0 ? a - g0 : i;  // (a branch root's label is the root itself)
     }
     __syncthreads();

@@ -100,6 +100,7 @@ struct SolveParams {
     int32_t *ws_lvl;       // [n_total + n_graphs] frame layers
     FtTmp *ft_tmp;         // [n_total] what k_first_tree leaves, in detection order (k_components_tree regroups it)
     FtTmp *ft;             // [n_total] ... and in the regrouped order, parents / branch labels as positions
+    int32_t *ft_anc;       // [n_total] the branch labels of ft_tmp once more (k_components_tree starts from them)
     // global staging area (components that do not fit shared memory; spilled arc lists of those that do)
     GRec *ws_rec;          // [n_total]
     int32_t *ws_tk;        // [n_total] layer keys
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(256, 5) k_first_tree(const SolveParams p) {
                 t.cert = cert;
                 t.pad = 0;
                 p.ft_tmp[g0 + j] = t;
+                p.ft_anc[g0 + j] = anc;
                 s_dp[j & (FT_W - 1)] = dpost;
                 s_an[j & (FT_W - 1)] = anc;
             }
@@ -864,6 +866,7 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
     p.job_meta = (int32_t *)take(JOB_META_INTS * sizeof(int32_t));
     p.comp_class = (int32_t *)take(n_cap * 4);
     p.ft_tmp = (FtTmp *)take(n_cap * sizeof(FtTmp));
+    p.ft_anc = (int32_t *)take(n_cap * 4);
     p.big_res_e = (longlong2 *)take(n_cap * 16);
     p.big_res_f = (int4 *)take(n_cap * 16);
     p.big_listed = (unsigned *)take((n_cap / 16 + n_cap + 8) * 4);
@@ -908,6 +911,7 @@ int32_t solve_batch_phased(int phases, int32_t g_first, int32_t g_count, int32_t
     //    and tree regrouped by component
     FtOut tree;
     tree.tmp = p.ft_tmp;
+    tree.anc = p.ft_anc;
     tree.out = p.ft;
     int32_t rc = components_run(n_graphs, n_total, graph_ptr, max_graph_nodes, in_ptr, in_src, arc_capacity, comp_perm,
                                 comp_inv, cgraph_ptr, cgraph_win, win_cbase, n_cgraphs, cws, cws_bytes, stream, g_first,
