@@ -17,7 +17,7 @@ extern "C" size_t mot3d_components_workspace_bytes(int64_t n_total, int32_t n_gr
 
 namespace m3 {
 
-constexpr int CC_TPB = 256;
+constexpr int CC_TPB = 512;
 constexpr int CC_MAX_SORT = 8192;
 
 struct CompParams {
