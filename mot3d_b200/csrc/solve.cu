@@ -31,7 +31,10 @@
 
 namespace m3 {
 
-constexpr int LPN = 4;  // lanes cooperating on one node's in-arcs (first tree, initial labels)
+#ifndef M3_LPN
+#define M3_LPN 4
+#endif
+constexpr int LPN = M3_LPN;  // lanes cooperating on one node's in-arcs (staging, relabelling rounds)
 
 // state markers (slots / positions are >= 0)
 constexpr int NONE = -1;  // detection unused

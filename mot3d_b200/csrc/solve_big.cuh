@@ -26,7 +26,7 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
                                                  int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
-    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
+    const unsigned gmask = ((1u << LPN) - 1u) << ((tid & 31) / LPN * LPN);
     SRec *const rec = (SRec *)(p.ws_rec + c0);  // (an 80-byte slot per record of the area solve_global.cuh uses)
     longlong2 *const res_e = p.big_res_e + c0;  // staged results of a round: new labels ...
     int4 *const res_f = p.big_res_f + c0;       // ... parent, branches, what moved (1 = pre, 2 = post)

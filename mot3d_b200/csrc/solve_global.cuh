@@ -65,7 +65,7 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
     typedef typename S::slot_t Slot;
     const int T = blockDim.x, tid = threadIdx.x;
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
-    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
+    const unsigned gmask = ((1u << LPN) - 1u) << ((tid & 31) / LPN * LPN);
     // slot lists: bl = the branch in layer order, hop = detections whose matched in-arc changed, pl = the branch's
     // unused records with a post node to re-label ("producers" of the ascending sweep)
     Rec *const rec = (Rec *)(p.ws_rec + c0);

@@ -74,7 +74,7 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
                                                 int *s_scan, KeyIdx *s_red, int *s_ok, long long *s_work) {
     const int T = blockDim.x, tid = threadIdx.x;
     const int sub = tid % LPN, grp = tid / LPN, ngrp = T / LPN;
-    const unsigned gmask = 0xFu << ((tid & 31) / LPN * LPN);
+    const unsigned gmask = ((1u << LPN) - 1u) << ((tid & 31) / LPN * LPN);
     const int n8 = (n + 7) & ~7;
     SRec *const rec = (SRec *)smem_raw;
     int32_t *const tk = (int32_t *)(smem_raw + (size_t)n8 * sizeof(SRec));
