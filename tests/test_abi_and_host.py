@@ -368,3 +368,19 @@ def test_costs_on_real_items_and_input_checks(built):
         quantise_scalar(float("nan"))
     with pytest.raises(NotImplementedError):
         wf.weight_distance_tracklets_auto(trk, mot3d.DetectionTracklet3D([mot3d.Detection3D(5, (0.0, 0.0, 0.0))]))
+
+
+def test_options_and_release_without_gpu(built):
+    """mot3d_set_option: known names take a value or NaN (= default), unknown names are an error with a message;
+    mot3d_host_release on a thread that never ran the host call does nothing. No CUDA call involved."""
+    L = built.lib()
+    for name in ("host_chunks", "host_pieces", "host_split", "host_edge_weight", "host_trace", "host_no_pack",
+                 "edge_cap", "edge_acap", "solve_no_fast", "big_delta"):
+        assert L.mot3d_set_option(name.encode(), 1.0) == 0
+        assert L.mot3d_set_option(name.encode(), float("nan")) == 0
+    assert L.mot3d_set_option(b"no_such_option", 1.0) == built.E_INVALID
+    assert b"no_such_option" in L.mot3d_last_error()
+    assert L.mot3d_set_option(None, 1.0) == built.E_INVALID
+    with pytest.raises(built.Mot3dError):
+        built.set_option("nope", 3)
+    assert L.mot3d_host_release() == 0
