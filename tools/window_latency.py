@@ -7,7 +7,8 @@ stand-alone:
 Cases (fixtures made by the reference itself, tests/golden/, unless noted):
   C1 simple_2d, C3 soldiers_3d pass 1 with max_jump 8 (the example's value) and 4 (BASELINE.json's), the two real PETS
   windows (C4), one C5 window, C5-whole (synthetic 100 000 detections / 1 000 frames as ONE graph, generated), a long
-  thin synthetic graph (F=1000, P=10, generated) and muSSP's own sample graph input_MOT_seq07 (solve only).
+  thin synthetic graph (F=1000, P=10, generated), the online loop of config 4 per batch (Tracker2D.update) and muSSP's
+  own sample graph input_MOT_seq07 (solve only).
 Per case:
   gpu_ms.objects   p50 / p99 of mot3d_b200.build_graph + solve_graph on Detection objects: the drop-in call, host packing,
                    H2D, kernels, D2H and unpacking included (small cases only)
@@ -161,6 +162,34 @@ def measure(reps=50, budget_s=6.0, cpu=True, log=None):
     detection_case("long_thin_f1000_p10", frame, pos, np.full(len(frame), 0.9), s5, objects=False)
     frame, pos = _gen(1000, 100, 0)
     detection_case("c5_whole_f1000_p100", frame, pos, np.full(len(frame), 0.9), s5, objects=False)
+
+    # the online window loop (BASELINE config 4): Tracker2D.update per batch of 50 frames on C4-synth, the scene carried
+    # from batch to batch (two graph builds + solves per batch and the host glue between them)
+    import json as _json
+    from mot3d_b200.online import Scene, Tracker2D
+    d = gu.load("c4_online_loop")
+    cfg = _json.loads(str(d["config"]))
+    ptr, det = d["det_ptr"], d["det"]
+    B = cfg["batch_size"]
+    t_batches = []
+    for rep in range(3):
+        scene = Scene(cfg["completed_after"])
+        tracker = Tracker2D(scene, None, cfg, image_size=(768, 576))
+        for b in range((len(ptr) - 1) // B):
+            dets = [[mot3d.Detection2D(f, det[r, :2].copy(), confidence=float(det[r, 2]), bbox=tuple(det[r, 3:7]))
+                     for r in range(int(ptr[f]), int(ptr[f + 1]))] for f in range(b * B, (b + 1) * B)]
+            t0 = time.perf_counter()
+            tracker.update((b + 1) * B, dets)
+            if rep:
+                t_batches.append((time.perf_counter() - t0) * 1e3)
+    rec = {"case": "c4_online_loop_per_batch", "detections": int(len(det) // ((len(ptr) - 1) // B)),
+           "gpu_ms": {"update": _pct(t_batches)},
+           "what": "mot3d_b200.online.Tracker2D.update: detection pass, tracklet pass against the active trajectories, "
+                   "interpolation, scene update; 50 frames per batch",
+           "totals_agree": bool(len(scene.completed) == 2 and len(scene.active) == 6)}
+    if log:
+        log(rec)
+    out.append(rec)
 
     # muSSP's own sample graph (solve only): arcs in, flow out
     d = gu.load("mussp_seq07")
