@@ -14,6 +14,8 @@ Per case:
                    H2D, kernels, D2H and unpacking included (small cases only)
   gpu_ms.arrays    p50 / p99 of DetectionBatch.from_arrays -> build_graphs -> solve_graphs -> extract_tracks -> host
                    lists: host arrays in, tracks out
+  gpu_ms.host_call p50 / p99 of the C-ABI host-buffer call (HostTracker.load + mot3d_track_batch_host + tracks()): one
+                   call per window, pinned buffers held by the caller (2-D cases without histograms)
   cpu_ms           the same graph through the numpy port of build_graph (oracle/oracle.py) + the reference's muSSP
                    (oracle/_ref, arrays in) on one core; `cpu_text_ms` = muSSP through the reference's text interface
                    (graph_to_text lines -> wrapper.cpp's parse -> solve: what mot3d itself pays per solve_graph call)
@@ -95,6 +97,19 @@ def measure(reps=50, budget_s=6.0, cpu=True, log=None):
 
         rec = {"case": label, "detections": n, "max_jump": s["max_jump"]}
         gpu = {"arrays": _pct(_time(arrays_once, reps, budget_s))}
+        if hist is None and s["kind"] == "2d" and n <= 20000:
+            # the C-ABI host-buffer call (mot3d_track_batch_host through HostTracker): load into pinned buffers, one call,
+            # tracks out; sized once (arc capacity from the array path above), as a service would hold it
+            ht = mot3d.HostTracker(n_max=n, g_max=1, edge_capacity=int(res["arcs"]) + 64, dim=2, with_bbox=bbox is not None)
+            hb, _ = mot3d.DetectionBatch.from_arrays(gp, frame, pos, conf, bbox=bbox)
+            spec_c = spec.to_c()
+
+            def host_once():
+                ht.load(hb)
+                ht.run(spec_c)
+                return ht.tracks()
+            gpu["host_call"] = _pct(_time(host_once, reps, budget_s))
+            res["host_total"] = int(ht.h_total[0].item())
         if objects:
             if s["kind"] == "3d":
                 dets = [mot3d.Detection3D(int(frame[i]), pos[i], confidence=float(conf[i])) for i in range(n)]
@@ -144,7 +159,8 @@ def measure(reps=50, budget_s=6.0, cpu=True, log=None):
                                               "(wrapper.cpp:39-88 parse + solve)"}
             # muSSP's float tolerances may leave it a few units above the exact optimum
             rec["total_cost_units"] = {"gpu": int(res["total"]), "mussp_same_arcs": int(ref_total)}
-            rec["totals_agree"] = bool(0 <= int(ref_total) - int(res["total"]) <= 2)
+            rec["totals_agree"] = bool(0 <= int(ref_total) - int(res["total"]) <= 2 and
+                                       res.get("host_total", res["total"]) == res["total"])
         if log:
             log(rec)
         out.append(rec)
