@@ -394,6 +394,37 @@ int32_t mot3d_tracklets_from_tracks(int32_t n, int32_t dim, const int32_t *frame
                                     int32_t *tail_ptr_out, int32_t *head_idx_out, int32_t *tail_idx_out,
                                     double *head_pos_out, double *tail_pos_out, void *ws, size_t ws_bytes, void *stream);
 
+/* The same for the online loop (projects/PETS2009S2L1/singleview_tracking.py:94-121): the tracklet set is the n_carry
+ * trajectories carried over from earlier batches (Scene.active, whole, in id order) followed by the new pieces, as in the
+ * reference's list; ranks are by (start frame, list position). carry_ptr [n_carry + 1] / carry_frame [points] /
+ * carry_pos [dim][carry_stride] planar describe the carried trajectories (device arrays, typically the output of the
+ * previous mot3d_online_concat). head_pos_out / tail_pos_out are planar with stride out_stride (>= the points any
+ * window set can hold: carried points + n). item_out [n_carry + n]: per rank, c < n_carry = carried trajectory c, else
+ * n_carry + number of the new piece in track order; for a carried trajectory trk_first_out addresses carry_frame.
+ * span_out (may be NULL) [2][..] interleaved: first and last frame of the tracklet at every rank.
+ * n = 0 (a batch without detections) is allowed: track_count must then point at a zero. */
+int32_t mot3d_online_tracklets(int32_t n, int32_t dim, const int32_t *frame, const double *pos,
+                               const int32_t *track_count, const int32_t *track_ptr, const int32_t *track_det,
+                               int32_t split_length, int32_t th_length, int32_t window, int32_t n_carry,
+                               const int32_t *carry_ptr, const int32_t *carry_frame, const double *carry_pos,
+                               int64_t carry_stride, int64_t out_stride, int32_t *n_tracklets_out, int32_t *item_out,
+                               int32_t *trk_first_out, int32_t *trk_len_out, int32_t *key_out, int32_t *head_ptr_out,
+                               int32_t *tail_ptr_out, int32_t *head_idx_out, int32_t *tail_idx_out, double *head_pos_out,
+                               double *tail_pos_out, int32_t *span_out, void *ws, size_t ws_bytes, void *stream);
+
+/* The online loop's write-back: concat_tracklets + interpolate_trajectory(position, bbox)
+ * (mot3d/utils/trajectory.py:11-69) for n_out output trajectories at once. Trajectory t is the chain of tracklets
+ * chain[chain_ptr[t] .. chain_ptr[t+1]) (ranks of mot3d_online_tracklets, in time order) and occupies points
+ * [out_ptr[t], out_ptr[t+1]) of the new arrays: one point per frame from its first to its last, skipped frames filled
+ * by v1 + (v2 - v1) / (t2 - t1) * (t - t1). bbox / carry_bbox / new_bbox are planar [4][stride] like the positions.
+ * *error_flag |= 1 if a chain does not cover its range exactly (wrong out_ptr, tracklets out of order). */
+int32_t mot3d_online_concat(int32_t n_out, const int32_t *chain_ptr, const int32_t *chain, const int32_t *out_ptr,
+                            const int32_t *item, const int32_t *trk_first, const int32_t *trk_len, int32_t n_carry,
+                            int32_t n, int32_t dim, const int32_t *track_det, const int32_t *frame, const double *pos,
+                            const double *bbox, const int32_t *carry_frame, const double *carry_pos,
+                            const double *carry_bbox, int64_t carry_stride, int32_t *new_frame, double *new_pos,
+                            double *new_bbox, int64_t new_stride, int32_t *error_flag, void *stream);
+
 /* Out-CSR of mot3d_tracklet_edge_fill (rows = arc tails) -> the solver's inputs for one graph of *n_nodes_dev nodes
  * (<= n_nodes_max): in-CSR, constant entry / node / exit costs, graph_ptr = {0, n}. ws: int32 [n_nodes_max + 1]. */
 int32_t mot3d_tracklet_graph_in_csr(const int32_t *n_nodes_dev, int32_t n_nodes_max, const int32_t *row_ptr,

@@ -19,4 +19,5 @@ from .batch import (DetectionBatch, GraphBatch, HostTracker, build_graphs, solve
 from .scheduler import shard_graphs, gather_tracks, TrackGather, pack_tracks_host, unpack_tracks_host  # noqa: F401
 from . import online  # noqa: F401
 from .twopass import link_tracks  # noqa: F401
+from .online_device import DeviceTracker2D  # noqa: F401
 from ._lib import Mot3dError, version  # noqa: F401

@@ -28,6 +28,14 @@ struct SplitParams {
     int32_t *head_ptr, *tail_ptr, *head_idx, *tail_idx;
     double *head_pos, *tail_pos;
     int32_t *w_flag, *w_first, *w_len, *w_keep;  // scratch [n + 1] each
+    // trajectories carried over from earlier batches (the online loop: Scene.active) join the tracklet set as they are
+    int32_t n_carry;
+    const int32_t *carry_ptr, *carry_frame;  // [n_carry + 1], [points]
+    const double *carry_pos;                 // [dim][carry_stride] planar
+    int64_t carry_stride;
+    int32_t *item;  // out [n_carry + kept]: what the tracklet at a rank is: c < n_carry = carried trajectory c, else
+                    // n_carry + number of the new tracklet in track order (the order the reference lists them in)
+    int64_t out_stride;  // planar stride of head_pos / tail_pos
 };
 
 __device__ __forceinline__ int py_mod(int a, int m) {
@@ -80,33 +88,43 @@ __global__ void __launch_bounds__(TP_T) k_split_tracks(const SplitParams p) {
         Mk += tot;
     }
     __syncthreads();
-    // (4) order by (start frame, number): rank by counting
-    for (int i = tid; i < Mk; i += TP_T) {
-        const int fi = p.frame[p.track_det[p.w_keep[i]]];
+    // (4) the tracklet set = carried trajectories, then the new tracklets (the reference's list order); ordered by
+    //     (start frame, list index): rank by counting. For a carried trajectory first / len address carry_frame.
+    const int A = p.n_carry, Mt = A + Mk;
+    auto first_frame = [&](int it) {
+        return it < A ? p.carry_frame[p.carry_ptr[it]] : p.frame[p.track_det[p.w_keep[it - A]]];
+    };
+    for (int i = tid; i < Mt; i += TP_T) {
+        const int fi = first_frame(i);
         int rank = 0;
-        for (int j = 0; j < Mk; j++) {
-            const int fj = p.frame[p.track_det[p.w_keep[j]]];
+        for (int j = 0; j < Mt; j++) {
+            const int fj = first_frame(j);
             rank += (fj < fi || (fj == fi && j < i)) ? 1 : 0;
         }
-        p.trk_first[rank] = p.w_keep[i];
-        p.trk_len[rank] = p.w_len[i];
+        p.trk_first[rank] = i < A ? p.carry_ptr[i] : p.w_keep[i - A];
+        p.trk_len[rank] = i < A ? p.carry_ptr[i + 1] - p.carry_ptr[i] : p.w_len[i - A];
         p.key[rank] = fi;
+        if (p.item) p.item[rank] = i;
     }
     __syncthreads();
     // (5) the windows at both ends: head = detections with index > last - window, tail = index < first + window
     //     (window 0 = None: the whole tracklet at both ends, mot3d/types.py:100-112); offsets by a scan, then the points
+    auto is_carried = [&](int r) { return p.item && p.item[r] < A; };
+    auto frame_of = [&](int r, int k) {
+        return is_carried(r) ? p.carry_frame[p.trk_first[r] + k] : p.frame[p.track_det[p.trk_first[r] + k]];
+    };
     int run_h = 0, run_t = 0;
-    for (int base = 0; base < Mk; base += TP_T) {
+    for (int base = 0; base < Mt; base += TP_T) {
         const int i = base + tid;
         int nh = 0, nt = 0;
-        if (i < Mk) {
-            const int first = p.trk_first[i], len = p.trk_len[i];
+        if (i < Mt) {
+            const int len = p.trk_len[i];
             if (p.window <= 0) {
                 nh = nt = len;
             } else {
-                const int f_last = p.frame[p.track_det[first + len - 1]], f_first = p.frame[p.track_det[first]];
+                const int f_last = frame_of(i, len - 1), f_first = frame_of(i, 0);
                 for (int k = 0; k < len; k++) {
-                    const int f = p.frame[p.track_det[first + k]];
+                    const int f = frame_of(i, k);
                     nh += f > f_last - p.window ? 1 : 0;
                     nt += f < f_first + p.window ? 1 : 0;
                 }
@@ -115,7 +133,7 @@ __global__ void __launch_bounds__(TP_T) k_split_tracks(const SplitParams p) {
         int tot_h, tot_t;
         const int eh = tp_block_excl_scan(nh, s_scan, &tot_h);
         const int et = tp_block_excl_scan(nt, s_scan, &tot_t);
-        if (i < Mk) {
+        if (i < Mt) {
             p.head_ptr[i] = run_h + eh;
             p.tail_ptr[i] = run_t + et;
         }
@@ -123,26 +141,29 @@ __global__ void __launch_bounds__(TP_T) k_split_tracks(const SplitParams p) {
         run_t += tot_t;
     }
     if (tid == 0) {
-        p.head_ptr[Mk] = run_h;
-        p.tail_ptr[Mk] = run_t;
-        p.n_tracklets[0] = Mk;
+        p.head_ptr[Mt] = run_h;
+        p.tail_ptr[Mt] = run_t;
+        p.n_tracklets[0] = Mt;
     }
     __syncthreads();
-    for (int i = tid; i < Mk; i += TP_T) {
+    for (int i = tid; i < Mt; i += TP_T) {
         const int first = p.trk_first[i], len = p.trk_len[i];
-        const int f_last = p.frame[p.track_det[first + len - 1]], f_first = p.frame[p.track_det[first]];
+        const bool carried = is_carried(i);
+        const int f_last = frame_of(i, len - 1), f_first = frame_of(i, 0);
         int h = p.head_ptr[i], t = p.tail_ptr[i];
         for (int k = 0; k < len; k++) {
-            const int d = p.track_det[first + k];
-            const int f = p.frame[d];
+            const int d = carried ? first + k : p.track_det[first + k];
+            const int f = carried ? p.carry_frame[d] : p.frame[d];
+            const double *src = carried ? p.carry_pos : p.pos;
+            const int64_t stride = carried ? p.carry_stride : (int64_t)p.n;
             if (p.window <= 0 || f > f_last - p.window) {
                 p.head_idx[h] = f;
-                for (int c = 0; c < p.dim; c++) p.head_pos[(size_t)c * p.n + h] = p.pos[(size_t)c * p.n + d];
+                for (int c = 0; c < p.dim; c++) p.head_pos[(size_t)c * p.out_stride + h] = src[(size_t)c * stride + d];
                 h++;
             }
             if (p.window <= 0 || f < f_first + p.window) {
                 p.tail_idx[t] = f;
-                for (int c = 0; c < p.dim; c++) p.tail_pos[(size_t)c * p.n + t] = p.pos[(size_t)c * p.n + d];
+                for (int c = 0; c < p.dim; c++) p.tail_pos[(size_t)c * p.out_stride + t] = src[(size_t)c * stride + d];
                 t++;
             }
         }
@@ -232,6 +253,136 @@ __global__ void __launch_bounds__(TP_T) k_concat_tracklets(const int32_t *__rest
     }
 }
 
+// The online loop's write-back: every output trajectory is a chain of tracklets (carried
+// trajectories and pieces of this batch's tracks); its points are the points of the chain in time order with the
+// skipped frames filled by linear interpolation of position and box -- concat_tracklets + interpolate_trajectory
+// (reference mot3d/utils/trajectory.py:11-69: v1 + (v2 - v1) / (t2 - t1) * (t - t1)). One block per trajectory, one
+// thread per source point: it writes its own point and the fill up to the next one.
+struct OnlineConcatParams {
+    int32_t n_out;
+    const int32_t *chain_ptr, *chain;  // [n_out + 1], ranks of the tracklets of every chain
+    const int32_t *out_ptr;            // [n_out + 1] first point of every output trajectory
+    const int32_t *item, *trk_first, *trk_len;
+    int32_t n_carry;
+    // this batch
+    int32_t n;
+    const int32_t *track_det, *frame;
+    const double *pos, *bbox;  // planar, stride n
+    // carried
+    const int32_t *carry_frame;
+    const double *carry_pos, *carry_bbox;  // planar, stride carry_stride
+    int64_t carry_stride;
+    int32_t dim;
+    // out
+    int32_t *new_frame;
+    double *new_pos, *new_bbox;  // planar, stride new_stride
+    int64_t new_stride;
+    int32_t *error;  // |= 1 when a chain does not fill its range exactly
+};
+
+constexpr int OC_T = 128;
+constexpr int OC_CHAIN = 256;  // chain prefix kept in shared memory; longer chains re-walk the list
+
+__global__ void __launch_bounds__(OC_T) k_online_concat(const OnlineConcatParams p) {
+    __shared__ int s_pre[OC_CHAIN + 1];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int c0 = p.chain_ptr[t], c1 = p.chain_ptr[t + 1], nc = c1 - c0;
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < nc; k++) {
+            if (k <= OC_CHAIN) s_pre[k] = run;
+            run += p.trk_len[p.chain[c0 + k]];
+        }
+        if (nc <= OC_CHAIN) s_pre[nc] = run;
+        else s_pre[OC_CHAIN] = run;  // total, whatever the length
+    }
+    __syncthreads();
+    const int total = s_pre[nc <= OC_CHAIN ? nc : OC_CHAIN];
+    const int o0 = p.out_ptr[t], o1 = p.out_ptr[t + 1];
+    // point k of the chain -> (source, index there)
+    auto locate = [&](int k, bool *carried) {
+        int j = 0, base = 0;
+        if (nc <= OC_CHAIN) {
+            while (j + 1 < nc && s_pre[j + 1] <= k) j++;
+            base = s_pre[j];
+        } else {
+            while (j + 1 < nc && base + p.trk_len[p.chain[c0 + j]] <= k) base += p.trk_len[p.chain[c0 + j++]];
+        }
+        const int r = p.chain[c0 + j];
+        *carried = p.item[r] < p.n_carry;
+        const int at = p.trk_first[r] + (k - base);
+        return *carried ? at : p.track_det[at];
+    };
+    auto load = [&](int d, bool carried, int *f, double *v) {
+        if (carried) {
+            *f = p.carry_frame[d];
+            for (int c = 0; c < p.dim; c++) v[c] = p.carry_pos[(size_t)c * p.carry_stride + d];
+            for (int c = 0; c < 4; c++) v[3 + c] = p.carry_bbox[(size_t)c * p.carry_stride + d];
+        } else {
+            *f = p.frame[d];
+            for (int c = 0; c < p.dim; c++) v[c] = p.pos[(size_t)c * p.n + d];
+            for (int c = 0; c < 4; c++) v[3 + c] = p.bbox[(size_t)c * p.n + d];
+        }
+    };
+    int f_first = 0;
+    {
+        bool cr;
+        double v[7];
+        const int d = locate(0, &cr);
+        load(d, cr, &f_first, v);
+    }
+    for (int k = tid; k < total; k += OC_T) {
+        bool cr1, cr2;
+        int f1, f2;
+        double v1[7], v2[7];
+        const int d1 = locate(k, &cr1);
+        load(d1, cr1, &f1, v1);
+        int at = o0 + (f1 - f_first);
+        if (at < o0 || at >= o1) {
+            atomicOr(p.error, 1);
+            continue;
+        }
+        p.new_frame[at] = f1;
+        for (int c = 0; c < p.dim; c++) p.new_pos[(size_t)c * p.new_stride + at] = v1[c];
+        for (int c = 0; c < 4; c++) p.new_bbox[(size_t)c * p.new_stride + at] = v1[3 + c];
+        if (k + 1 < total) {
+            const int d2 = locate(k + 1, &cr2);
+            load(d2, cr2, &f2, v2);
+            if (f2 <= f1 || at + (f2 - f1) >= o1) {
+                atomicOr(p.error, 1);
+                continue;
+            }
+            const double dt = (double)(f2 - f1);
+            for (int f = f1 + 1; f < f2; f++) {
+                const int a2 = at + (f - f1);
+                const double x = (double)(f - f1);
+                p.new_frame[a2] = f;
+                for (int c = 0; c < p.dim; c++)
+                    p.new_pos[(size_t)c * p.new_stride + a2] = (v2[c] - v1[c]) / dt * x + v1[c];
+                for (int c = 0; c < 4; c++)
+                    p.new_bbox[(size_t)c * p.new_stride + a2] = (v2[3 + c] - v1[3 + c]) / dt * x + v1[3 + c];
+            }
+        } else if (at != o1 - 1) {
+            atomicOr(p.error, 1);
+        }
+    }
+}
+
+// first / last frame of the tracklet at every rank (the host lays the output trajectories out from these)
+__global__ void k_tracklet_spans(const int32_t *__restrict__ n_tracklets, const int32_t *__restrict__ item,
+                                 const int32_t *__restrict__ trk_first, const int32_t *__restrict__ trk_len,
+                                 int32_t n_carry, const int32_t *__restrict__ carry_frame,
+                                 const int32_t *__restrict__ track_det, const int32_t *__restrict__ frame,
+                                 int32_t *__restrict__ span) {
+    const int M = n_tracklets[0];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+        const int first = trk_first[r], last = first + trk_len[r] - 1;
+        const bool carried = item[r] < n_carry;
+        span[2 * r] = carried ? carry_frame[first] : frame[track_det[first]];
+        span[2 * r + 1] = carried ? carry_frame[last] : frame[track_det[last]];
+    }
+}
+
 }  // namespace m3
 
 using namespace m3;
@@ -249,18 +400,37 @@ int32_t mot3d_tracklets_from_tracks(int32_t n, int32_t dim, const int32_t *frame
                                     int32_t *trk_first_out, int32_t *trk_len_out, int32_t *key_out, int32_t *head_ptr_out,
                                     int32_t *tail_ptr_out, int32_t *head_idx_out, int32_t *tail_idx_out,
                                     double *head_pos_out, double *tail_pos_out, void *ws, size_t ws_bytes, void *stream) {
-    M3_CHECK_ARG(n >= 0 && (dim == 2 || dim == 3), "n >= 0, dim 2 or 3");
-    M3_CHECK_ARG(split_length >= 1, "split length must be >= 1");
-    M3_CHECK_ARG(n_tracklets_out, "NULL output");
     if (n == 0) {
+        M3_CHECK_ARG(n_tracklets_out, "NULL output");
         M3_CUDA(cudaMemsetAsync(n_tracklets_out, 0, 4, (cudaStream_t)stream));
         return MOT3D_OK;
     }
-    M3_CHECK_ARG(frame && pos && track_count && track_ptr && track_det, "NULL input");
+    return mot3d_online_tracklets(n, dim, frame, pos, track_count, track_ptr, track_det, split_length, th_length, window,
+                                  0, nullptr, nullptr, nullptr, 0, n, n_tracklets_out, nullptr, trk_first_out,
+                                  trk_len_out, key_out, head_ptr_out, tail_ptr_out, head_idx_out, tail_idx_out,
+                                  head_pos_out, tail_pos_out, nullptr, ws, ws_bytes, stream);
+}
+
+int32_t mot3d_online_tracklets(int32_t n, int32_t dim, const int32_t *frame, const double *pos,
+                               const int32_t *track_count, const int32_t *track_ptr, const int32_t *track_det,
+                               int32_t split_length, int32_t th_length, int32_t window, int32_t n_carry,
+                               const int32_t *carry_ptr, const int32_t *carry_frame, const double *carry_pos,
+                               int64_t carry_stride, int64_t out_stride, int32_t *n_tracklets_out, int32_t *item_out,
+                               int32_t *trk_first_out, int32_t *trk_len_out, int32_t *key_out, int32_t *head_ptr_out,
+                               int32_t *tail_ptr_out, int32_t *head_idx_out, int32_t *tail_idx_out, double *head_pos_out,
+                               double *tail_pos_out, int32_t *span_out, void *ws, size_t ws_bytes, void *stream) {
+    M3_CHECK_ARG(n >= 0 && (dim == 2 || dim == 3), "n >= 0, dim 2 or 3");
+    M3_CHECK_ARG(split_length >= 1, "split length must be >= 1");
+    M3_CHECK_ARG(n_tracklets_out, "NULL output");
+    M3_CHECK_ARG(n_carry >= 0, "negative number of carried trajectories");
+    M3_CHECK_ARG(n_carry == 0 || (carry_ptr && carry_frame && carry_pos && item_out), "NULL carried input");
+    M3_CHECK_ARG(out_stride >= 1, "out_stride");
+    M3_CHECK_ARG(track_count && track_ptr, "NULL input");
+    M3_CHECK_ARG(n == 0 || (frame && pos && track_det), "NULL input");
     M3_CHECK_ARG(trk_first_out && trk_len_out && key_out && head_ptr_out && tail_ptr_out && head_idx_out && tail_idx_out &&
                      head_pos_out && tail_pos_out && ws,
                  "NULL output");
-    if (ws_bytes < mot3d_tracklets_from_tracks_workspace_bytes(n)) {
+    if (!ws || ws_bytes < mot3d_tracklets_from_tracks_workspace_bytes(n)) {
         set_error("tracklet workspace too small");
         return MOT3D_E_CAPACITY;
     }
@@ -290,8 +460,63 @@ int32_t mot3d_tracklets_from_tracks(int32_t n, int32_t dim, const int32_t *frame
     p.w_first = w + (n + 1);
     p.w_len = w + 2 * (size_t)(n + 1);
     p.w_keep = w + 3 * (size_t)(n + 1);
+    p.n_carry = n_carry;
+    p.carry_ptr = carry_ptr;
+    p.carry_frame = carry_frame;
+    p.carry_pos = carry_pos;
+    p.carry_stride = carry_stride;
+    p.item = item_out;
+    p.out_stride = out_stride;
     k_split_tracks<<<1, TP_T, 0, (cudaStream_t)stream>>>(p);
     M3_LAUNCH_CHECK("k_split_tracks");
+    if (span_out) {
+        M3_CHECK_ARG(item_out, "spans need the item array");
+        k_tracklet_spans<<<4, 256, 0, (cudaStream_t)stream>>>(n_tracklets_out, item_out, trk_first_out, trk_len_out, n_carry,
+                                                             carry_frame, track_det, frame, span_out);
+        M3_LAUNCH_CHECK("k_tracklet_spans");
+    }
+    return MOT3D_OK;
+}
+
+int32_t mot3d_online_concat(int32_t n_out, const int32_t *chain_ptr, const int32_t *chain, const int32_t *out_ptr,
+                            const int32_t *item, const int32_t *trk_first, const int32_t *trk_len, int32_t n_carry,
+                            int32_t n, int32_t dim, const int32_t *track_det, const int32_t *frame, const double *pos,
+                            const double *bbox, const int32_t *carry_frame, const double *carry_pos,
+                            const double *carry_bbox, int64_t carry_stride, int32_t *new_frame, double *new_pos,
+                            double *new_bbox, int64_t new_stride, int32_t *error_flag, void *stream) {
+    M3_CHECK_ARG(n_out >= 0 && (dim == 2 || dim == 3), "n_out >= 0, dim 2 or 3");
+    if (n_out == 0) return MOT3D_OK;
+    M3_CHECK_ARG(chain_ptr && chain && out_ptr && item && trk_first && trk_len && new_frame && new_pos && new_bbox &&
+                     error_flag,
+                 "NULL pointer");
+    M3_CHECK_ARG(n_carry == 0 || (carry_frame && carry_pos && carry_bbox), "NULL carried input");
+    M3_CHECK_ARG(n == 0 || (track_det && frame && pos && bbox), "NULL batch input");
+    OnlineConcatParams p;
+    p.n_out = n_out;
+    p.chain_ptr = chain_ptr;
+    p.chain = chain;
+    p.out_ptr = out_ptr;
+    p.item = item;
+    p.trk_first = trk_first;
+    p.trk_len = trk_len;
+    p.n_carry = n_carry;
+    p.n = n;
+    p.track_det = track_det;
+    p.frame = frame;
+    p.pos = pos;
+    p.bbox = bbox;
+    p.carry_frame = carry_frame;
+    p.carry_pos = carry_pos;
+    p.carry_bbox = carry_bbox;
+    p.carry_stride = carry_stride;
+    p.dim = dim;
+    p.new_frame = new_frame;
+    p.new_pos = new_pos;
+    p.new_bbox = new_bbox;
+    p.new_stride = new_stride;
+    p.error = error_flag;
+    k_online_concat<<<n_out, OC_T, 0, (cudaStream_t)stream>>>(p);
+    M3_LAUNCH_CHECK("k_online_concat");
     return MOT3D_OK;
 }
 

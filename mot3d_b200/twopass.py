@@ -20,6 +20,63 @@ from .batch import _ptr, _stream
 from .spec import quantise_scalar
 
 
+def tracklet_pass(dev, dim, M, n_trk, stride, head_ptr, tail_ptr, head_idx, tail_idx, head_pos, tail_pos, key, tspec):
+    """Arcs between M tracklets (windows in the mot3d_tracklets arrays, planar stride `stride`), solve, chains.
+    Returns (t_count, t_ptr, t_trk, total_cost, n_arcs): device tensors except n_arcs."""
+    L = _lib.lib()
+    st = _stream(dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    i64 = dict(dtype=torch.int64, device=dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+    n = stride
+    # ---- arcs between tracklets (csrc/tracklet.cu), rows = arc tails
+    trk = _lib.Tracklets()
+    trk.n, trk.dim = M, dim
+    trk.n_head_points = trk.n_tail_points = n  # planar stride of head_pos / tail_pos
+    trk.head_ptr, trk.tail_ptr = head_ptr.data_ptr(), tail_ptr.data_ptr()
+    trk.head_idx, trk.tail_idx = head_idx.data_ptr(), tail_idx.data_ptr()
+    trk.head_pos, trk.tail_pos = head_pos.data_ptr(), tail_pos.data_ptr()
+    access = torch.zeros(M, dtype=torch.uint8, device=dev)  # tracklets built from solved tracks: no access points
+    trk.tail_access_point = access.data_ptr()
+    fit_h, fit_t = torch.empty(M * dim * 2, **f64), torch.empty(M * dim * 2, **f64)
+    trk.head_fit_ws, trk.tail_fit_ws = fit_h.data_ptr(), fit_t.data_ptr()
+    cs = tspec.to_c()
+    cs.use_hist = 0
+    row_count = torch.zeros(M, **i32)
+    _lib.check(L.mot3d_tracklet_edge_count(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_count), st))
+    row_ptr = torch.empty(M + 1, **i32)
+    sb = L.mot3d_scan_workspace_bytes(M)
+    sws = torch.empty(sb, dtype=torch.uint8, device=dev)
+    _lib.check(L.mot3d_exclusive_scan_i32(_ptr(row_count), M, _ptr(row_ptr), _ptr(sws), sb, st))
+    E = int(row_ptr[M].item())
+    col, cost = torch.empty(max(E, 1), **i32), torch.empty(max(E, 1), **i64)
+    weight = torch.empty(max(E, 1), **f64)
+    overflow = torch.zeros(1, **i32)
+    _lib.check(L.mot3d_tracklet_edge_fill(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_ptr), E, _ptr(col), _ptr(cost),
+                                          _ptr(weight), _ptr(overflow), st))
+    # ---- the solver's inputs: in-CSR, constant node costs (DetectionTracklet's default confidence 0.5,
+    #      mot3d/types.py:49), time key = first frame of every tracklet
+    in_ptr, in_src, in_cost = torch.empty(M + 1, **i32), torch.empty(max(E, 1), **i32), torch.empty(max(E, 1), **i64)
+    en, cn, ex = torch.empty(M, **i64), torch.empty(M, **i64), torch.empty(M, **i64)
+    gptr = torch.empty(2, **i32)
+    cur = torch.empty(M + 1, **i32)
+    conf = 0.5
+    _lib.check(L.mot3d_tracklet_graph_in_csr(
+        _ptr(n_trk), M, _ptr(row_ptr), _ptr(col), _ptr(cost), quantise_scalar(tspec.weight_source_sink),
+        quantise_scalar(-(conf * tspec.confidence["mul"] + tspec.confidence["bias"])), 0, _ptr(in_ptr), _ptr(in_src),
+        _ptr(in_cost), _ptr(en), _ptr(cn), _ptr(ex), _ptr(gptr), _ptr(cur), st))
+    nxt, prv = torch.empty(M, **i32), torch.empty(M, **i32)
+    n_paths, total = torch.zeros(1, **i32), torch.zeros(1, **i64)
+    swb = L.mot3d_solve_workspace_bytes(M, 1, E)
+    sw = torch.empty(swb, dtype=torch.uint8, device=dev)
+    _lib.check(L.mot3d_solve_batch(1, M, _ptr(gptr), M, _ptr(key), E, _ptr(in_ptr), _ptr(in_src), _ptr(in_cost), _ptr(en),
+                                   _ptr(cn), _ptr(ex), _ptr(nxt), _ptr(prv), _ptr(n_paths), _ptr(total), None, None,
+                                   _ptr(sw), swb, st))
+    t_count, t_ptr, t_trk = torch.zeros(1, **i32), torch.zeros(M + 2, **i32), torch.zeros(M, **i32)
+    _lib.check(L.mot3d_extract_tracks(1, _ptr(gptr), _ptr(nxt), _ptr(prv), _ptr(t_count), _ptr(t_ptr), _ptr(t_trk), st))
+    return t_count, t_ptr, t_trk, total, E
+
+
 def link_tracks(batch, sol, tspec, split_length=10, th_length=10, window=None):
     """batch: DetectionBatch on a CUDA device holding ONE graph; sol: its Solution after extract_tracks;
     tspec: TrackletCostSpec (kind, distance kwargs, confidence kwargs, weight_source_sink, max_jump) of pass 2.
@@ -54,52 +111,9 @@ def link_tracks(batch, sol, tspec, split_length=10, th_length=10, window=None):
     info = dict(n_tracklets=M, n_arcs=0, total_cost=0, tracklets=(trk_first[:M], trk_len[:M], key[:M]))
     if M == 0:
         return [], info
-    # ---- arcs between tracklets (csrc/tracklet.cu), rows = arc tails
-    trk = _lib.Tracklets()
-    trk.n, trk.dim = M, dim
-    trk.n_head_points = trk.n_tail_points = n  # planar stride of head_pos / tail_pos
-    trk.head_ptr, trk.tail_ptr = head_ptr.data_ptr(), tail_ptr.data_ptr()
-    trk.head_idx, trk.tail_idx = head_idx.data_ptr(), tail_idx.data_ptr()
-    trk.head_pos, trk.tail_pos = head_pos.data_ptr(), tail_pos.data_ptr()
-    access = torch.zeros(M, dtype=torch.uint8, device=dev)  # tracklets built from solved tracks: no access points
-    trk.tail_access_point = access.data_ptr()
-    fit_h, fit_t = torch.empty(M * dim * 2, **f64), torch.empty(M * dim * 2, **f64)
-    trk.head_fit_ws, trk.tail_fit_ws = fit_h.data_ptr(), fit_t.data_ptr()
-    cs = tspec.to_c()
-    cs.use_hist = 0
-    row_count = torch.zeros(M, **i32)
-    _lib.check(L.mot3d_tracklet_edge_count(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_count), st))
-    row_ptr = torch.empty(M + 1, **i32)
-    sb = L.mot3d_scan_workspace_bytes(M)
-    sws = torch.empty(sb, dtype=torch.uint8, device=dev)
-    _lib.check(L.mot3d_exclusive_scan_i32(_ptr(row_count), M, _ptr(row_ptr), _ptr(sws), sb, st))
-    E = int(row_ptr[M].item())
+    t_count, t_ptr, t_trk, total, E = tracklet_pass(dev, dim, M, n_trk, n, head_ptr, tail_ptr, head_idx, tail_idx,
+                                                    head_pos, tail_pos, key, tspec)
     info["n_arcs"] = E
-    col, cost = torch.empty(max(E, 1), **i32), torch.empty(max(E, 1), **i64)
-    weight = torch.empty(max(E, 1), **f64)
-    overflow = torch.zeros(1, **i32)
-    _lib.check(L.mot3d_tracklet_edge_fill(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_ptr), E, _ptr(col), _ptr(cost),
-                                          _ptr(weight), _ptr(overflow), st))
-    # ---- the solver's inputs: in-CSR, constant node costs (DetectionTracklet's default confidence 0.5,
-    #      mot3d/types.py:49), time key = first frame of every tracklet
-    in_ptr, in_src, in_cost = torch.empty(M + 1, **i32), torch.empty(max(E, 1), **i32), torch.empty(max(E, 1), **i64)
-    en, cn, ex = torch.empty(M, **i64), torch.empty(M, **i64), torch.empty(M, **i64)
-    gptr = torch.empty(2, **i32)
-    cur = torch.empty(M + 1, **i32)
-    conf = 0.5
-    _lib.check(L.mot3d_tracklet_graph_in_csr(
-        _ptr(n_trk), M, _ptr(row_ptr), _ptr(col), _ptr(cost), quantise_scalar(tspec.weight_source_sink),
-        quantise_scalar(-(conf * tspec.confidence["mul"] + tspec.confidence["bias"])), 0, _ptr(in_ptr), _ptr(in_src),
-        _ptr(in_cost), _ptr(en), _ptr(cn), _ptr(ex), _ptr(gptr), _ptr(cur), st))
-    nxt, prv = torch.empty(M, **i32), torch.empty(M, **i32)
-    n_paths, total = torch.zeros(1, **i32), torch.zeros(1, **i64)
-    swb = L.mot3d_solve_workspace_bytes(M, 1, E)
-    sw = torch.empty(swb, dtype=torch.uint8, device=dev)
-    _lib.check(L.mot3d_solve_batch(1, M, _ptr(gptr), M, _ptr(key), E, _ptr(in_ptr), _ptr(in_src), _ptr(in_cost), _ptr(en),
-                                   _ptr(cn), _ptr(ex), _ptr(nxt), _ptr(prv), _ptr(n_paths), _ptr(total), None, None,
-                                   _ptr(sw), swb, st))
-    t_count, t_ptr, t_trk = torch.zeros(1, **i32), torch.zeros(M + 2, **i32), torch.zeros(M, **i32)
-    _lib.check(L.mot3d_extract_tracks(1, _ptr(gptr), _ptr(nxt), _ptr(prv), _ptr(t_count), _ptr(t_ptr), _ptr(t_trk), st))
     # ---- chains of tracklets -> chains of detections
     o_count, o_ptr, o_det = torch.zeros(1, **i32), torch.zeros(M + 2, **i32), torch.zeros(n + 1, **i32)
     _lib.check(L.mot3d_concat_tracklets(_ptr(t_count), _ptr(t_ptr), _ptr(t_trk), _ptr(trk_first), _ptr(trk_len),

@@ -865,6 +865,100 @@ def test_online_window_loop_matches_reference():
     assert len(scene.completed) == 2 and len(scene.active) == 6
 
 
+def _scene_arrays(store):
+    ids = sorted(store)
+    ptr = np.cumsum([0] + [len(store[i][0]) for i in ids]).tolist()
+    cat = lambda k, w: (np.concatenate([store[i][k] for i in ids]) if ids else np.zeros((0, w))).reshape(-1, w)
+    return ids, ptr, cat(0, 1).reshape(-1).astype(np.int64).tolist(), cat(1, 2), cat(2, 4)
+
+
+def test_online_loop_with_device_resident_scene_matches_reference():
+    """DeviceTracker2D keeps the active trajectories in device memory between updates and does the
+    cutting, windowing, linking, concatenation and hole filling in kernels (csrc/twopass.cu: k_split_tracks with carried
+    trajectories, k_online_concat). Same golden as the object loop: after every batch of C4-synth the ids, frames,
+    interpolated positions and boxes of the active and the completed trajectories are what the reference's own loop
+    left (tests/golden/c4_online_loop.npz)."""
+    import json
+    from mot3d_b200.online_device import DeviceTracker2D
+    d = gu.load("c4_online_loop")
+    cfg = json.loads(str(d["config"]))
+    tracker = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
+    ptr, det = d["det_ptr"], d["det"]
+    B = cfg["batch_size"]
+    n_frames = len(ptr) - 1
+    for b in range(n_frames // B):
+        lo, hi = int(ptr[b * B]), int(ptr[(b + 1) * B])
+        frame = np.repeat(np.arange(b * B, (b + 1) * B), np.diff(ptr[b * B:(b + 1) * B + 1]))
+        tracker.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7])
+        for name, store in (("active", tracker.active()), ("completed", tracker.completed)):
+            ids, p_, index, pos, box = _scene_arrays(store)
+            assert ids == d["b%d_%s_ids" % (b, name)].tolist(), (b, name)
+            assert p_ == d["b%d_%s_ptr" % (b, name)].tolist()
+            assert index == d["b%d_%s_index" % (b, name)].tolist()
+            np.testing.assert_allclose(pos, d["b%d_%s_pos" % (b, name)].reshape(-1, 2), rtol=1e-12, atol=1e-9)
+            np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)].reshape(-1, 4), rtol=1e-12, atol=1e-9)
+    assert tracker.n_tracklets_seen == int(d["n_tracklets"])
+    assert len(tracker.completed) == 2 and len(tracker.ids) == 6
+
+
+def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
+    """The same two loops (objects: mot3d_b200.online.Tracker2D, pinned to the reference above; arrays on the device:
+    DeviceTracker2D) over 12 batches of a sequence where people enter, leave for good and come back after gaps, with
+    some empty batches: trajectories complete, ids are never reused, carried trajectories are extended, left alone or
+    linked behind another one. Scenes must agree after every batch."""
+    import mot3d_b200 as mot3d
+    from mot3d_b200.online import Scene, Tracker2D
+    from mot3d_b200.online_device import DeviceTracker2D
+    cfg = dict(batch_size=20, completed_after=30,
+               detections=dict(weight_source_sink=1, max_jump=4, verbose=False,
+                               weight_distance=dict(sigma_distance=10, sigma_jump=4, sigma_color_histogram=0.1,
+                                                    sigma_box_size=0.1, max_distance=30, use_color_histogram=False,
+                                                    use_bbox=True),
+                               weight_confidence=dict(mul=0, bias=0)),
+               tracklets=dict(weight_source_sink=0.1, max_jump=40, length_endpoints=5, verbose=False,
+                              weight_distance=dict(sigma_color_histogram=0.3, sigma_motion=100, alpha=0.2,
+                                                   cutoff_motion=0.1, cutoff_appearance=0.1, use_color_histogram=True),
+                              weight_confidence=dict(mul=0, bias=0.11)))
+    rng = np.random.RandomState(5)
+    B, n_batches = cfg["batch_size"], 12
+    people = []
+    for k in range(14):
+        t0 = int(rng.randint(0, 160))
+        people.append(dict(t0=t0, t1=t0 + int(rng.randint(25, 110)), p=rng.uniform(50, 700, 2), v=rng.uniform(-3, 3, 2),
+                           gap=(int(rng.randint(t0 + 10, t0 + 60)), int(rng.randint(4, 25))), wh=rng.uniform(20, 60, 2)))
+    rows = []
+    for f in range(B * n_batches):
+        if 100 <= f < 120:
+            continue  # an empty batch
+        for q in people:
+            if not (q["t0"] <= f < q["t1"]) or (q["gap"][0] <= f < q["gap"][0] + q["gap"][1]) or rng.rand() < 0.08:
+                continue
+            c = q["p"] + q["v"] * (f - q["t0"]) + rng.normal(0, 0.7, 2)
+            w, h = q["wh"] * (1 + rng.normal(0, 0.02, 2))
+            rows.append((f, c[0], c[1], rng.uniform(0.5, 1), c[0] - w / 2, c[1] - h / 2, c[0] + w / 2, c[1] + h / 2))
+    rows = np.array(rows)
+    scene = Scene(cfg["completed_after"])
+    t_obj = Tracker2D(scene, None, cfg, image_size=(768, 576))
+    t_dev = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
+    n_done = 0
+    for b in range(n_batches):
+        sel = rows[(rows[:, 0] >= b * B) & (rows[:, 0] < (b + 1) * B)]
+        dets = [[mot3d.Detection2D(int(r[0]), r[1:3].copy(), confidence=float(r[3]), bbox=tuple(r[4:8]))
+                 for r in sel if int(r[0]) == f] for f in range(b * B, (b + 1) * B)]
+        t_obj.update((b + 1) * B, dets)
+        t_dev.update((b + 1) * B, sel[:, 0].astype(np.int64), sel[:, 1:3], sel[:, 3], sel[:, 4:8])
+        for name, want, got in (("active", scene.active, t_dev.active()), ("completed", scene.completed, t_dev.completed)):
+            assert sorted(want) == sorted(got), (b, name)
+            for i in want:
+                assert [x.index for x in want[i]] == got[i][0].tolist(), (b, name, i)
+                np.testing.assert_allclose(np.array([np.asarray(x.position, dtype=np.float64) for x in want[i]]),
+                                           got[i][1], rtol=1e-12, atol=1e-9)
+                np.testing.assert_allclose(np.array([np.asarray(x.bbox, dtype=np.float64) for x in want[i]]),
+                                           got[i][2], rtol=1e-12, atol=1e-9)
+        n_done = len(scene.completed)
+    assert n_done >= 3 and scene.id_last == t_dev.id_last and len(scene.tracklets) == t_dev.n_tracklets_seen
+
+
 def test_single_track_pass_equals_full_solver(monkeypatch):
     """k_single_track finishes most components of crowded windows straight from the first tree; what it writes must
     be what the staged solver writes for the same components. 60 C5 windows (5 000 detections each, ~88 components

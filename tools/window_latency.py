@@ -203,6 +203,21 @@ def measure(reps=50, budget_s=6.0, cpu=True, log=None):
            "what": "mot3d_b200.online.Tracker2D.update: detection pass, tracklet pass against the active trajectories, "
                    "interpolation, scene update; 50 frames per batch",
            "totals_agree": bool(len(scene.completed) == 2 and len(scene.active) == 6)}
+    # the same loop with the scene kept on the device (DeviceTracker2D: arrays in, no objects; N1)
+    from mot3d_b200.online_device import DeviceTracker2D
+    t_dev = []
+    for rep in range(3):
+        trk = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
+        for b in range((len(ptr) - 1) // B):
+            lo, hi = int(ptr[b * B]), int(ptr[(b + 1) * B])
+            fr = np.repeat(np.arange(b * B, (b + 1) * B), np.diff(ptr[b * B:(b + 1) * B + 1]))
+            t0 = time.perf_counter()
+            trk.update((b + 1) * B, fr, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7])
+            torch.cuda.synchronize()
+            if rep:
+                t_dev.append((time.perf_counter() - t0) * 1e3)
+    rec["gpu_ms"]["update_device_scene"] = _pct(t_dev)
+    rec["totals_agree"] = bool(rec["totals_agree"] and len(trk.completed) == 2 and len(trk.ids) == 6)
     if log:
         log(rec)
     out.append(rec)
