@@ -10,15 +10,19 @@ k_online_concat writes the joined, hole-filled trajectories into the next state 
 bookkeeping the reference does in Scene.update / update_completed - which id a chain continues, which trajectories
 are completed - from a few integers per tracklet (item, first frame, last frame) and the chains.
 
-Scope: 2-D detections with boxes, no valid_region, no colour histograms on the tracklets (a tracklet cost with
-use_color_histogram=True falls back to the motion term alone, as the reference does when no tracklet has one)."""
+Scope: 2-D detections with boxes, no colour histograms on the tracklets (a tracklet cost with
+use_color_histogram=True falls back to the motion term alone, as the reference does when no tracklet has one).
+valid_region (an object with is_inside(point), singleview_tracking.py:28-38) filters the detections of a batch on the
+host before they are uploaded; the reference's second test, on the two ends of every new tracklet (:104-118), can
+then never fail - every detection of a tracklet already passed the first - so nothing is skipped there."""
 import ctypes
 
 import numpy as np
 import torch
 
 from . import _lib
-from .batch import DetectionBatch, _ptr, _stream, build_graphs, solve_graphs, extract_tracks
+from .batch import DetectionBatch, _ptr, _stream
+from .pipeline import TrackPipeline
 from .spec import CostSpec, TrackletCostSpec
 from .twopass import tracklet_pass
 
@@ -30,7 +34,8 @@ class DeviceTracker2D(object):
     completed_after: Scene's. update(time_index, frame, pos, conf, bbox) takes the detections of one batch as arrays
     (frame int[n], pos float[n, 2], conf float[n], bbox float[n, 4], any order)."""
 
-    def __init__(self, config, completed_after=30, device=None, split_length=10, th_length=2):
+    def __init__(self, config, completed_after=30, device=None, split_length=10, th_length=2, valid_region=None):
+        self.valid_region = valid_region
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         cfgd, cfgt = config["detections"], config["tracklets"]
         self.spec = CostSpec(kind="detections_2d", distance=cfgd["weight_distance"],
@@ -51,8 +56,16 @@ class DeviceTracker2D(object):
         self._cap = 0
         self._state = None          # dict(ptr=int32 device [A+1], frame, pos, bbox) of the active trajectories
         self._spare = None
+        self._pipe = None
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._zero = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def _pipeline(self, n):
+        """The preallocated, synchronisation-free detection pass (pipeline.TrackPipeline), grown when a batch is larger."""
+        if self._pipe is None or self._pipe.n_max < n:
+            n_max = max(1024, 2 * n)
+            self._pipe = TrackPipeline(n_max, 1, 64 * n_max, device=self.device, dim=2)
+        return self._pipe
 
     # ---- state buffers --------------------------------------------------------------------------------------------
     def _buffers(self, points):
@@ -74,6 +87,10 @@ class DeviceTracker2D(object):
         st = _stream(dev)
         i32 = dict(dtype=torch.int32, device=dev)
         f64 = dict(dtype=torch.float64, device=dev)
+        if self.valid_region is not None and len(frame):
+            inside = np.fromiter((bool(self.valid_region.is_inside(p)) for p in np.asarray(pos)), dtype=bool,
+                                 count=len(frame))
+            frame, pos, conf, bbox = (np.asarray(a)[inside] for a in (frame, pos, conf, bbox))
         n = int(len(frame))
         A = len(self.ids)
         P = int(self.ptr[-1])
@@ -81,10 +98,9 @@ class DeviceTracker2D(object):
         if n > 0:
             hb, _ = DetectionBatch.from_arrays(np.array([0, n]), frame, pos, conf, bbox=bbox)
             db = hb.to(dev)
-            gb = build_graphs(db, self.spec)
-            sol = solve_graphs(gb)
-            extract_tracks(gb, sol)
-            t_count, t_ptr, t_det = sol.track_count, sol.track_ptr, sol.track_det
+            pipe = self._pipeline(n)
+            pipe.run(db, self.spec)   # no host synchronisation; its flag word is read with the tracklet count below
+            t_count, t_ptr, t_det = pipe.track_count, pipe.track_ptr, pipe.track_det
             b_frame, b_pos, b_bbox = db.frame, db.pos, db.bbox
         else:
             t_count, t_ptr, t_det = self._zero[:1], self._zero, self._zero
@@ -109,7 +125,16 @@ class DeviceTracker2D(object):
             _ptr(s["pos"]) if A else None, s["cap"] if A else 0, stride, _ptr(n_trk), _ptr(item), _ptr(trk_first),
             _ptr(trk_len), _ptr(key), _ptr(head_ptr), _ptr(tail_ptr), _ptr(head_idx), _ptr(tail_idx), _ptr(head_pos),
             _ptr(tail_pos), _ptr(span), _ptr(ws), wsb, st))
-        M = int(n_trk.item())
+        if n > 0:
+            M, flag = torch.cat([n_trk, pipe.overflow]).tolist()
+            if flag:
+                if flag & (_lib.ERR_ARC_CAPACITY | _lib.ERR_WINDOW):
+                    # the arc buffer was a guess: size it from what the build counted and run the batch again
+                    self._pipe = TrackPipeline(pipe.n_max, 1, 2 * pipe.n_edges() + 1024, device=dev, dim=2)
+                    return self.update(time_index, frame, pos, conf, bbox)
+                pipe.check_overflow()
+        else:
+            M = int(n_trk.item())
         self.n_tracklets_seen += M - A
         if M == 0:
             return 0

@@ -899,6 +899,19 @@ def test_online_loop_with_device_resident_scene_matches_reference():
             np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)].reshape(-1, 4), rtol=1e-12, atol=1e-9)
     assert tracker.n_tracklets_seen == int(d["n_tracklets"])
     assert len(tracker.completed) == 2 and len(tracker.ids) == 6
+    # the detection pass runs in preallocated buffers sized by a guess: too small an arc buffer is noticed, the buffers
+    # are re-sized from the build's own count and the batch runs again - same scene
+    from mot3d_b200.pipeline import TrackPipeline
+    again = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
+    again._pipe = TrackPipeline(1024, 1, 64, dim=2)
+    for b in range(n_frames // B):
+        lo, hi = int(ptr[b * B]), int(ptr[(b + 1) * B])
+        frame = np.repeat(np.arange(b * B, (b + 1) * B), np.diff(ptr[b * B:(b + 1) * B + 1]))
+        again.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7])
+    assert again._pipe.edge_capacity > 64
+    a, b_ = _scene_arrays(tracker.active()), _scene_arrays(again.active())
+    assert a[:3] == b_[:3] and (a[3] == b_[3]).all() and (a[4] == b_[4]).all()
+    assert again.n_tracklets_seen == tracker.n_tracklets_seen and sorted(again.completed) == sorted(tracker.completed)
 
 
 def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
@@ -937,15 +950,20 @@ def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
             w, h = q["wh"] * (1 + rng.normal(0, 0.02, 2))
             rows.append((f, c[0], c[1], rng.uniform(0.5, 1), c[0] - w / 2, c[1] - h / 2, c[0] + w / 2, c[1] + h / 2))
     rows = np.array(rows)
+    class Region(object):  # valid_region: everything but a strip on the left
+        @staticmethod
+        def is_inside(p):
+            return p[0] > 90
+
     scene = Scene(cfg["completed_after"])
-    t_obj = Tracker2D(scene, None, cfg, image_size=(768, 576))
-    t_dev = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
+    t_obj = Tracker2D(scene, Region, cfg, image_size=(768, 576))
+    t_dev = DeviceTracker2D(cfg, completed_after=cfg["completed_after"], valid_region=Region)
     n_done = 0
     for b in range(n_batches):
         sel = rows[(rows[:, 0] >= b * B) & (rows[:, 0] < (b + 1) * B)]
         dets = [[mot3d.Detection2D(int(r[0]), r[1:3].copy(), confidence=float(r[3]), bbox=tuple(r[4:8]))
                  for r in sel if int(r[0]) == f] for f in range(b * B, (b + 1) * B)]
-        t_obj.update((b + 1) * B, dets)
+        assert t_obj.update((b + 1) * B, dets) == 0   # (no tracklet is skipped at the second valid_region test)
         t_dev.update((b + 1) * B, sel[:, 0].astype(np.int64), sel[:, 1:3], sel[:, 3], sel[:, 4:8])
         for name, want, got in (("active", scene.active, t_dev.active()), ("completed", scene.completed, t_dev.completed)):
             assert sorted(want) == sorted(got), (b, name)
