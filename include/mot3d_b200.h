@@ -417,13 +417,30 @@ int32_t mot3d_online_tracklets(int32_t n, int32_t dim, const int32_t *frame, con
  * chain[chain_ptr[t] .. chain_ptr[t+1]) (ranks of mot3d_online_tracklets, in time order) and occupies points
  * [out_ptr[t], out_ptr[t+1]) of the new arrays: one point per frame from its first to its last, skipped frames filled
  * by v1 + (v2 - v1) / (t2 - t1) * (t - t1). bbox / carry_bbox / new_bbox are planar [4][stride] like the positions.
+ * hist_len > 0: the points' colour histograms travel too (hist [n][hist_len] of this batch or NULL, carry_hist /
+ * carry_has of the carried points, new_hist [points][hist_len] / new_has out); filled points have none.
  * *error_flag |= 1 if a chain does not cover its range exactly (wrong out_ptr, tracklets out of order). */
 int32_t mot3d_online_concat(int32_t n_out, const int32_t *chain_ptr, const int32_t *chain, const int32_t *out_ptr,
                             const int32_t *item, const int32_t *trk_first, const int32_t *trk_len, int32_t n_carry,
                             int32_t n, int32_t dim, const int32_t *track_det, const int32_t *frame, const double *pos,
                             const double *bbox, const int32_t *carry_frame, const double *carry_pos,
                             const double *carry_bbox, int64_t carry_stride, int32_t *new_frame, double *new_pos,
-                            double *new_bbox, int64_t new_stride, int32_t *error_flag, void *stream);
+                            double *new_bbox, int64_t new_stride, int32_t hist_len, const double *hist,
+                            const double *carry_hist, const uint8_t *carry_has, double *new_hist, uint8_t *new_has,
+                            int32_t *error_flag, void *stream);
+
+/* Median colour histogram of the head window and of the tail window of every tracklet (ranks of
+ * mot3d_online_tracklets / mot3d_tracklets_from_tracks, same `window`): DetectionTracklet2D's head.color_histogram /
+ * tail.color_histogram, np.median over the detections of the window that have one (mot3d/types.py:69-86,109-125).
+ * hist [n][hist_len] are the histograms of this batch's detections (NULL = none has one); carry_hist / carry_has those
+ * of the carried points (points filled by interpolation have none). Outputs [n_tracklets][hist_len] and the has-flags
+ * struct mot3d_tracklets takes. item may be NULL when n_carry = 0. */
+int32_t mot3d_tracklet_window_hist(int32_t n_tracklets, const int32_t *item, const int32_t *trk_first,
+                                   const int32_t *trk_len, int32_t n_carry, int32_t window, int32_t hist_len,
+                                   const int32_t *track_det, const int32_t *frame, const double *hist,
+                                   const int32_t *carry_frame, const double *carry_hist, const uint8_t *carry_has,
+                                   double *head_hist_out, double *tail_hist_out, uint8_t *head_has_out,
+                                   uint8_t *tail_has_out, void *stream);
 
 /* Out-CSR of mot3d_tracklet_edge_fill (rows = arc tails) -> the solver's inputs for one graph of *n_nodes_dev nodes
  * (<= n_nodes_max): in-CSR, constant entry / node / exit costs, graph_ptr = {0, n}. ws: int32 [n_nodes_max + 1]. */

@@ -132,7 +132,9 @@ SIGNATURES = {
     "mot3d_online_tracklets": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mot3d_online_concat": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                   _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+                                   _i64, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mot3d_tracklet_window_hist": (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _vp, _vp]),
     "mot3d_color_histograms": (_i32, [_vp, _i32, _i32, _i64, _vp, _i32, ctypes.POINTER(ctypes.c_int32), _i32, _i32, _vp, _vp,
                                       _vp]),
     "mot3d_track_batch_workspace_bytes": (_sz, [_i64, _i32, _i64]),

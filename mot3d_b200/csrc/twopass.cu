@@ -278,6 +278,13 @@ struct OnlineConcatParams {
     double *new_pos, *new_bbox;  // planar, stride new_stride
     int64_t new_stride;
     int32_t *error;  // |= 1 when a chain does not fill its range exactly
+    // colour histograms of the points (optional): hist_len doubles per point; filled points have none
+    int32_t hist_len;
+    const double *hist;        // this batch [n][hist_len] or NULL (no detection has one)
+    const double *carry_hist;  // [carried points][hist_len]
+    const uint8_t *carry_has;
+    double *new_hist;
+    uint8_t *new_has;
 };
 
 constexpr int OC_T = 128;
@@ -345,6 +352,14 @@ __global__ void __launch_bounds__(OC_T) k_online_concat(const OnlineConcatParams
         p.new_frame[at] = f1;
         for (int c = 0; c < p.dim; c++) p.new_pos[(size_t)c * p.new_stride + at] = v1[c];
         for (int c = 0; c < 4; c++) p.new_bbox[(size_t)c * p.new_stride + at] = v1[3 + c];
+        if (p.new_has) {
+            const bool has = cr1 ? (p.carry_has[d1] != 0) : (p.hist != nullptr);
+            p.new_has[at] = has ? 1 : 0;
+            if (has) {
+                const double *src = cr1 ? p.carry_hist + (size_t)d1 * p.hist_len : p.hist + (size_t)d1 * p.hist_len;
+                for (int c = 0; c < p.hist_len; c++) p.new_hist[(size_t)at * p.hist_len + c] = src[c];
+            }
+        }
         if (k + 1 < total) {
             const int d2 = locate(k + 1, &cr2);
             load(d2, cr2, &f2, v2);
@@ -357,6 +372,7 @@ __global__ void __launch_bounds__(OC_T) k_online_concat(const OnlineConcatParams
                 const int a2 = at + (f - f1);
                 const double x = (double)(f - f1);
                 p.new_frame[a2] = f;
+                if (p.new_has) p.new_has[a2] = 0;
                 for (int c = 0; c < p.dim; c++)
                     p.new_pos[(size_t)c * p.new_stride + a2] = (v2[c] - v1[c]) / dt * x + v1[c];
                 for (int c = 0; c < 4; c++)
@@ -365,6 +381,69 @@ __global__ void __launch_bounds__(OC_T) k_online_concat(const OnlineConcatParams
         } else if (at != o1 - 1) {
             atomicOr(p.error, 1);
         }
+    }
+}
+
+// Median colour histogram of the head and of the tail window of every tracklet: what DetectionTracklet2D keeps as
+// head.color_histogram / tail.color_histogram (reference mot3d/types.py:69-86,109-125: np.median over the detections of
+// the window that have a histogram; none of them -> None). One block per (tracklet, end), one thread per bin; the
+// median by counting ranks (windows are a handful of points; a long carried trajectory with window None still works).
+struct WindowHistParams {
+    const int32_t *item, *trk_first, *trk_len;
+    int32_t n_carry, window, hist_len;
+    const int32_t *track_det, *frame;
+    const double *hist;
+    const int32_t *carry_frame;
+    const double *carry_hist;
+    const uint8_t *carry_has;
+    double *head_hist, *tail_hist;
+    uint8_t *head_has, *tail_has;
+};
+
+__global__ void __launch_bounds__(128) k_window_median_hist(const WindowHistParams p) {
+    const int r = blockIdx.x >> 1, tail = blockIdx.x & 1;
+    const int first = p.trk_first[r], len = p.trk_len[r];
+    const bool carried = p.item && p.item[r] < p.n_carry;
+    auto frame_of = [&](int k) { return carried ? p.carry_frame[first + k] : p.frame[p.track_det[first + k]]; };
+    // the window is a run of points at one end (frames ascend along a tracklet)
+    int lo = 0, hi = len;
+    if (p.window > 0) {
+        if (tail) {
+            const int cut = frame_of(0) + p.window;
+            hi = 0;
+            while (hi < len && frame_of(hi) < cut) hi++;
+        } else {
+            const int cut = frame_of(len - 1) - p.window;
+            lo = len;
+            while (lo > 0 && frame_of(lo - 1) > cut) lo--;
+        }
+    }
+    auto has = [&](int k) { return carried ? p.carry_has[first + k] != 0 : p.hist != nullptr; };
+    auto row = [&](int k) {
+        return carried ? p.carry_hist + (size_t)(first + k) * p.hist_len
+                       : p.hist + (size_t)p.track_det[first + k] * p.hist_len;
+    };
+    int m = 0;
+    for (int k = lo; k < hi; k++) m += has(k) ? 1 : 0;
+    double *out = (tail ? p.tail_hist : p.head_hist) + (size_t)r * p.hist_len;
+    if (threadIdx.x == 0) (tail ? p.tail_has : p.head_has)[r] = m > 0 ? 1 : 0;
+    if (m == 0) return;
+    const int want_a = (m - 1) >> 1, want_b = m >> 1;  // the middle one(s) in sorted order
+    for (int c = threadIdx.x; c < p.hist_len; c += blockDim.x) {
+        double va = 0.0, vb = 0.0;
+        for (int i = lo; i < hi; i++) {
+            if (!has(i)) continue;
+            const double vi = row(i)[c];
+            int rank = 0;
+            for (int j = lo; j < hi; j++) {
+                if (!has(j)) continue;
+                const double vj = row(j)[c];
+                rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+            }
+            if (rank == want_a) va = vi;
+            if (rank == want_b) vb = vi;
+        }
+        out[c] = want_a == want_b ? va : (va + vb) / 2.0;
     }
 }
 
@@ -483,8 +562,12 @@ int32_t mot3d_online_concat(int32_t n_out, const int32_t *chain_ptr, const int32
                             int32_t n, int32_t dim, const int32_t *track_det, const int32_t *frame, const double *pos,
                             const double *bbox, const int32_t *carry_frame, const double *carry_pos,
                             const double *carry_bbox, int64_t carry_stride, int32_t *new_frame, double *new_pos,
-                            double *new_bbox, int64_t new_stride, int32_t *error_flag, void *stream) {
+                            double *new_bbox, int64_t new_stride, int32_t hist_len, const double *hist,
+                            const double *carry_hist, const uint8_t *carry_has, double *new_hist, uint8_t *new_has,
+                            int32_t *error_flag, void *stream) {
     M3_CHECK_ARG(n_out >= 0 && (dim == 2 || dim == 3), "n_out >= 0, dim 2 or 3");
+    M3_CHECK_ARG(hist_len >= 0 && (hist_len == 0 || (new_hist && new_has)), "histograms: NULL output");
+    M3_CHECK_ARG(hist_len == 0 || n_carry == 0 || (carry_hist && carry_has), "histograms: NULL carried input");
     if (n_out == 0) return MOT3D_OK;
     M3_CHECK_ARG(chain_ptr && chain && out_ptr && item && trk_first && trk_len && new_frame && new_pos && new_bbox &&
                      error_flag,
@@ -515,8 +598,46 @@ int32_t mot3d_online_concat(int32_t n_out, const int32_t *chain_ptr, const int32
     p.new_bbox = new_bbox;
     p.new_stride = new_stride;
     p.error = error_flag;
+    p.hist_len = hist_len;
+    p.hist = hist;
+    p.carry_hist = carry_hist;
+    p.carry_has = carry_has;
+    p.new_hist = hist_len ? new_hist : nullptr;
+    p.new_has = hist_len ? new_has : nullptr;
     k_online_concat<<<n_out, OC_T, 0, (cudaStream_t)stream>>>(p);
     M3_LAUNCH_CHECK("k_online_concat");
+    return MOT3D_OK;
+}
+
+int32_t mot3d_tracklet_window_hist(int32_t n_tracklets, const int32_t *item, const int32_t *trk_first,
+                                   const int32_t *trk_len, int32_t n_carry, int32_t window, int32_t hist_len,
+                                   const int32_t *track_det, const int32_t *frame, const double *hist,
+                                   const int32_t *carry_frame, const double *carry_hist, const uint8_t *carry_has,
+                                   double *head_hist_out, double *tail_hist_out, uint8_t *head_has_out,
+                                   uint8_t *tail_has_out, void *stream) {
+    M3_CHECK_ARG(n_tracklets >= 0 && hist_len >= 1 && n_carry >= 0, "sizes");
+    if (n_tracklets == 0) return MOT3D_OK;
+    M3_CHECK_ARG(trk_first && trk_len && head_hist_out && tail_hist_out && head_has_out && tail_has_out, "NULL pointer");
+    M3_CHECK_ARG(n_carry == 0 || (item && carry_frame && carry_hist && carry_has), "NULL carried input");
+    WindowHistParams p;
+    p.item = item;
+    p.trk_first = trk_first;
+    p.trk_len = trk_len;
+    p.n_carry = n_carry;
+    p.window = window;
+    p.hist_len = hist_len;
+    p.track_det = track_det;
+    p.frame = frame;
+    p.hist = hist;
+    p.carry_frame = carry_frame;
+    p.carry_hist = carry_hist;
+    p.carry_has = carry_has;
+    p.head_hist = head_hist_out;
+    p.tail_hist = tail_hist_out;
+    p.head_has = head_has_out;
+    p.tail_has = tail_has_out;
+    k_window_median_hist<<<2 * n_tracklets, 128, 0, (cudaStream_t)stream>>>(p);
+    M3_LAUNCH_CHECK("k_window_median_hist");
     return MOT3D_OK;
 }
 

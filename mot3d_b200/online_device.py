@@ -10,8 +10,10 @@ k_online_concat writes the joined, hole-filled trajectories into the next state 
 bookkeeping the reference does in Scene.update / update_completed - which id a chain continues, which trajectories
 are completed - from a few integers per tracklet (item, first frame, last frame) and the chains.
 
-Scope: 2-D detections with boxes, no colour histograms on the tracklets (a tracklet cost with
-use_color_histogram=True falls back to the motion term alone, as the reference does when no tracklet has one).
+Scope: 2-D detections with boxes. Colour histograms are optional: with them, every point of the scene keeps its
+histogram on the device (filled points have none) and the tracklet cost's appearance term compares the median
+histograms of the windows (k_window_median_hist); without them a tracklet cost with use_color_histogram=True falls
+back to the motion term alone, as the reference does when no tracklet has one.
 valid_region (an object with is_inside(point), singleview_tracking.py:28-38) filters the detections of a batch on the
 host before they are uploaded; the reference's second test, on the two ends of every new tracklet (:104-118), can
 then never fail - every detection of a tracklet already passed the first - so nothing is skipped there."""
@@ -24,7 +26,7 @@ from . import _lib
 from .batch import DetectionBatch, _ptr, _stream
 from .pipeline import TrackPipeline
 from .spec import CostSpec, TrackletCostSpec
-from .twopass import tracklet_pass
+from .twopass import tracklet_pass, window_hist
 
 __all__ = ["DeviceTracker2D"]
 
@@ -57,6 +59,7 @@ class DeviceTracker2D(object):
         self._state = None          # dict(ptr=int32 device [A+1], frame, pos, bbox) of the active trajectories
         self._spare = None
         self._pipe = None
+        self._hist_shape = None     # (C, B) once a batch came with histograms
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._zero = torch.zeros(2, dtype=torch.int32, device=dev)
 
@@ -72,16 +75,21 @@ class DeviceTracker2D(object):
         """A state buffer (not the live one) with room for `points` points."""
         dev = self.device
         b = self._spare
-        if b is None or b["cap"] < points:
+        if b is None or b["cap"] < points or (self._hist_shape is not None and b["hist"] is None):
             cap = max(1024, int(points * 1.5))
             b = dict(cap=cap, frame=torch.empty(cap, dtype=torch.int32, device=dev),
                      pos=torch.empty(2 * cap, dtype=torch.float64, device=dev),
-                     bbox=torch.empty(4 * cap, dtype=torch.float64, device=dev), ptr=None)
+                     bbox=torch.empty(4 * cap, dtype=torch.float64, device=dev), ptr=None, hist=None, has=None)
+            if self._hist_shape is not None:
+                b["hist"] = torch.empty((cap,) + self._hist_shape, dtype=torch.float64, device=dev)
+                b["has"] = torch.empty(cap, dtype=torch.uint8, device=dev)
         self._spare = None
         return b
 
     # ---- one batch ------------------------------------------------------------------------------------------------
-    def update(self, time_index, frame, pos, conf, bbox):
+    def update(self, time_index, frame, pos, conf, bbox, hist=None):
+        """hist: None or float[n, C, B], the colour histograms of the detections (mot3d_b200.color_histograms writes
+        that layout); every batch of a run must come with or without them."""
         L = _lib.lib()
         dev = self.device
         st = _stream(dev)
@@ -91,20 +99,28 @@ class DeviceTracker2D(object):
             inside = np.fromiter((bool(self.valid_region.is_inside(p)) for p in np.asarray(pos)), dtype=bool,
                                  count=len(frame))
             frame, pos, conf, bbox = (np.asarray(a)[inside] for a in (frame, pos, conf, bbox))
+            hist = None if hist is None else np.asarray(hist)[inside]
+        if hist is not None:
+            shape = tuple(np.shape(hist)[1:])
+            if len(shape) != 2 or (self._hist_shape not in (None, shape)) or (self._hist_shape is None and self.id_last):
+                raise ValueError("histograms must be [n, C, B] with the same C, B in every batch of a run")
+            self._hist_shape = shape
+        elif self._hist_shape is not None and len(frame):
+            raise ValueError("earlier batches came with histograms, this one does not")
         n = int(len(frame))
         A = len(self.ids)
         P = int(self.ptr[-1])
         # (1) pass 1: the tracks of this batch (compute_trajectories, tracking_routines.py:16-34)
         if n > 0:
-            hb, _ = DetectionBatch.from_arrays(np.array([0, n]), frame, pos, conf, bbox=bbox)
+            hb, _ = DetectionBatch.from_arrays(np.array([0, n]), frame, pos, conf, bbox=bbox, hist=hist)
             db = hb.to(dev)
             pipe = self._pipeline(n)
             pipe.run(db, self.spec)   # no host synchronisation; its flag word is read with the tracklet count below
             t_count, t_ptr, t_det = pipe.track_count, pipe.track_ptr, pipe.track_det
-            b_frame, b_pos, b_bbox = db.frame, db.pos, db.bbox
+            b_frame, b_pos, b_bbox, b_hist = db.frame, db.pos, db.bbox, db.hist
         else:
             t_count, t_ptr, t_det = self._zero[:1], self._zero, self._zero
-            b_frame = b_pos = b_bbox = None
+            b_frame = b_pos = b_bbox = b_hist = None
         if A == 0 and n == 0:
             return 0
         # (2) the tracklet set: carried trajectories + pieces of the new tracks (singleview_tracking.py:94-121)
@@ -131,7 +147,7 @@ class DeviceTracker2D(object):
                 if flag & (_lib.ERR_ARC_CAPACITY | _lib.ERR_WINDOW):
                     # the arc buffer was a guess: size it from what the build counted and run the batch again
                     self._pipe = TrackPipeline(pipe.n_max, 1, 2 * pipe.n_edges() + 1024, device=dev, dim=2)
-                    return self.update(time_index, frame, pos, conf, bbox)
+                    return self.update(time_index, frame, pos, conf, bbox, hist)
                 pipe.check_overflow()
         else:
             M = int(n_trk.item())
@@ -139,8 +155,12 @@ class DeviceTracker2D(object):
         if M == 0:
             return 0
         # (3) pass 2 (concatenate_tracklets, tracking_routines.py:36-52)
+        wh = None
+        if self._hist_shape is not None and self.tspec.use_hist:
+            wh = window_hist(dev, M, self._hist_shape, self.window, item, trk_first, trk_len, t_det, b_frame, b_hist, A,
+                             s["frame"] if A else None, s["hist"] if A else None, s["has"] if A else None)
         c_count, c_ptr, c_trk, _total, _E = tracklet_pass(dev, 2, M, n_trk, stride, head_ptr, tail_ptr, head_idx,
-                                                          tail_idx, head_pos, tail_pos, key, self.tspec)
+                                                          tail_idx, head_pos, tail_pos, key, self.tspec, hist=wh)
         meta = torch.cat([c_count, c_ptr[:M + 1], c_trk[:M], item[:M], span[:2 * M]]).cpu().numpy()
         K = int(meta[0])
         c_ptr_h = meta[1:M + 2]
@@ -180,7 +200,10 @@ class DeviceTracker2D(object):
             n_out, _ptr(d_ch_ptr), _ptr(d_ch), _ptr(d_out_ptr), _ptr(item), _ptr(trk_first), _ptr(trk_len), A, n, 2,
             _ptr(t_det), _ptr(b_frame), _ptr(b_pos), _ptr(b_bbox), _ptr(s["frame"]) if A else None,
             _ptr(s["pos"]) if A else None, _ptr(s["bbox"]) if A else None, s["cap"] if A else 0, _ptr(nb["frame"]),
-            _ptr(nb["pos"]), _ptr(nb["bbox"]), nb["cap"], _ptr(self._err), st))
+            _ptr(nb["pos"]), _ptr(nb["bbox"]), nb["cap"],
+            0 if self._hist_shape is None else self._hist_shape[0] * self._hist_shape[1], _ptr(b_hist),
+            _ptr(s["hist"]) if A else None, _ptr(s["has"]) if A else None, _ptr(nb["hist"]), _ptr(nb["has"]),
+            _ptr(self._err), st))
         nb["ptr"] = d_out_ptr
         # completed trajectories leave the device
         if done:

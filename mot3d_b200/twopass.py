@@ -8,8 +8,9 @@ on the GPU: csrc/twopass.cu cuts and windows the tracks, csrc/tracklet.cu builds
 extraction are the ones of pass 1, and only the final trajectories (indices of pass-1 detections) come back. Between
 the passes the host reads two integers (the number of tracklets and the number of arcs, to size the launches).
 
-Scope: one graph per call; tracklet costs without the appearance term (use_color_histogram=False, what the 3-D example
-uses): the median histograms of DetectionTracklet2D's windows are not computed on the device."""
+Scope: one graph per call. 2-D tracklet costs with the appearance term use the median histograms of the windows
+(k_window_median_hist) when the batch carries histograms; 3-D tracklets with use_color_histogram=True (per-view 2-D
+tracklets) take the object path."""
 import ctypes
 
 import numpy as np
@@ -20,8 +21,11 @@ from .batch import _ptr, _stream
 from .spec import quantise_scalar
 
 
-def tracklet_pass(dev, dim, M, n_trk, stride, head_ptr, tail_ptr, head_idx, tail_idx, head_pos, tail_pos, key, tspec):
+def tracklet_pass(dev, dim, M, n_trk, stride, head_ptr, tail_ptr, head_idx, tail_idx, head_pos, tail_pos, key, tspec,
+                  hist=None):
     """Arcs between M tracklets (windows in the mot3d_tracklets arrays, planar stride `stride`), solve, chains.
+    hist: None, or (head_hist [M, C, B], tail_hist, head_has uint8[M], tail_has) from window_hist() - the appearance
+    term of the tracklet cost then counts wherever both ends have a histogram.
     Returns (t_count, t_ptr, t_trk, total_cost, n_arcs): device tensors except n_arcs."""
     L = _lib.lib()
     st = _stream(dev)
@@ -42,6 +46,11 @@ def tracklet_pass(dev, dim, M, n_trk, stride, head_ptr, tail_ptr, head_idx, tail
     trk.head_fit_ws, trk.tail_fit_ws = fit_h.data_ptr(), fit_t.data_ptr()
     cs = tspec.to_c()
     cs.use_hist = 0
+    if hist is not None and tspec.use_hist:
+        cs.use_hist = 1
+        trk.hist_channels, trk.hist_bins = int(hist[0].shape[1]), int(hist[0].shape[2])
+        trk.head_hist, trk.tail_hist = hist[0].data_ptr(), hist[1].data_ptr()
+        trk.head_has_hist, trk.tail_has_hist = hist[2].data_ptr(), hist[3].data_ptr()
     row_count = torch.zeros(M, **i32)
     _lib.check(L.mot3d_tracklet_edge_count(ctypes.byref(trk), ctypes.byref(cs), _ptr(row_count), st))
     row_ptr = torch.empty(M + 1, **i32)
@@ -77,6 +86,21 @@ def tracklet_pass(dev, dim, M, n_trk, stride, head_ptr, tail_ptr, head_idx, tail
     return t_count, t_ptr, t_trk, total, E
 
 
+def window_hist(dev, M, shape, window, item, trk_first, trk_len, track_det, frame, hist, n_carry=0, carry_frame=None,
+                carry_hist=None, carry_has=None):
+    """Median histograms of the head / tail windows of M tracklets (csrc/twopass.cu k_window_median_hist).
+    shape = (C, B). Returns the tuple tracklet_pass(hist=...) takes."""
+    L = _lib.lib()
+    C, B = shape
+    hh, th = (torch.empty((M, C, B), dtype=torch.float64, device=dev) for _ in range(2))
+    hs, ts = (torch.empty(M, dtype=torch.uint8, device=dev) for _ in range(2))
+    _lib.check(L.mot3d_tracklet_window_hist(M, _ptr(item), _ptr(trk_first), _ptr(trk_len), n_carry,
+                                            0 if window is None else int(window), C * B, _ptr(track_det), _ptr(frame),
+                                            _ptr(hist), _ptr(carry_frame), _ptr(carry_hist), _ptr(carry_has), _ptr(hh),
+                                            _ptr(th), _ptr(hs), _ptr(ts), _stream(dev)))
+    return hh, th, hs, ts
+
+
 def link_tracks(batch, sol, tspec, split_length=10, th_length=10, window=None):
     """batch: DetectionBatch on a CUDA device holding ONE graph; sol: its Solution after extract_tracks;
     tspec: TrackletCostSpec (kind, distance kwargs, confidence kwargs, weight_source_sink, max_jump) of pass 2.
@@ -86,9 +110,9 @@ def link_tracks(batch, sol, tspec, split_length=10, th_length=10, window=None):
     L = _lib.lib()
     if batch.n_graphs != 1:
         raise ValueError("link_tracks takes one graph per call")
-    if tspec.use_hist:
-        raise NotImplementedError("link_tracks: tracklet costs with use_color_histogram=True need the median histograms "
-                                  "of the tracklet windows (host path: build_graph on DetectionTracklet objects)")
+    if tspec.use_hist and tspec.kind != "tracklets_2d":
+        raise NotImplementedError("link_tracks: 3-D tracklet costs with use_color_histogram=True average over the "
+                                  "per-view 2-D tracklets (host path: build_graph on DetectionTracklet3D objects)")
     dev = batch.frame.device
     n, dim = batch.n, batch.dim
     st = _stream(dev)
@@ -111,8 +135,12 @@ def link_tracks(batch, sol, tspec, split_length=10, th_length=10, window=None):
     info = dict(n_tracklets=M, n_arcs=0, total_cost=0, tracklets=(trk_first[:M], trk_len[:M], key[:M]))
     if M == 0:
         return [], info
+    hist = None
+    if tspec.use_hist and batch.hist is not None:
+        hist = window_hist(dev, M, tuple(batch.hist.shape[1:]), window, None, trk_first, trk_len, sol.track_det,
+                           batch.frame, batch.hist)
     t_count, t_ptr, t_trk, total, E = tracklet_pass(dev, dim, M, n_trk, n, head_ptr, tail_ptr, head_idx, tail_idx,
-                                                    head_pos, tail_pos, key, tspec)
+                                                    head_pos, tail_pos, key, tspec, hist=hist)
     info["n_arcs"] = E
     # ---- chains of tracklets -> chains of detections
     o_count, o_ptr, o_det = torch.zeros(1, **i32), torch.zeros(M + 2, **i32), torch.zeros(n + 1, **i32)

@@ -288,9 +288,11 @@ def gen_online(F=200, P=8, seed=0):
     return frames
 
 
-def case_online(mot3d):
+def case_online(mot3d, with_hist=False):
     """(4d) the reference's own online loop (projects/PETS2009S2L1/singleview_tracking.py:76-134 Tracker2D.update,
-    tracking_routines.py, scene.py) on C4-synth, 4 batches of 50 frames; the scene after every batch is frozen."""
+    tracking_routines.py, scene.py) on C4-synth, 4 batches of 50 frames; the scene after every batch is frozen.
+    with_hist: every detection also carries a colour histogram [3, 8] (a per-person pattern + noise; false positives
+    random) and both costs use their appearance terms - c4_online_loop_hist."""
     import collections
     import collections.abc
     collections.Iterable = collections.abc.Iterable  # tracking_routines.py:9 predates Python 3.10
@@ -300,6 +302,26 @@ def case_online(mot3d):
     import singleview_tracking as sv
     frames = gen_online()
     cfg = ONLINE_CONFIG
+    hists = None
+    if with_hist:
+        import copy
+        cfg = copy.deepcopy(ONLINE_CONFIG)
+        cfg["detections"]["weight_distance"].update(use_color_histogram=True, sigma_color_histogram=0.5)
+        cfg["tracklets"]["weight_distance"].update(alpha=0.5, sigma_color_histogram=0.4)
+        # who made each detection is not recorded by gen_online: give nearby detections alike patterns instead - a
+        # smooth random field of the position (people move ~1 px per frame) plus noise
+        rng = np.random.RandomState(11)
+        W = rng.randn(4, 24)
+        hists = []
+        for f, fr in enumerate(frames):
+            ph = np.stack([np.sin(fr[:, 0] / 60.0), np.cos(fr[:, 0] / 60.0), np.sin(fr[:, 1] / 60.0),
+                           np.cos(fr[:, 1] / 60.0)], 1) if len(fr) else np.zeros((0, 4))
+            # from frame 120 on everybody in the left half of the image looks different (the pattern flips): links
+            # that motion alone would make across that frame are cut by the appearance terms
+            sign = np.where((f >= 120) & (fr[:, 0] < 384), -1.0, 1.0)[:, None] if len(fr) else np.zeros((0, 1))
+            h = sign * (ph @ W) + rng.randn(len(fr), 24) * 0.25
+            h = h.reshape(-1, 3, 8)
+            hists.append(h - h.mean(axis=2, keepdims=True))
     scene = sv.Scene(cfg["completed_after"])
     tracker = sv.Tracker2D(scene, None, cfg, image_size=(768, 576))
     out = dict(det_ptr=np.cumsum([0] + [len(f) for f in frames]).astype(np.int64),
@@ -308,8 +330,9 @@ def case_online(mot3d):
     import io
     import contextlib
     for b in range(len(frames) // B):
-        dets = [[mot3d.Detection2D(f, r[:2].copy(), confidence=float(r[2]), bbox=tuple(r[3:7]))
-                 for r in frames[f]] for f in range(b * B, (b + 1) * B)]
+        dets = [[mot3d.Detection2D(f, r[:2].copy(), confidence=float(r[2]), bbox=tuple(r[3:7]),
+                                   color_histogram=None if hists is None else hists[f][k].copy())
+                 for k, r in enumerate(frames[f])] for f in range(b * B, (b + 1) * B)]
         with contextlib.redirect_stdout(io.StringIO()):
             tracker.update((b + 1) * B, dets)  # iterator.idx after the batch (feeders.py)
         for name, store in (("active", scene.active), ("completed", scene.completed)):
@@ -324,9 +347,12 @@ def case_online(mot3d):
         print("online batch %d: active %d completed %d tracklets %d" % (b, len(scene.active), len(scene.completed),
                                                                         len(scene.tracklets)))
     out["n_tracklets"] = len(scene.tracklets)
-    path = os.path.join(HERE, "c4_online_loop.npz")
+    name = "c4_online_loop_hist" if with_hist else "c4_online_loop"
+    if with_hist:
+        out["det_hist"] = np.concatenate(hists)
+    path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
-    print("%-22s (%d KB)" % ("c4_online_loop", os.path.getsize(path) // 1024))
+    print("%-22s (%d KB)" % (name, os.path.getsize(path) // 1024))
 
 
 def case_multiview_tracklets(mot3d, wf):
@@ -471,6 +497,8 @@ def main():
         return case_multiview_tracklets(mot3d, wf)
     if "c4_online_loop" in sys.argv[1:]:
         return case_online(mot3d)
+    if "c4_online_loop_hist" in sys.argv[1:]:
+        return case_online(mot3d, with_hist=True)
     if "c3_synth_multiview" in sys.argv[1:]:
         return case_multiview(mot3d, wf)
     case_color_histogram(mot3d)
@@ -479,6 +507,7 @@ def main():
     case_multiview(mot3d, wf)
     case_multiview_tracklets(mot3d, wf)
     case_online(mot3d)
+    case_online(mot3d, with_hist=True)
     from mot3d.utils import utils as ref_utils
     from mot3d.utils import trajectory as ref_traj
 

@@ -832,7 +832,8 @@ def test_two_pass_pipeline_drop_in():
         assert [d.index for d in j] == sorted(d.index for d in j)
 
 
-def test_online_window_loop_matches_reference():
+@pytest.mark.parametrize("case", ["c4_online_loop", "c4_online_loop_hist"])
+def test_online_window_loop_matches_reference(case):
     """BASELINE config 4 (PETS-shaped online sliding-window tracking): mot3d_b200.online.Tracker2D / Scene, the mirror
     of the reference's loop (projects/PETS2009S2L1/singleview_tracking.py:76-134, tracking_routines.py:16-52,
     scene.py:8-52), over 4 batches of 50 frames of C4-synth. After every batch the scene - ids, frames, interpolated
@@ -841,15 +842,17 @@ def test_online_window_loop_matches_reference():
     import json
     import mot3d_b200 as mot3d
     from mot3d_b200.online import Scene, Tracker2D
-    d = gu.load("c4_online_loop")
+    d = gu.load(case)
     cfg = json.loads(str(d["config"]))
     scene = Scene(cfg["completed_after"])
     tracker = Tracker2D(scene, None, cfg, image_size=(768, 576))
     ptr, det = d["det_ptr"], d["det"]
+    hist = d["det_hist"] if "det_hist" in d else None   # (_hist: both costs use their appearance terms)
     B = cfg["batch_size"]
     n_frames = len(ptr) - 1
     for b in range(n_frames // B):
-        dets = [[mot3d.Detection2D(f, det[r, :2].copy(), confidence=float(det[r, 2]), bbox=tuple(det[r, 3:7]))
+        dets = [[mot3d.Detection2D(f, det[r, :2].copy(), confidence=float(det[r, 2]), bbox=tuple(det[r, 3:7]),
+                                   color_histogram=None if hist is None else hist[r].copy())
                  for r in range(int(ptr[f]), int(ptr[f + 1]))] for f in range(b * B, (b + 1) * B)]
         tracker.update((b + 1) * B, dets)
         for name, store in (("active", scene.active), ("completed", scene.completed)):
@@ -862,7 +865,7 @@ def test_online_window_loop_matches_reference():
             np.testing.assert_allclose(pos, d["b%d_%s_pos" % (b, name)], rtol=1e-12, atol=1e-9)
             np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)], rtol=1e-12, atol=1e-9)
     assert len(scene.tracklets) == int(d["n_tracklets"])
-    assert len(scene.completed) == 2 and len(scene.active) == 6
+    assert len(scene.completed) == (5 if hist is not None else 2) and len(scene.active) == 6
 
 
 def _scene_arrays(store):
@@ -872,15 +875,19 @@ def _scene_arrays(store):
     return ids, ptr, cat(0, 1).reshape(-1).astype(np.int64).tolist(), cat(1, 2), cat(2, 4)
 
 
-def test_online_loop_with_device_resident_scene_matches_reference():
+@pytest.mark.parametrize("case", ["c4_online_loop", "c4_online_loop_hist"])
+def test_online_loop_with_device_resident_scene_matches_reference(case):
     """DeviceTracker2D keeps the active trajectories in device memory between updates and does the
     cutting, windowing, linking, concatenation and hole filling in kernels (csrc/twopass.cu: k_split_tracks with carried
     trajectories, k_online_concat). Same golden as the object loop: after every batch of C4-synth the ids, frames,
     interpolated positions and boxes of the active and the completed trajectories are what the reference's own loop
-    left (tests/golden/c4_online_loop.npz)."""
+    left (tests/golden/c4_online_loop.npz). _hist: the detections carry colour histograms and both costs use them - the
+    scene keeps a histogram per point and the tracklet cost compares window medians (k_window_median_hist)."""
     import json
     from mot3d_b200.online_device import DeviceTracker2D
-    d = gu.load("c4_online_loop")
+    d = gu.load(case)
+    hist = d["det_hist"] if "det_hist" in d else None
+    hs = lambda lo, hi: None if hist is None else hist[lo:hi]
     cfg = json.loads(str(d["config"]))
     tracker = DeviceTracker2D(cfg, completed_after=cfg["completed_after"])
     ptr, det = d["det_ptr"], d["det"]
@@ -889,7 +896,7 @@ def test_online_loop_with_device_resident_scene_matches_reference():
     for b in range(n_frames // B):
         lo, hi = int(ptr[b * B]), int(ptr[(b + 1) * B])
         frame = np.repeat(np.arange(b * B, (b + 1) * B), np.diff(ptr[b * B:(b + 1) * B + 1]))
-        tracker.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7])
+        tracker.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7], hs(lo, hi))
         for name, store in (("active", tracker.active()), ("completed", tracker.completed)):
             ids, p_, index, pos, box = _scene_arrays(store)
             assert ids == d["b%d_%s_ids" % (b, name)].tolist(), (b, name)
@@ -898,7 +905,7 @@ def test_online_loop_with_device_resident_scene_matches_reference():
             np.testing.assert_allclose(pos, d["b%d_%s_pos" % (b, name)].reshape(-1, 2), rtol=1e-12, atol=1e-9)
             np.testing.assert_allclose(box, d["b%d_%s_bbox" % (b, name)].reshape(-1, 4), rtol=1e-12, atol=1e-9)
     assert tracker.n_tracklets_seen == int(d["n_tracklets"])
-    assert len(tracker.completed) == 2 and len(tracker.ids) == 6
+    assert len(tracker.completed) == (5 if hist is not None else 2) and len(tracker.ids) == 6
     # the detection pass runs in preallocated buffers sized by a guess: too small an arc buffer is noticed, the buffers
     # are re-sized from the build's own count and the batch runs again - same scene
     from mot3d_b200.pipeline import TrackPipeline
@@ -907,7 +914,7 @@ def test_online_loop_with_device_resident_scene_matches_reference():
     for b in range(n_frames // B):
         lo, hi = int(ptr[b * B]), int(ptr[(b + 1) * B])
         frame = np.repeat(np.arange(b * B, (b + 1) * B), np.diff(ptr[b * B:(b + 1) * B + 1]))
-        again.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7])
+        again.update((b + 1) * B, frame, det[lo:hi, :2], det[lo:hi, 2], det[lo:hi, 3:7], hs(lo, hi))
     assert again._pipe.edge_capacity > 64
     a, b_ = _scene_arrays(tracker.active()), _scene_arrays(again.active())
     assert a[:3] == b_[:3] and (a[3] == b_[3]).all() and (a[4] == b_[4]).all()
@@ -918,7 +925,8 @@ def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
     """The same two loops (objects: mot3d_b200.online.Tracker2D, pinned to the reference above; arrays on the device:
     DeviceTracker2D) over 12 batches of a sequence where people enter, leave for good and come back after gaps, with
     some empty batches: trajectories complete, ids are never reused, carried trajectories are extended, left alone or
-    linked behind another one. Scenes must agree after every batch."""
+    linked behind another one. Every detection carries a colour histogram and the tracklet cost uses it: the windows of
+    carried trajectories mix points with a histogram and filled points without. Scenes must agree after every batch."""
     import mot3d_b200 as mot3d
     from mot3d_b200.online import Scene, Tracker2D
     from mot3d_b200.online_device import DeviceTracker2D
@@ -939,7 +947,9 @@ def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
         t0 = int(rng.randint(0, 160))
         people.append(dict(t0=t0, t1=t0 + int(rng.randint(25, 110)), p=rng.uniform(50, 700, 2), v=rng.uniform(-3, 3, 2),
                            gap=(int(rng.randint(t0 + 10, t0 + 60)), int(rng.randint(4, 25))), wh=rng.uniform(20, 60, 2)))
-    rows = []
+    rows, hists = [], []
+    for q in people:
+        q["h"] = rng.normal(0, 1, (3, 6))
     for f in range(B * n_batches):
         if 100 <= f < 120:
             continue  # an empty batch
@@ -949,7 +959,10 @@ def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
             c = q["p"] + q["v"] * (f - q["t0"]) + rng.normal(0, 0.7, 2)
             w, h = q["wh"] * (1 + rng.normal(0, 0.02, 2))
             rows.append((f, c[0], c[1], rng.uniform(0.5, 1), c[0] - w / 2, c[1] - h / 2, c[0] + w / 2, c[1] + h / 2))
-    rows = np.array(rows)
+            # a histogram per detection: the person's pattern + noise; half the people change clothes after a gap
+            flip = -1.0 if (people.index(q) % 2 and f >= q["gap"][0]) else 1.0
+            hists.append(flip * q["h"] + rng.normal(0, 0.3, (3, 6)))
+    rows, hists = np.array(rows), np.array(hists)
     class Region(object):  # valid_region: everything but a strip on the left
         @staticmethod
         def is_inside(p):
@@ -960,11 +973,13 @@ def test_online_loop_device_scene_equals_object_loop_on_a_long_sequence():
     t_dev = DeviceTracker2D(cfg, completed_after=cfg["completed_after"], valid_region=Region)
     n_done = 0
     for b in range(n_batches):
-        sel = rows[(rows[:, 0] >= b * B) & (rows[:, 0] < (b + 1) * B)]
-        dets = [[mot3d.Detection2D(int(r[0]), r[1:3].copy(), confidence=float(r[3]), bbox=tuple(r[4:8]))
-                 for r in sel if int(r[0]) == f] for f in range(b * B, (b + 1) * B)]
+        m = (rows[:, 0] >= b * B) & (rows[:, 0] < (b + 1) * B)
+        sel, hsel = rows[m], hists[m]
+        dets = [[mot3d.Detection2D(int(r[0]), r[1:3].copy(), confidence=float(r[3]), bbox=tuple(r[4:8]),
+                                   color_histogram=hh.copy())
+                 for r, hh in zip(sel, hsel) if int(r[0]) == f] for f in range(b * B, (b + 1) * B)]
         assert t_obj.update((b + 1) * B, dets) == 0   # (no tracklet is skipped at the second valid_region test)
-        t_dev.update((b + 1) * B, sel[:, 0].astype(np.int64), sel[:, 1:3], sel[:, 3], sel[:, 4:8])
+        t_dev.update((b + 1) * B, sel[:, 0].astype(np.int64), sel[:, 1:3], sel[:, 3], sel[:, 4:8], hsel)
         for name, want, got in (("active", scene.active, t_dev.active()), ("completed", scene.completed, t_dev.completed)):
             assert sorted(want) == sorted(got), (b, name)
             for i in want:
@@ -1287,7 +1302,7 @@ def test_track_pipeline_with_appearance_costs(name):
         small.check_overflow()
 
 
-@pytest.mark.parametrize("case", ["c3_soldiers_3d", "c5_small_2d_window"])
+@pytest.mark.parametrize("case", ["c3_soldiers_3d", "c5_small_2d_window", "c5_small_2d_window_hist"])
 def test_device_resident_two_pass_equals_host_glue(case):
     """link_tracks (pass 1 -> tracklets -> pass 2 -> trajectories on the device, csrc/twopass.cu) against the drop-in
     path on Python objects (split_trajectory_modulo / remove_short_trajectories / DetectionTracklet / build_graph /
@@ -1306,10 +1321,18 @@ def test_device_resident_two_pass_equals_host_glue(case):
         d = gu.load("c5_small_f30_p12")
         length, th, window = 5, 1, 3
         tkw = dict(sigma_color_histogram=0.3, sigma_motion=20, alpha=0.7, cutoff_motion=0.1, cutoff_appearance=0.1,
-                   max_distance=60, use_color_histogram=False)
+                   max_distance=60, use_color_histogram=case.endswith("_hist"))
         kind, wss2, mj2 = "tracklets_2d", 0.2, 12
     spec = _spec_from(d["spec"], mot3d)
     n = len(d["frame"])
+    hist = None
+    if case.endswith("_hist"):
+        # _hist: every detection carries a histogram (a smooth pattern of its position + noise) and the tracklet cost
+        # compares the medians over the 3-frame windows (k_window_median_hist vs DetectionTracklet2D's np.median)
+        rng = np.random.RandomState(3)
+        ph = np.concatenate([np.sin(d["pos"] / 40.0), np.cos(d["pos"] / 40.0)], 1)
+        hist = (ph @ rng.randn(4, 12) + rng.randn(n, 12) * 0.4).reshape(n, 3, 4)
+        d = dict(d, hist=hist)
     b = _batch_from(d, mot3d).to("cuda")
     gb, sol = mot3d.track_batch(b, spec)
     tracks1 = mot3d.tracks_to_lists(np.array([0, n]), sol.track_count.cpu().numpy(), sol.track_ptr.cpu().numpy(),
@@ -1321,6 +1344,9 @@ def test_device_resident_two_pass_equals_host_glue(case):
     three_d = kind == "tracklets_3d"
     Det = mot3d.Detection3D if three_d else mot3d.Detection2D
     dets = [Det(int(d["frame"][i]), d["pos"][i], confidence=float(d["conf"][i])) for i in range(n)]
+    if hist is not None:
+        for i, x in enumerate(dets):
+            x.color_histogram = hist[i]
     index_of = {id(x): i for i, x in enumerate(dets)}
     pieces = []
     for t in tracks1:
