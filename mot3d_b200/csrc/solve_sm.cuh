@@ -8,13 +8,22 @@
 //               The work queue only hands a block components that fit (staging_bytes); costs fit 32 bits
 //               (k_first_tree checked), distances are exact int64.
 //   next path   block arg-min over dpost + exit cost (muSSP's sink heap, Graph.cpp:508-541); stop when the path does
-//               not pay (wrapper.cpp:263-267).
+//               not pay (wrapper.cpp:263-267). SEVERAL paths are taken from one set of labels: after a path through
+//               the branch of S -> pre_r is flipped, every residual arc still has a non-negative reduced cost under
+//               the old labels (the reversed arcs are tight), so no label falls, the labels outside that branch stay
+//               exact and the ones inside are lower bounds. The next sink in (cost, slot) order is therefore the next
+//               shortest path as long as it lies in a branch no path of the batch went through (the vendored
+//               wrapper.cpp:237-300 re-labels after every single path; the result is the same, see below); the
+//               first sink in a used branch ends the batch, and a next sink that does not pay ends the
+//               component without a last re-labelling. The path costs and their order are those of one-by-one
+//               successive shortest paths.
 //   path update one thread walks the path back from T and rewrites next / prev (Graph::flip_path, Graph.cpp:266-335).
 //   certificate once every detection is on a track: if every matched arc is the cheapest in-arc of its head, costs
 //               mc <= 0, cn + mc <= 0, and no entry / exit cost is negative, no further path can pay (every piece of
 //               a residual S -> T path is >= 0): finished without a last re-labelling.
 //   re-label    muSSP's observation (Graph.cpp:341-343, 394-503): only the branch of the shortest-path tree that hung
-//               from the path's first arc loses its labels. Its nodes start unlabelled and are relaxed in SYNCHRONOUS
+//               from the path's first arc loses its labels (here: the branches of all paths of the batch, at
+//               once). Their nodes start unlabelled and are relaxed in SYNCHRONOUS
 //               ROUNDS in pull mode: a round computes, from the labels of the round before, the best label of a
 //               record's pre node (in-arcs, S arc, reversed node arc) and post node (own pre node when unused,
 //               reversed matched arc of the successor when on a track); all changes are published at once. Labels
@@ -172,6 +181,12 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
     int K = 0, n_used = 0;
     int64_t total = 0;
     for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+        // ---- a batch of paths from ONE set of labels (see "next path" in the header): sinks in ascending order, each
+        //      in a branch no earlier path of the batch went through. pl[] marks the roots of those branches.
+        for (int s = tid; s < n; s += T) pl[s] = 0;
+        bool finished = false;
+#pragma unroll 1
+        for (;;) {
         // ---- cheapest way into T
         KeyIdx best;
         best.key = INF;
@@ -202,20 +217,26 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
             const KeyIdx o = s_red[k];
             if (o.key < sink.key || (o.key == sink.key && (unsigned)o.idx < (unsigned)sink.idx)) sink = o;
         }
+        // (read before the barrier: thread 0 marks the root right after it)
+        const int root = (sink.idx >= 0 && sink.key < 0) ? rec[sink.idx].F.z : -1;
+        const bool root_used = root >= 0 && pl[root] != 0;
         __syncthreads();  // s_red is rewritten next iteration
         cnt.tick(0);
+        finished = true;
         if (sink.idx < 0) break;  // T unreachable
-        if (sink.key >= 0) {      // the first-path rule belongs to the whole graph (k_first_path_rule)
-            if (K == 0 && tid == 0) {
+        if (sink.key >= 0) {      // no sink pays, now or (the stale labels are lower bounds) after a re-labelling.
+            if (K == 0 && tid == 0) {  // the first-path rule belongs to the whole graph (k_first_path_rule)
                 p.first_cost[cg] = sink.key;
                 p.first_sink[cg] = c0 + sink.idx;
             }
             break;
         }
-        const int root = rec[sink.idx].F.z;
         if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        finished = false;
+        if (root_used) break;  // its branch already carries a path of this batch: its labels are stale, re-label first
         // ---- augment: walk the path back from T and rewrite next / prev
         if (tid == 0) {
+            pl[root] = 1;
             int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
             for (int step = 0; step <= n; step++) {
                 const int4 A = rec[cur].A;         // z = prev, w = next
@@ -256,7 +277,10 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
         }
         __syncthreads();
         cnt.tick(3);
-        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        if (!s_ok[0]) {  // defensive: inconsistent state, stop with what we have
+            finished = true;
+            break;
+        }
         n_used += s_ok[7];
         for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
             const int m = hop[h], q = rec[m].A.z;
@@ -271,6 +295,8 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
         K++;
         total += sink.key;
         __syncthreads();
+        }  // (batch)
+        if (finished) break;
         // ---- finished? (every detection on a track + the certificate of the header)
         if (n_used == n) {
             bool good = true;
@@ -295,11 +321,12 @@ __device__ __noinline__ bool solve_component_sm(const SolveParams &p, const int 
                 break;
             }
         }
-        // ---- the branch hanging from S -> pre_root loses its labels
+        // ---- the branches hanging from the S -> pre_root arcs of the batch lose their labels
         int n_mine = 0;
         for (int s = tid; s < n; s += T) {
             int4 F = rec[s].F;
-            const int f = (F.y == root ? 1 : 0) | (F.z == root ? 2 : 0);  // 1 = pre node, 2 = post node in the branch
+            // 1 = pre node, 2 = post node in one of the branches
+            const int f = ((F.y >= 0 && pl[F.y]) ? 1 : 0) | ((F.z >= 0 && pl[F.z]) ? 2 : 0);
             flg[s] = (unsigned char)f;
             if (f) {
                 longlong2 E = rec[s].E;

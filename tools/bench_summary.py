@@ -1,8 +1,8 @@
-"""One line per bench JSON line on stdin: value, step, solve stage, k_ssp_solve, e2e."""
+"""One line per bench JSON line (files given as arguments, else stdin): value, step, solve stage, k_ssp_solve, e2e."""
+import fileinput
 import json
-import sys
 
-for line in sys.stdin:
+for line in fileinput.input():
     line = line.strip()
     if not line.startswith("{"):
         continue
