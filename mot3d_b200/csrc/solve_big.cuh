@@ -134,6 +134,13 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
     int K = 0, n_used = 0;
     int64_t total = 0;
     for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+        // ---- a batch of paths from ONE set of labels (solve_sm.cuh, "next path"): sinks in ascending order, each in a
+        //      branch no earlier path of the batch went through. The root of a used branch carries the batch's stamp
+        //      in F.w (free after staging; a first-arc index there is never negative).
+        const int stamp = -2 - iter;
+        bool finished = false;
+#pragma unroll 1
+        for (;;) {
         // ---- cheapest way into T
         KeyIdx best;
         best.key = INF;
@@ -164,8 +171,12 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
             const KeyIdx o = s_red[k];
             if (o.key < sink.key || (o.key == sink.key && (unsigned)o.idx < (unsigned)sink.idx)) sink = o;
         }
+        // (read before the barrier: thread 0 stamps the root right after it)
+        const int root = (sink.idx >= 0 && sink.key < 0) ? rec[sink.idx].F.z : -1;
+        const bool root_used = root >= 0 && rec[root].F.w == stamp;
         __syncthreads();  // s_red is rewritten next iteration
         cnt.tick(0);
+        finished = true;
         if (sink.idx < 0) break;  // T unreachable
         if (sink.key >= 0) {      // the first-path rule belongs to the whole graph (k_first_path_rule)
             if (K == 0 && tid == 0) {
@@ -174,10 +185,12 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
             }
             break;
         }
-        const int root = rec[sink.idx].F.z;
         if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        finished = false;
+        if (root_used) break;  // its branch already carries a path of this batch: stale labels, re-label first
         // ---- augment: walk the path back from T and rewrite next / prev
         if (tid == 0) {
+            rec[root].F.w = stamp;
             int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
             for (int step = 0; step <= n; step++) {
                 const int4 A = rec[cur].A;         // z = prev, w = next
@@ -218,7 +231,10 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
         }
         __syncthreads();
         cnt.tick(3);
-        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        if (!s_ok[0]) {  // defensive: inconsistent state, stop with what we have
+            finished = true;
+            break;
+        }
         n_used += s_ok[7];
         for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
             const int m = hop[h], q = rec[m].A.z;
@@ -233,6 +249,8 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
         K++;
         total += sink.key;
         __syncthreads();
+        }  // (batch)
+        if (finished) break;
         // ---- finished? (every detection on a track + the certificate of the header)
         if (n_used == n) {
             bool good = true;
@@ -266,7 +284,8 @@ __device__ __noinline__ void solve_component_big(const SolveParams &p, const int
             int f = 0;
             if (s < n) {
                 int4 F = rec[s].F;
-                f = (F.y == root ? 1 : 0) | (F.z == root ? 2 : 0);  // 1 = pre node, 2 = post node in the branch
+                // 1 = pre node, 2 = post node in one of the batch's branches
+                f = ((F.y >= 0 && rec[F.y].F.w == stamp) ? 1 : 0) | ((F.z >= 0 && rec[F.z].F.w == stamp) ? 2 : 0);
                 flg[s] = (unsigned char)f;
                 if (f) {
                     longlong2 E = rec[s].E;
