@@ -160,6 +160,13 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
     int K = 0, n_used = 0;
     int64_t total = 0;
     for (int iter = 0; iter <= n; iter++) {  // at most one path per detection
+        // ---- a batch of paths from ONE set of labels (solve_sm.cuh, "next path"): sinks in ascending order, each in a
+        //      branch no earlier path of the batch went through. The root of a used branch carries the batch's stamp
+        //      in F.w (free after staging; a first-arc index there is never negative).
+        const int stamp = -2 - iter;
+        bool finished = false;
+#pragma unroll 1
+        for (;;) {
         // ---- cheapest way into T
         KeyIdx best;
         best.key = INF;
@@ -190,8 +197,12 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
             const KeyIdx o = s_red[k];
             if (o.key < sink.key || (o.key == sink.key && (unsigned)o.idx < (unsigned)sink.idx)) sink = o;
         }
+        // (read before the barrier: thread 0 stamps the root right after it)
+        const int root = (sink.idx >= 0 && sink.key < 0) ? rec[sink.idx].F.z : -1;
+        const bool root_used = root >= 0 && rec[root].F.w == stamp;
         __syncthreads();  // s_red is rewritten next iteration
         cnt.tick(0);
+        finished = true;
         if (sink.idx < 0) break;  // T unreachable
         if (sink.key >= 0) {      // see k_ssp_solve: the first-path rule belongs to the whole graph
             if (K == 0 && tid == 0) {
@@ -200,10 +211,12 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
             }
             break;
         }
-        const int root = rec[sink.idx].F.z;
         if (root < 0) break;  // cannot happen: a labelled node always has a branch
+        finished = false;
+        if (root_used) break;  // its branch already carries a path of this batch: stale labels, re-label first
         // ---- augment: walk the path back from T and rewrite next/prev (Graph::flip_path, Graph.cpp:266-335)
         if (tid == 0) {
+            rec[root].F.w = stamp;
             int ok = 0, nhop = 0, nxt_new = TERM, cur = sink.idx, joined = 0;
             for (int step = 0; step <= n; step++) {
                 const int4 A = rec[cur].A;         // z = prev, w = next
@@ -244,7 +257,10 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
         }
         __syncthreads();
         cnt.tick(3);
-        if (!s_ok[0]) break;  // defensive: inconsistent state, stop with what we have
+        if (!s_ok[0]) {  // defensive: inconsistent state, stop with what we have
+            finished = true;
+            break;
+        }
         n_used += s_ok[7];
         for (int h = tid; h < s_ok[1]; h += T) {  // cost of every newly matched arc prev -> m
             const int m = hop[h], q = rec[m].A.z;
@@ -258,7 +274,12 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
                 }
             }
         }
+        if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
+        K++;
+        total += sink.key;
         __syncthreads();
+        }  // (batch)
+        if (finished) break;
         // ---- Is this component finished? Once every detection is on a track, a further S -> T path in the residual
         //      network has the shape  S -> pre_i, (pre -> post of the predecessor: cancels a matched arc, -mc), then
         //      any number of hops post_a -> pre_b -> post_prev(b) (an unused arc and the cancellation of b's matched
@@ -287,9 +308,6 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
                 }
             }
             if (__syncthreads_and(good)) {
-                if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
-                K++;
-                total += sink.key;
                 cnt.n_cert++;
                 cnt.tick(6);
                 break;
@@ -302,7 +320,8 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
             int my_nd = 0;
             for (int i = i0; i < i1; i++) {
                 const int4 F = rec[i].F;
-                const int f = (F.y == root ? DL_PRE : 0) | (F.z == root ? DL_POST : 0);
+                const int f = ((F.y >= 0 && rec[F.y].F.w == stamp) ? DL_PRE : 0) |
+                              ((F.z >= 0 && rec[F.z].F.w == stamp) ? DL_POST : 0);
                 rec[i].A.x = f;
                 my_nd += f ? 1 : 0;
             }
@@ -314,7 +333,6 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
         __syncthreads();
         for (int lp = tid; lp < nd; lp += T)
             if (lp == 0 || tk[bl[lp]] != tk[bl[lp - 1]]) rec[bl[lp]].A.x |= DL_FIRST;
-        if (tid == 0 && p.path_cost) p.path_cost[c0 + K] = sink.key;
         cnt.n_branch++;
         cnt.n_rec += nd;
         cnt.tick(1);
@@ -654,8 +672,6 @@ __device__ __noinline__ void solve_component_global(const SolveParams &p, const 
         }
         __syncthreads();
         cnt.tick(4);
-        K++;
-        total += sink.key;
     }
     // ---- results of this component: flow in detection indices, totals added to its graph
     __syncthreads();
