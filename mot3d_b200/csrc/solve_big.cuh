@@ -2,9 +2,9 @@
 // bits: the staging area lives in GLOBAL memory (it stays in L2: 150 bytes per record, 12 per arc), slots are 32 bits,
 // any size. Included by solve.cu. Costs beyond 32 bits, and thin components, go to solve_global.cuh (k_ssp_solve picks).
 //
-// Same successive shortest paths as solve_sm.cuh (arg-min over the sinks, path walk, certificate, exact re-labelling of
-// the branch that hung from the path's first arc by synchronous pull rounds), with two differences that matter at this
-// size:
+// Same successive shortest paths as solve_sm.cuh (arg-min over the sinks, several paths per re-labelling as long as
+// their branches differ, path walk, certificate, exact re-labelling of the branches that hung from the paths' first
+// arcs by synchronous pull rounds), with two differences that matter at this size:
 //   pushed work lists   a round only touches the records whose inputs moved in the round before. Publishing a post label
 //                       puts the heads of the node's out-arcs on the next round's work list (the out-arc lists are
 //                       staged next to the in-arc lists); publishing a pre label on a track lists the track's previous

@@ -2,8 +2,8 @@
 // solve_sm.cuh or whose costs need more than 32 bits. Any size, any cost: 80-byte records, 16-byte arcs, 64-bit costs,
 // 32-bit slots. Included by solve.cu.
 //
-// After a path through S -> pre_a is flipped, the branch of the shortest-path tree that hung from that arc is listed in
-// frame-layer order and re-labelled by an exact Bellman-Ford fix-point in pull mode: ascending layer order settles the
+// After a path through S -> pre_a is flipped (several paths per re-labelling as long as their branches differ, see
+// solve_sm.cuh), the branch of the shortest-path tree that hung from that arc is listed in frame-layer order and re-labelled by an exact Bellman-Ford fix-point in pull mode: ascending layer order settles the
 // forward arcs (one warp, layer by layer, for the records that pass a fresh label on; everything else at once), a
 // descending pass settles the reversed arcs (independent chain walks down the tracks); the two alternate until nothing
 // moves (Graph::update_shortest_path_tree_recursive, Graph.cpp:394-503, without heap or tolerances). Work is
@@ -29,7 +29,8 @@ struct GStaging {
 };
 // A record, in 16-byte groups so that a relaxation is a handful of 128-bit loads:
 //   A  x = DL_* flags of the current branch, y = arc list (see arcs_of), z = prev, w = next (slots / NONE / TERM)
-//   F  x = parent of the pre node (slot / PAR_*), y = branch of pre, z = branch of post
+//   F  x = parent of the pre node (slot / PAR_*), y = branch of pre, z = branch of post, w = first arc while staging,
+//      then the stamp of the batch of paths that last went through the branch rooted here
 //   E  exact distances from S of pre and post (the invariant the incremental update relies on)
 //   W  costs: S -> pre, pre -> post, post -> T, matched arc prev -> this
 struct __align__(16) GRec {
