@@ -56,6 +56,8 @@ def _oracle():
         lib.oracle_ssp_solve.restype = ctypes.c_int
         lib.oracle_ssp_solve.argtypes = [ctypes.c_int32, ctypes.c_int32, _i32p, _i32p, _i64p, _i32p, _i32p, _i64p,
                                          ctypes.c_int32, _i64p]
+        lib.oracle_ssp_solve_batched.restype = ctypes.c_int
+        lib.oracle_ssp_solve_batched.argtypes = lib.oracle_ssp_solve.argtypes + [_i32p]
         _oracle_lib = lib
     return _oracle_lib
 
@@ -429,8 +431,9 @@ def merge_close_points(points, eps=0.3, return_indexes=False):
 
 
 # ------------------------------------------------------------------------------------------------- solve
-def ssp_solve(n_nodes, tail1, head1, cost_units, path_cap=None):
-    """C restatement on int64 units. tail1/head1 are 1-based as in the text. -> dict(flow, K, path_cost, total)."""
+def ssp_solve(n_nodes, tail1, head1, cost_units, path_cap=None, batched=False):
+    """C restatement on int64 units. tail1/head1 are 1-based as in the text. -> dict(flow, K, path_cost, total).
+    batched=True: several paths per search (the rule of the CUDA solver, see ssp_oracle.c); also returns `searches`."""
     tail = np.ascontiguousarray(np.asarray(tail1, dtype=np.int32) - 1)
     head = np.ascontiguousarray(np.asarray(head1, dtype=np.int32) - 1)
     cost = np.ascontiguousarray(cost_units, dtype=np.int64)
@@ -441,6 +444,15 @@ def ssp_solve(n_nodes, tail1, head1, cost_units, path_cap=None):
     pc = np.zeros(path_cap, dtype=np.int64)
     K = ctypes.c_int32(0)
     total = ctypes.c_int64(0)
+    if batched:
+        searches = ctypes.c_int32(0)
+        rc = _oracle().oracle_ssp_solve_batched(int(n_nodes), int(m), _p(tail, _i32p), _p(head, _i32p),
+                                                _p(cost, _i64p), _p(flow, _i32p), ctypes.byref(K), _p(pc, _i64p),
+                                                int(path_cap), ctypes.byref(total), ctypes.byref(searches))
+        if rc != 0:
+            raise RuntimeError("oracle_ssp_solve_batched failed: %d" % rc)
+        return dict(flow=flow[:m], K=K.value, path_cost=pc[:K.value].copy(), total=total.value,
+                    searches=searches.value)
     rc = _oracle().oracle_ssp_solve(int(n_nodes), int(m), _p(tail, _i32p), _p(head, _i32p), _p(cost, _i64p),
                                     _p(flow, _i32p), ctypes.byref(K), _p(pc, _i64p), int(path_cap),
                                     ctypes.byref(total))

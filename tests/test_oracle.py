@@ -30,6 +30,62 @@ def test_ssp_restatement_matches_mussp(name):
     assert (r["path_cost"][1:] < 0).all()
 
 
+@pytest.mark.parametrize("name", gu.GRAPH_CASES)
+def test_several_paths_per_search_equal_one_by_one(name):
+    """The CUDA solver takes several paths from one set of labels (csrc/solve_sm.cuh "next path": sinks in ascending
+    order while each lies in a first-level branch of the tree no earlier path of the batch went through). The rule,
+    restated on the generic residual graph (ssp_oracle.c: oracle_ssp_solve_batched), must give exactly the paths of
+    one-by-one successive shortest paths: same K, same path costs in the same order, same flow - with fewer searches."""
+    d = gu.load(name)
+    one = oracle.ssp_solve(int(d["n_nodes"]), d["tail"], d["head"], d["cost"])
+    many = oracle.ssp_solve(int(d["n_nodes"]), d["tail"], d["head"], d["cost"], batched=True)
+    assert many["K"] == one["K"] and many["total"] == one["total"]
+    assert (many["path_cost"] == one["path_cost"]).all()
+    assert (many["flow"] == one["flow"]).all()
+    assert many["searches"] <= one["K"] + 1
+    if name == "c5_window_f50_p100":
+        assert many["searches"] < 15  # 100 paths
+
+
+def test_several_paths_per_search_on_random_windows():
+    """The same on 40 seeded crowded windows (people crossing, misses, clutter; costs in 1e-7 units): total, K and the
+    sequence of path costs are those of one-by-one successive shortest paths, the flow costs the same."""
+    n_batched = n_paths = 0
+    for seed in range(40):
+        rng = np.random.RandomState(seed)
+        F, P = int(rng.randint(6, 25)), int(rng.randint(2, 12))
+        pos = rng.rand(P, 2) * rng.choice([40.0, 120.0, 400.0])
+        vel = rng.randn(P, 2) * 2.0
+        frame, pts = [], []
+        for f in range(F):
+            pos = pos + vel + rng.randn(P, 2) * 0.5
+            for q in range(P):
+                if rng.rand() < 0.85:
+                    frame.append(f)
+                    pts.append(pos[q] + rng.randn(2))
+            for _ in range(rng.poisson(0.5)):
+                frame.append(f)
+                pts.append(rng.rand(2) * 400.0)
+        frame, pts = np.array(frame), np.array(pts).reshape(-1, 2)
+        n = len(frame)
+        spec = oracle.CostSpec(sigma_jump=1, sigma_distance=10, max_distance=30, use_color_histogram=False,
+                               use_bbox=False, mul=1, bias=0, weight_source_sink=float(rng.choice([0.5, 1.0, 2.0])),
+                               max_jump=int(rng.randint(1, 5)))
+        conf = rng.uniform(0.3, 1.0, n)
+        row_ptr, col, w = oracle.build_transitions(frame, pts, spec)
+        tail, head, ww = oracle.graph_arcs(n, float(spec.weight_source_sink), oracle.node_weights(conf, spec), 0.0,
+                                           row_ptr, col, w)
+        cost = oracle.quantise(ww)
+        one = oracle.ssp_solve(2 * n + 2, tail, head, cost)
+        many = oracle.ssp_solve(2 * n + 2, tail, head, cost, batched=True)
+        assert many["K"] == one["K"] and many["total"] == one["total"], seed
+        assert (many["path_cost"] == one["path_cost"]).all(), seed
+        assert oracle.flow_cost(cost, many["flow"]) == many["total"], seed
+        n_batched += many["searches"]
+        n_paths += one["K"]
+    assert n_paths > 150 and n_batched < n_paths  # the batches do happen
+
+
 @pytest.mark.parametrize("name", ["c1_simple_2d", "c4_pets_view1_w0", "c4_pets_view1_w1", "c4_synth_appearance",
                                   "c5_small_f30_p12", "wrapper_test_graph", "c2_tracklets_pass2"])
 def test_exact_optimum_network_simplex(name):
