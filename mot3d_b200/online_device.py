@@ -148,7 +148,8 @@ class DeviceTracker2D(object):
                     # the arc buffer was a guess: size it from what the build counted and run the batch again
                     self._pipe = TrackPipeline(pipe.n_max, 1, 2 * pipe.n_edges() + 1024, device=dev, dim=2)
                     return self.update(time_index, frame, pos, conf, bbox, hist)
-                pipe.check_overflow()
+                self._pipe = None   # (its flag word is sticky: the next batch gets fresh buffers)
+                pipe.check_overflow()   # raises: frames out of the key range
         else:
             M = int(n_trk.item())
         self.n_tracklets_seen += M - A
